@@ -1,0 +1,602 @@
+/*
+ * kv_oracle.c — CPU restatement of KnightVision's custom chess rules (TEST INFRASTRUCTURE ONLY).
+ *
+ * This file is the parity oracle for the B200 hot path.  It is NOT a product code path:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load it.  The product library (libkv_b200.so) never links or calls it.
+ *
+ * It restates, as a plain mailbox engine in C, the algorithm of the reference
+ * `core/chessEngine.py` (all file:line citations are relative to /root/reference):
+ *   - state                       core/chessEngine.py:34-84
+ *   - getValidMoves               core/chessEngine.py:277-321
+ *   - checkForPinsAndChecks       core/chessEngine.py:325-383   (7-entry knight table, :373-374)
+ *   - inCheck / squareUnderAttack core/chessEngine.py:388-415   (re-entrancy guard :401-402)
+ *   - getAllPossibleMoves         core/chessEngine.py:433-441
+ *   - piece generators            core/chessEngine.py:447-601
+ *   - addPieceMovesConsideringPins core/chessEngine.py:604-630
+ *   - makeMove                    core/chessEngine.py:127-197
+ *   - checkForEndConditions       core/chessEngine.py:632-651   (mate/stalemate/draw50 only;
+ *                                  the repetition dictionary lives in the host shim)
+ *   - isDraw (only-kings clause)  core/chessEngine.py:21-33
+ *   - encode_board / encode_move  ai/ai.py:17-57
+ * The quirks of that file are reproduced on purpose.
+ *
+ * Parity pinning: tests/test_oracle_golden.py checks this file against fixtures generated
+ * by running the UNMODIFIED Python reference in the build container
+ * (oracle/gen_golden.py -> tests/golden/).  The MCTS part (kvo_mcts_*) has no reference
+ * counterpart ("parity unpinned" — the reference has no tree search); it is the
+ * executable specification of SPEC.md §MCTS.
+ */
+#include <stdint.h>
+#include <string.h>
+#include <stdlib.h>
+#include <math.h>
+
+#define KVO_API __attribute__((visibility("default")))
+
+/* piece codes: 0 empty, 1+PIECE_TO_INDEX (ai/ai.py:7-10): wK wQ wR wB wN wp bK bQ bR bB bN bp */
+enum { EMPTY = 0, WK = 1, WQ, WR, WB, WN, WP, BK, BQ, BR, BB, BN, BP };
+enum { T_K = 0, T_Q, T_R, T_B, T_N, T_P };
+
+#define IS_WHITE(p) ((p) >= WK && (p) <= WP)
+#define IS_BLACK(p) ((p) >= BK)
+#define PTYPE(p) (((p) - 1) % 6)
+
+/* moved-flag bits (core/chessEngine.py:66-71) */
+enum { F_WK = 1, F_BK = 2, F_WRK = 4, F_WRQ = 8, F_BRK = 16, F_BRQ = 32 };
+/* move flags */
+enum { MF_EP = 1, MF_CASTLE = 2, MF_PROMO = 4 };
+/* result flags of getValidMoves */
+enum { RF_CHECKMATE = 1, RF_STALEMATE = 2, RF_DRAW50 = 4, RF_E3_CHECK = 8, RF_ONLY_KINGS = 16,
+       RF_STATE_MUTATED = 32, RF_OVERFLOW = 64 };
+
+typedef struct {
+    uint8_t board[64];      /* index = row*8+col, row 0 = rank 8 */
+    uint8_t white_to_move;
+    uint8_t wk_sq, bk_sq;   /* whiteKingLocation / blackKingLocation (independent of the board) */
+    uint8_t moved;          /* F_* bits */
+    int8_t ep_sq;           /* enPassantPossible, -1 = () */
+    uint8_t pad[3];
+    uint32_t clock;         /* halfMoveClock */
+} kvo_state;
+
+typedef struct {
+    uint8_t from, to, flags;
+    uint8_t piece_moved, piece_captured;
+} kvo_move;
+
+#define KVO_MAX_MOVES 512
+
+typedef struct {
+    kvo_move m[KVO_MAX_MOVES];
+    int n;
+} movelist;
+
+typedef struct {
+    int r, c, dr, dc;
+} ray4;
+
+/* ------------------------------------------------------------------------------------------ */
+
+KVO_API void kvo_init_start(kvo_state *s) {
+    static const uint8_t back_b[8] = { BR, BN, BB, BQ, BK, BB, BN, BR };
+    static const uint8_t back_w[8] = { WR, WN, WB, WQ, WK, WB, WN, WR };
+    memset(s, 0, sizeof(*s));
+    for (int c = 0; c < 8; c++) {
+        s->board[0 * 8 + c] = back_b[c];
+        s->board[1 * 8 + c] = BP;
+        s->board[6 * 8 + c] = WP;
+        s->board[7 * 8 + c] = back_w[c];
+    }
+    s->white_to_move = 1;
+    s->wk_sq = 7 * 8 + 4;
+    s->bk_sq = 0 * 8 + 4;
+    s->ep_sq = -1;
+}
+
+static inline int is_ally(const kvo_state *s, uint8_t p) {
+    return s->white_to_move ? IS_WHITE(p) : IS_BLACK(p);
+}
+static inline int is_enemy(const kvo_state *s, uint8_t p) {
+    return s->white_to_move ? IS_BLACK(p) : IS_WHITE(p);
+}
+
+static inline void push_move(const kvo_state *s, movelist *ml, int from, int to, int flags) {
+    /* Move.__init__, core/chessEngine.py:693-713 */
+    if (ml->n >= KVO_MAX_MOVES) return;
+    kvo_move *m = &ml->m[ml->n++];
+    m->from = (uint8_t)from;
+    m->to = (uint8_t)to;
+    m->piece_moved = s->board[from];
+    m->piece_captured = s->board[to];
+    m->flags = (uint8_t)flags;
+    if (flags & MF_EP) m->piece_captured = (m->piece_moved == WP) ? BP : WP;
+    if ((m->piece_moved == WP && (to >> 3) == 0) || (m->piece_moved == BP && (to >> 3) == 7))
+        m->flags |= MF_PROMO;
+}
+
+typedef struct {
+    kvo_state *s;
+    int inside_sua; /* insideSquareUnderAttack, core/chessEngine.py:61 */
+} ctx_t;
+
+static int square_under_attack(ctx_t *cx, int r, int c);
+static void gen_all(ctx_t *cx, movelist *ml, const ray4 *pins, int npins);
+
+/* getPawnMoves, core/chessEngine.py:447-472.  has_pin: pinDirection given. */
+static void gen_pawn(ctx_t *cx, int r, int c, movelist *ml, int has_pin, int pr, int pc) {
+    kvo_state *s = cx->s;
+    int ma = s->white_to_move ? -1 : 1;
+    int start_row = s->white_to_move ? 6 : 1;
+    if (!has_pin || (pr == ma && pc == 0)) {
+        int r1 = r + ma;
+        if (r1 >= 0 && r1 < 8 && s->board[r1 * 8 + c] == EMPTY) {
+            push_move(s, ml, r * 8 + c, r1 * 8 + c, 0);
+            if (r == start_row && s->board[(r + 2 * ma) * 8 + c] == EMPTY)
+                push_move(s, ml, r * 8 + c, (r + 2 * ma) * 8 + c, 0);
+        }
+    }
+    for (int k = 0; k < 2; k++) {
+        int dc = k ? 1 : -1;
+        if (c + dc < 0 || c + dc >= 8) continue;
+        if (has_pin && !(pr == ma && pc == dc)) continue;
+        int r1 = r + ma;
+        if (r1 < 0 || r1 >= 8) continue;
+        int t = r1 * 8 + c + dc;
+        if (is_enemy(s, s->board[t]))
+            push_move(s, ml, r * 8 + c, t, 0);
+        else if (t == s->ep_sq)
+            push_move(s, ml, r * 8 + c, t, MF_EP);
+    }
+}
+
+/* getRookMoves :477-494 / getBishopMoves :516-531 share the same walk */
+static void gen_slider(ctx_t *cx, int r, int c, movelist *ml, const int (*dirs)[2]) {
+    kvo_state *s = cx->s;
+    for (int k = 0; k < 4; k++) {
+        for (int i = 1; i < 8; i++) {
+            int er = r + dirs[k][0] * i, ec = c + dirs[k][1] * i;
+            if (er < 0 || er >= 8 || ec < 0 || ec >= 8) break;
+            uint8_t p = s->board[er * 8 + ec];
+            if (p == EMPTY) {
+                push_move(s, ml, r * 8 + c, er * 8 + ec, 0);
+            } else if (is_enemy(s, p)) {
+                push_move(s, ml, r * 8 + c, er * 8 + ec, 0);
+                break;
+            } else {
+                break;
+            }
+        }
+    }
+}
+static const int ROOK_DIRS[4][2] = { { -1, 0 }, { 1, 0 }, { 0, -1 }, { 0, 1 } };
+static const int BISHOP_DIRS[4][2] = { { -1, -1 }, { -1, 1 }, { 1, -1 }, { 1, 1 } };
+
+/* getKnightMoves :500-512 */
+static void gen_knight(ctx_t *cx, int r, int c, movelist *ml) {
+    static const int km[8][2] = { { -2, -1 }, { -1, -2 }, { -2, 1 }, { -1, 2 },
+                                  { 1, -2 },  { 2, -1 },  { 1, 2 },  { 2, 1 } };
+    kvo_state *s = cx->s;
+    for (int k = 0; k < 8; k++) {
+        int er = r + km[k][0], ec = c + km[k][1];
+        if (er < 0 || er >= 8 || ec < 0 || ec >= 8) continue;
+        uint8_t p = s->board[er * 8 + ec];
+        if (p == EMPTY || !is_ally(s, p)) push_move(s, ml, r * 8 + c, er * 8 + ec, 0);
+    }
+}
+
+/* getCastleMoves :575-601 */
+static void gen_castle(ctx_t *cx, int r, int c, movelist *ml) {
+    kvo_state *s = cx->s;
+    if (square_under_attack(cx, r, c)) return;
+    if (s->white_to_move) {
+        if (s->wk_sq != 60 || (s->moved & F_WK)) return;
+        if (!(s->moved & F_WRK) && s->board[61] == EMPTY && s->board[62] == EMPTY)
+            if (!square_under_attack(cx, 7, 5) && !square_under_attack(cx, 7, 6))
+                if (s->board[63] == WR) push_move(s, ml, 60, 62, MF_CASTLE);
+        if (!(s->moved & F_WRQ) && s->board[57] == EMPTY && s->board[58] == EMPTY && s->board[59] == EMPTY)
+            if (!square_under_attack(cx, 7, 2) && !square_under_attack(cx, 7, 3))
+                if (s->board[56] == WR) push_move(s, ml, 60, 58, MF_CASTLE);
+    } else {
+        if (s->bk_sq != 4 || (s->moved & F_BK)) return;
+        if (!(s->moved & F_BRK) && s->board[5] == EMPTY && s->board[6] == EMPTY)
+            if (!square_under_attack(cx, 0, 5) && !square_under_attack(cx, 0, 6))
+                if (s->board[7] == BR) push_move(s, ml, 4, 6, MF_CASTLE);
+        if (!(s->moved & F_BRQ) && s->board[1] == EMPTY && s->board[2] == EMPTY && s->board[3] == EMPTY)
+            if (!square_under_attack(cx, 0, 2) && !square_under_attack(cx, 0, 3))
+                if (s->board[0] == BR) push_move(s, ml, 4, 2, MF_CASTLE);
+    }
+}
+
+/* getKingMoves :543-573.  NOTE the restore at :564 copies the placed king back to (r,c):
+ * when (r,c) did not hold a king (stale king location in the >=2-checks branch, :315) this
+ * permanently writes a king there.  Reproduced. */
+static void gen_king(ctx_t *cx, int r, int c, movelist *ml) {
+    static const int kd[8][2] = { { -1, -1 }, { -1, 0 }, { -1, 1 }, { 0, -1 },
+                                  { 0, 1 },   { 1, -1 }, { 1, 0 },  { 1, 1 } };
+    kvo_state *s = cx->s;
+    for (int k = 0; k < 8; k++) {
+        int er = r + kd[k][0], ec = c + kd[k][1];
+        if (er < 0 || er >= 8 || ec < 0 || ec >= 8) continue;
+        uint8_t p = s->board[er * 8 + ec];
+        if (p == EMPTY || !is_ally(s, p)) {
+            uint8_t orig = p;
+            s->board[r * 8 + c] = EMPTY;
+            s->board[er * 8 + ec] = s->white_to_move ? WK : BK;
+            uint8_t orig_loc = s->white_to_move ? s->wk_sq : s->bk_sq;
+            if (s->white_to_move) s->wk_sq = (uint8_t)(er * 8 + ec);
+            else s->bk_sq = (uint8_t)(er * 8 + ec);
+            int in_check = square_under_attack(cx, er, ec);
+            s->board[r * 8 + c] = s->board[er * 8 + ec];
+            s->board[er * 8 + ec] = orig;
+            if (s->white_to_move) s->wk_sq = orig_loc;
+            else s->bk_sq = orig_loc;
+            if (!in_check) push_move(s, ml, r * 8 + c, er * 8 + ec, 0);
+        }
+    }
+    gen_castle(cx, r, c, ml);
+}
+
+static void gen_piece(ctx_t *cx, int type, int r, int c, movelist *ml) {
+    switch (type) {
+    case T_R: gen_slider(cx, r, c, ml, ROOK_DIRS); break;
+    case T_B: gen_slider(cx, r, c, ml, BISHOP_DIRS); break;
+    case T_Q:
+        gen_slider(cx, r, c, ml, ROOK_DIRS);
+        gen_slider(cx, r, c, ml, BISHOP_DIRS);
+        break;
+    case T_N: gen_knight(cx, r, c, ml); break;
+    case T_K: gen_king(cx, r, c, ml); break;
+    default: break;
+    }
+}
+
+/* addPieceMovesConsideringPins :604-630 */
+static void add_piece_moves(ctx_t *cx, int type, int r, int c, movelist *ml, const ray4 *pins, int npins) {
+    int pinned = 0, pr = 0, pc = 0;
+    for (int i = npins - 1; i >= 0; i--) {
+        if (pins[i].r == r && pins[i].c == c) {
+            pinned = 1;
+            pr = pins[i].dr;
+            pc = pins[i].dc;
+            break;
+        }
+    }
+    if (pinned) {
+        if (type == T_N) return;
+        movelist tmp;
+        tmp.n = 0;
+        if (type == T_P) gen_pawn(cx, r, c, &tmp, 1, pr, pc);
+        else gen_piece(cx, type, r, c, &tmp);
+        for (int i = 0; i < tmp.n; i++) {
+            int mr = (tmp.m[i].to >> 3) - r, mc = (tmp.m[i].to & 7) - c;
+            if (mr * pc == mc * pr && ml->n < KVO_MAX_MOVES) ml->m[ml->n++] = tmp.m[i];
+        }
+    } else {
+        if (type == T_P) gen_pawn(cx, r, c, ml, 0, 0, 0);
+        else gen_piece(cx, type, r, c, ml);
+    }
+}
+
+/* getAllPossibleMoves :433-441 */
+static void gen_all(ctx_t *cx, movelist *ml, const ray4 *pins, int npins) {
+    kvo_state *s = cx->s;
+    ml->n = 0;
+    for (int r = 0; r < 8; r++)
+        for (int c = 0; c < 8; c++) {
+            uint8_t p = s->board[r * 8 + c];
+            if (p != EMPTY && is_ally(s, p)) add_piece_moves(cx, PTYPE(p), r, c, ml, pins, npins);
+        }
+}
+
+/* squareUnderAttack :400-415 */
+static int square_under_attack(ctx_t *cx, int r, int c) {
+    if (cx->inside_sua) return 0;
+    cx->inside_sua = 1;
+    kvo_state *s = cx->s;
+    uint8_t orig = s->white_to_move;
+    s->white_to_move = !orig;
+    movelist opp;
+    gen_all(cx, &opp, NULL, 0);
+    s->white_to_move = orig;
+    cx->inside_sua = 0;
+    int t = r * 8 + c;
+    for (int i = 0; i < opp.n; i++)
+        if (opp.m[i].to == t) return 1;
+    return 0;
+}
+
+/* checkForPinsAndChecks :325-383 */
+static int pins_and_checks(const kvo_state *s, ray4 *pins, int *npins, ray4 *checks, int *nchecks) {
+    static const int dirs[8][2] = { { -1, 0 }, { 0, -1 }, { 1, 0 }, { 0, 1 },
+                                    { -1, -1 }, { -1, 1 }, { 1, -1 }, { 1, 1 } };
+    static const int kn[7][2] = { { -2, -1 }, { -1, -2 }, { -1, 2 }, { 1, -2 }, { 2, -1 }, { 1, 2 }, { 2, 1 } };
+    int in_check = 0;
+    *npins = 0;
+    *nchecks = 0;
+    int ksq = s->white_to_move ? s->wk_sq : s->bk_sq;
+    int kr = ksq >> 3, kc = ksq & 7;
+    int enemy_white = !s->white_to_move;
+    for (int d = 0; d < 8; d++) {
+        int have_pin = 0;
+        ray4 pp = { 0, 0, 0, 0 };
+        for (int i = 1; i < 8; i++) {
+            int er = kr + dirs[d][0] * i, ec = kc + dirs[d][1] * i;
+            if (er < 0 || er >= 8 || ec < 0 || ec >= 8) break;
+            uint8_t p = s->board[er * 8 + ec];
+            if (p == EMPTY) continue;
+            if (is_ally(s, p)) {
+                if (!have_pin) {
+                    have_pin = 1;
+                    pp.r = er; pp.c = ec; pp.dr = dirs[d][0]; pp.dc = dirs[d][1];
+                } else {
+                    break;
+                }
+            } else {
+                int t = PTYPE(p);
+                int orth = d < 4;
+                int pawn_dir_ok = enemy_white ? (dirs[d][0] == 1 && dirs[d][1] != 0)
+                                              : (dirs[d][0] == -1 && dirs[d][1] != 0);
+                if ((orth && (t == T_R || t == T_Q)) || (!orth && (t == T_B || t == T_Q)) ||
+                    (i == 1 && t == T_P && pawn_dir_ok)) {
+                    if (!have_pin) {
+                        in_check = 1;
+                        checks[*nchecks].r = er; checks[*nchecks].c = ec;
+                        checks[*nchecks].dr = dirs[d][0]; checks[*nchecks].dc = dirs[d][1];
+                        (*nchecks)++;
+                    } else {
+                        pins[(*npins)++] = pp;
+                    }
+                }
+                break;
+            }
+        }
+    }
+    for (int k = 0; k < 7; k++) {
+        int er = kr + kn[k][0], ec = kc + kn[k][1];
+        if (er < 0 || er >= 8 || ec < 0 || ec >= 8) continue;
+        uint8_t p = s->board[er * 8 + ec];
+        if (p != EMPTY && is_enemy(s, p) && PTYPE(p) == T_N) {
+            in_check = 1;
+            checks[*nchecks].r = er; checks[*nchecks].c = ec;
+            checks[*nchecks].dr = kn[k][0]; checks[*nchecks].dc = kn[k][1];
+            (*nchecks)++;
+        }
+    }
+    return in_check;
+}
+
+static int only_kings(const kvo_state *s) {
+    for (int i = 0; i < 64; i++)
+        if (s->board[i] != EMPTY && s->board[i] != WK && s->board[i] != BK) return 0;
+    return 1;
+}
+
+/* getValidMoves :277-321.  Returns the number of moves; *rflags gets RF_* bits. */
+static int valid_moves(kvo_state *s, movelist *out, int *rflags) {
+    ctx_t cx = { s, 0 };
+    ray4 pins[8], checks[16];
+    int npins, nchecks;
+    kvo_state before = *s;
+    int in_check = pins_and_checks(s, pins, &npins, checks, &nchecks);
+    int ksq = s->white_to_move ? s->wk_sq : s->bk_sq;
+    int kr = ksq >> 3, kc = ksq & 7;
+    out->n = 0;
+    if (in_check) {
+        if (nchecks == 1) {
+            movelist all;
+            gen_all(&cx, &all, pins, npins);
+            uint64_t valid = 0;
+            ray4 ck = checks[0];
+            uint8_t checker = s->board[ck.r * 8 + ck.c];
+            if (PTYPE(checker) == T_N) {
+                valid = 1ull << (ck.r * 8 + ck.c);
+            } else {
+                for (int i = 1; i < 8; i++) {
+                    int r = kr + ck.dr * i, c = kc + ck.dc * i;
+                    /* the reference appends tuples without bounds checks; the walk always
+                       terminates at the checker square, which is on the board */
+                    if (r >= 0 && r < 8 && c >= 0 && c < 8) valid |= 1ull << (r * 8 + c);
+                    if (r == ck.r && c == ck.c) break;
+                }
+            }
+            for (int i = 0; i < all.n; i++) {
+                kvo_move *m = &all.m[i];
+                if (m->piece_moved != EMPTY && PTYPE(m->piece_moved) == T_K) {
+                    if (!square_under_attack(&cx, m->to >> 3, m->to & 7)) out->m[out->n++] = *m;
+                } else if ((valid >> m->to) & 1) {
+                    out->m[out->n++] = *m;
+                }
+            }
+        } else {
+            gen_king(&cx, kr, kc, out);
+        }
+    } else {
+        gen_all(&cx, out, pins, npins);
+    }
+    int f = 0;
+    if (in_check) f |= RF_E3_CHECK;
+    /* checkForEndConditions :632-651 (repetition handled by the host shim) */
+    if (out->n == 0) {
+        if (square_under_attack(&cx, ksq >> 3, ksq & 7)) f |= RF_CHECKMATE;
+        else f |= RF_STALEMATE;
+    } else if (s->clock >= 100) {
+        f |= RF_DRAW50;
+    }
+    if (only_kings(s)) f |= RF_ONLY_KINGS;
+    if (memcmp(before.board, s->board, 64) != 0) f |= RF_STATE_MUTATED;
+    *rflags = f;
+    return out->n;
+}
+
+/* makeMove :127-197 (no legality check).  promo_type: T_Q by default (Move.promotionChoice). */
+static void make_move(kvo_state *s, int from, int to, int flags, int promo_type) {
+    uint8_t pm = s->board[from];
+    uint8_t pcap = s->board[to];
+    if (flags & MF_EP) pcap = (pm == WP) ? BP : WP;
+    int sr = from >> 3, sc = from & 7, er = to >> 3, ec = to & 7;
+    s->board[from] = EMPTY;
+    s->board[to] = pm;
+    if (pm == WK) s->moved |= F_WK;
+    else if (pm == BK) s->moved |= F_BK;
+    else if (pm == WR) {
+        if (from == 56) s->moved |= F_WRQ;
+        else if (from == 63) s->moved |= F_WRK;
+    } else if (pm == BR) {
+        if (from == 0) s->moved |= F_BRQ;
+        else if (from == 7) s->moved |= F_BRK;
+    }
+    if (flags & MF_EP) s->board[sr * 8 + ec] = EMPTY;
+    if (flags & MF_CASTLE) {
+        if (ec - sc == 2) {
+            if (ec + 1 < 8) { /* the reference would raise IndexError otherwise */
+                s->board[er * 8 + ec - 1] = s->board[er * 8 + ec + 1];
+                s->board[er * 8 + ec + 1] = EMPTY;
+            }
+        } else {
+            if (ec - 2 >= 0 && ec + 1 < 8) {
+                s->board[er * 8 + ec + 1] = s->board[er * 8 + ec - 2];
+                s->board[er * 8 + ec - 2] = EMPTY;
+            }
+        }
+    }
+    if (pm != EMPTY && PTYPE(pm) == T_P && abs(sr - er) == 2) s->ep_sq = (int8_t)(((sr + er) / 2) * 8 + sc);
+    else s->ep_sq = -1;
+    if (pcap != EMPTY) s->clock = 0; /* 'P' typo at :178 — pawn moves never reset */
+    else s->clock += 1;
+    s->white_to_move = !s->white_to_move;
+    if (pm == WK) s->wk_sq = (uint8_t)to;
+    else if (pm == BK) s->bk_sq = (uint8_t)to;
+    if (flags & MF_PROMO) s->board[to] = (uint8_t)((IS_WHITE(pm) ? 1 : 7) + promo_type);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Packed 128-byte board line (the device layout, include/kv_b200.h):
+ *   w[0..11]  bitboards in PIECE_TO_INDEX order, bit = row*8+col
+ *   w[12]     meta: bit0 whiteToMove | bits1-6 moved flags | bits8-14 ep (64=none)
+ *             | bits16-21 wk_sq | bits24-29 bk_sq | bits32-47 clock
+ *   w[13..15] reserved (0)
+ * ------------------------------------------------------------------------------------------ */
+KVO_API void kvo_pack(const kvo_state *s, uint64_t *w) {
+    memset(w, 0, 16 * sizeof(uint64_t));
+    for (int i = 0; i < 64; i++)
+        if (s->board[i]) w[s->board[i] - 1] |= 1ull << i;
+    uint64_t ep = s->ep_sq < 0 ? 64 : (uint64_t)s->ep_sq;
+    uint32_t clk = s->clock > 0xFFFF ? 0xFFFF : s->clock;
+    w[12] = (uint64_t)(s->white_to_move & 1) | ((uint64_t)(s->moved & 63) << 1) | (ep << 8) |
+            ((uint64_t)s->wk_sq << 16) | ((uint64_t)s->bk_sq << 24) | ((uint64_t)clk << 32);
+}
+
+KVO_API void kvo_unpack(const uint64_t *w, kvo_state *s) {
+    memset(s, 0, sizeof(*s));
+    for (int p = 0; p < 12; p++)
+        for (int i = 0; i < 64; i++)
+            if ((w[p] >> i) & 1) s->board[i] = (uint8_t)(p + 1);
+    uint64_t m = w[12];
+    s->white_to_move = m & 1;
+    s->moved = (m >> 1) & 63;
+    int ep = (m >> 8) & 127;
+    s->ep_sq = ep >= 64 ? -1 : (int8_t)ep;
+    s->wk_sq = (m >> 16) & 63;
+    s->bk_sq = (m >> 24) & 63;
+    s->clock = (m >> 32) & 0xFFFF;
+}
+
+static inline uint16_t pack_move(const kvo_move *m) {
+    return (uint16_t)(m->from | (m->to << 6) | ((m->flags & 7) << 12));
+}
+
+/* Batched API over packed lines (same shapes as the device C-ABI). */
+KVO_API void kvo_movegen(uint64_t *lines, int n, uint16_t *moves, int stride, int32_t *counts, int32_t *flags) {
+    for (int i = 0; i < n; i++) {
+        kvo_state s;
+        movelist ml;
+        int f;
+        kvo_unpack(lines + 16 * (size_t)i, &s);
+        int cnt = valid_moves(&s, &ml, &f);
+        if (cnt > stride) { f |= RF_OVERFLOW; }
+        for (int k = 0; k < cnt && k < stride; k++) moves[(size_t)i * stride + k] = pack_move(&ml.m[k]);
+        counts[i] = cnt;
+        flags[i] = f;
+        if (f & RF_STATE_MUTATED) kvo_pack(&s, lines + 16 * (size_t)i);
+    }
+}
+
+KVO_API void kvo_make_moves(uint64_t *lines, int n, const uint16_t *mv) {
+    for (int i = 0; i < n; i++) {
+        kvo_state s;
+        kvo_unpack(lines + 16 * (size_t)i, &s);
+        make_move(&s, mv[i] & 63, (mv[i] >> 6) & 63, (mv[i] >> 12) & 7, T_Q);
+        kvo_pack(&s, lines + 16 * (size_t)i);
+    }
+}
+
+KVO_API int kvo_square_under_attack(const uint64_t *line, int r, int c) {
+    kvo_state s;
+    kvo_unpack(line, &s);
+    ctx_t cx = { &s, 0 };
+    return square_under_attack(&cx, r, c);
+}
+
+KVO_API int kvo_in_check(const uint64_t *line) {
+    kvo_state s;
+    kvo_unpack(line, &s);
+    ctx_t cx = { &s, 0 };
+    int k = s.white_to_move ? s.wk_sq : s.bk_sq;
+    return square_under_attack(&cx, k >> 3, k & 7);
+}
+
+/* perft: copy-make DFS over getValidMoves/makeMove with bulk counting at depth 1.
+ * out[0] nodes, out[1] captures, out[2] ep, out[3] castles, out[4] promos (of leaf moves),
+ * out[5] order digest: FNV-1a-64 over (from,to,flags) bytes of every move list visited, in DFS order. */
+#define FNV_OFFSET 0xcbf29ce484222325ull
+#define FNV_PRIME 0x100000001b3ull
+
+static void perft_rec(const kvo_state *s, int depth, uint64_t *out) {
+    kvo_state cur = *s;
+    movelist ml;
+    int f;
+    int n = valid_moves(&cur, &ml, &f);
+    uint64_t h = out[5];
+    for (int i = 0; i < n; i++) {
+        h = (h ^ ml.m[i].from) * FNV_PRIME;
+        h = (h ^ ml.m[i].to) * FNV_PRIME;
+        h = (h ^ (ml.m[i].flags & 7)) * FNV_PRIME;
+    }
+    out[5] = h;
+    if (depth == 1) {
+        out[0] += (uint64_t)n;
+        for (int i = 0; i < n; i++) {
+            if (ml.m[i].piece_captured != EMPTY) out[1]++;
+            if (ml.m[i].flags & MF_EP) out[2]++;
+            if (ml.m[i].flags & MF_CASTLE) out[3]++;
+            if (ml.m[i].flags & MF_PROMO) out[4]++;
+        }
+        return;
+    }
+    for (int i = 0; i < n; i++) {
+        kvo_state child = cur;
+        make_move(&child, ml.m[i].from, ml.m[i].to, ml.m[i].flags, T_Q);
+        perft_rec(&child, depth - 1, out);
+    }
+}
+
+KVO_API void kvo_perft(const uint64_t *line, int depth, uint64_t *out6) {
+    kvo_state s;
+    kvo_unpack(line, &s);
+    memset(out6, 0, 6 * sizeof(uint64_t));
+    out6[5] = FNV_OFFSET;
+    if (depth <= 0) { out6[0] = 1; return; }
+    perft_rec(&s, depth, out6);
+}
+
+/* encode_board, ai/ai.py:17-41 (list branch): float32 [12,8,8] one-hot */
+KVO_API void kvo_encode(const uint64_t *lines, int n, float *planes) {
+    for (int i = 0; i < n; i++)
+        for (int p = 0; p < 12; p++)
+            for (int sq = 0; sq < 64; sq++)
+                planes[((size_t)i * 12 + p) * 64 + sq] = (float)((lines[16 * (size_t)i + p] >> sq) & 1);
+}
+
+/* encode_move ai/ai.py:51-57 */
+KVO_API int kvo_move_index(uint16_t mv) { return (mv & 63) * 64 + ((mv >> 6) & 63); }
