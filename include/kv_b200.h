@@ -1,0 +1,105 @@
+/*
+ * kv_b200.h — C ABI of libkv_b200.so, the B200 (sm_100a) self-play hot path for KnightVision.
+ *
+ * The reference (TheRealShamsaba/KnightVision) is pure Python and has no FFI; its callers bind to four
+ * Python objects.  This header is the boundary a maintainer would bind with ctypes/cffi
+ * (see INTEGRATION.md); each entry point names the reference interface it replaces (paths relative to the
+ * reference root).  Plain pointers and sizes only; all `d_*` pointers are device pointers on the ctx's
+ * GPU (e.g. torch tensor .data_ptr()), all `h_*` pointers are host pointers; `stream` is a cudaStream_t
+ * (NULL = default stream).  Every function returns 0 on success, <0 on error (kv_last_error()).
+ * There is no CPU fallback: without a CUDA device kv_create fails.
+ *
+ * Board line (128 B = 16 little-endian u64, one cache line, lane i of the owning warp loads word i):
+ *   w[0..11]  bitboards in ai/ai.py:7-10 order  wK wQ wR wB wN wp bK bQ bR bB bN bp;
+ *             bit = row*8+col, row 0 = rank 8 (board[row][col], core/chessEngine.py:39-47)
+ *   w[12]     bit0 whiteToMove | bits1-6 moved flags wK,bK,wRk,wRq,bRk,bRq (:66-71) | bits8-14
+ *             enPassantPossible (64 = none, :72) | bits16-21 whiteKingLocation | bits24-29
+ *             blackKingLocation (:59-60) | bits32-47 halfMoveClock (:79)
+ *   w[13..15] owned by the engine (perft root id / path hash, MCTS bookkeeping); 0 on input
+ * Move word (u16): from | to<<6 | isEnPassantMove<<12 | isCastleMove<<13 | isPawnPromotion<<14
+ * (Move, core/chessEngine.py:683-733).  Policy index = from*64+to (ai/ai.py:51-57).
+ */
+#ifndef KV_B200_H
+#define KV_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kv_ctx kv_ctx;
+
+#if defined(__GNUC__)
+#define KV_API __attribute__((visibility("default")))
+#else
+#define KV_API
+#endif
+
+#define KV_LINE_WORDS 16
+#define KV_MAX_MOVES 256
+/* result flags of kv_movegen: checkMate, staleMate, draw50 (core/chessEngine.py:632-651), E3 = the
+ * inCheck returned by checkForPinsAndChecks (:325-383), only-kings = isDraw() (:21-33), state-mutated =
+ * getKingMoves' restore quirk rewrote the board (:564), overflow = more than KV_MAX_MOVES moves */
+#define KV_RF_CHECKMATE 1
+#define KV_RF_STALEMATE 2
+#define KV_RF_DRAW50 4
+#define KV_RF_E3_CHECK 8
+#define KV_RF_ONLY_KINGS 16
+#define KV_RF_STATE_MUTATED 32
+#define KV_RF_OVERFLOW 64
+
+/* ---- context ------------------------------------------------------------------------------------ */
+KV_API int kv_create(int device, kv_ctx** out);
+KV_API void kv_destroy(kv_ctx* ctx);
+KV_API const char* kv_last_error(kv_ctx* ctx);       /* ctx may be NULL: error of the last failed kv_create */
+KV_API int kv_abi_version(void);
+KV_API int kv_sm_count(kv_ctx* ctx);
+/* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
+KV_API uint64_t kv_launch_count(kv_ctx* ctx);
+
+/* per-kernel device timing with CUDA events on the launching stream (bench.py's roofline numbers).
+ * kv_profile_read synchronises and returns, per kernel category (KV_K_*), the summed duration in ms and
+ * the launch count since the previous read; returns the number of categories. */
+#define KV_K_MOVEGEN 0
+#define KV_K_MAKE_MOVES 1
+#define KV_K_PERFT_EXPAND 2
+#define KV_K_PERFT_LEAF 3
+#define KV_K_ENCODE 4
+#define KV_K_NET_STEM 5
+#define KV_K_NET_CONV 6
+#define KV_K_NET_HEAD 7
+#define KV_K_MCTS_SELECT 8
+#define KV_K_MCTS_EXPAND 9
+#define KV_K_MCTS_MISC 10
+#define KV_K_COUNT 11
+KV_API int kv_profile_enable(kv_ctx* ctx, int on);
+KV_API int kv_profile_read(kv_ctx* ctx, double* ms, uint64_t* n, int cap);
+
+/* ---- rules (replaces GameState.getValidMoves / makeMove, core/chessEngine.py:277-321, :127-197) --- */
+/* d_lines [n][16] (rewritten only where KV_RF_STATE_MUTATED), d_moves [n][stride] u16 (stride even,
+ * entries >= count unspecified), d_counts [n], d_flags [n] */
+KV_API int kv_movegen(kv_ctx* ctx, uint64_t* d_lines, int n, uint16_t* d_moves, int stride, int32_t* d_counts,
+               int32_t* d_flags, void* stream);
+/* in place; d_moves [n] one move word per board, 0xFFFF = leave the board untouched */
+KV_API int kv_make_moves(kv_ctx* ctx, uint64_t* d_lines, int n, const uint16_t* d_moves, void* stream);
+/* host-buffer forms (copies inside): what a ctypes binding of GameState would call */
+KV_API int kv_movegen_host(kv_ctx* ctx, uint64_t* h_lines, int n, uint16_t* h_moves, int stride, int32_t* h_counts,
+                    int32_t* h_flags);
+KV_API int kv_make_moves_host(kv_ctx* ctx, uint64_t* h_lines, int n, const uint16_t* h_moves);
+
+/* perft over getValidMoves/makeMove with bulk counting at depth 1 (no reference counterpart: the golden
+ * counts of SURVEY.md §8c were produced by exactly this driver over the unmodified engine).
+ * d_roots [n][16]; out [n][8] u64: nodes, captures, e.p., castles, promotions (of the leaf moves),
+ * order digest (order-sensitive hash of every move list visited), movegen calls, 0.
+ * chunk = boards per launch (0 = 65536). */
+KV_API int kv_perft(kv_ctx* ctx, const uint64_t* d_roots, int n, int depth, uint64_t* d_out, int chunk, void* stream);
+KV_API int kv_perft_host(kv_ctx* ctx, const uint64_t* h_roots, int n, int depth, uint64_t* h_out, int chunk);
+
+/* ---- encoders (replaces encode_board, ai/ai.py:17-41) ---------------------------------------------- */
+/* d_planes [n][12][8][8] float32 one-hot, the reference's record/input format */
+KV_API int kv_encode(kv_ctx* ctx, const uint64_t* d_lines, int n, float* d_planes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KV_B200_H */

@@ -1,0 +1,59 @@
+"""ctypes binding of libkv_b200.so (include/kv_b200.h).  Fails loudly when the CUDA library is missing:
+there is no CPU fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libkv_b200.so")
+
+_lib = None
+
+c_void_p, c_int, c_u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
+
+# name -> (restype, argtypes); every symbol include/kv_b200.h declares
+SIGNATURES = {
+    "kv_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
+    "kv_destroy": (None, [c_void_p]),
+    "kv_last_error": (ctypes.c_char_p, [c_void_p]),
+    "kv_abi_version": (c_int, []),
+    "kv_sm_count": (c_int, [c_void_p]),
+    "kv_launch_count": (c_u64, [c_void_p]),
+    "kv_profile_enable": (c_int, [c_void_p, c_int]),
+    "kv_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
+    "kv_movegen": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "kv_make_moves": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "kv_movegen_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "kv_make_moves_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "kv_perft": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "kv_perft_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int]),
+    "kv_encode": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+}
+
+
+def lib():
+    """Load the library (no CUDA call is made by loading it)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m knightvision_b200.build` "
+                "(knightvision_b200 has no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class KVError(RuntimeError):
+    pass
+
+
+def check(ctx, rc: int, what: str):
+    if rc != 0:
+        msg = lib().kv_last_error(ctx)
+        raise KVError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")

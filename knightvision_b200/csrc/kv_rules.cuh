@@ -1,0 +1,612 @@
+// kv_rules.cuh — KnightVision's custom chess rules as warp-per-board bitboard device code.
+//
+// One warp owns one board.  The 128-byte board line (16 x u64, see include/kv_b200.h) is loaded with
+// one coalesced request (lane i loads word i) and broadcast by shuffles; every lane then holds the
+// whole position in registers.  Work is spread over lanes by *work item*:
+//   - checkForPinsAndChecks  (core/chessEngine.py:325-383): lanes 0-7 walk one king ray each
+//   - getKingMoves/getCastleMoves (:543-601): lanes 0-7 test one king step each on the "king placed"
+//     board, lanes 8-12 test the castle squares, all through attacked()
+//   - getAllPossibleMoves (:433-441): lane l owns squares 2l and 2l+1 (row-major scan order falls out
+//     of a warp prefix sum), emitting moves in the reference's per-piece direction order
+// squareUnderAttack (:400-415) — "some opponent pseudo-move ENDS on the square", with all its quirks
+// (pawn pushes attack, pawn diagonals onto empty squares do not, opponent castling attacks c/g,
+// nested calls see the re-entrancy guard) — is restated in closed form in attacked().
+// The quirk list this file reproduces on purpose is SURVEY.md §8a-Q.
+//
+// The same source compiles under KV_HOST_EMU (tests/simt_emu) where the warp collectives are routed
+// to a 32-fiber lock-step emulator, so the integer kernels are parity-checked on a box without a GPU.
+#pragma once
+#include "kv_tables.cuh"
+#include "kv_warp.cuh"
+
+namespace kv {
+
+constexpr int F_WK = 1, F_BK = 2, F_WRK = 4, F_WRQ = 8, F_BRK = 16, F_BRQ = 32;   // core/chessEngine.py:66-71
+constexpr int MF_EP = 1, MF_CASTLE = 2, MF_PROMO = 4;
+constexpr int RF_CHECKMATE = 1, RF_STALEMATE = 2, RF_DRAW50 = 4, RF_E3_CHECK = 8, RF_ONLY_KINGS = 16,
+              RF_STATE_MUTATED = 32, RF_OVERFLOW = 64;
+constexpr int T_K = 0, T_Q = 1, T_R = 2, T_B = 3, T_N = 4, T_P = 5;               // ai/ai.py:7-10 order
+constexpr int MAX_MOVES = 256;
+constexpr int LINE_WORDS = 16;
+constexpr int EP_NONE = 64;
+
+constexpr uint64_t FILE_A = 0x0101010101010101ull;
+constexpr uint64_t FILE_H = FILE_A << 7;
+
+KV_DEV uint64_t bit(int s) { return 1ull << s; }
+KV_DEV bool dir_asc(int d) { return (0xCA >> d) & 1; }   // S, E, SW, SE walk towards higher square indices
+KV_DEV int dir_opp(int d) { return d < 4 ? (d ^ 1) : 11 - d; }
+KV_DEV int first_on_ray(uint64_t b, int d) { return dir_asc(d) ? ctz64(b) : msb64(b); }
+
+// Squares a slider on s reaches in direction d (up to and including the first blocker).
+KV_DEV uint64_t ray_att(const Tables& T, int d, int s, uint64_t occ) {
+    uint64_t r = T.ray[d][s];
+    uint64_t b = r & occ;
+    if (b) r ^= T.ray[d][first_on_ray(b, d)];
+    return r;
+}
+KV_DEV uint64_t rook_att(const Tables& T, int s, uint64_t occ) {
+    return ray_att(T, 0, s, occ) | ray_att(T, 1, s, occ) | ray_att(T, 2, s, occ) | ray_att(T, 3, s, occ);
+}
+KV_DEV uint64_t bishop_att(const Tables& T, int s, uint64_t occ) {
+    return ray_att(T, 4, s, occ) | ray_att(T, 5, s, occ) | ray_att(T, 6, s, occ) | ray_att(T, 7, s, occ);
+}
+
+// What attacked() needs to know about a (possibly hypothetical) board: "own" = side to move.
+struct Agg {
+    uint64_t occ, own, opp;
+    uint64_t eN, eK, eRQ, eBQ, eP, eR;
+};
+
+// squareUnderAttack(r,c), core/chessEngine.py:400-415, for attacker = opponent of the side to move:
+// true iff getAllPossibleMoves() of the opponent (pins=[], nested guard on) contains a move ending on t.
+//   wtm    side to move is white (so the attacker is black and its pawns move towards higher rows)
+//   ep     enPassantPossible square or EP_NONE;  moved: moved-flag bits;  akloc: attacker's king *location variable*
+KV_DEV bool attacked(const Tables& T, const Agg& g, int t, bool wtm, int ep, int moved, int akloc) {
+    const uint64_t tb = bit(t);
+    bool res = false;
+    if (!(g.opp & tb)) {   // knight / king / slider moves end on empty or enemy squares only
+        uint64_t a = (T.knight[t] & g.eN) | (T.king[t] & g.eK);
+        a |= rook_att(T, t, g.occ) & g.eRQ;
+        a |= bishop_att(T, t, g.occ) & g.eBQ;
+        res = a != 0;
+    }
+    uint64_t capsrc, p1src, p2src, mid;
+    bool row2;
+    if (wtm) {   // black pawns: moveAmount +1, startRow 1 (core/chessEngine.py:452-455)
+        capsrc = ((tb >> 7) & ~FILE_A) | ((tb >> 9) & ~FILE_H);
+        p1src = tb >> 8;
+        p2src = tb >> 16;
+        mid = tb >> 8;
+        row2 = (t >> 3) == 3;
+    } else {     // white pawns: moveAmount -1, startRow 6
+        capsrc = ((tb << 7) & ~FILE_H) | ((tb << 9) & ~FILE_A);
+        p1src = tb << 8;
+        p2src = tb << 16;
+        mid = tb << 8;
+        row2 = (t >> 3) == 4;
+    }
+    // pawn capture: target holds a piece of the side to move, or is the e.p. square (:466-472)
+    if ((capsrc & g.eP) && ((g.own & tb) || t == ep)) res = true;
+    // pawn pushes count as "attacks" on empty squares (:459-462)
+    if (!(g.occ & tb)) {
+        if (p1src & g.eP) res = true;
+        if (row2 && (p2src & g.eP) && !(g.occ & mid)) res = true;
+    }
+    // the opponent's available castling "attacks" its king-destination square (:575-601);
+    // getKingMoves is only reached when the board scan finds an opponent king
+    if (g.eK) {
+        if (wtm) {
+            if (akloc == 4 && !(moved & F_BK)) {
+                if (t == 6 && !(moved & F_BRK) && !(g.occ & (bit(5) | bit(6))) && (g.eR & bit(7))) res = true;
+                if (t == 2 && !(moved & F_BRQ) && !(g.occ & (bit(1) | bit(2) | bit(3))) && (g.eR & bit(0))) res = true;
+            }
+        } else {
+            if (akloc == 60 && !(moved & F_WK)) {
+                if (t == 62 && !(moved & F_WRK) && !(g.occ & (bit(61) | bit(62))) && (g.eR & bit(63))) res = true;
+                if (t == 58 && !(moved & F_WRQ) && !(g.occ & (bit(57) | bit(58) | bit(59))) && (g.eR & bit(56))) res = true;
+            }
+        }
+    }
+    return res;
+}
+
+// A position as every lane of the owning warp sees it.
+struct Pos {
+    uint64_t o[6];   // side to move: K Q R B N P
+    uint64_t e[6];   // opponent
+    uint64_t meta;
+    bool wtm;
+    int ep, moved, kloc, akloc, clock;
+};
+
+KV_DEV void make_agg(const Pos& p, Agg& g) {
+    g.own = p.o[0] | p.o[1] | p.o[2] | p.o[3] | p.o[4] | p.o[5];
+    g.opp = p.e[0] | p.e[1] | p.e[2] | p.e[3] | p.e[4] | p.e[5];
+    g.occ = g.own | g.opp;
+    g.eN = p.e[T_N];
+    g.eK = p.e[T_K];
+    g.eRQ = p.e[T_R] | p.e[T_Q];
+    g.eBQ = p.e[T_B] | p.e[T_Q];
+    g.eP = p.e[T_P];
+    g.eR = p.e[T_R];
+}
+
+// Broadcast the line (lane i < 16 passes word i in w) to every lane.
+KV_DEV void load_pos(uint64_t w, Pos& p) {
+    uint64_t bb[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) bb[i] = shfl64(w, i);
+    p.meta = shfl64(w, 12);
+    p.wtm = p.meta & 1;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        p.o[i] = p.wtm ? bb[i] : bb[6 + i];
+        p.e[i] = p.wtm ? bb[6 + i] : bb[i];
+    }
+    p.moved = (int)((p.meta >> 1) & 63);
+    p.ep = (int)((p.meta >> 8) & 127);
+    if (p.ep > EP_NONE) p.ep = EP_NONE;
+    int wk = (int)((p.meta >> 16) & 63), bk = (int)((p.meta >> 24) & 63);
+    p.kloc = p.wtm ? wk : bk;
+    p.akloc = p.wtm ? bk : wk;
+    p.clock = (int)((p.meta >> 32) & 0xFFFF);
+}
+
+struct KingOut {
+    uint32_t steps;    // bit k: king step k (getKingMoves order) is legal
+    uint32_t castle;   // bit0 king side, bit1 queen side
+};
+
+// getKingMoves + getCastleMoves for the king-like piece on ks (core/chessEngine.py:543-601), plus the
+// extra in-check filter of getValidMoves (:306-309) when mode == 1.  Warp-collective; result is uniform.
+KV_DEV KingOut king_phase(const Tables& T, int lane, const Pos& p, const Agg& g, int ks, int mode,
+                          uint64_t valid, uint64_t pinned) {
+    const int home = p.wtm ? 60 : 4;
+    bool ok = false, att = false;
+    if (lane < 8) {
+        const int dr = (lane < 3) ? -1 : (lane < 5 ? 0 : 1);
+        const int dc = (lane == 0 || lane == 3 || lane == 5) ? -1 : ((lane == 1 || lane == 6) ? 0 : 1);
+        const int er = (ks >> 3) + dr, ec = (ks & 7) + dc;
+        if (er >= 0 && er < 8 && ec >= 0 && ec < 8) {
+            const int t = er * 8 + ec;
+            const uint64_t tb = bit(t), ksb = bit(ks);
+            if (!(g.own & tb)) {
+                Agg h;   // the king placed on t, whatever stood there removed (:556-563)
+                h.occ = (g.occ & ~ksb) | tb;
+                h.own = (g.own & ~ksb) | tb;
+                h.opp = g.opp & ~tb;
+                h.eN = g.eN & ~tb;
+                h.eK = g.eK & ~tb;
+                h.eRQ = g.eRQ & ~tb;
+                h.eBQ = g.eBQ & ~tb;
+                h.eP = g.eP & ~tb;
+                h.eR = g.eR & ~tb;
+                ok = !attacked(T, h, t, p.wtm, p.ep, p.moved, p.akloc);
+                if (ok && mode == 1) ok = !attacked(T, g, t, p.wtm, p.ep, p.moved, p.akloc);
+            }
+        }
+    } else if (lane < 13) {
+        // lane 8: the king's own square; 9,10: f,g; 11,12: c,d  — on the unmodified board (:576-599)
+        const int sq = lane == 8 ? ks : (lane == 9 ? home + 1 : (lane == 10 ? home + 2 : (lane == 11 ? home - 2 : home - 1)));
+        att = attacked(T, g, sq, p.wtm, p.ep, p.moved, p.akloc);
+    }
+    const uint32_t okb = ballot(ok) & 0xFFu;
+    const uint32_t ab = ballot(att) >> 8;
+    KingOut out;
+    out.steps = okb;
+    out.castle = 0;
+    const int f_k = p.wtm ? F_WK : F_BK, f_rk = p.wtm ? F_WRK : F_BRK, f_rq = p.wtm ? F_WRQ : F_BRQ;
+    if (!(ab & 1) && p.kloc == home && !(p.moved & f_k)) {
+        bool ck = !(p.moved & f_rk) && !(g.occ & (bit(home + 1) | bit(home + 2))) && !(ab & 2) && !(ab & 4) &&
+                  (p.o[T_R] & bit(home + 3));
+        bool cq = !(p.moved & f_rq) && !(g.occ & (bit(home - 1) | bit(home - 2) | bit(home - 3))) && !(ab & 8) &&
+                  !(ab & 16) && (p.o[T_R] & bit(home - 4));
+        if (mode == 1) {
+            // getValidMoves :306-310: Move.pieceMoved is board[home]; a king (either colour) is re-tested
+            // with squareUnderAttack(to) — already false here — anything else must land on validSquares
+            const bool home_is_k = ((p.o[T_K] | p.e[T_K]) & bit(home)) != 0;
+            if (!home_is_k) {
+                ck = ck && (valid & bit(home + 2));
+                cq = cq && (valid & bit(home - 2));
+            }
+        }
+        out.castle = (ck ? 1u : 0u) | (cq ? 2u : 0u);
+    }
+    if (pinned & bit(ks)) {
+        // a king piece standing on a ray from a stale king location can be "pinned" (:604-630): colinearity filter
+        int pd = 0;
+        for (int d = 0; d < 8; d++)
+            if (T.ray[d][p.kloc] & bit(ks)) pd = d;
+        const uint64_t line = T.ray[pd][ks] | T.ray[dir_opp(pd)][ks];
+        uint32_t keep = 0;
+        for (int k = 0; k < 8; k++) {
+            const int dr = (k < 3) ? -1 : (k < 5 ? 0 : 1);
+            const int dc = (k == 0 || k == 3 || k == 5) ? -1 : ((k == 1 || k == 6) ? 0 : 1);
+            const int er = (ks >> 3) + dr, ec = (ks & 7) + dc;
+            if (er >= 0 && er < 8 && ec >= 0 && ec < 8 && (line & bit(er * 8 + ec))) keep |= 1u << k;
+        }
+        out.steps &= keep;
+        if (!(line & bit(home + 2))) out.castle &= ~1u;
+        if (!(line & bit(home - 2))) out.castle &= ~2u;
+    }
+    return out;
+}
+
+KV_DEV uint64_t king_steps_to_mask(int ks, uint32_t steps) {
+    uint64_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int dr = (k < 3) ? -1 : (k < 5 ? 0 : 1);
+        const int dc = (k == 0 || k == 3 || k == 5) ? -1 : ((k == 1 || k == 6) ? 0 : 1);
+        if ((steps >> k) & 1) m |= bit(((ks >> 3) + dr) * 8 + (ks & 7) + dc);
+    }
+    return m;
+}
+
+enum SlotKind : int { K_NONE = 0, K_PAWN = 1, K_KNIGHT = 2, K_SLIDER = 3, K_KING = 4 };
+
+struct Slot {
+    int kind;
+    uint64_t tgt;      // destination squares
+    uint64_t epm;      // pawn: destinations that are e.p. captures
+    uint32_t aux;      // slider: direction mask; king: castle bits
+};
+
+KV_DEV int slot_count(const Slot& s) {
+    return s.kind == K_NONE ? 0 : popc64(s.tgt) + (s.kind == K_KING ? popc32(s.aux) : 0);
+}
+
+// Write the slot's moves to mv[off..] in the reference's emission order.  Returns the new offset.
+KV_DEV int slot_emit(const Tables& T, const Pos& p, const Slot& sl, int s, uint16_t* mv, int off) {
+    auto put = [&](int from, int to, int fl) {
+        if (off < MAX_MOVES) mv[off] = (uint16_t)(from | (to << 6) | (fl << 12));
+        off++;
+    };
+    if (sl.kind == K_PAWN) {
+        // push1, push2, capture dc=-1, capture dc=+1 (core/chessEngine.py:458-472); promotion by rank (:706-710)
+        const int fwd = p.wtm ? -8 : 8;
+        const int last = p.wtm ? 0 : 7;
+        const int cand[4] = {s + fwd, s + 2 * fwd, s + fwd - 1, s + fwd + 1};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int t = cand[k];
+            if (t >= 0 && t < 64 && (sl.tgt & bit(t))) {
+                int fl = ((sl.epm & bit(t)) ? MF_EP : 0) | (((t >> 3) == last) ? MF_PROMO : 0);
+                put(s, t, fl);
+            }
+        }
+    } else if (sl.kind == K_KNIGHT) {
+        const int dl[8] = {-17, -10, -15, -6, 6, 15, 10, 17};   // :501-502 order
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int t = s + dl[k];
+            if (t >= 0 && t < 64 && (sl.tgt & bit(t))) put(s, t, 0);
+        }
+    } else if (sl.kind == K_SLIDER) {
+        for (int d = 0; d < 8; d++) {
+            if (!((sl.aux >> d) & 1)) continue;
+            uint64_t m = sl.tgt & T.ray[d][s];
+            while (m) {
+                const int t = first_on_ray(m, d);
+                m ^= bit(t);
+                put(s, t, 0);
+            }
+        }
+    } else if (sl.kind == K_KING) {
+        const int dl[8] = {-9, -8, -7, -1, 1, 7, 8, 9};          // :544-546 order
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int t = s + dl[k];
+            if (t >= 0 && t < 64 && (sl.tgt & bit(t))) put(s, t, 0);
+        }
+        const int home = p.wtm ? 60 : 4;
+        if (sl.aux & 1) put(home, home + 2, MF_CASTLE);
+        if (sl.aux & 2) put(home, home - 2, MF_CASTLE);
+    }
+    return off;
+}
+
+struct GenOut {
+    int n;       // number of legal moves (may exceed MAX_MOVES; only MAX_MOVES are stored)
+    int flags;   // RF_*
+};
+
+// getValidMoves (core/chessEngine.py:277-321) + checkForEndConditions (:632-651, repetition excluded).
+//   w       lane i < 16: word i of the board line; updated in place when the getKingMoves restore quirk
+//           (:564, stale king location) rewrites the board (flags & RF_STATE_MUTATED)
+//   mv      this warp's move buffer (shared memory), MAX_MOVES u16: from | to<<6 | ep<<12 | castle<<13 | promo<<14
+KV_DEV GenOut movegen_warp(const Tables& T, int lane, uint64_t& w, uint16_t* mv) {
+    Pos p;
+    load_pos(w, p);
+    Agg g;
+    make_agg(p, g);
+    int flags = 0;
+
+    // ---- checkForPinsAndChecks: lanes 0-7 one ray each -------------------------------------------------
+    uint64_t pinb = 0, validm = 0;
+    bool chk = false;
+    if (lane < 8) {
+        const int d = lane;
+        const uint64_t r = T.ray[d][p.kloc];
+        const uint64_t b = r & g.occ;
+        if (b) {
+            const int f = first_on_ray(b, d);
+            const uint64_t fb = bit(f);
+            const uint64_t sliders = d < 4 ? g.eRQ : g.eBQ;
+            if (g.own & fb) {
+                const uint64_t b2 = T.ray[d][f] & g.occ;
+                if (b2) {
+                    const int s2 = first_on_ray(b2, d);
+                    if (sliders & bit(s2)) pinb = fb;
+                }
+            } else {
+                bool m = (sliders & fb) != 0;
+                const bool pawn_dir = p.wtm ? (d == D_NW || d == D_NE) : (d == D_SW || d == D_SE);
+                if (!m && pawn_dir && (g.eP & fb) && (T.king[p.kloc] & fb)) m = true;
+                if (m) {
+                    chk = true;
+                    validm = r ^ T.ray[d][f];
+                }
+            }
+        }
+    }
+    const uint32_t chkb = ballot(chk);
+    const uint64_t kn = T.knight7[p.kloc] & g.eN;   // 7-entry table: (-2,+1) is missing
+    const int nchecks = popc32(chkb) + popc64(kn);
+    const uint64_t pinned = warp_or64(pinb, lane);
+    const int src = chkb ? ffs32(chkb) - 1 : 0;
+    uint64_t valid = shfl64(validm, src);
+    if (kn) valid = kn;
+    const int mode = nchecks == 0 ? 0 : (nchecks == 1 ? 1 : 2);
+    if (nchecks) flags |= RF_E3_CHECK;
+
+    // ---- >= 2 checks: getKingMoves(kingRow, kingCol) on whatever stands there (:315).  Its restore step
+    // (:564) leaves a king on the square once any step qualified; apply that rewrite up front. -----------
+    if (mode == 2) {
+        const uint64_t kb = bit(p.kloc);
+        if ((T.king[p.kloc] & ~g.own) && !(p.o[T_K] & kb)) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                p.o[i] &= ~kb;
+                p.e[i] &= ~kb;
+            }
+            p.o[T_K] |= kb;
+            make_agg(p, g);
+            flags |= RF_STATE_MUTATED;
+            // write the rewritten board back into the line words held by lanes 0-11
+            if (lane < 12) {
+                w &= ~kb;
+                if (lane == (p.wtm ? 0 : 6)) w |= kb;
+            }
+        }
+    }
+
+    // ---- king phases --------------------------------------------------------------------------------
+    Slot sl[2];
+    sl[0].kind = sl[1].kind = K_NONE;
+    sl[0].tgt = sl[1].tgt = sl[0].epm = sl[1].epm = 0;
+    sl[0].aux = sl[1].aux = 0;
+    {
+        uint64_t kings = mode == 2 ? bit(p.kloc) : p.o[T_K];
+        while (kings) {   // warp-uniform; one iteration on any reachable position
+            const int ks = ctz64(kings);
+            kings &= kings - 1;
+            const KingOut ko = king_phase(T, lane, p, g, ks, mode, valid, pinned);
+            if (lane == (ks >> 1)) {
+                Slot& s = (ks & 1) ? sl[1] : sl[0];
+                s.kind = K_KING;
+                s.tgt = king_steps_to_mask(ks, ko.steps);
+                s.aux = ko.castle;
+            }
+        }
+    }
+
+    // ---- every other piece: lane l owns squares 2l, 2l+1 ---------------------------------------------
+    if (mode != 2) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int s = 2 * lane + j;
+            const uint64_t sb = bit(s);
+            Slot& o = j ? sl[1] : sl[0];
+            if (!(g.own & sb) || (p.o[T_K] & sb)) continue;
+            const bool is_pinned = (pinned & sb) != 0;
+            int pd = 0;
+            if (is_pinned)
+                for (int d = 0; d < 8; d++)
+                    if (T.ray[d][p.kloc] & sb) pd = d;
+            uint64_t tgt = 0;
+            if (p.o[T_P] & sb) {
+                o.kind = K_PAWN;
+                const int r = s >> 3, c = s & 7;
+                const int dr = p.wtm ? -1 : 1;
+                const int fwd = dr * 8;
+                const int r1 = r + dr;
+                if (r1 >= 0 && r1 < 8) {
+                    if (!is_pinned || pd == (p.wtm ? D_N : D_S)) {
+                        if (!(g.occ & bit(s + fwd))) {
+                            tgt |= bit(s + fwd);
+                            if (r == (p.wtm ? 6 : 1) && !(g.occ & bit(s + 2 * fwd))) tgt |= bit(s + 2 * fwd);
+                        }
+                    }
+                    if (c > 0 && (!is_pinned || pd == (p.wtm ? D_NW : D_SW))) {
+                        const int t = s + fwd - 1;
+                        if (g.opp & bit(t)) tgt |= bit(t);
+                        else if (t == p.ep) { tgt |= bit(t); o.epm |= bit(t); }
+                    }
+                    if (c < 7 && (!is_pinned || pd == (p.wtm ? D_NE : D_SE))) {
+                        const int t = s + fwd + 1;
+                        if (g.opp & bit(t)) tgt |= bit(t);
+                        else if (t == p.ep) { tgt |= bit(t); o.epm |= bit(t); }
+                    }
+                }
+            } else if (p.o[T_N] & sb) {
+                o.kind = K_KNIGHT;
+                if (!is_pinned) tgt = T.knight[s] & ~g.own;
+            } else {
+                o.kind = K_SLIDER;
+                o.aux = (p.o[T_R] & sb) ? 0x0Fu : ((p.o[T_B] & sb) ? 0xF0u : 0xFFu);
+                if (o.aux & 0x0F) tgt |= rook_att(T, s, g.occ);
+                if (o.aux & 0xF0) tgt |= bishop_att(T, s, g.occ);
+                tgt &= ~g.own;
+                if (is_pinned) tgt &= T.ray[pd][s] | T.ray[dir_opp(pd)][s];
+            }
+            if (mode == 1) tgt &= valid;
+            o.tgt = tgt;
+            o.epm &= tgt;
+        }
+    }
+
+    // ---- ordered emission ------------------------------------------------------------------------------
+    const int c0 = slot_count(sl[0]), c1 = slot_count(sl[1]);
+    const int incl = warp_incl_scan(c0 + c1, lane);
+    const int n = shfl32(incl, 31);
+    int off = incl - (c0 + c1);
+    off = slot_emit(T, p, sl[0], (mode == 2) ? p.kloc : 2 * lane, mv, off);
+    off = slot_emit(T, p, sl[1], (mode == 2) ? p.kloc : 2 * lane + 1, mv, off);
+    syncwarp();
+
+    // ---- checkForEndConditions (:632-651) ---------------------------------------------------------------
+    if (n == 0) {
+        const bool ic = attacked(T, g, p.kloc, p.wtm, p.ep, p.moved, p.akloc);   // inCheck(), :388-394
+        flags |= ic ? RF_CHECKMATE : RF_STALEMATE;
+    } else if (p.clock >= 100) {
+        flags |= RF_DRAW50;
+    }
+    if (g.occ == (p.o[T_K] | p.e[T_K])) flags |= RF_ONLY_KINGS;   // isDraw(), :21-33 (the only satisfiable clause)
+    if (n > MAX_MOVES) flags |= RF_OVERFLOW;
+    GenOut out;
+    out.n = n;
+    out.flags = flags;
+    return out;
+}
+
+// makeMove (core/chessEngine.py:127-197), no legality check, mailbox write order preserved.
+// Lane l < 12 holds bitboard l in w, lane 12 the meta word; returns the lane's new word.
+KV_DEV uint64_t make_move_warp(int lane, uint64_t w, int mvw, int promo_type) {
+    const int from = mvw & 63, to = (mvw >> 6) & 63, fl = (mvw >> 12) & 7;
+    const uint64_t fb = bit(from), tb = bit(to);
+    const bool bbl = lane < 12;
+    const uint32_t has_f = ballot(bbl && (w & fb));
+    const uint32_t has_t = ballot(bbl && (w & tb));
+    const int pm = has_f ? ffs32(has_f) - 1 : -1;
+    const bool captured = (fl & MF_EP) || has_t;
+    const int sr = from >> 3, sc = from & 7, er = to >> 3, ec = to & 7;
+    if (bbl) {
+        w &= ~fb;                       // board[start] = "--"
+        w &= ~tb;                       // board[end] = pieceMoved
+        if (lane == pm) w |= tb;
+        if (fl & MF_EP) w &= ~bit(sr * 8 + ec);   // :152-153
+    }
+    if (fl & MF_CASTLE) {               // rook hop, :156-164
+        int rs = -1, rd = -1;
+        if (ec - sc == 2) {
+            if (ec + 1 < 8) { rs = er * 8 + ec + 1; rd = er * 8 + ec - 1; }
+        } else if (ec - 2 >= 0 && ec + 1 < 8) {
+            rs = er * 8 + ec - 2; rd = er * 8 + ec + 1;
+        }
+        if (rs >= 0) {
+            const uint32_t has_r = ballot(bbl && (w & bit(rs)));
+            const int rp = has_r ? ffs32(has_r) - 1 : -1;
+            if (bbl) {
+                w &= ~bit(rd);
+                if (lane == rp) w |= bit(rd);
+                w &= ~bit(rs);
+            }
+        }
+    }
+    if (fl & MF_PROMO) {                // :190-191, promotionChoice defaults to 'Q'
+        const int pp = ((pm >= 0 && pm < 6) ? 0 : 6) + promo_type;
+        if (bbl) {
+            w &= ~tb;
+            if (lane == pp) w |= tb;
+        }
+    }
+    if (lane == 12) {
+        uint64_t m = w;
+        int moved = (int)((m >> 1) & 63);
+        int wk = (int)((m >> 16) & 63), bk = (int)((m >> 24) & 63);
+        int clock = (int)((m >> 32) & 0xFFFF);
+        const bool wtm = m & 1;
+        if (pm == 0) { moved |= F_WK; wk = to; }
+        else if (pm == 6) { moved |= F_BK; bk = to; }
+        else if (pm == 2) { if (from == 56) moved |= F_WRQ; else if (from == 63) moved |= F_WRK; }
+        else if (pm == 8) { if (from == 0) moved |= F_BRQ; else if (from == 7) moved |= F_BRK; }
+        int ep = EP_NONE;
+        if ((pm == 5 || pm == 11) && (sr - er == 2 || er - sr == 2)) ep = ((sr + er) >> 1) * 8 + sc;   // :169-173
+        clock = captured ? 0 : (clock + 1 > 0xFFFF ? 0xFFFF : clock + 1);   // :178 resets on captures only
+        w = (m & 0xFFFF000000000000ull) | (uint64_t)(wtm ? 0 : 1) | ((uint64_t)moved << 1) | ((uint64_t)ep << 8) |
+            ((uint64_t)wk << 16) | ((uint64_t)bk << 24) | ((uint64_t)clock << 32);
+    }
+    return w;
+}
+
+// ---- perft (kv_perft): one frontier board per warp -----------------------------------------------------
+KV_DEV uint64_t mix64(uint64_t x) {
+    x ^= x >> 30;
+    x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27;
+    x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+// order digest of one move list under path hash `path`: sum_k mix64(path + (k+1)*G + (mv_k << 32))
+KV_DEV uint64_t list_digest(const uint16_t* mv, int n, uint64_t path, int lane) {
+    uint64_t h = 0;
+    for (int k = lane; k < n; k += 32)
+        h += mix64(path + (uint64_t)(k + 1) * 0x9E3779B97F4A7C15ull + ((uint64_t)mv[k] << 32));
+    return warp_sum64(h, lane);
+}
+KV_DEV uint64_t child_path(uint64_t path, int k) { return mix64(path ^ ((uint64_t)(k + 1) * 0xD6E8FEB86659FD93ull)); }
+
+// lane k of the warp owns accumulator k: nodes, captures, ep, castles, promos, digest, movegen calls
+KV_DEV void perft_acc_flush(uint64_t& accv, int root, uint64_t* out, int lane) {
+    if (root >= 0 && lane < 7 && accv) atomic_add_u64(out + (size_t)root * 8 + lane, accv);
+    accv = 0;
+}
+
+// Visit one frontier board.  LEAF: bulk-count its move list.  Otherwise: write every child board to `next`
+// (slots claimed with one atomic add per parent; the frontier is an unordered multiset and every output is an
+// order-independent sum).  w[13] = root id, w[14] = path hash.
+template <bool LEAF>
+KV_DEV void perft_visit_warp(const Tables& T, int lane, uint64_t w, uint16_t* mv, uint64_t& accv, int& acc_root,
+                             uint64_t* next, uint32_t* next_count, uint64_t* out) {
+    const int root = (int)(uint32_t)shfl64(w, 13);
+    const uint64_t path = shfl64(w, 14);
+    if (root != acc_root) {
+        perft_acc_flush(accv, acc_root, out, lane);
+        acc_root = root;
+    }
+    // w reflects the :564 rewrite afterwards, as the reference's makeMove would see it
+    const GenOut g = movegen_warp(T, lane, w, mv);
+    const int n = g.n < MAX_MOVES ? g.n : MAX_MOVES;
+    const uint64_t dig = list_digest(mv, n, path, lane);
+    if (LEAF) {
+        const uint64_t occ = warp_or64(lane < 12 ? w : 0ull, lane);
+        uint64_t cats = 0;   // captures | ep<<16 | castles<<32 | promos<<48 (each <= 256)
+        for (int k = lane; k < n; k += 32) {
+            const int x = mv[k];
+            const int fl = x >> 12;
+            const uint64_t cap = ((fl & 1) || ((occ >> ((x >> 6) & 63)) & 1)) ? 1 : 0;
+            cats += cap | ((uint64_t)(fl & 1) << 16) | ((uint64_t)((fl >> 1) & 1) << 32) |
+                    ((uint64_t)((fl >> 2) & 1) << 48);
+        }
+        cats = warp_sum64(cats, lane);
+        if (lane == 0) accv += (unsigned)n;
+        if (lane >= 1 && lane <= 4) accv += (cats >> (16 * (lane - 1))) & 0xFFFF;
+    } else {
+        uint32_t base = 0;
+        if (lane == 0 && n) base = atomic_add_u32(next_count, (uint32_t)n);
+        base = (uint32_t)shfl32((int)base, 0);
+        for (int k = 0; k < n; k++) {
+            uint64_t c = make_move_warp(lane, w, mv[k], T_Q);
+            if (lane == 14) c = child_path(path, k);
+            if (lane < LINE_WORDS) next[(size_t)(base + k) * LINE_WORDS + lane] = c;
+        }
+    }
+    if (lane == 5) accv += dig;
+    if (lane == 6) accv += 1;
+    syncwarp();
+}
+
+}  // namespace kv

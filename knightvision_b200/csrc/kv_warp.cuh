@@ -1,0 +1,99 @@
+// kv_warp.cuh — warp-collective wrappers used by the warp-per-board kernels.
+//
+// On the device these are the sm_100a intrinsics.  When KV_HOST_EMU is defined (tests/simt_emu only —
+// a CI harness that runs the *kernel source* lane-by-lane on the CPU so the integer kernels can be
+// checked against the oracle on a box without a GPU) they are routed to a 32-fiber lock-step emulator.
+// The product library is never built with KV_HOST_EMU.
+#pragma once
+#include <cstdint>
+
+#ifdef KV_HOST_EMU
+#include <cstring>
+#define KV_DEV inline
+#define KV_DEVFN
+namespace kvemu {
+uint64_t collective_shfl(uint64_t v, int src);
+uint32_t collective_ballot(bool p);
+void collective_sync();
+int lane_id();
+}  // namespace kvemu
+namespace kv {
+KV_DEV int popc32(uint32_t x) { return __builtin_popcount(x); }
+KV_DEV int popc64(uint64_t x) { return __builtin_popcountll(x); }
+KV_DEV int ctz64(uint64_t x) { return __builtin_ctzll(x); }        // x != 0
+KV_DEV int msb64(uint64_t x) { return 63 - __builtin_clzll(x); }   // x != 0
+KV_DEV int ffs32(uint32_t x) { return __builtin_ffs((int)x); }
+KV_DEV uint64_t shfl64(uint64_t v, int src) { return kvemu::collective_shfl(v, src); }
+KV_DEV int shfl32(int v, int src) { return (int)(int64_t)kvemu::collective_shfl((uint64_t)(int64_t)v, src); }
+KV_DEV float shflf(float v, int src) {
+    uint32_t u; memcpy(&u, &v, 4);
+    u = (uint32_t)kvemu::collective_shfl(u, src);
+    float r; memcpy(&r, &u, 4); return r;
+}
+KV_DEV uint32_t ballot(bool p) { return kvemu::collective_ballot(p); }
+KV_DEV void syncwarp() { kvemu::collective_sync(); }
+KV_DEV int shfl_up32(int v, int delta, int lane) {
+    int r = (int)(int64_t)kvemu::collective_shfl((uint64_t)(int64_t)v, lane >= delta ? lane - delta : lane);
+    return r;
+}
+KV_DEV uint64_t shfl_xor64(uint64_t v, int m, int lane) { return kvemu::collective_shfl(v, lane ^ m); }
+KV_DEV int shfl_xor32(int v, int m, int lane) { return (int)(int64_t)kvemu::collective_shfl((uint64_t)(int64_t)v, lane ^ m); }
+KV_DEV float shfl_xorf(float v, int m, int lane) { return shflf(v, lane ^ m); }
+// lanes run one at a time in the emulator, so plain read-modify-write is atomic
+KV_DEV uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+KV_DEV void atomic_add_u64(uint64_t* p, uint64_t v) { *p += v; }
+KV_DEV uint64_t ldg64(const uint64_t* p) { return *p; }
+}  // namespace kv
+#else
+#define KV_DEV __device__ __forceinline__
+#define KV_DEVFN __device__
+namespace kv {
+constexpr unsigned FULL = 0xffffffffu;
+KV_DEV int popc32(uint32_t x) { return __popc(x); }
+KV_DEV int popc64(uint64_t x) { return __popcll(x); }
+KV_DEV int ctz64(uint64_t x) { return __ffsll((long long)x) - 1; }
+KV_DEV int msb64(uint64_t x) { return 63 - __clzll((long long)x); }
+KV_DEV int ffs32(uint32_t x) { return __ffs((int)x); }
+KV_DEV uint64_t shfl64(uint64_t v, int src) { return __shfl_sync(FULL, v, src); }
+KV_DEV int shfl32(int v, int src) { return __shfl_sync(FULL, v, src); }
+KV_DEV float shflf(float v, int src) { return __shfl_sync(FULL, v, src); }
+KV_DEV uint32_t ballot(bool p) { return __ballot_sync(FULL, p); }
+KV_DEV void syncwarp() { __syncwarp(); }
+KV_DEV int shfl_up32(int v, int delta, int /*lane*/) { return __shfl_up_sync(FULL, v, delta); }
+KV_DEV uint64_t shfl_xor64(uint64_t v, int m, int /*lane*/) { return __shfl_xor_sync(FULL, v, m); }
+KV_DEV int shfl_xor32(int v, int m, int /*lane*/) { return __shfl_xor_sync(FULL, v, m); }
+KV_DEV float shfl_xorf(float v, int m, int /*lane*/) { return __shfl_xor_sync(FULL, v, m); }
+KV_DEV uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+KV_DEV void atomic_add_u64(uint64_t* p, uint64_t v) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+KV_DEV uint64_t ldg64(const uint64_t* p) { return __ldg(p); }
+}  // namespace kv
+#endif
+
+namespace kv {
+// inclusive prefix sum over the warp
+KV_DEV int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = shfl_up32(v, d, lane);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+KV_DEV uint64_t warp_or64(uint64_t v, int lane) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v |= shfl_xor64(v, m, lane);
+    return v;
+}
+KV_DEV uint64_t warp_sum64(uint64_t v, int lane) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += shfl_xor64(v, m, lane);
+    return v;
+}
+KV_DEV int warp_sum32(int v, int lane) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += shfl_xor32(v, m, lane);
+    return v;
+}
+}  // namespace kv

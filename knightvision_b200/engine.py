@@ -1,0 +1,143 @@
+"""Batched device engine: thin Python host over the C ABI (include/kv_b200.h).
+
+torch is used for device memory and streams only; every computation is a hand-written sm_100a kernel
+inside libkv_b200.so.  Board lines are uint64 [n,16] (see knightvision_b200.layout).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+MOVE_STRIDE = 256
+
+
+def _ptr(t):
+    if isinstance(t, torch.Tensor):
+        return ctypes.c_void_p(t.data_ptr())
+    return t.ctypes.data_as(ctypes.c_void_p)
+
+
+def lines_to_device(lines: np.ndarray, device) -> torch.Tensor:
+    a = np.ascontiguousarray(lines, dtype=np.uint64).view(np.int64)
+    return torch.from_numpy(a).to(device)
+
+
+def lines_to_host(t: torch.Tensor) -> np.ndarray:
+    return t.cpu().numpy().view(np.uint64)
+
+
+class Engine:
+    """One context per GPU (kv_create).  Raises if there is no CUDA device or the library is missing."""
+
+    def __init__(self, device: int | str | torch.device = 0):
+        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if dev.type != "cuda":
+            raise N.KVError("knightvision_b200 runs on CUDA devices only (no CPU fallback)")
+        self.device = dev
+        self.index = dev.index or 0
+        self._lib = N.lib()
+        ctx = ctypes.c_void_p()
+        rc = self._lib.kv_create(self.index, ctypes.byref(ctx))
+        if rc != 0:
+            raise N.KVError(f"kv_create failed ({rc}): {self._lib.kv_last_error(None).decode()}")
+        self.ctx = ctx
+        torch.cuda.set_device(dev)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self._lib.kv_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers -------------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.kv_launch_count(self.ctx))
+
+    @property
+    def sm_count(self) -> int:
+        return int(self._lib.kv_sm_count(self.ctx))
+
+    KERNELS = ("movegen", "make_moves", "perft_expand", "perft_leaf", "encode", "net_stem", "net_conv", "net_head",
+               "mcts_select", "mcts_expand", "mcts_misc")
+
+    def profile(self, on: bool):
+        N.check(self.ctx, self._lib.kv_profile_enable(self.ctx, int(on)), "kv_profile_enable")
+
+    def profile_read(self) -> dict:
+        """{kernel: (total_ms, launches)} recorded with CUDA events since the last read."""
+        ms = np.zeros(16, dtype=np.float64)
+        n = np.zeros(16, dtype=np.uint64)
+        k = self._lib.kv_profile_read(self.ctx, _ptr(ms), _ptr(n), 16)
+        return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(self.KERNELS[:k])}
+
+    # ---- rules ---------------------------------------------------------------------------------
+    def movegen(self, lines: torch.Tensor, moves=None, counts=None, flags=None, stride: int = MOVE_STRIDE):
+        """getValidMoves for every board.  lines: int64/uint64 view [n,16] on this device (rewritten in
+        place only in the RF_STATE_MUTATED corner).  Returns (moves int16 [n,stride], counts, flags)."""
+        n = lines.shape[0]
+        if moves is None:
+            moves = torch.empty((n, stride), dtype=torch.int16, device=self.device)
+        if counts is None:
+            counts = torch.empty(n, dtype=torch.int32, device=self.device)
+        if flags is None:
+            flags = torch.empty(n, dtype=torch.int32, device=self.device)
+        N.check(self.ctx, self._lib.kv_movegen(self.ctx, _ptr(lines), n, _ptr(moves), stride, _ptr(counts),
+                                               _ptr(flags), self._stream()), "kv_movegen")
+        return moves, counts, flags
+
+    def make_moves(self, lines: torch.Tensor, mv: torch.Tensor):
+        """makeMove in place; mv int16 [n] move words (0xFFFF = skip)."""
+        N.check(self.ctx, self._lib.kv_make_moves(self.ctx, _ptr(lines), lines.shape[0], _ptr(mv), self._stream()),
+                "kv_make_moves")
+        return lines
+
+    def perft(self, roots: torch.Tensor, depth: int, chunk: int = 0) -> torch.Tensor:
+        n = roots.shape[0]
+        out = torch.empty((n, 8), dtype=torch.int64, device=self.device)
+        N.check(self.ctx, self._lib.kv_perft(self.ctx, _ptr(roots), n, depth, _ptr(out), chunk, self._stream()),
+                "kv_perft")
+        return out
+
+    def encode(self, lines: torch.Tensor) -> torch.Tensor:
+        n = lines.shape[0]
+        out = torch.empty((n, 12, 8, 8), dtype=torch.float32, device=self.device)
+        N.check(self.ctx, self._lib.kv_encode(self.ctx, _ptr(lines), n, _ptr(out), self._stream()), "kv_encode")
+        return out
+
+    # ---- host-buffer forms (numpy in / numpy out; copies happen inside the C call) ---------------
+    def movegen_host(self, lines: np.ndarray, stride: int = MOVE_STRIDE):
+        lines = np.ascontiguousarray(lines, dtype=np.uint64).copy()
+        n = lines.shape[0]
+        moves = np.zeros((n, stride), dtype=np.uint16)
+        counts = np.zeros(n, dtype=np.int32)
+        flags = np.zeros(n, dtype=np.int32)
+        N.check(self.ctx, self._lib.kv_movegen_host(self.ctx, _ptr(lines), n, _ptr(moves), stride, _ptr(counts),
+                                                    _ptr(flags)), "kv_movegen_host")
+        return moves, counts, flags, lines
+
+    def make_moves_host(self, lines: np.ndarray, mv: np.ndarray) -> np.ndarray:
+        out = np.ascontiguousarray(lines, dtype=np.uint64).copy()
+        mv = np.ascontiguousarray(mv, dtype=np.uint16)
+        N.check(self.ctx, self._lib.kv_make_moves_host(self.ctx, _ptr(out), out.shape[0], _ptr(mv)),
+                "kv_make_moves_host")
+        return out
+
+    def perft_host(self, roots: np.ndarray, depth: int, chunk: int = 0) -> np.ndarray:
+        roots = np.ascontiguousarray(roots, dtype=np.uint64)
+        out = np.zeros((roots.shape[0], 8), dtype=np.uint64)
+        N.check(self.ctx, self._lib.kv_perft_host(self.ctx, _ptr(roots), roots.shape[0], depth, _ptr(out), chunk),
+                "kv_perft_host")
+        return out

@@ -590,6 +590,52 @@ KVO_API void kvo_perft(const uint64_t *line, int depth, uint64_t *out6) {
     perft_rec(&s, depth, out6);
 }
 
+/* perft2: the quantities the GPU perft driver reports (include/kv_b200.h, kv_perft).  The GPU frontier is an
+ * unordered multiset, so the order digest is an order-independent SUM of per-list hashes, each seeded by the
+ * hash of the path that leads to the list: still sensitive to the order of moves inside every list.
+ * out[0] nodes, [1] captures, [2] ep, [3] castles, [4] promos, [5] digest, [6] movegen calls, [7] 0. */
+static uint64_t mix64(uint64_t x) {
+    x ^= x >> 30;
+    x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27;
+    x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+
+static void perft2_rec(const kvo_state *s, int depth, uint64_t path, uint64_t *out) {
+    kvo_state cur = *s;
+    movelist ml;
+    int f;
+    int n = valid_moves(&cur, &ml, &f);
+    if (n > 256) n = 256;
+    out[6]++;
+    for (int k = 0; k < n; k++)
+        out[5] += mix64(path + (uint64_t)(k + 1) * 0x9E3779B97F4A7C15ull + ((uint64_t)pack_move(&ml.m[k]) << 32));
+    if (depth == 1) {
+        out[0] += (uint64_t)n;
+        for (int i = 0; i < n; i++) {
+            if (ml.m[i].piece_captured != EMPTY) out[1]++;
+            if (ml.m[i].flags & MF_EP) out[2]++;
+            if (ml.m[i].flags & MF_CASTLE) out[3]++;
+            if (ml.m[i].flags & MF_PROMO) out[4]++;
+        }
+        return;
+    }
+    for (int k = 0; k < n; k++) {
+        kvo_state child = cur;
+        make_move(&child, ml.m[k].from, ml.m[k].to, ml.m[k].flags, T_Q);
+        perft2_rec(&child, depth - 1, mix64(path ^ ((uint64_t)(k + 1) * 0xD6E8FEB86659FD93ull)), out);
+    }
+}
+
+KVO_API void kvo_perft2(const uint64_t *line, int depth, uint64_t *out8) {
+    kvo_state s;
+    kvo_unpack(line, &s);
+    memset(out8, 0, 8 * sizeof(uint64_t));
+    perft2_rec(&s, depth, 0, out8);
+}
+
 /* encode_board, ai/ai.py:17-41 (list branch): float32 [12,8,8] one-hot */
 KVO_API void kvo_encode(const uint64_t *lines, int n, float *planes) {
     for (int i = 0; i < n; i++)

@@ -69,6 +69,14 @@ def perft(line: np.ndarray, depth: int) -> np.ndarray:
     return out
 
 
+def perft2(line: np.ndarray, depth: int) -> np.ndarray:
+    """Returns uint64[8] in the layout of kv_perft (include/kv_b200.h)."""
+    line = np.ascontiguousarray(line, dtype=np.uint64)
+    out = np.zeros(8, dtype=np.uint64)
+    lib().kvo_perft2(_p(line), ctypes.c_int(depth), _p(out))
+    return out
+
+
 def square_under_attack(line: np.ndarray, r: int, c: int) -> bool:
     line = np.ascontiguousarray(line, dtype=np.uint64)
     return bool(lib().kvo_square_under_attack(_p(line), ctypes.c_int(r), ctypes.c_int(c)))

@@ -1,0 +1,58 @@
+"""ctypes wrapper of the CPU lock-step emulator of the warp-per-board kernels (TEST INFRASTRUCTURE ONLY)."""
+from __future__ import annotations
+
+import ctypes
+import glob
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SO = os.path.join(HERE, "libkv_emu.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    deps = [os.path.join(HERE, "kvemu.cpp")] + glob.glob(os.path.join(ROOT, "knightvision_b200", "csrc", "*.cuh"))
+    if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
+                               "-ffp-contract=off", "-fvisibility=hidden", "-o", SO,
+                               os.path.join(HERE, "kvemu.cpp")])
+    return SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def movegen(lines, stride=256):
+    lines = np.ascontiguousarray(lines, dtype=np.uint64).copy()
+    n = lines.shape[0]
+    moves = np.zeros((n, stride), dtype=np.uint16)
+    counts = np.zeros(n, dtype=np.int32)
+    flags = np.zeros(n, dtype=np.int32)
+    lib().kvemu_movegen(_p(lines), ctypes.c_int(n), _p(moves), ctypes.c_int(stride), _p(counts), _p(flags))
+    return moves, counts, flags, lines
+
+
+def make_moves(lines, mv):
+    out = np.ascontiguousarray(lines, dtype=np.uint64).copy()
+    mv = np.ascontiguousarray(mv, dtype=np.uint16)
+    lib().kvemu_make_moves(_p(out), ctypes.c_int(out.shape[0]), _p(mv))
+    return out
+
+
+def perft(roots, depth):
+    roots = np.ascontiguousarray(roots, dtype=np.uint64)
+    out = np.zeros((roots.shape[0], 8), dtype=np.uint64)
+    lib().kvemu_perft(_p(roots), ctypes.c_int(roots.shape[0]), ctypes.c_int(depth), _p(out))
+    return out

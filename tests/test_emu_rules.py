@@ -1,0 +1,52 @@
+"""The warp-per-board kernel SOURCE (knightvision_b200/csrc/kv_rules.cuh), run lane-by-lane on the CPU by
+tests/simt_emu, against the golden fixtures of the unmodified reference and against the oracle.  CPU only —
+the same checks run on the real kernels in tests/test_gpu_rules.py."""
+import numpy as np
+import pytest
+
+from knightvision_b200 import layout as L
+from oracle import kv_oracle as O
+import helpers as H
+from simt_emu import emu
+
+
+@pytest.mark.parametrize("name,step", [("playouts", 4), ("synthetic", 1)])
+def test_emu_movegen_golden(name, step):
+    rows = H.load_rows(name)
+    sel = slice(None, None, step)
+    sub = {k: rows[k][sel] for k in ("line_in", "line_mid", "counts", "flags", "moves")}
+    H.check_movegen_against(sub, emu.movegen(sub["line_in"]))
+
+
+@pytest.mark.parametrize("name", ["playouts", "synthetic"])
+def test_emu_make_move_golden(name):
+    rows = H.load_rows(name)
+    ok = rows["played"] != 0xFFFF
+    out = emu.make_moves(rows["line_mid"][ok][::2], rows["played"][ok][::2])
+    assert np.array_equal(out[:, :13], rows["line_out"][ok][::2][:, :13])
+
+
+def test_emu_movegen_random_playouts_vs_oracle():
+    lines = H.random_playout_positions(n_games=12, max_plies=120, seed=5)
+    H.check_movegen_against(lines, emu.movegen(lines))
+
+
+def test_emu_perft_vs_oracle():
+    gold = H.perft_gold()
+    names = list(gold)
+    roots = np.array([gold[k]["line"] for k in names], dtype=np.uint64)
+    for depth in (1, 2, 3):
+        got = emu.perft(roots, depth)
+        for i, k in enumerate(names):
+            assert int(got[i, 0]) == H.PERFT_EXPECT[k][depth - 1], (k, depth)
+            assert np.array_equal(got[i], O.perft2(roots[i], depth)), (k, depth)
+            assert [int(x) for x in got[i, 1:5]] == gold[k]["depths"][str(depth)]["cats"]
+
+
+def test_emu_skip_move_and_promotion_choice_default():
+    # 0xFFFF is "no move" only at the kernel level (kv_make_moves); make_move_warp itself applies any word
+    line = L.start_line()[None]
+    out = emu.make_moves(line, np.array([L.move_word(6, 4, 4, 4)], dtype=np.uint16))   # e2e4
+    f = L.unpack_fields(out[0])
+    assert f["board"][4][4] == "wp" and f["board"][6][4] == "--" and f["ep"] == (5, 4) and not f["white_to_move"]
+    assert f["clock"] == 1   # pawn moves do not reset the clock (core/chessEngine.py:178)
