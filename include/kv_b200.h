@@ -99,6 +99,26 @@ KV_API int kv_perft_host(kv_ctx* ctx, const uint64_t* h_roots, int n, int depth,
 /* d_planes [n][12][8][8] float32 one-hot, the reference's record/input format */
 KV_API int kv_encode(kv_ctx* ctx, const uint64_t* d_lines, int n, float* d_planes, void* stream);
 
+/* ---- policy/value network (replaces ChessNet, ai/model.py:27-77) ----------------------------------- */
+/* Architecture: conv 12->stem_channels, [conv stem->tower if has_conv2], n_blocks x ResidualBlock(tower),
+ * heads as in the reference.  The reference net is (256, 512, 5, 1).  max_boards = largest batch. */
+KV_API int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_blocks, int has_conv2, int max_boards);
+/* Weights: the fp32 tensors of ChessNet.state_dict() concatenated in key order (every *.num_batches_tracked
+ * skipped): conv w,b then bn weight,bias,running_mean,running_var for each layer; policy_fc / value_fc as stored.
+ * BatchNorm is folded (eval mode, eps 1e-5) and the tower weights are converted to bf16 on the device. */
+KV_API uint64_t kv_net_blob_floats(kv_ctx* ctx);
+KV_API int kv_net_load(kv_ctx* ctx, const float* h_blob, uint64_t n_floats);
+/* Device staging buffer of kv_net_blob_floats() floats: write the blob there (e.g. as the target of an NCCL
+ * broadcast) and call kv_net_commit_weights. */
+KV_API void* kv_net_blob_device_ptr(kv_ctx* ctx);
+KV_API int kv_net_commit_weights(kv_ctx* ctx, void* stream);
+/* forward(x) -> (policy logits [n][4096] fp32, value [n] fp32 after tanh); either output may be NULL.
+ * Input = board lines (the stem kernel fuses encode_board), or the reference's fp32 one-hot planes. */
+KV_API int kv_net_forward(kv_ctx* ctx, const uint64_t* d_lines, int n, float* d_policy, float* d_value, void* stream);
+/* test hook: stem + the first n_convs tower convolutions; copies the NHWC bf16 activations [n*64][*channels] out */
+KV_API int kv_net_forward_partial(kv_ctx* ctx, const uint64_t* d_lines, int n, int n_convs, void* d_act_out, int* channels);
+KV_API int kv_net_forward_planes(kv_ctx* ctx, const float* d_planes, int n, float* d_policy, float* d_value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

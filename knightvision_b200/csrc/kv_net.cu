@@ -1,0 +1,677 @@
+// kv_net.cu — the policy/value network (reference: ai/model.py:8-77) for sm_100a.
+//
+//   stem      conv1 12->C1 + bn1 + relu, fused with board encoding (ai/ai.py:17-41): the input planes are
+//             one-hot, so a 3x3 conv is at most 9 table rows added per output pixel; reads 96 B of bitboards
+//             per board instead of 3 072 B of fp32 planes.  CUDA cores (0.11 % of the FLOPs).
+//   tower     every other 3x3 conv (conv2 and the residual blocks, 99.8 % of the FLOPs) is ONE kernel:
+//             a persistent, warp-specialised implicit GEMM on the 5th-gen tensor cores.
+//               A  activations, NHWC bf16.  One TMA 4-D box {64 ch, 8, 8, 2 boards} per (filter tap, 64-channel
+//                  block) with start coordinates (c0, dx, dy, b0), dx,dy in {-1,0,1}: the TMA unit zero-fills
+//                  out-of-board pixels, i.e. the conv padding, so there is no im2col anywhere.  The box lands
+//                  in shared memory as 128 rows x 128 B in the canonical K-major SWIZZLE_128B UMMA layout.
+//               B  BN-folded weights [Cout][9*Cin] bf16 (K-major), TMA 2-D boxes {64, 256}.
+//               D  128 x 256 fp32 accumulator in TMEM, double-buffered (2 x 256 of the 512 columns) so the
+//                  epilogue of tile i overlaps the main loop of tile i+1.
+//             warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue
+//             (tcgen05.ld -> +bias (+residual) -> relu -> bf16 -> global).
+//   heads     policy 1x1 conv + bn + relu + FC(128->4096) and value 1x1 conv + bn + relu + FC + relu + FC + tanh
+//             fused in one CUDA-core kernel per board (0.04 % of the FLOPs); in search mode only the legal
+//             moves' logits are computed and soft-maxed (kv_mcts.cu).
+// BatchNorm is folded with running statistics (eval mode, eps 1e-5), as the reference runs self-play.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "kv_internal.h"
+#include "kv_net.h"
+#include "kv_umma.cuh"
+
+using bf16 = __nv_bfloat16;
+
+namespace kvn {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int CONV_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int CONV_THREADS = 256;
+
+struct ConvParams {
+    const float* bias;
+    const bf16* residual;
+    bf16* out;
+    int m_tiles, n_tiles, kb_per_tap, cout, m_valid, relu;
+};
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        kvu::prefetch_tmap(&tmA);
+        kvu::prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            kvu::mbar_init(&full[s], 1);
+            kvu::mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            kvu::mbar_init(&tfull[a], 1);
+            kvu::mbar_init(&tempty[a], 128);
+        }
+        kvu::fence_barrier_init();
+    }
+    if (warp == 2) kvu::tmem_alloc(tmem_slot, 512);
+    kvu::tc_fence_before();
+    __syncthreads();
+    kvu::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int total = P.m_tiles * P.n_tiles;
+    const int ksteps = 9 * P.kb_per_tap;
+
+    if (warp == 0) {
+        // ---- TMA producer ---------------------------------------------------------------------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const int m_tile = tile / P.n_tiles, n_tile = tile % P.n_tiles;
+            for (int ks = 0; ks < ksteps; ks++) {
+                const int tap = ks / P.kb_per_tap, kb = ks - tap * P.kb_per_tap;
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                kvu::mbar_wait(&empty[stage], phase ^ 1);
+                if (lane == 0) {
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    kvu::mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+                    kvu::tma_load_4d(sa, &tmA, &full[stage], kb * BK, dx, dy, m_tile * 2);
+                    kvu::tma_load_2d(sa + A_BYTES, &tmB, &full[stage], ks * BK, n_tile * BN);
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer -----------------------------------------------------------------------------
+        constexpr uint32_t idesc = kvu::make_idesc_bf16(BM, BN);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            kvu::mbar_wait(&tempty[acc], acc_phase ^ 1);
+            kvu::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+            for (int ks = 0; ks < ksteps; ks++) {
+                kvu::mbar_wait(&full[stage], phase);
+                kvu::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = kvu::smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t adesc = kvu::make_sw128_kmajor_desc(sa);
+                    const uint64_t bdesc = kvu::make_sw128_kmajor_desc(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++)   // +32 B per UMMA_K inside the 128 B swizzle atom
+                        kvu::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+                    kvu::umma_commit(&empty[stage]);
+                    if (ks == ksteps - 1) kvu::umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue: TMEM -> registers -> bias/residual/relu -> bf16 -> global ------------------------
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const int m_tile = tile / P.n_tiles, n_tile = tile % P.n_tiles;
+            kvu::mbar_wait(&tfull[acc], acc_phase);
+            kvu::tc_fence_after();
+            const int row = m_tile * BM + q * 32 + lane;
+            const bool valid = row < P.m_valid;
+            const size_t rbase = (size_t)row * P.cout + (size_t)n_tile * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t v[32];
+                kvu::tmem_ld_32x32(tmem_base + (uint32_t)acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
+                kvu::tmem_ld_wait();
+                if (valid) {
+                    const float4* bp = reinterpret_cast<const float4*>(P.bias + n_tile * BN + c * 32);
+                    uint4 res[4];
+                    if (P.residual) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(P.residual + rbase + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) res[j] = __ldg(rp + j);
+                    }
+                    uint4 o[4];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 b = __ldg(bp + j);
+                        float x0 = __uint_as_float(v[4 * j + 0]) + b.x, x1 = __uint_as_float(v[4 * j + 1]) + b.y;
+                        float x2 = __uint_as_float(v[4 * j + 2]) + b.z, x3 = __uint_as_float(v[4 * j + 3]) + b.w;
+                        if (P.residual) {
+                            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&res[j >> 1]) + (j & 1) * 2;
+                            const __nv_bfloat162 r01 = *reinterpret_cast<const __nv_bfloat162*>(&rw[0]);
+                            const __nv_bfloat162 r23 = *reinterpret_cast<const __nv_bfloat162*>(&rw[1]);
+                            x0 += __low2float(r01); x1 += __high2float(r01);
+                            x2 += __low2float(r23); x3 += __high2float(r23);
+                        }
+                        if (P.relu) {
+                            x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+                        }
+                        const __nv_bfloat162 p01 = __floats2bfloat162_rn(x0, x1), p23 = __floats2bfloat162_rn(x2, x3);
+                        uint32_t* ow = reinterpret_cast<uint32_t*>(&o[j >> 1]) + (j & 1) * 2;
+                        ow[0] = *reinterpret_cast<const uint32_t*>(&p01);
+                        ow[1] = *reinterpret_cast<const uint32_t*>(&p23);
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(P.out + rbase + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) op[j] = o[j];
+                }
+            }
+            kvu::tc_fence_before();
+            kvu::mbar_arrive(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    kvu::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) kvu::tmem_dealloc(tmem_base, 512);
+}
+
+// ---- stem: encode + conv1 + bn1 + relu ------------------------------------------------------------------
+// table [9 taps][12 pieces][C1] fp32 (BN scale folded), bias [C1].  One CTA per board, thread = channel.
+__global__ void __launch_bounds__(256) stem_kernel(const uint64_t* __restrict__ lines, int n,
+                                                   const float* __restrict__ table, const float* __restrict__ bias,
+                                                   bf16* __restrict__ out, int C1) {
+    __shared__ int8_t piece[64];
+    const int b = blockIdx.x;
+    if (b >= n) return;
+    if (threadIdx.x < 64) {
+        int pc = -1;
+#pragma unroll
+        for (int p = 0; p < 12; p++)
+            if ((__ldg(lines + (size_t)b * 16 + p) >> threadIdx.x) & 1) pc = p;
+        piece[threadIdx.x] = (int8_t)pc;
+    }
+    __syncthreads();
+    for (int co = threadIdx.x; co < C1; co += blockDim.x) {
+        const float bs = bias[co];
+        for (int px = 0; px < 64; px++) {
+            const int y = px >> 3, x = px & 7;
+            float acc = bs;
+#pragma unroll
+            for (int tap = 0; tap < 9; tap++) {
+                const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+                if (yy >= 0 && yy < 8 && xx >= 0 && xx < 8) {
+                    const int pc = piece[yy * 8 + xx];
+                    if (pc >= 0) acc += __ldg(table + ((size_t)tap * 12 + pc) * C1 + co);
+                }
+            }
+            out[((size_t)b * 64 + px) * C1 + co] = __float2bfloat16(fmaxf(acc, 0.f));
+        }
+    }
+}
+
+// ---- heads ---------------------------------------------------------------------------------------------------
+// wh [3][C] fp32 (policy ch0, policy ch1, value; BN folded), bh [3].  One CTA (256 threads) per board.
+// feat out: hp[128] (index c*64 + pixel, torch.flatten order of [2,8,8]) and hv[64], both after relu.
+__device__ __forceinline__ void head_features(const bf16* __restrict__ act, int C, const float* __restrict__ wh,
+                                              const float* __restrict__ bh, float* hp, float* hv) {
+    const int px = threadIdx.x >> 2, part = threadIdx.x & 3;   // 64 pixels x 4 channel quarters
+    const int cq = C >> 2;
+    const bf16* row = act + (size_t)px * C + part * cq;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int c = 0; c < cq; c += 8) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + c));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float a0 = __low2float(h[j]), a1 = __high2float(h[j]);
+            const int ci = part * cq + c + 2 * j;
+            s0 += a0 * __ldg(wh + ci) + a1 * __ldg(wh + ci + 1);
+            s1 += a0 * __ldg(wh + C + ci) + a1 * __ldg(wh + C + ci + 1);
+            s2 += a0 * __ldg(wh + 2 * C + ci) + a1 * __ldg(wh + 2 * C + ci + 1);
+        }
+    }
+#pragma unroll
+    for (int m = 1; m <= 2; m <<= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+    }
+    if (part == 0) {
+        hp[px] = fmaxf(s0 + bh[0], 0.f);
+        hp[64 + px] = fmaxf(s1 + bh[1], 0.f);
+        hv[px] = fmaxf(s2 + bh[2], 0.f);
+    }
+}
+
+__device__ __forceinline__ float value_mlp(const float* hv, const float* __restrict__ w1, const float* __restrict__ b1,
+                                           const float* __restrict__ w2, const float* __restrict__ b2, float* red) {
+    // value_fc1 64->512 + relu, value_fc2 512->1, tanh (ai/model.py:70-73)
+    float part = 0.f;
+    for (int j = threadIdx.x; j < 512; j += blockDim.x) {
+        float a = __ldg(b1 + j);
+        const float4* wr = reinterpret_cast<const float4*>(w1 + (size_t)j * 64);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const float4 w = __ldg(wr + i);
+            a += w.x * hv[4 * i] + w.y * hv[4 * i + 1] + w.z * hv[4 * i + 2] + w.w * hv[4 * i + 3];
+        }
+        part += fmaxf(a, 0.f) * __ldg(w2 + j);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += red[w];
+    return tanhf(tot + __ldg(b2));
+}
+
+__global__ void __launch_bounds__(256) head_full_kernel(const bf16* __restrict__ act, int n, int C,
+                                                        const float* __restrict__ wh, const float* __restrict__ bh,
+                                                        const float* __restrict__ wfc, const float* __restrict__ bfc,
+                                                        const float* __restrict__ w1, const float* __restrict__ b1,
+                                                        const float* __restrict__ w2, const float* __restrict__ b2,
+                                                        float* __restrict__ policy, float* __restrict__ value) {
+    __shared__ float hp[128], hv[64], red[8];
+    const int b = blockIdx.x;
+    if (b >= n) return;
+    head_features(act + (size_t)b * 64 * C, C, wh, bh, hp, hv);
+    __syncthreads();
+    const float v = value_mlp(hv, w1, b1, w2, b2, red);
+    if (threadIdx.x == 0 && value) value[b] = v;
+    if (policy) {
+        for (int o = threadIdx.x; o < 4096; o += blockDim.x) {
+            float a = __ldg(bfc + o);
+            const float4* wr = reinterpret_cast<const float4*>(wfc + (size_t)o * 128);
+#pragma unroll 8
+            for (int i = 0; i < 32; i++) {
+                const float4 w = __ldg(wr + i);
+                a += w.x * hp[4 * i] + w.y * hp[4 * i + 1] + w.z * hp[4 * i + 2] + w.w * hp[4 * i + 3];
+            }
+            policy[(size_t)b * 4096 + o] = a;
+        }
+    }
+}
+
+// ---- weight preparation (device side) ------------------------------------------------------------------------
+// conv weight [Cout][Cin][3][3] fp32 + conv bias + BN(gamma, beta, mean, var) -> [Cout][9][Cin] bf16 + bias fp32
+__global__ void fold_conv3x3_kernel(const float* __restrict__ w, const float* __restrict__ cb,
+                                    const float* __restrict__ g, const float* __restrict__ be,
+                                    const float* __restrict__ mu, const float* __restrict__ var, int cout, int cin,
+                                    bf16* __restrict__ wout, float* __restrict__ bout) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t tot = (size_t)cout * 9 * cin;
+    if (i < tot) {
+        const int ci = (int)(i % cin), tap = (int)((i / cin) % 9), co = (int)(i / ((size_t)cin * 9));
+        const float s = g[co] / sqrtf(var[co] + 1e-5f);
+        wout[i] = __float2bfloat16(w[((size_t)co * cin + ci) * 9 + tap] * s);
+    }
+    if (i < (size_t)cout) {
+        const float s = g[i] / sqrtf(var[i] + 1e-5f);
+        bout[i] = (cb[i] - mu[i]) * s + be[i];
+    }
+}
+// stem: [C1][12][3][3] -> table [9][12][C1] fp32
+__global__ void fold_stem_kernel(const float* __restrict__ w, const float* __restrict__ cb, const float* __restrict__ g,
+                                 const float* __restrict__ be, const float* __restrict__ mu,
+                                 const float* __restrict__ var, int c1, float* __restrict__ table,
+                                 float* __restrict__ bout) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 9 * 12 * c1) {
+        const int co = i % c1, pc = (i / c1) % 12, tap = i / (c1 * 12);
+        const float s = g[co] / sqrtf(var[co] + 1e-5f);
+        table[i] = w[((size_t)co * 12 + pc) * 9 + tap] * s;
+    }
+    if (i < c1) {
+        const float s = g[i] / sqrtf(var[i] + 1e-5f);
+        bout[i] = (cb[i] - mu[i]) * s + be[i];
+    }
+}
+// 1x1 head convs: rows [r0, r0+rows) of wh [3][C]
+__global__ void fold_head_kernel(const float* __restrict__ w, const float* __restrict__ cb, const float* __restrict__ g,
+                                 const float* __restrict__ be, const float* __restrict__ mu,
+                                 const float* __restrict__ var, int rows, int C, float* __restrict__ wh,
+                                 float* __restrict__ bh) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * C) {
+        const int r = i / C;
+        const float s = g[r] / sqrtf(var[r] + 1e-5f);
+        wh[i] = w[i] * s;
+    }
+    if (i < rows) {
+        const float s = g[i] / sqrtf(var[i] + 1e-5f);
+        bh[i] = (cb[i] - mu[i]) * s + be[i];
+    }
+}
+
+// planes [n][12][8][8] float (one-hot) -> board lines (bitboards only; meta = 0)
+__global__ void planes_to_lines_kernel(const float* __restrict__ planes, int n, uint64_t* __restrict__ lines,
+                                       int* __restrict__ not_onehot) {
+    const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;   // 12 warps, one per plane
+    if (b >= n || wid >= 12) return;
+    const float* p = planes + ((size_t)b * 12 + wid) * 64;
+    const float a = p[lane], c = p[32 + lane];
+    if ((a != 0.f && a != 1.f) || (c != 0.f && c != 1.f)) atomicExch(not_onehot, 1);
+    const uint32_t lo = __ballot_sync(0xffffffffu, a != 0.f), hi = __ballot_sync(0xffffffffu, c != 0.f);
+    if (lane == 0) lines[(size_t)b * 16 + wid] = (uint64_t)lo | ((uint64_t)hi << 32);
+    if (wid == 0 && lane < 4) lines[(size_t)b * 16 + 12 + lane] = 0;
+}
+
+}  // namespace kvn
+
+using namespace kvn;
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+static int make_act_map(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boards) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return kv_fail_msg(ctx, "cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[4] = {(cuuint64_t)C, 8, 8, (cuuint64_t)boards};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 16, (cuuint64_t)C * 128};
+    cuuint32_t box[4] = {64, 8, 8, 2};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return kv_fail_msg(ctx, "cuTensorMapEncodeTiled(activations) failed");
+    return 0;
+}
+static int make_w_map(kv_ctx* ctx, CUtensorMap* m, void* base, int cout, int K) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return kv_fail_msg(ctx, "cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cout};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {64, 256};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return kv_fail_msg(ctx, "cuTensorMapEncodeTiled(weights) failed");
+    return 0;
+}
+
+static size_t net_blob_floats(const kv_net* n) {
+    auto conv_bn = [](size_t cout, size_t cin, size_t k) { return cout * cin * k * k + cout + 4 * cout; };
+    size_t t = conv_bn(n->C1, 12, 3);
+    if (n->has_conv2) t += conv_bn(n->C, n->C1, 3);
+    t += (size_t)n->blocks * 2 * conv_bn(n->C, n->C, 3);
+    t += conv_bn(2, n->C, 1) + 4096 * 128 + 4096;
+    t += conv_bn(1, n->C, 1) + 512 * 64 + 512 + 512 + 1;
+    return t;
+}
+
+void kv_net_destroy(kv_ctx* ctx) {
+    kv_net* n = ctx->net;
+    if (!n) return;
+    for (auto& L : n->convs) {
+        if (L.w) cudaFree(L.w);
+        if (L.b) cudaFree(L.b);
+    }
+    for (int i = 0; i < 3; i++)
+        if (n->act[i]) cudaFree(n->act[i]);
+    void* ptrs[] = {n->stem_table, n->stem_bias, n->wh, n->bh, n->wfc, n->bfc, n->w1, n->b1, n->w2, n->b2, n->d_blob,
+                    n->d_flag, n->d_lines_tmp};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete n;
+    ctx->net = nullptr;
+}
+
+extern "C" {
+
+int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_blocks, int has_conv2, int max_boards) {
+    if (!ctx) return -3;
+    KV_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (stem_channels % 64 || tower_channels % 256 || stem_channels > 512 || tower_channels > 512 || n_blocks < 0 ||
+        max_boards < 1)
+        return kv_fail_msg(ctx, "kv_net_create: channels must be multiples of 64 (stem) / 256 (tower), <= 512");
+    if (!has_conv2 && stem_channels != tower_channels)
+        return kv_fail_msg(ctx, "kv_net_create: without conv2 the stem must produce the tower width");
+    kv_net_destroy(ctx);
+    kv_net* n = new kv_net();
+    ctx->net = n;
+    n->C1 = stem_channels;
+    n->C = tower_channels;
+    n->blocks = n_blocks;
+    n->has_conv2 = has_conv2 != 0;
+    n->cap = (max_boards + 1) & ~1;
+    const int cmax = n->C > n->C1 ? n->C : n->C1;
+    for (int i = 0; i < 3; i++) {
+        KV_CUDA(ctx, cudaMalloc(&n->act[i], (size_t)n->cap * 64 * cmax * sizeof(bf16)));
+        KV_CUDA(ctx, cudaMemset(n->act[i], 0, (size_t)n->cap * 64 * cmax * sizeof(bf16)));
+        if (int rc = make_act_map(ctx, &n->map_act[i][0], n->act[i], n->C1, n->cap)) return rc;
+        if (int rc = make_act_map(ctx, &n->map_act[i][1], n->act[i], n->C, n->cap)) return rc;
+    }
+    const int nconv = (n->has_conv2 ? 1 : 0) + 2 * n->blocks;
+    n->convs.resize(nconv);
+    for (int l = 0; l < nconv; l++) {
+        kv_conv& L = n->convs[l];
+        L.cin = (n->has_conv2 && l == 0) ? n->C1 : n->C;
+        L.cout = n->C;
+        KV_CUDA(ctx, cudaMalloc(&L.w, (size_t)L.cout * 9 * L.cin * sizeof(bf16)));
+        KV_CUDA(ctx, cudaMalloc(&L.b, (size_t)L.cout * sizeof(float)));
+        if (int rc = make_w_map(ctx, &L.map, L.w, L.cout, 9 * L.cin)) return rc;
+    }
+    KV_CUDA(ctx, cudaMalloc(&n->stem_table, (size_t)9 * 12 * n->C1 * sizeof(float)));
+    KV_CUDA(ctx, cudaMalloc(&n->stem_bias, (size_t)n->C1 * sizeof(float)));
+    KV_CUDA(ctx, cudaMalloc(&n->wh, (size_t)3 * n->C * sizeof(float)));
+    KV_CUDA(ctx, cudaMalloc(&n->bh, 4 * sizeof(float)));
+    KV_CUDA(ctx, cudaMalloc(&n->wfc, (size_t)4096 * 128 * sizeof(float)));
+    KV_CUDA(ctx, cudaMalloc(&n->bfc, 4096 * sizeof(float)));
+    KV_CUDA(ctx, cudaMalloc(&n->w1, 512 * 64 * sizeof(float)));
+    KV_CUDA(ctx, cudaMalloc(&n->b1, 512 * sizeof(float)));
+    KV_CUDA(ctx, cudaMalloc(&n->w2, 512 * sizeof(float)));
+    KV_CUDA(ctx, cudaMalloc(&n->b2, 4 * sizeof(float)));
+    KV_CUDA(ctx, cudaMalloc(&n->d_flag, 4 * sizeof(int)));
+    KV_CUDA(ctx, cudaMalloc(&n->d_lines_tmp, (size_t)n->cap * 128));
+    n->blob_floats = net_blob_floats(n);
+    KV_CUDA(ctx, cudaMalloc(&n->d_blob, n->blob_floats * sizeof(float)));
+    KV_CUDA(ctx, cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
+    return 0;
+}
+
+uint64_t kv_net_blob_floats(kv_ctx* ctx) { return (ctx && ctx->net) ? ctx->net->blob_floats : 0; }
+void* kv_net_blob_device_ptr(kv_ctx* ctx) { return (ctx && ctx->net) ? ctx->net->d_blob : nullptr; }
+
+// Fold the fp32 state_dict blob that sits in the net's device staging buffer (kv_net_blob_device_ptr).
+int kv_net_commit_weights(kv_ctx* ctx, void* stream) {
+    if (!ctx || !ctx->net) return kv_fail_msg(ctx, "kv_net_commit_weights: no net");
+    kv_net* n = ctx->net;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* p = n->d_blob;
+    auto take = [&](size_t k) {
+        const float* r = p;
+        p += k;
+        return r;
+    };
+    {   // conv1 + bn1
+        const float* w = take((size_t)n->C1 * 12 * 9);
+        const float* cb = take(n->C1);
+        const float *g = take(n->C1), *be = take(n->C1), *mu = take(n->C1), *var = take(n->C1);
+        const int tot = 9 * 12 * n->C1;
+        fold_stem_kernel<<<(tot + 255) / 256, 256, 0, st>>>(w, cb, g, be, mu, var, n->C1, n->stem_table, n->stem_bias);
+        KV_LAUNCH_CHECK(ctx);
+    }
+    for (auto& L : n->convs) {
+        const float* w = take((size_t)L.cout * L.cin * 9);
+        const float* cb = take(L.cout);
+        const float *g = take(L.cout), *be = take(L.cout), *mu = take(L.cout), *var = take(L.cout);
+        const size_t tot = (size_t)L.cout * 9 * L.cin;
+        fold_conv3x3_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w, cb, g, be, mu, var, L.cout, L.cin, L.w, L.b);
+        KV_LAUNCH_CHECK(ctx);
+    }
+    {   // policy head
+        const float* w = take((size_t)2 * n->C);
+        const float* cb = take(2);
+        const float *g = take(2), *be = take(2), *mu = take(2), *var = take(2);
+        fold_head_kernel<<<(2 * n->C + 255) / 256, 256, 0, st>>>(w, cb, g, be, mu, var, 2, n->C, n->wh, n->bh);
+        KV_LAUNCH_CHECK(ctx);
+        KV_CUDA(ctx, cudaMemcpyAsync(n->wfc, take((size_t)4096 * 128), (size_t)4096 * 128 * 4, cudaMemcpyDeviceToDevice, st));
+        KV_CUDA(ctx, cudaMemcpyAsync(n->bfc, take(4096), 4096 * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    {   // value head
+        const float* w = take((size_t)n->C);
+        const float* cb = take(1);
+        const float *g = take(1), *be = take(1), *mu = take(1), *var = take(1);
+        fold_head_kernel<<<(n->C + 255) / 256, 256, 0, st>>>(w, cb, g, be, mu, var, 1, n->C, n->wh + 2 * n->C, n->bh + 2);
+        KV_LAUNCH_CHECK(ctx);
+        KV_CUDA(ctx, cudaMemcpyAsync(n->w1, take(512 * 64), 512 * 64 * 4, cudaMemcpyDeviceToDevice, st));
+        KV_CUDA(ctx, cudaMemcpyAsync(n->b1, take(512), 512 * 4, cudaMemcpyDeviceToDevice, st));
+        KV_CUDA(ctx, cudaMemcpyAsync(n->w2, take(512), 512 * 4, cudaMemcpyDeviceToDevice, st));
+        KV_CUDA(ctx, cudaMemcpyAsync(n->b2, take(1), 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if ((size_t)(p - n->d_blob) != n->blob_floats) return kv_fail_msg(ctx, "kv_net_commit_weights: blob size mismatch");
+    n->loaded = true;
+    return 0;
+}
+
+int kv_net_load(kv_ctx* ctx, const float* h_blob, uint64_t n_floats) {
+    if (!ctx || !ctx->net) return kv_fail_msg(ctx, "kv_net_load: no net");
+    if (n_floats != ctx->net->blob_floats) return kv_fail_msg(ctx, "kv_net_load: blob has the wrong number of floats");
+    KV_CUDA(ctx, cudaSetDevice(ctx->device));
+    KV_CUDA(ctx, cudaMemcpy(ctx->net->d_blob, h_blob, n_floats * sizeof(float), cudaMemcpyHostToDevice));
+    if (int rc = kv_net_commit_weights(ctx, nullptr)) return rc;
+    KV_CUDA(ctx, cudaDeviceSynchronize());
+    return 0;
+}
+
+}  // extern "C"
+
+// Runs stem + tower for n boards; returns the buffer index holding the final activations.
+int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, int* final_buf, int max_convs) {
+    kv_net* net = ctx->net;
+    if (!net || !net->loaded) return kv_fail_msg(ctx, "net: weights not loaded");
+    if (n > net->cap) return kv_fail_msg(ctx, "net: batch exceeds max_boards given to kv_net_create");
+    {
+        KvTimed t_(ctx, KVK_NET_STEM, st);
+        stem_kernel<<<n, 256, 0, st>>>(d_lines, n, net->stem_table, net->stem_bias, net->act[0], net->C1);
+    }
+    KV_LAUNCH_CHECK(ctx);
+    int x = 0;   // buffer holding the current block input
+    auto conv = [&](int layer, int in, int out, int res, int relu) -> int {
+        kv_conv& L = net->convs[layer];
+        ConvParams P;
+        P.bias = L.b;
+        P.residual = res >= 0 ? net->act[res] : nullptr;
+        P.out = net->act[out];
+        P.m_tiles = (n + 1) / 2;
+        P.n_tiles = L.cout / BN;
+        P.kb_per_tap = L.cin / BK;
+        P.cout = L.cout;
+        P.m_valid = n * 64;
+        P.relu = relu;
+        const int total = P.m_tiles * P.n_tiles;
+        const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+        {
+            KvTimed t_(ctx, KVK_NET_CONV, st);
+            conv3x3_umma_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(net->map_act[in][L.cin == net->C1 && L.cin != net->C ? 0 : 1],
+                                                                       L.map, P);
+        }
+        KV_LAUNCH_CHECK(ctx);
+        return 0;
+    };
+    int layer = 0;
+    *final_buf = 0;
+    if (max_convs == 0) return 0;
+    if (net->has_conv2) {
+        if (int rc = conv(layer++, 0, 1, -1, 1)) return rc;
+        x = 1;
+        *final_buf = x;
+        if (layer == max_convs) return 0;
+    }
+    for (int b = 0; b < net->blocks; b++) {
+        const int t = (x + 1) % 3, o = (x + 2) % 3;
+        if (int rc = conv(layer++, x, t, -1, 1)) return rc;
+        if (layer == max_convs) {   // debug stop inside a block: expose the intermediate
+            *final_buf = t;
+            return 0;
+        }
+        if (int rc = conv(layer++, t, o, x, 1)) return rc;
+        x = o;
+        *final_buf = x;
+        if (layer == max_convs) return 0;
+    }
+    return 0;
+}
+
+extern "C" {
+
+int kv_net_forward(kv_ctx* ctx, const uint64_t* d_lines, int n, float* d_policy, float* d_value, void* stream) {
+    if (!ctx) return -3;
+    if (n <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int fb = 0;
+    if (int rc = kv_net_tower(ctx, d_lines, n, st, &fb, -1)) return rc;
+    kv_net* net = ctx->net;
+    {
+        KvTimed t_(ctx, KVK_NET_HEAD, st);
+        head_full_kernel<<<n, 256, 0, st>>>(net->act[fb], n, net->C, net->wh, net->bh, net->wfc, net->bfc, net->w1,
+                                            net->b1, net->w2, net->b2, d_policy, d_value);
+    }
+    KV_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// Debug/test hook: run the stem and the first n_convs tower convolutions, copy the bf16 NHWC activations out.
+int kv_net_forward_partial(kv_ctx* ctx, const uint64_t* d_lines, int n, int n_convs, void* d_act_out, int* channels) {
+    if (!ctx || !ctx->net) return kv_fail_msg(ctx, "kv_net_forward_partial: no net");
+    int fb = 0;
+    if (int rc = kv_net_tower(ctx, d_lines, n, nullptr, &fb, n_convs)) return rc;
+    const int C = n_convs == 0 ? ctx->net->C1 : ctx->net->C;
+    if (channels) *channels = C;
+    KV_CUDA(ctx, cudaMemcpyAsync(d_act_out, ctx->net->act[fb], (size_t)n * 64 * C * 2, cudaMemcpyDeviceToDevice, nullptr));
+    KV_CUDA(ctx, cudaStreamSynchronize(nullptr));
+    return 0;
+}
+
+// ChessNet.forward drop-in: fp32 one-hot planes in (the reference's input format), logits + value out.
+int kv_net_forward_planes(kv_ctx* ctx, const float* d_planes, int n, float* d_policy, float* d_value, void* stream) {
+    if (!ctx || !ctx->net) return kv_fail_msg(ctx, "kv_net_forward_planes: no net");
+    if (n <= 0) return 0;
+    kv_net* net = ctx->net;
+    if (n > net->cap) return kv_fail_msg(ctx, "net: batch exceeds max_boards given to kv_net_create");
+    cudaStream_t st = (cudaStream_t)stream;
+    KV_CUDA(ctx, cudaMemsetAsync(net->d_flag, 0, sizeof(int), st));
+    planes_to_lines_kernel<<<n, 384, 0, st>>>(d_planes, n, net->d_lines_tmp, net->d_flag);
+    KV_LAUNCH_CHECK(ctx);
+    int flag = 0;
+    KV_CUDA(ctx, cudaMemcpyAsync(&flag, net->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    KV_CUDA(ctx, cudaStreamSynchronize(st));
+    if (flag) return kv_fail_msg(ctx, "kv_net_forward_planes: input planes are not 0/1 (encode_board output expected)");
+    return kv_net_forward(ctx, net->d_lines_tmp, n, d_policy, d_value, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,34 @@
+// kv_net.h — device-resident network state (kv_net.cu), shared with the MCTS translation unit
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <vector>
+
+struct kv_conv {
+    __nv_bfloat16* w = nullptr;   // [cout][9][cin], BN scale folded
+    float* b = nullptr;           // [cout]
+    int cin = 0, cout = 0;
+    CUtensorMap map;
+};
+
+struct kv_net {
+    int C1 = 256, C = 512, blocks = 5;
+    bool has_conv2 = true;
+    bool loaded = false;
+    int cap = 0;                           // boards (even)
+    std::vector<kv_conv> convs;
+    __nv_bfloat16* act[3] = {nullptr, nullptr, nullptr};   // NHWC bf16 [cap*64][max(C1,C)]
+    CUtensorMap map_act[3][2];             // [buffer][0: C1-channel view, 1: C-channel view]
+    float *stem_table = nullptr, *stem_bias = nullptr;
+    float *wh = nullptr, *bh = nullptr;    // head 1x1 convs [3][C], [3]
+    float *wfc = nullptr, *bfc = nullptr;  // policy_fc [4096][128], [4096]
+    float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;   // value_fc1 [512][64], value_fc2 [512]
+    float* d_blob = nullptr;               // fp32 state_dict staging (NCCL broadcast target)
+    size_t blob_floats = 0;
+    int* d_flag = nullptr;
+    uint64_t* d_lines_tmp = nullptr;
+};
+
+struct kv_ctx;
+int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, int* final_buf, int max_convs = -1);

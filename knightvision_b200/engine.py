@@ -117,6 +117,56 @@ class Engine:
         N.check(self.ctx, self._lib.kv_encode(self.ctx, _ptr(lines), n, _ptr(out), self._stream()), "kv_encode")
         return out
 
+    # ---- network ---------------------------------------------------------------------------------
+    def net_create(self, stem: int = 256, tower: int = 512, blocks: int = 5, conv2: bool = True, max_boards: int = 4096):
+        N.check(self.ctx, self._lib.kv_net_create(self.ctx, stem, tower, blocks, int(conv2), max_boards), "kv_net_create")
+        self.net_max_boards = max_boards
+
+    def net_load(self, blob: torch.Tensor):
+        """blob: fp32 CPU tensor, ChessNet.weight_blob()."""
+        blob = blob.detach().to(torch.float32).cpu().contiguous()
+        need = int(self._lib.kv_net_blob_floats(self.ctx))
+        if blob.numel() != need:
+            raise N.KVError(f"weight blob has {blob.numel()} floats, the architecture needs {need}")
+        N.check(self.ctx, self._lib.kv_net_load(self.ctx, ctypes.c_void_p(blob.data_ptr()), blob.numel()), "kv_net_load")
+
+    def net_blob_tensor(self) -> torch.Tensor:
+        """Device staging buffer for the fp32 weight blob as a torch tensor (NCCL broadcast target)."""
+        n = int(self._lib.kv_net_blob_floats(self.ctx))
+        ptr = int(self._lib.kv_net_blob_device_ptr(self.ctx))
+
+        class _Holder:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_Holder(), device=self.device)
+
+    def net_commit(self):
+        N.check(self.ctx, self._lib.kv_net_commit_weights(self.ctx, self._stream()), "kv_net_commit_weights")
+
+    def net_forward(self, lines: torch.Tensor, want_policy: bool = True):
+        n = lines.shape[0]
+        pol = torch.empty((n, 4096), dtype=torch.float32, device=self.device) if want_policy else None
+        val = torch.empty(n, dtype=torch.float32, device=self.device)
+        N.check(self.ctx, self._lib.kv_net_forward(self.ctx, _ptr(lines), n, _ptr(pol) if want_policy else None,
+                                                   _ptr(val), self._stream()), "kv_net_forward")
+        return pol, val
+
+    def net_forward_partial(self, lines: torch.Tensor, n_convs: int) -> torch.Tensor:
+        """Test hook: NHWC bf16 activations [n,8,8,C] after the stem and the first n_convs tower convolutions."""
+        n = lines.shape[0]
+        out = torch.empty((n, 8, 8, 512), dtype=torch.bfloat16, device=self.device)
+        ch = ctypes.c_int(0)
+        N.check(self.ctx, self._lib.kv_net_forward_partial(self.ctx, _ptr(lines), n, n_convs, _ptr(out), ctypes.byref(ch)),
+                "kv_net_forward_partial")
+        return out.reshape(-1)[: n * 64 * ch.value].reshape(n, 8, 8, ch.value)
+
+    def net_forward_planes(self, planes: torch.Tensor):
+        n = planes.shape[0]
+        pol = torch.empty((n, 4096), dtype=torch.float32, device=self.device)
+        val = torch.empty(n, dtype=torch.float32, device=self.device)
+        N.check(self.ctx, self._lib.kv_net_forward_planes(self.ctx, _ptr(planes), n, _ptr(pol), _ptr(val),
+                                                          self._stream()), "kv_net_forward_planes")
+        return pol, val
+
     # ---- host-buffer forms (numpy in / numpy out; copies happen inside the C call) ---------------
     def movegen_host(self, lines: np.ndarray, stride: int = MOVE_STRIDE):
         lines = np.ascontiguousarray(lines, dtype=np.uint64).copy()

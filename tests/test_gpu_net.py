@@ -1,0 +1,125 @@
+"""Policy/value network on the sm_100a kernels vs the fp32 reference graph (ai/model.py:51-77).
+Tolerance (north_star): 2e-2 absolute on policy logits and value, bf16 kernels against fp32."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import helpers as H
+from oracle import kv_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from knightvision_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _net(seed=0, bnrand=False, **kw):
+    from knightvision_b200.model import ChessNet
+    torch.manual_seed(seed)
+    net = ChessNet(**kw).eval()
+    if bnrand:   # same recipe as oracle/gen_golden.py: non-trivial BN statistics so folding is exercised
+        g = torch.Generator().manual_seed(1)
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.05)
+                m.running_var.copy_(1.0 + 0.2 * torch.rand(m.running_var.shape, generator=g))
+                m.weight.data.copy_(1.0 + 0.1 * torch.randn(m.weight.shape, generator=g))
+                m.bias.data.copy_(0.05 * torch.randn(m.bias.shape, generator=g))
+    return net
+
+
+def _lines(n, seed=3):
+    lines = H.random_playout_positions(n_games=max(2, n // 40), max_plies=80, seed=seed)
+    idx = np.random.default_rng(seed).permutation(len(lines))[:n]
+    return lines[idx]
+
+
+def test_layers_against_torch(eng):
+    """stem, conv2 and the first residual block, layer by layer (localises a GEMM/TMA/descriptor bug)."""
+    from knightvision_b200.engine import lines_to_device
+    from knightvision_b200.model import fp32_reference_forward  # noqa: F401
+    net = _net(bnrand=True).attach(eng, max_batch=64)
+    lines = _lines(37)
+    d = lines_to_device(lines, eng.device)
+    x = torch.from_numpy(O.encode(lines)).cuda()
+    netc = net.cuda()
+
+    def bn(m, t):
+        return F.batch_norm(t, m.running_mean, m.running_var, m.weight, m.bias, False, 0.0, m.eps)
+    with torch.no_grad():
+        a0 = F.relu(bn(netc.bn1, netc.conv1(x)))
+        g0 = eng.net_forward_partial(d, 0).float().permute(0, 3, 1, 2)
+        assert (g0 - a0).abs().max().item() < 1e-2
+        a1 = F.relu(bn(netc.bn2, netc.conv2(a0)))
+        g1 = eng.net_forward_partial(d, 1).float().permute(0, 3, 1, 2)
+        assert (g1 - a1).abs().max().item() < 2e-2, (g1 - a1).abs().max().item()
+        b = netc.res_blocks[0]
+        t = F.relu(bn(b.bn1, b.conv1(a1)))
+        g2 = eng.net_forward_partial(d, 2).float().permute(0, 3, 1, 2)
+        assert (g2 - t).abs().max().item() < 3e-2, (g2 - t).abs().max().item()
+        a2 = F.relu(bn(b.bn2, b.conv2(t)) + a1)
+        g3 = eng.net_forward_partial(d, 3).float().permute(0, 3, 1, 2)
+        assert (g3 - a2).abs().max().item() < 4e-2, (g3 - a2).abs().max().item()
+
+
+@pytest.mark.parametrize("variant", ["init", "bnrand"])
+def test_forward_matches_reference_golden(eng, variant):
+    """Golden outputs of the UNMODIFIED reference ChessNet (fp32, CPU) on 8 playout positions."""
+    from knightvision_b200.engine import lines_to_device
+    g = np.load(H.GOLDEN + "/net.npz")
+    net = _net(bnrand=(variant == "bnrand")).attach(eng, max_batch=64)
+    assert list(g["keys"]) == list(net.state_dict().keys())
+    pol, val = net.forward_lines(lines_to_device(g["lines"], eng.device))
+    torch.cuda.synchronize()
+    dp = np.abs(pol.cpu().numpy() - g["policy_" + variant]).max()
+    dv = np.abs(val.cpu().numpy() - g["value_" + variant]).max()
+    assert dp < TOL and dv < TOL, (dp, dv)
+    # the planes entry point (ChessNet.forward drop-in) gives the same numbers
+    x = torch.from_numpy(O.encode(g["lines"])).cuda()
+    pol2, val2 = net(x)
+    assert torch.equal(pol2, pol) and torch.equal(val2, val)
+
+
+def test_forward_batch_odd_sizes_and_determinism(eng):
+    from knightvision_b200.engine import lines_to_device
+    from knightvision_b200.model import fp32_reference_forward
+    net = _net(seed=5, bnrand=True).attach(eng, max_batch=700)
+    lines = _lines(611, seed=9)
+    d = lines_to_device(lines, eng.device)
+    pol, val = net.forward_lines(d)
+    pol_b, val_b = net.forward_lines(d)
+    assert torch.equal(pol, pol_b) and torch.equal(val, val_b)          # run-to-run deterministic
+    p1, v1 = net.forward_lines(d[:1])
+    assert torch.equal(p1[0], pol[0]) and torch.equal(v1[0], val[0])     # independent of batch composition
+    with torch.no_grad():
+        rp, rv = fp32_reference_forward(net.cuda(), torch.from_numpy(O.encode(lines)).cuda())
+    assert (pol - rp).abs().max().item() < TOL and (val - rv).abs().max().item() < TOL
+
+
+def test_rejects_training_mode_and_non_onehot(eng):
+    from knightvision_b200 import _native as N
+    net = _net().attach(eng, max_batch=8)
+    with pytest.raises(N.KVError):
+        net.train()(torch.zeros(1, 12, 8, 8).cuda())
+    net.eval()
+    with pytest.raises(N.KVError):
+        net(torch.full((1, 12, 8, 8), 0.5).cuda())
+
+
+def test_tower_20x256_variant(eng):
+    """BASELINE config 5's 20-block x 256-channel tower through the same kernels."""
+    from knightvision_b200.engine import lines_to_device
+    from knightvision_b200.model import fp32_reference_forward
+    net = _net(seed=2, bnrand=True, stem=256, tower=256, blocks=20, conv2=False).attach(eng, max_batch=64)
+    lines = _lines(33, seed=4)
+    pol, val = net.forward_lines(lines_to_device(lines, eng.device))
+    with torch.no_grad():
+        rp, rv = fp32_reference_forward(net.cuda(), torch.from_numpy(O.encode(lines)).cuda())
+    assert (pol - rp).abs().max().item() < TOL and (val - rv).abs().max().item() < TOL
