@@ -119,6 +119,31 @@ KV_API int kv_net_forward(kv_ctx* ctx, const uint64_t* d_lines, int n, float* d_
 KV_API int kv_net_forward_partial(kv_ctx* ctx, const uint64_t* d_lines, int n, int n_convs, void* d_act_out, int* channels);
 KV_API int kv_net_forward_planes(kv_ctx* ctx, const float* d_planes, int n, float* d_policy, float* d_value, void* stream);
 
+/* ---- self-play engine: batched PUCT search + game records (replaces the game loop of scripts/self_play.py:111-255;
+ *      the tree search itself is new functionality, specified in DESIGN.md §MCTS and oracle/kv_oracle.c) ----------- */
+/* n_games concurrent games on this GPU, `sims` simulations per move (one in flight per game), edges_per_node = edge
+ * pool sizing (0 = 48), max_plies = ply cap (draw), temp_plies = plies that sample the move from the visit counts,
+ * eval_mode 0 = hash test evaluator, 1 = the network of kv_net_create (max_boards >= n_games). */
+KV_API int kv_mcts_create(kv_ctx* ctx, int n_games, int sims, int edges_per_node, int max_plies, int temp_plies,
+                          float c_puct, float dir_alpha, float dir_eps, uint64_t seed, int eval_mode);
+/* d_start [n_games][16] start lines or NULL (initial position); game ids = game_id_base + local index (RNG keys) */
+KV_API int kv_mcts_reset(kv_ctx* ctx, const uint64_t* d_start, uint64_t game_id_base, void* stream);
+KV_API int kv_mcts_run_sims(kv_ctx* ctx, int n_waves, void* stream);   /* n_waves simulations for every live game */
+KV_API int kv_mcts_finish_move(kv_ctx* ctx, void* stream);            /* pick + record + play the move, reset trees */
+KV_API int kv_mcts_run_move(kv_ctx* ctx, void* stream);               /* sims waves + finish_move */
+/* h_out8: games done, sum of sims done in the current move, evaluator calls, plies played, games with edge-pool
+ * overflow, white wins, black wins, draws */
+KV_API int kv_mcts_status(kv_ctx* ctx, uint64_t* h_out8, void* stream);
+KV_API int kv_mcts_geometry(kv_ctx* ctx, int32_t* out4);              /* n_games, node_cap, edge_cap, rec_cap */
+/* records of every game in game order; d_lines [cap][16] board lines (kv_encode gives the reference's planes),
+ * d_move policy index (ai/ai.py:51-57), d_reward 1.0 / 0.2 / -1.0 (scripts/self_play.py:245-250), d_game index */
+KV_API int kv_mcts_records(kv_ctx* ctx, uint64_t* d_lines, int32_t* d_move, float* d_reward, int32_t* d_game, int cap,
+                           int32_t* h_count, void* stream);
+/* test hooks (host buffers): root edges of one game; per-node evaluator values / per-edge priors for oracle replay */
+KV_API int kv_mcts_read_root(kv_ctx* ctx, int game, uint16_t* h_moves, uint32_t* h_N, float* h_W, float* h_P, int32_t* h_info4);
+KV_API int kv_mcts_dump_tree(kv_ctx* ctx, int game, float* h_node_val, int32_t* h_node_first, float* h_edge_P,
+                             uint64_t* h_root_line16);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,17 @@ SIGNATURES = {
     "kv_net_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "kv_net_forward_partial": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, ctypes.POINTER(c_int)]),
     "kv_net_forward_planes": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "kv_mcts_create": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float,
+                               ctypes.c_float, c_u64, c_int]),
+    "kv_mcts_reset": (c_int, [c_void_p, c_void_p, c_u64, c_void_p]),
+    "kv_mcts_run_sims": (c_int, [c_void_p, c_int, c_void_p]),
+    "kv_mcts_finish_move": (c_int, [c_void_p, c_void_p]),
+    "kv_mcts_run_move": (c_int, [c_void_p, c_void_p]),
+    "kv_mcts_status": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "kv_mcts_geometry": (c_int, [c_void_p, c_void_p]),
+    "kv_mcts_records": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "kv_mcts_read_root": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kv_mcts_dump_tree": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -1,0 +1,69 @@
+// kv_heads.cuh — policy / value head device functions (ai/model.py:64-73), shared by the full-logits forward
+// (kv_net.cu) and the search-mode evaluator that only needs the legal moves' logits (kv_mcts.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace kvn {
+using bf16 = __nv_bfloat16;
+
+// wh [3][C] fp32 (policy ch0, policy ch1, value; BN folded), bh [3].  One CTA (256 threads) per board.
+// feat out: hp[128] (index c*64 + pixel, torch.flatten order of [2,8,8]) and hv[64], both after relu.
+__device__ __forceinline__ void head_features(const bf16* __restrict__ act, int C, const float* __restrict__ wh,
+                                              const float* __restrict__ bh, float* hp, float* hv) {
+    const int px = threadIdx.x >> 2, part = threadIdx.x & 3;   // 64 pixels x 4 channel quarters
+    const int cq = C >> 2;
+    const bf16* row = act + (size_t)px * C + part * cq;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int c = 0; c < cq; c += 8) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + c));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float a0 = __low2float(h[j]), a1 = __high2float(h[j]);
+            const int ci = part * cq + c + 2 * j;
+            s0 += a0 * __ldg(wh + ci) + a1 * __ldg(wh + ci + 1);
+            s1 += a0 * __ldg(wh + C + ci) + a1 * __ldg(wh + C + ci + 1);
+            s2 += a0 * __ldg(wh + 2 * C + ci) + a1 * __ldg(wh + 2 * C + ci + 1);
+        }
+    }
+#pragma unroll
+    for (int m = 1; m <= 2; m <<= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+    }
+    if (part == 0) {
+        hp[px] = fmaxf(s0 + bh[0], 0.f);
+        hp[64 + px] = fmaxf(s1 + bh[1], 0.f);
+        hv[px] = fmaxf(s2 + bh[2], 0.f);
+    }
+}
+
+__device__ __forceinline__ float value_mlp(const float* hv, const float* __restrict__ w1, const float* __restrict__ b1,
+                                           const float* __restrict__ w2, const float* __restrict__ b2, float* red) {
+    // value_fc1 64->512 + relu, value_fc2 512->1, tanh (ai/model.py:70-73)
+    float part = 0.f;
+    for (int j = threadIdx.x; j < 512; j += blockDim.x) {
+        float a = __ldg(b1 + j);
+        const float4* wr = reinterpret_cast<const float4*>(w1 + (size_t)j * 64);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const float4 w = __ldg(wr + i);
+            a += w.x * hv[4 * i] + w.y * hv[4 * i + 1] + w.z * hv[4 * i + 2] + w.w * hv[4 * i + 3];
+        }
+        part += fmaxf(a, 0.f) * __ldg(w2 + j);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += red[w];
+    return tanhf(tot + __ldg(b2));
+}
+
+
+}  // namespace kvn

@@ -1,0 +1,405 @@
+// kv_mcts.cu — self-play engine: batched PUCT search kernels (kv_mcts.cuh), the search-mode network evaluator
+// (legal-move logits + masked softmax fused with the heads), game records, and their C-ABI entry points.
+//
+// One search wave = one simulation for every live game:
+//   select_kernel      warp per game: descend / make-move / movegen / queue leaf       (integer + fp32 PUCT)
+//   network            stem + tcgen05 tower over the queued leaves (count stays on the device)      (kv_net.cu)
+//   eval_net_kernel    CTA per leaf: heads, logits of the LEGAL moves only, softmax priors, root noise, backup
+// cfg.sims waves, then finish_move_kernel picks / records / plays the move for every game.
+#include <cstring>
+#include <vector>
+
+#include "kv_heads.cuh"
+#include "kv_internal.h"
+#include "kv_mcts.cuh"
+#include "kv_net.h"
+#include "kv_tables_dev.cuh"
+
+namespace kv {
+
+
+constexpr int kMW = 8;   // warps (games) per CTA
+struct __align__(16) MctsSmem {
+    Tables tab;
+    uint16_t mv[kMW][MAX_MOVES];
+};
+
+__device__ __forceinline__ void stage_tables_m(Tables& dstT) {
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(&g_tables);
+    uint64_t* dst = reinterpret_cast<uint64_t*>(&dstT);
+    for (int i = threadIdx.x; i < kTableWords; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kMW * 32) mcts_select_kernel(MctsCfg cfg, MctsArrays A, int G) {
+    __shared__ MctsSmem sm;
+    stage_tables_m(sm.tab);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * kMW + wid;
+    if (g >= G) return;
+    mcts_select_warp(sm.tab, lane, cfg, A, g, sm.mv[wid]);
+}
+
+__global__ void __launch_bounds__(kMW * 32) mcts_hash_eval_kernel(MctsCfg cfg, MctsArrays A) {
+    __shared__ float scratch[kMW][MAX_MOVES];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int slot = blockIdx.x * kMW + wid;
+    if (slot >= (int)*A.n_eval) return;
+    mcts_hash_eval_warp(lane, cfg, A, slot, scratch[wid]);
+}
+
+__global__ void __launch_bounds__(kMW * 32) mcts_finish_move_kernel(MctsCfg cfg, MctsArrays A, int G) {
+    __shared__ MctsSmem sm;
+    stage_tables_m(sm.tab);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * kMW + wid;
+    if (g >= G) return;
+    mcts_finish_move_warp(sm.tab, lane, cfg, A, g, sm.mv[wid]);
+}
+
+struct HeadW {
+    const float *wh, *bh, *wfc, *bfc, *w1, *b1, *w2, *b2;
+    int C;
+};
+
+// CTA per queued leaf: heads on the tower output, logits of the legal moves, then the warp-level expand/backup.
+__global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArrays A, const __nv_bfloat16* __restrict__ act,
+                                                            HeadW H) {
+    __shared__ float hp[128], hv[64], red[8], logits[MAX_MOVES];
+    const int slot = blockIdx.x;
+    if (slot >= (int)*A.n_eval) return;
+    const int g = A.eval_game[slot];
+    kvn::head_features(act + (size_t)slot * 64 * H.C, H.C, H.wh, H.bh, hp, hv);
+    __syncthreads();
+    const float v_white = kvn::value_mlp(hv, H.w1, H.b1, H.w2, H.b2, red);
+    const GameHdr* h = &A.hdr[g];
+    const NodeMeta m = A.node_meta[(size_t)g * cfg.node_cap + h->pend_node];
+    const int n = m.ne_term & 0xFFFF;
+    const size_t e0 = (size_t)g * cfg.edge_cap + m.first_edge;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int idx = move_index(A.eMv[e0 + k]);
+        float a = __ldg(H.bfc + idx);
+        const float4* wr = reinterpret_cast<const float4*>(H.wfc + (size_t)idx * 128);
+#pragma unroll 8
+        for (int i = 0; i < 32; i++) {
+            const float4 w = __ldg(wr + i);
+            a += w.x * hp[4 * i] + w.y * hp[4 * i + 1] + w.z * hp[4 * i + 2] + w.w * hp[4 * i + 3];
+        }
+        logits[k] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) mcts_expand_warp((int)threadIdx.x, cfg, A, g, logits, v_white);
+}
+
+__global__ void mcts_init_kernel(MctsCfg cfg, MctsArrays A, int G, const uint64_t* __restrict__ start, uint64_t id_base) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    GameHdr h;
+    memset(&h, 0, sizeof(h));
+    h.pend_node = -1;
+    h.game_id = id_base + (uint64_t)g;
+    A.hdr[g] = h;
+    for (int i = 0; i < LINE_WORDS; i++) {
+        uint64_t v = start ? start[(size_t)g * LINE_WORDS + i] : 0ull;
+        if (i >= 13) v = 0;
+        A.root_line[(size_t)g * LINE_WORDS + i] = v;
+    }
+}
+
+// status: [0] games done, [1] sum sims_done, [2] sum evals, [3] sum plies, [4] overflow count, [5] white wins,
+// [6] black wins, [7] draws (among done)
+__global__ void mcts_status_kernel(MctsArrays A, int G, unsigned long long* out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const GameHdr h = A.hdr[g];
+    if (h.done) atomicAdd(out + 0, 1ull);
+    atomicAdd(out + 1, (unsigned long long)h.sims_done);
+    atomicAdd(out + 2, (unsigned long long)h.n_evals);
+    atomicAdd(out + 3, (unsigned long long)h.ply);
+    if (h.overflow) atomicAdd(out + 4, 1ull);
+    if (h.done && h.result > 0) atomicAdd(out + 5, 1ull);
+    if (h.done && h.result < 0) atomicAdd(out + 6, 1ull);
+    if (h.done && h.result == 0) atomicAdd(out + 7, 1ull);
+}
+
+// Records of all games, in game order: lines [N][16] (bitboards, rest 0), move index, reward (self_play.py:245-250:
+// white's perspective, win 1.0 / draw 0.2 / loss -1.0, same value on every ply), game id.
+__global__ void mcts_record_offsets_kernel(MctsArrays A, int G, int rec_cap, int* offsets /*[G+1]*/) {
+    // single CTA, sequential scan by thread 0 over <= 32 768 games is fine (once per generation)
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int acc = 0;
+        for (int g = 0; g < G; g++) {
+            offsets[g] = acc;
+            int p = A.hdr[g].ply;
+            acc += p < rec_cap ? p : rec_cap;
+        }
+        offsets[G] = acc;
+    }
+}
+__global__ void mcts_record_gather_kernel(MctsArrays A, int G, int rec_cap, const int* __restrict__ offsets,
+                                          uint64_t* __restrict__ out_lines, int32_t* __restrict__ out_move,
+                                          float* __restrict__ out_reward, int32_t* __restrict__ out_game, int cap) {
+    const int g = blockIdx.x;
+    if (g >= G) return;
+    const GameHdr h = A.hdr[g];
+    const int np = h.ply < rec_cap ? h.ply : rec_cap;
+    const float reward = h.result > 0 ? 1.0f : (h.result < 0 ? -1.0f : 0.2f);
+    for (int i = threadIdx.x; i < np * 16; i += blockDim.x) {
+        const int p = i >> 4, wd = i & 15;
+        const int o = offsets[g] + p;
+        if (o >= cap) continue;
+        out_lines[(size_t)o * 16 + wd] = wd < 12 ? A.rec_line[((size_t)g * rec_cap + p) * 12 + wd] : 0ull;
+        if (wd == 0) {
+            out_move[o] = move_index(A.rec_move[(size_t)g * rec_cap + p]);
+            out_reward[o] = reward;
+            out_game[o] = g;
+        }
+    }
+}
+
+}  // namespace kv
+
+using namespace kv;
+
+struct kv_mcts {
+    MctsCfg cfg;
+    MctsArrays A;
+    int G = 0;
+    std::vector<void*> allocs;
+    unsigned long long* d_status = nullptr;
+    int* d_offsets = nullptr;
+};
+
+void kv_mcts_destroy(kv_ctx* ctx) {
+    kv_mcts* m = ctx->mcts;
+    if (!m) return;
+    for (void* p : m->allocs) cudaFree(p);
+    delete m;
+    ctx->mcts = nullptr;
+}
+
+template <class T>
+static int dalloc(kv_ctx* ctx, kv_mcts* m, T** p, size_t count) {
+    KV_CUDA(ctx, cudaMalloc((void**)p, count * sizeof(T)));
+    m->allocs.push_back(*p);
+    return 0;
+}
+
+extern "C" {
+
+int kv_mcts_create(kv_ctx* ctx, int n_games, int sims, int edges_per_node, int max_plies, int temp_plies, float c_puct,
+                   float dir_alpha, float dir_eps, uint64_t seed, int eval_mode) {
+    if (!ctx) return -3;
+    KV_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_games < 1 || sims < 1 || max_plies < 1) return kv_fail_msg(ctx, "kv_mcts_create: bad sizes");
+    if (eval_mode == 1 && (!ctx->net || ctx->net->cap < n_games))
+        return kv_fail_msg(ctx, "kv_mcts_create: network evaluator needs kv_net_create(max_boards >= n_games) first");
+    kv_mcts_destroy(ctx);
+    kv_mcts* m = new kv_mcts();
+    ctx->mcts = m;
+    m->G = n_games;
+    MctsCfg& c = m->cfg;
+    c.sims = sims;
+    c.node_cap = sims;
+    if (edges_per_node <= 0) edges_per_node = 48;
+    c.edge_cap = sims * edges_per_node;
+    if (c.edge_cap < MAX_MOVES) c.edge_cap = MAX_MOVES;
+    c.temp_plies = temp_plies;
+    c.max_plies = max_plies;
+    c.rec_cap = max_plies;
+    c.eval_mode = eval_mode;
+    c.c_puct = c_puct;
+    c.dir_alpha = dir_alpha;
+    c.dir_eps = dir_eps;
+    c.seed = seed;
+    MctsArrays& A = m->A;
+    const size_t G = (size_t)n_games;
+    if (dalloc(ctx, m, &A.hdr, G)) return -1;
+    if (dalloc(ctx, m, &A.root_line, G * 16)) return -1;
+    if (dalloc(ctx, m, &A.node_line, G * c.node_cap * 16)) return -1;
+    if (dalloc(ctx, m, &A.node_meta, G * c.node_cap)) return -1;
+    if (dalloc(ctx, m, &A.eP, G * c.edge_cap)) return -1;
+    if (dalloc(ctx, m, &A.eN, G * c.edge_cap)) return -1;
+    if (dalloc(ctx, m, &A.eW, G * c.edge_cap)) return -1;
+    if (dalloc(ctx, m, &A.eChild, G * c.edge_cap)) return -1;
+    if (dalloc(ctx, m, &A.eMv, G * c.edge_cap)) return -1;
+    if (dalloc(ctx, m, &A.path_edge, G * (c.node_cap + 1))) return -1;
+    if (dalloc(ctx, m, &A.path_node, G * (c.node_cap + 1))) return -1;
+    if (dalloc(ctx, m, &A.n_eval, 4)) return -1;
+    if (dalloc(ctx, m, &A.eval_game, G)) return -1;
+    if (dalloc(ctx, m, &A.eval_lines, (G + 1) * 16)) return -1;
+    if (dalloc(ctx, m, &A.rec_line, G * c.rec_cap * 12)) return -1;
+    if (dalloc(ctx, m, &A.rec_move, G * c.rec_cap)) return -1;
+    if (dalloc(ctx, m, &m->d_status, 8)) return -1;
+    if (dalloc(ctx, m, &m->d_offsets, G + 1)) return -1;
+    KV_CUDA(ctx, cudaMemset(A.n_eval, 0, 16));
+    return 0;
+}
+
+// start lines: d_start [n_games][16] or NULL for the initial position of GameState() (core/chessEngine.py:34-84)
+int kv_mcts_reset(kv_ctx* ctx, const uint64_t* d_start, uint64_t game_id_base, void* stream) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_reset: no search context");
+    kv_mcts* m = ctx->mcts;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t* tmp = nullptr;
+    if (!d_start) {
+        // the standard initial position as a board line, replicated
+        static const uint64_t start[16] = {
+            1ull << 60, 1ull << 59, (1ull << 56) | (1ull << 63), (1ull << 58) | (1ull << 61), (1ull << 57) | (1ull << 62),
+            0xFFull << 48, 1ull << 4, 1ull << 3, (1ull << 0) | (1ull << 7), (1ull << 2) | (1ull << 5),
+            (1ull << 1) | (1ull << 6), 0xFFull << 8,
+            1ull | (64ull << 8) | (60ull << 16) | (4ull << 24), 0, 0, 0};
+        std::vector<uint64_t> h((size_t)m->G * 16);
+        for (int g = 0; g < m->G; g++) memcpy(&h[(size_t)g * 16], start, sizeof(start));
+        KV_CUDA(ctx, cudaMalloc(&tmp, h.size() * 8));
+        KV_CUDA(ctx, cudaMemcpyAsync(tmp, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
+        KV_CUDA(ctx, cudaStreamSynchronize(st));
+        d_start = tmp;
+    }
+    mcts_init_kernel<<<(m->G + 255) / 256, 256, 0, st>>>(m->cfg, m->A, m->G, d_start, game_id_base);
+    KV_LAUNCH_CHECK(ctx);
+    if (tmp) {
+        KV_CUDA(ctx, cudaStreamSynchronize(st));
+        cudaFree(tmp);
+    }
+    return 0;
+}
+
+static int mcts_wave(kv_ctx* ctx, cudaStream_t st) {
+    kv_mcts* m = ctx->mcts;
+    const int G = m->G;
+    const int grid = (G + kMW - 1) / kMW;
+    KV_CUDA(ctx, cudaMemsetAsync(m->A.n_eval, 0, sizeof(uint32_t), st));
+    {
+        KvTimed t_(ctx, KVK_MCTS_SELECT, st);
+        mcts_select_kernel<<<grid, kMW * 32, 0, st>>>(m->cfg, m->A, G);
+    }
+    KV_LAUNCH_CHECK(ctx);
+    if (m->cfg.eval_mode == 0) {
+        KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
+        mcts_hash_eval_kernel<<<grid, kMW * 32, 0, st>>>(m->cfg, m->A);
+        KV_LAUNCH_CHECK(ctx);
+    } else {
+        int fb = 0;
+        if (int rc = kv_net_tower(ctx, m->A.eval_lines, G, st, &fb, -1, reinterpret_cast<const int*>(m->A.n_eval))) return rc;
+        kv_net* net = ctx->net;
+        HeadW H{net->wh, net->bh, net->wfc, net->bfc, net->w1, net->b1, net->w2, net->b2, net->C};
+        KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
+        mcts_eval_net_kernel<<<G, 256, 0, st>>>(m->cfg, m->A, net->act[fb], H);
+        KV_LAUNCH_CHECK(ctx);
+    }
+    return 0;
+}
+
+int kv_mcts_run_sims(kv_ctx* ctx, int n_waves, void* stream) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_run_sims: no search context");
+    for (int i = 0; i < n_waves; i++)
+        if (int rc = mcts_wave(ctx, (cudaStream_t)stream)) return rc;
+    return 0;
+}
+
+int kv_mcts_finish_move(kv_ctx* ctx, void* stream) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_finish_move: no search context");
+    kv_mcts* m = ctx->mcts;
+    KvTimed t_(ctx, KVK_MCTS_MISC, (cudaStream_t)stream);
+    mcts_finish_move_kernel<<<(m->G + kMW - 1) / kMW, kMW * 32, 0, (cudaStream_t)stream>>>(m->cfg, m->A, m->G);
+    KV_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// one move for every live game: cfg.sims waves, then pick / record / play
+int kv_mcts_run_move(kv_ctx* ctx, void* stream) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_run_move: no search context");
+    if (int rc = kv_mcts_run_sims(ctx, ctx->mcts->cfg.sims, stream)) return rc;
+    return kv_mcts_finish_move(ctx, stream);
+}
+
+int kv_mcts_status(kv_ctx* ctx, uint64_t* h_out8, void* stream) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_status: no search context");
+    kv_mcts* m = ctx->mcts;
+    cudaStream_t st = (cudaStream_t)stream;
+    KV_CUDA(ctx, cudaMemsetAsync(m->d_status, 0, 8 * sizeof(unsigned long long), st));
+    mcts_status_kernel<<<(m->G + 255) / 256, 256, 0, st>>>(m->A, m->G, m->d_status);
+    KV_LAUNCH_CHECK(ctx);
+    KV_CUDA(ctx, cudaMemcpyAsync(h_out8, m->d_status, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    KV_CUDA(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+// test hook: root edges of one game (host buffers of 256 entries): move words, visits, W, P; info = {n, nodes, edges, ply}
+int kv_mcts_read_root(kv_ctx* ctx, int game, uint16_t* h_moves, uint32_t* h_N, float* h_W, float* h_P, int32_t* h_info4) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_read_root: no search context");
+    kv_mcts* m = ctx->mcts;
+    KV_CUDA(ctx, cudaDeviceSynchronize());
+    GameHdr h;
+    KV_CUDA(ctx, cudaMemcpy(&h, m->A.hdr + game, sizeof(h), cudaMemcpyDeviceToHost));
+    NodeMeta nm;
+    KV_CUDA(ctx, cudaMemcpy(&nm, m->A.node_meta + (size_t)game * m->cfg.node_cap, sizeof(nm), cudaMemcpyDeviceToHost));
+    int n = (h.n_nodes && !(nm.ne_term >> 16)) ? (nm.ne_term & 0xFFFF) : 0;
+    h_info4[0] = n;
+    h_info4[1] = h.n_nodes;
+    h_info4[2] = h.n_edges;
+    h_info4[3] = h.ply;
+    if (n) {
+        const size_t e0 = (size_t)game * m->cfg.edge_cap + nm.first_edge;
+        KV_CUDA(ctx, cudaMemcpy(h_moves, m->A.eMv + e0, n * 2, cudaMemcpyDeviceToHost));
+        KV_CUDA(ctx, cudaMemcpy(h_N, m->A.eN + e0, n * 4, cudaMemcpyDeviceToHost));
+        KV_CUDA(ctx, cudaMemcpy(h_W, m->A.eW + e0, n * 4, cudaMemcpyDeviceToHost));
+        KV_CUDA(ctx, cudaMemcpy(h_P, m->A.eP + e0, n * 4, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+// test hook: what the oracle needs to replay a search "given identical net outputs": per node the evaluator's value
+// and first edge, per edge the prior.  Host buffers sized node_cap / node_cap / edge_cap.
+int kv_mcts_dump_tree(kv_ctx* ctx, int game, float* h_node_val, int32_t* h_node_first, float* h_edge_P,
+                      uint64_t* h_root_line16) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_dump_tree: no search context");
+    kv_mcts* m = ctx->mcts;
+    KV_CUDA(ctx, cudaDeviceSynchronize());
+    std::vector<NodeMeta> nm(m->cfg.node_cap);
+    KV_CUDA(ctx, cudaMemcpy(nm.data(), m->A.node_meta + (size_t)game * m->cfg.node_cap, nm.size() * sizeof(NodeMeta),
+                            cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m->cfg.node_cap; i++) {
+        h_node_val[i] = nm[i].val;
+        h_node_first[i] = nm[i].first_edge;
+    }
+    KV_CUDA(ctx, cudaMemcpy(h_edge_P, m->A.eP + (size_t)game * m->cfg.edge_cap, (size_t)m->cfg.edge_cap * 4,
+                            cudaMemcpyDeviceToHost));
+    if (h_root_line16)
+        KV_CUDA(ctx, cudaMemcpy(h_root_line16, m->A.root_line + (size_t)game * 16, 128, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int kv_mcts_geometry(kv_ctx* ctx, int32_t* out4) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_geometry: no search context");
+    out4[0] = ctx->mcts->G;
+    out4[1] = ctx->mcts->cfg.node_cap;
+    out4[2] = ctx->mcts->cfg.edge_cap;
+    out4[3] = ctx->mcts->cfg.rec_cap;
+    return 0;
+}
+
+// Game records in game order (scripts/self_play.py:253 tuple fields, packed): returns the record count in *h_count.
+// d_lines [cap][16] (feed to kv_encode for the reference's float planes), d_move [cap] policy index, d_reward [cap],
+// d_game [cap] local game index.
+int kv_mcts_records(kv_ctx* ctx, uint64_t* d_lines, int32_t* d_move, float* d_reward, int32_t* d_game, int cap,
+                    int32_t* h_count, void* stream) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_records: no search context");
+    kv_mcts* m = ctx->mcts;
+    cudaStream_t st = (cudaStream_t)stream;
+    mcts_record_offsets_kernel<<<1, 32, 0, st>>>(m->A, m->G, m->cfg.rec_cap, m->d_offsets);
+    KV_LAUNCH_CHECK(ctx);
+    int total = 0;
+    KV_CUDA(ctx, cudaMemcpyAsync(&total, m->d_offsets + m->G, sizeof(int), cudaMemcpyDeviceToHost, st));
+    KV_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h_count) *h_count = total;
+    if (d_lines && cap > 0) {
+        mcts_record_gather_kernel<<<m->G, 128, 0, st>>>(m->A, m->G, m->cfg.rec_cap, m->d_offsets, d_lines, d_move, d_reward,
+                                                        d_game, cap);
+        KV_LAUNCH_CHECK(ctx);
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,354 @@
+// kv_mcts.cuh — batched PUCT tree search over a GPU-resident node pool: warp-per-game device code.
+//
+// The reference has no tree search; the algorithm is specified in DESIGN.md §MCTS and restated
+// sequentially in oracle/kv_oracle.c (mcts_search), which these functions must match bit-for-bit.
+// One simulation is in flight per game (4 096 concurrent games already fill the network batch), so the search
+// inside a game is sequential and needs no virtual loss; a warp owns a game:
+//   select   warp-level argmax of the PUCT score over a node's edges (lane k handles edges k, k+32, ...),
+//            ties broken towards the lowest edge index = the reference's move order
+//   expand   make-move + legal move generation for the new leaf (kv_rules.cuh), edges appended to the game's pool
+//   evaluate the leaf is queued (one atomic add) for the batched network pass; terminal leaves back up at once
+//   backup   lane 0 walks the recorded path: W += +/-v, N += 1 in the oracle's order (fp32, no atomics needed)
+// All floating point that steers the search goes through include/kv_detmath.h (no FMA, fixed order).
+// Compiles for the device and, with KV_HOST_EMU, for the CPU lock-step emulator (tests/simt_emu).
+#pragma once
+#include "../../include/kv_detmath.h"
+#include "kv_rules.cuh"
+
+namespace kv {
+
+struct MctsCfg {
+    int sims, node_cap, edge_cap, temp_plies, max_plies, eval_mode;   // eval_mode: 0 hash evaluator, 1 network
+    float c_puct, dir_alpha, dir_eps;
+    int rec_cap;          // records per game (>= max_plies)
+    uint64_t seed;
+};
+
+struct GameHdr {          // 64 B
+    int n_nodes, n_edges, ply, done;
+    int result, pend_node, pend_depth, overflow;
+    int sims_done, n_evals, cache_hits, pad0;
+    uint64_t game_id;
+    uint64_t pad1;
+};
+
+struct NodeMeta {         // 16 B: first_edge | n_edges + (term << 16) | visits N | value (terminal or evaluator's)
+    int first_edge;
+    int ne_term;
+    uint32_t N;
+    float val;
+};
+
+struct MctsArrays {
+    GameHdr* hdr;          // [G]
+    uint64_t* root_line;   // [G][16]
+    uint64_t* node_line;   // [G][node_cap][16]
+    NodeMeta* node_meta;   // [G][node_cap]
+    float* eP;             // [G][edge_cap]
+    uint32_t* eN;
+    float* eW;
+    int* eChild;
+    uint16_t* eMv;
+    int* path_edge;        // [G][node_cap + 1] (edge index inside the game's pool)
+    int* path_node;
+    // evaluation queue of the current wave
+    uint32_t* n_eval;      // device counter
+    int* eval_game;        // [G]
+    uint64_t* eval_lines;  // [G][16]
+    // game records (scripts/self_play.py:173-174): position bitboards + the move played
+    uint64_t* rec_line;    // [G][rec_cap][12]
+    uint16_t* rec_move;    // [G][rec_cap]
+};
+
+KV_DEV float f_from_bits(uint32_t u) { return kvd_u2f(u); }
+
+KV_DEV uint64_t pos_hash_warp(uint64_t w, int lane) {
+    // same fold as the oracle's pos_hash: sequential over the 12 bitboards (cheap: 12 steps)
+    uint64_t h = 0x243F6A8885A308D3ull;
+#pragma unroll
+    for (int p = 0; p < 12; p++) h = kvd_mix64(h ^ (shfl64(w, p) + (uint64_t)(p + 1) * 0x9E3779B97F4A7C15ull));
+    return h;
+}
+KV_DEV float hash_logit(uint64_t ph, int idx) {
+    return (float)kvd_rand24(ph, (uint64_t)idx, 1, 0) * (4.0f / 16777216.0f) - 2.0f;
+}
+KV_DEV float hash_value(uint64_t ph) { return (float)kvd_rand24(ph, 4096, 2, 0) * (2.0f / 16777216.0f) - 1.0f; }
+KV_DEV int move_index(int mv) { return (mv & 63) * 64 + ((mv >> 6) & 63); }   // encode_move, ai/ai.py:51-57
+
+// lane 0: walk the path, newest edge first
+KV_DEV void mcts_backup_lane0(const MctsArrays& A, size_t ebase, size_t nbase, size_t pbase, int depth, float v) {
+    for (int i = depth - 1; i >= 0; i--) {
+        v = -v;
+        const size_t e = ebase + (size_t)A.path_edge[pbase + i];
+        A.eW[e] = A.eW[e] + v;
+        A.eN[e] = A.eN[e] + 1;
+        A.node_meta[nbase + (size_t)A.path_node[pbase + i]].N += 1;
+    }
+}
+
+// One simulation step for game g: descend, create the leaf, queue it for evaluation or back up a terminal value.
+KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, const MctsArrays& A, int g, uint16_t* mv) {
+    GameHdr* h = &A.hdr[g];
+    if (h->done) return;
+    const size_t nbase = (size_t)g * cfg.node_cap, ebase = (size_t)g * cfg.edge_cap;
+    const size_t pbase = (size_t)g * (cfg.node_cap + 1);
+    const int n_nodes = h->n_nodes;
+    if (n_nodes >= cfg.node_cap) return;   // cannot happen: sims <= node_cap
+    int depth = 0, node = 0, leaf = -1;
+    float v = 0.0f;
+    uint64_t w = 0;
+    if (n_nodes == 0) {
+        w = lane < LINE_WORDS ? A.root_line[(size_t)g * LINE_WORDS + lane] : 0ull;
+        leaf = 0;
+    } else {
+        for (;;) {
+            const NodeMeta m = A.node_meta[nbase + node];
+            const int ne = m.ne_term & 0xFFFF;
+            if (m.ne_term >> 16) {
+                v = m.val;
+                if (lane == 0) A.node_meta[nbase + node].N = m.N + 1;
+                break;
+            }
+            const float sq = KVD_SQRTF((float)m.N);
+            float bs = 0.0f;
+            int bi = 0x7FFFFFFF;
+            for (int k = lane; k < ne; k += 32) {
+                const size_t e = ebase + m.first_edge + k;
+                const float sc = kvd_puct(A.eW[e], A.eN[e], A.eP[e], sq, cfg.c_puct);
+                if (bi == 0x7FFFFFFF || sc > bs) {
+                    bs = sc;
+                    bi = k;
+                }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const float os = shfl_xorf(bs, d, lane);
+                const int oi = shfl_xor32(bi, d, lane);
+                if (oi != 0x7FFFFFFF && (bi == 0x7FFFFFFF || os > bs || (os == bs && oi < bi))) {
+                    bs = os;
+                    bi = oi;
+                }
+            }
+            const int ei = m.first_edge + bi;
+            if (lane == 0) {
+                A.path_node[pbase + depth] = node;
+                A.path_edge[pbase + depth] = ei;
+            }
+            depth++;
+            const int child = A.eChild[ebase + ei];
+            if (child < 0) {
+                w = lane < LINE_WORDS ? A.node_line[(nbase + node) * LINE_WORDS + lane] : 0ull;
+                w = make_move_warp(lane, w, A.eMv[ebase + ei], T_Q);
+                leaf = n_nodes;
+                if (lane == 0) A.eChild[ebase + ei] = leaf;
+                break;
+            }
+            node = child;
+        }
+    }
+    bool queued = false;
+    if (leaf >= 0) {
+        const GenOut go = movegen_warp(T, lane, w, mv);   // w carries the :564 rewrite, as the reference's state would
+        const int n = go.n < MAX_MOVES ? go.n : MAX_MOVES;
+        if (lane < LINE_WORDS) A.node_line[(nbase + leaf) * LINE_WORDS + lane] = w;
+        NodeMeta nm;
+        nm.N = 1;
+        nm.first_edge = -1;
+        nm.ne_term = 1 << 16;
+        nm.val = 0.0f;
+        const int n_edges = h->n_edges;
+        if (n == 0) {
+            nm.val = (go.flags & RF_CHECKMATE) ? -1.0f : 0.0f;
+        } else if (go.flags & RF_ONLY_KINGS) {
+            nm.val = 0.0f;
+        } else if (n_edges + n > cfg.edge_cap) {
+            nm.val = 0.0f;
+            if (lane == 0) h->overflow = 1;
+        } else {
+            nm.first_edge = n_edges;
+            nm.ne_term = n;
+            for (int k = lane; k < n; k += 32) {
+                const size_t e = ebase + n_edges + k;
+                A.eMv[e] = mv[k];
+                A.eN[e] = 0;
+                A.eW[e] = 0.0f;
+                A.eP[e] = 0.0f;
+                A.eChild[e] = -1;
+            }
+            uint32_t slot = 0;
+            if (lane == 0) slot = atomic_add_u32(A.n_eval, 1u);
+            slot = (uint32_t)shfl32((int)slot, 0);
+            if (lane < LINE_WORDS) A.eval_lines[(size_t)slot * LINE_WORDS + lane] = w;
+            if (lane == 0) {
+                A.eval_game[slot] = g;
+                h->n_edges = n_edges + n;
+                h->pend_node = leaf;
+                h->pend_depth = depth;
+            }
+            queued = true;
+        }
+        v = nm.val;
+        if (lane == 0) {
+            A.node_meta[nbase + leaf] = nm;
+            h->n_nodes = n_nodes + 1;
+        }
+    }
+    syncwarp();
+    if (!queued && lane == 0) {
+        mcts_backup_lane0(A, ebase, nbase, pbase, depth, v);
+        h->sims_done += 1;
+    }
+    syncwarp();
+}
+
+// Finish the pending simulation of game g given the leaf's legal-move logits (n floats, edge order) and the
+// evaluator's white-perspective value: softmax priors (+ root Dirichlet noise), then backup.
+KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int g, const float* logits, float v_white) {
+    GameHdr* h = &A.hdr[g];
+    const size_t nbase = (size_t)g * cfg.node_cap, ebase = (size_t)g * cfg.edge_cap;
+    const size_t pbase = (size_t)g * (cfg.node_cap + 1);
+    const int c = h->pend_node, depth = h->pend_depth;
+    const NodeMeta m = A.node_meta[nbase + c];
+    const int n = m.ne_term & 0xFFFF;
+    const size_t e0 = ebase + m.first_edge;
+    const bool wtm = A.node_line[(nbase + c) * LINE_WORDS + 12] & 1;
+    float mx = -3.0e38f;
+    for (int k = lane; k < n; k += 32) mx = logits[k] > mx ? logits[k] : mx;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const float o = shfl_xorf(mx, d, lane);
+        mx = o > mx ? o : mx;
+    }
+    for (int k = lane; k < n; k += 32) A.eP[e0 + k] = kvd_expf(logits[k] - mx);
+    syncwarp();
+    float s = 0.0f;
+    if (lane == 0)
+        for (int k = 0; k < n; k++) s = s + A.eP[e0 + k];
+    s = shflf(s, 0);
+    for (int k = lane; k < n; k += 32) A.eP[e0 + k] = A.eP[e0 + k] / s;
+    if (c == 0 && cfg.dir_eps > 0.0f) {
+        // root Dirichlet(alpha) noise over the legal moves (scripts/self_play.py:153-154 mixes with eps = 0.25)
+        for (int k = lane; k < n; k += 32)
+            A.eW[e0 + k] = kvd_gamma_small(cfg.dir_alpha, cfg.seed, h->game_id, (uint64_t)h->ply * 256 + (uint64_t)k);
+        syncwarp();
+        float gs = 0.0f;
+        if (lane == 0)
+            for (int k = 0; k < n; k++) gs = gs + A.eW[e0 + k];
+        gs = shflf(gs, 0);
+        for (int k = lane; k < n; k += 32) {
+            const float eta = A.eW[e0 + k] / gs;
+            A.eP[e0 + k] = (1.0f - cfg.dir_eps) * A.eP[e0 + k] + cfg.dir_eps * eta;
+            A.eW[e0 + k] = 0.0f;
+        }
+    }
+    syncwarp();
+    const float v = wtm ? v_white : -v_white;
+    if (lane == 0) {
+        A.node_meta[nbase + c].val = v;
+        mcts_backup_lane0(A, ebase, nbase, pbase, depth, v);
+        h->sims_done += 1;
+        h->n_evals += 1;
+        h->pend_node = -1;
+    }
+    syncwarp();
+}
+
+// Hash evaluator (test evaluator, oracle mode 0): logits and value from a hash of the position.
+// scratch: n floats of per-warp scratch (shared memory on the device).
+KV_DEV void mcts_hash_eval_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int slot, float* scratch) {
+    const int g = A.eval_game[slot];
+    const uint64_t w = lane < LINE_WORDS ? A.eval_lines[(size_t)slot * LINE_WORDS + lane] : 0ull;
+    const uint64_t ph = pos_hash_warp(w, lane);
+    const GameHdr* h = &A.hdr[g];
+    const NodeMeta m = A.node_meta[(size_t)g * cfg.node_cap + h->pend_node];
+    const int n = m.ne_term & 0xFFFF;
+    const size_t e0 = (size_t)g * cfg.edge_cap + m.first_edge;
+    for (int k = lane; k < n; k += 32) scratch[k] = hash_logit(ph, move_index(A.eMv[e0 + k]));
+    syncwarp();
+    mcts_expand_warp(lane, cfg, A, g, scratch, hash_value(ph));
+}
+
+// After cfg.sims simulations: pick the move from the root visit counts, record (position, move), play it,
+// detect the end of the game (scripts/self_play.py:122-238 control flow) and reset the tree.
+KV_DEV void mcts_finish_move_warp(const Tables& T, int lane, const MctsCfg& cfg, const MctsArrays& A, int g, uint16_t* mv) {
+    GameHdr* h = &A.hdr[g];
+    if (h->done) return;
+    const size_t nbase = (size_t)g * cfg.node_cap, ebase = (size_t)g * cfg.edge_cap;
+    const NodeMeta m = A.node_meta[nbase];
+    const int ply = h->ply;
+    uint64_t w = lane < LINE_WORDS ? A.root_line[(size_t)g * LINE_WORDS + lane] : 0ull;
+    if (h->n_nodes == 0 || (m.ne_term >> 16)) {   // root had no move at all: the game is over as it stands
+        if (lane == 0) {
+            h->done = 1;
+            h->result = (h->n_nodes && m.val < 0.0f) ? ((w & 1) ? -1 : 1) : 0;
+        }
+        syncwarp();
+        return;
+    }
+    const int n = m.ne_term & 0xFFFF;
+    const size_t e0 = ebase + m.first_edge;
+    // total visits
+    int tot = 0;
+    for (int k = lane; k < n; k += 32) tot += (int)A.eN[e0 + k];
+    tot = warp_sum32(tot, lane);
+    int pick = 0;
+    if (ply < cfg.temp_plies && tot > 0) {
+        const uint64_t r = ((uint64_t)kvd_rand24(cfg.seed, h->game_id, (uint64_t)ply, 0xC0FFEEull) * (uint64_t)tot) >> 24;
+        int base = 0;
+        pick = -1;
+        for (int k0 = 0; k0 < n; k0 += 32) {   // warp-uniform trip count
+            const int k = k0 + lane;
+            const int c = k < n ? (int)A.eN[e0 + k] : 0;
+            const int incl = warp_incl_scan(c, lane) + base;
+            const uint32_t hit = ballot(k < n && (uint64_t)incl > r);
+            if (pick < 0 && hit) pick = k0 + ffs32(hit) - 1;
+            base = shfl32(incl, 31);
+        }
+        if (pick < 0) pick = 0;
+    } else {
+        int bc = -1, bi = 0x7FFFFFFF;
+        for (int k = lane; k < n; k += 32) {
+            const int c = (int)A.eN[e0 + k];
+            if (c > bc) {
+                bc = c;
+                bi = k;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const int oc = shfl_xor32(bc, d, lane), oi = shfl_xor32(bi, d, lane);
+            if (oc > bc || (oc == bc && oi < bi)) {
+                bc = oc;
+                bi = oi;
+            }
+        }
+        pick = bi;
+    }
+    const int mvw = A.eMv[e0 + pick];
+    if (ply < cfg.rec_cap) {
+        if (lane < 12) A.rec_line[((size_t)g * cfg.rec_cap + ply) * 12 + lane] = w;
+        if (lane == 0) A.rec_move[(size_t)g * cfg.rec_cap + ply] = (uint16_t)mvw;
+    }
+    w = make_move_warp(lane, w, mvw, T_Q);
+    const GenOut go = movegen_warp(T, lane, w, mv);
+    if (lane < LINE_WORDS) A.root_line[(size_t)g * LINE_WORDS + lane] = w;
+    const bool wtm_new = shfl64(w, 12) & 1;
+    if (lane == 0) {
+        const int np = ply + 1;
+        h->ply = np;
+        h->n_nodes = 0;
+        h->n_edges = 0;
+        h->sims_done = 0;
+        h->pend_node = -1;
+        if (go.n == 0) {
+            h->done = 1;
+            h->result = (go.flags & RF_CHECKMATE) ? (wtm_new ? -1 : 1) : 0;   // self_play.py:217-220
+        } else if ((go.flags & RF_ONLY_KINGS) || np >= cfg.max_plies) {
+            h->done = 1;
+            h->result = 0;
+        }
+    }
+    syncwarp();
+}
+
+}  // namespace kv

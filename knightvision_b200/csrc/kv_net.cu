@@ -27,6 +27,7 @@
 
 #include "kv_internal.h"
 #include "kv_net.h"
+#include "kv_heads.cuh"
 #include "kv_umma.cuh"
 
 using bf16 = __nv_bfloat16;
@@ -43,6 +44,7 @@ struct ConvParams {
     const bf16* residual;
     bf16* out;
     int m_tiles, n_tiles, kb_per_tap, cout, m_valid, relu;
+    const int* n_ptr;   // optional device-side board count (search waves): overrides m_tiles / m_valid
 };
 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
@@ -76,6 +78,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     kvu::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (P.n_ptr) {
+        const int nb = *P.n_ptr;
+        P.m_tiles = (nb + 1) >> 1;
+        P.m_valid = nb * 64;
+    }
     const int total = P.m_tiles * P.n_tiles;
     const int ksteps = 9 * P.kb_per_tap;
 
@@ -198,10 +205,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ---- stem: encode + conv1 + bn1 + relu ------------------------------------------------------------------
 // table [9 taps][12 pieces][C1] fp32 (BN scale folded), bias [C1].  One CTA per board, thread = channel.
 __global__ void __launch_bounds__(256) stem_kernel(const uint64_t* __restrict__ lines, int n,
+                                                   const int* __restrict__ n_ptr,
                                                    const float* __restrict__ table, const float* __restrict__ bias,
                                                    bf16* __restrict__ out, int C1) {
     __shared__ int8_t piece[64];
     const int b = blockIdx.x;
+    if (n_ptr) n = *n_ptr;
     if (b >= n) return;
     if (threadIdx.x < 64) {
         int pc = -1;
@@ -229,63 +238,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint64_t* __restrict__ 
     }
 }
 
-// ---- heads ---------------------------------------------------------------------------------------------------
-// wh [3][C] fp32 (policy ch0, policy ch1, value; BN folded), bh [3].  One CTA (256 threads) per board.
-// feat out: hp[128] (index c*64 + pixel, torch.flatten order of [2,8,8]) and hv[64], both after relu.
-__device__ __forceinline__ void head_features(const bf16* __restrict__ act, int C, const float* __restrict__ wh,
-                                              const float* __restrict__ bh, float* hp, float* hv) {
-    const int px = threadIdx.x >> 2, part = threadIdx.x & 3;   // 64 pixels x 4 channel quarters
-    const int cq = C >> 2;
-    const bf16* row = act + (size_t)px * C + part * cq;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int c = 0; c < cq; c += 8) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + c));
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float a0 = __low2float(h[j]), a1 = __high2float(h[j]);
-            const int ci = part * cq + c + 2 * j;
-            s0 += a0 * __ldg(wh + ci) + a1 * __ldg(wh + ci + 1);
-            s1 += a0 * __ldg(wh + C + ci) + a1 * __ldg(wh + C + ci + 1);
-            s2 += a0 * __ldg(wh + 2 * C + ci) + a1 * __ldg(wh + 2 * C + ci + 1);
-        }
-    }
-#pragma unroll
-    for (int m = 1; m <= 2; m <<= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, m);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, m);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, m);
-    }
-    if (part == 0) {
-        hp[px] = fmaxf(s0 + bh[0], 0.f);
-        hp[64 + px] = fmaxf(s1 + bh[1], 0.f);
-        hv[px] = fmaxf(s2 + bh[2], 0.f);
-    }
-}
-
-__device__ __forceinline__ float value_mlp(const float* hv, const float* __restrict__ w1, const float* __restrict__ b1,
-                                           const float* __restrict__ w2, const float* __restrict__ b2, float* red) {
-    // value_fc1 64->512 + relu, value_fc2 512->1, tanh (ai/model.py:70-73)
-    float part = 0.f;
-    for (int j = threadIdx.x; j < 512; j += blockDim.x) {
-        float a = __ldg(b1 + j);
-        const float4* wr = reinterpret_cast<const float4*>(w1 + (size_t)j * 64);
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const float4 w = __ldg(wr + i);
-            a += w.x * hv[4 * i] + w.y * hv[4 * i + 1] + w.z * hv[4 * i + 2] + w.w * hv[4 * i + 3];
-        }
-        part += fmaxf(a, 0.f) * __ldg(w2 + j);
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
-    __syncthreads();
-    float tot = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += red[w];
-    return tanhf(tot + __ldg(b2));
-}
-
+// ---- heads: head_features / value_mlp live in kv_heads.cuh (shared with the search-mode evaluator) ----------
 __global__ void __launch_bounds__(256) head_full_kernel(const bf16* __restrict__ act, int n, int C,
                                                         const float* __restrict__ wh, const float* __restrict__ bh,
                                                         const float* __restrict__ wfc, const float* __restrict__ bfc,
@@ -571,13 +524,14 @@ int kv_net_load(kv_ctx* ctx, const float* h_blob, uint64_t n_floats) {
 }  // extern "C"
 
 // Runs stem + tower for n boards; returns the buffer index holding the final activations.
-int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, int* final_buf, int max_convs) {
+int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, int* final_buf, int max_convs,
+                 const int* n_ptr) {
     kv_net* net = ctx->net;
     if (!net || !net->loaded) return kv_fail_msg(ctx, "net: weights not loaded");
     if (n > net->cap) return kv_fail_msg(ctx, "net: batch exceeds max_boards given to kv_net_create");
     {
         KvTimed t_(ctx, KVK_NET_STEM, st);
-        stem_kernel<<<n, 256, 0, st>>>(d_lines, n, net->stem_table, net->stem_bias, net->act[0], net->C1);
+        stem_kernel<<<n, 256, 0, st>>>(d_lines, n, n_ptr, net->stem_table, net->stem_bias, net->act[0], net->C1);
     }
     KV_LAUNCH_CHECK(ctx);
     int x = 0;   // buffer holding the current block input
@@ -593,6 +547,7 @@ int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, i
         P.cout = L.cout;
         P.m_valid = n * 64;
         P.relu = relu;
+        P.n_ptr = n_ptr;
         const int total = P.m_tiles * P.n_tiles;
         const int grid = total < ctx->sm_count ? total : ctx->sm_count;
         {

@@ -31,4 +31,6 @@ struct kv_net {
 };
 
 struct kv_ctx;
-int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, int* final_buf, int max_convs = -1);
+// n = boards (grid sizing / upper bound); n_ptr = optional device-side count that overrides n inside the kernels
+int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, int* final_buf, int max_convs = -1,
+                 const int* n_ptr = nullptr);

@@ -9,10 +9,10 @@
 
 #include "kv_internal.h"
 #include "kv_rules.cuh"
+#include "kv_tables_dev.cuh"
 
 namespace kv {
 
-__device__ const Tables g_tables = make_tables();
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;

@@ -167,6 +167,66 @@ class Engine:
                                                           self._stream()), "kv_net_forward_planes")
         return pol, val
 
+    # ---- self-play search ---------------------------------------------------------------------------
+    def mcts_create(self, n_games: int, sims: int, max_plies: int, temp_plies: int = 30, c_puct: float = 1.5,
+                    dir_alpha: float = 0.3, dir_eps: float = 0.25, seed: int = 42, eval_mode: int = 1,
+                    edges_per_node: int = 0):
+        N.check(self.ctx, self._lib.kv_mcts_create(self.ctx, n_games, sims, edges_per_node, max_plies, temp_plies,
+                                                   c_puct, dir_alpha, dir_eps, seed, eval_mode), "kv_mcts_create")
+        g = np.zeros(4, dtype=np.int32)
+        N.check(self.ctx, self._lib.kv_mcts_geometry(self.ctx, _ptr(g)), "kv_mcts_geometry")
+        self.mcts_games, self.mcts_node_cap, self.mcts_edge_cap, self.mcts_rec_cap = (int(x) for x in g)
+        self.mcts_sims = sims
+
+    def mcts_reset(self, start_lines: torch.Tensor | None = None, game_id_base: int = 0):
+        N.check(self.ctx, self._lib.kv_mcts_reset(self.ctx, _ptr(start_lines) if start_lines is not None else None,
+                                                  game_id_base, self._stream()), "kv_mcts_reset")
+
+    def mcts_run_sims(self, n_waves: int):
+        N.check(self.ctx, self._lib.kv_mcts_run_sims(self.ctx, n_waves, self._stream()), "kv_mcts_run_sims")
+
+    def mcts_finish_move(self):
+        N.check(self.ctx, self._lib.kv_mcts_finish_move(self.ctx, self._stream()), "kv_mcts_finish_move")
+
+    def mcts_run_move(self):
+        N.check(self.ctx, self._lib.kv_mcts_run_move(self.ctx, self._stream()), "kv_mcts_run_move")
+
+    def mcts_status(self) -> dict:
+        out = np.zeros(8, dtype=np.uint64)
+        N.check(self.ctx, self._lib.kv_mcts_status(self.ctx, _ptr(out), self._stream()), "kv_mcts_status")
+        keys = ("done", "sims_in_move", "evals", "plies", "overflow", "white_wins", "black_wins", "draws")
+        return {k: int(v) for k, v in zip(keys, out)}
+
+    def mcts_read_root(self, game: int) -> dict:
+        mv = np.zeros(256, np.uint16); n_ = np.zeros(256, np.uint32); w = np.zeros(256, np.float32)
+        p = np.zeros(256, np.float32); info = np.zeros(4, np.int32)
+        N.check(self.ctx, self._lib.kv_mcts_read_root(self.ctx, game, _ptr(mv), _ptr(n_), _ptr(w), _ptr(p), _ptr(info)),
+                "kv_mcts_read_root")
+        n = int(info[0])
+        return dict(moves=mv[:n], N=n_[:n], W=w[:n], P=p[:n], nodes=int(info[1]), edges=int(info[2]), ply=int(info[3]))
+
+    def mcts_dump_tree(self, game: int):
+        nv = np.zeros(self.mcts_node_cap, np.float32); nf = np.zeros(self.mcts_node_cap, np.int32)
+        ep = np.zeros(self.mcts_edge_cap, np.float32); root = np.zeros(16, np.uint64)
+        N.check(self.ctx, self._lib.kv_mcts_dump_tree(self.ctx, game, _ptr(nv), _ptr(nf), _ptr(ep), _ptr(root)),
+                "kv_mcts_dump_tree")
+        return nv, nf, ep, root
+
+    def mcts_records(self):
+        """(lines int64 [N,16], move_index int32 [N], reward float32 [N], game int32 [N]) device tensors, game order."""
+        cnt = ctypes.c_int32(0)
+        N.check(self.ctx, self._lib.kv_mcts_records(self.ctx, None, None, None, None, 0, ctypes.byref(cnt), self._stream()),
+                "kv_mcts_records")
+        n = int(cnt.value)
+        lines = torch.zeros((max(n, 1), 16), dtype=torch.int64, device=self.device)
+        move = torch.zeros(max(n, 1), dtype=torch.int32, device=self.device)
+        reward = torch.zeros(max(n, 1), dtype=torch.float32, device=self.device)
+        game = torch.zeros(max(n, 1), dtype=torch.int32, device=self.device)
+        if n:
+            N.check(self.ctx, self._lib.kv_mcts_records(self.ctx, _ptr(lines), _ptr(move), _ptr(reward), _ptr(game), n,
+                                                        ctypes.byref(cnt), self._stream()), "kv_mcts_records")
+        return lines[:n], move[:n], reward[:n], game[:n]
+
     # ---- host-buffer forms (numpy in / numpy out; copies happen inside the C call) ---------------
     def movegen_host(self, lines: np.ndarray, stride: int = MOVE_STRIDE):
         lines = np.ascontiguousarray(lines, dtype=np.uint64).copy()

@@ -1,0 +1,122 @@
+"""Drop-in for the reference's self-play entry points (scripts/self_play.py:258-311), on the B200 engine.
+
+    self_play(model, num_games, device, max_moves=None, model_path=None) -> list[(np.float32[12,8,8], int, float)]
+    generate_self_play_data(model, num_games, device, max_moves=None)     -> same, decisive-only filter (:304-310)
+
+Every game runs concurrently on the GPU: bitboard rules kernels, a GPU-resident PUCT tree per game and the
+tcgen05 policy/value tower evaluate one leaf per game per wave.  The reference picks each move by sampling the raw
+policy; here the move comes from `KV_SIMS` PUCT simulations (default 800; the tree search is new functionality,
+DESIGN.md §MCTS) with the reference's Dirichlet parameters (DIR_NOISE_EPS / DIR_NOISE_ALPHA, :12-13) at the root.
+Record format, reward map (win 1.0 / draw 0.2 / loss -1.0 from white's side, same on every ply, :245-250), error
+behaviour (ValueError without model and path, FileNotFoundError for a missing checkpoint) follow the reference.
+"""
+from __future__ import annotations
+
+import logging
+import os
+
+import numpy as np
+import torch
+
+from .engine import Engine
+from .model import ChessNet
+
+logger = logging.getLogger(__name__)
+
+DIR_NOISE_EPS = float(os.getenv("DIR_NOISE_EPS", "0.25"))      # scripts/self_play.py:12
+DIR_NOISE_ALPHA = float(os.getenv("DIR_NOISE_ALPHA", "0.3"))   # :13
+SEED = int(os.getenv("SEED", "42"))                            # :24
+DEFAULT_SIMS = int(os.getenv("KV_SIMS", "800"))
+DEFAULT_PLY_CAP = int(os.getenv("KV_MAX_PLIES", "512"))        # the reference has no cap when max_moves is None
+TEMP_PLIES = int(os.getenv("KV_TEMP_PLIES", "30"))
+C_PUCT = float(os.getenv("KV_CPUCT", "1.5"))
+
+_engines: dict[int, Engine] = {}
+
+
+def engine_for(device) -> Engine:
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("knightvision_b200 self-play needs a CUDA device (there is no CPU fallback)")
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _engines:
+        _engines[idx] = Engine(idx)
+    return _engines[idx]
+
+
+def _load_model(model_path: str) -> ChessNet:
+    if not os.path.exists(model_path):
+        raise FileNotFoundError(f"Model checkpoint not found: {model_path}")   # scripts/self_play.py:67-68
+    ckpt = torch.load(model_path, map_location="cpu")
+    sd = ckpt["model_state_dict"] if isinstance(ckpt, dict) and "model_state_dict" in ckpt else ckpt   # :72-76
+    sd = {k[len("module."):] if k.startswith("module.") else k: v for k, v in sd.items()}               # DataParallel
+    net = ChessNet()
+    net.load_state_dict(sd)
+    return net.eval()
+
+
+class SelfPlay:
+    """n_games concurrent self-play games on one GPU."""
+
+    def __init__(self, model: ChessNet, n_games: int, device, sims: int = DEFAULT_SIMS, max_plies: int = DEFAULT_PLY_CAP,
+                 temp_plies: int = TEMP_PLIES, c_puct: float = C_PUCT, dir_alpha: float = DIR_NOISE_ALPHA,
+                 dir_eps: float = DIR_NOISE_EPS, seed: int = SEED, eval_mode: int = 1, engine: Engine | None = None):
+        self.eng = engine or engine_for(device)
+        self.n_games, self.sims, self.max_plies = n_games, sims, max_plies
+        if eval_mode == 1:
+            inner = model.module if hasattr(model, "module") else model
+            if not isinstance(inner, ChessNet):
+                # a reference ai.model.ChessNet (or any module with its state_dict layout): adopt its weights
+                net = ChessNet()
+                net.load_state_dict(inner.state_dict())
+                inner = net
+            inner.eval()
+            inner.attach(self.eng, max_batch=max(n_games, 2))
+            self.model = inner
+        self.eng.mcts_create(n_games, sims, max_plies, temp_plies, c_puct, dir_alpha, dir_eps, seed, eval_mode)
+
+    def play(self, start_lines: torch.Tensor | None = None, game_id_base: int = 0, progress=None) -> dict:
+        eng = self.eng
+        eng.mcts_reset(start_lines, game_id_base)
+        st = eng.mcts_status()
+        moves = 0
+        while st["done"] < self.n_games and moves < self.max_plies + 1:
+            eng.mcts_run_move()
+            moves += 1
+            st = eng.mcts_status()
+            if progress:
+                progress(moves, st)
+        return st
+
+    def records_device(self):
+        return self.eng.mcts_records()
+
+    def records(self):
+        """The reference's list of (state float32 (12,8,8), move_index, reward) tuples, in game order."""
+        lines, move, reward, game = self.eng.mcts_records()
+        if lines.shape[0] == 0:
+            return []
+        planes = self.eng.encode(lines).cpu().numpy()
+        mv = move.cpu().numpy()
+        rw = reward.cpu().numpy()
+        return [(planes[i], int(mv[i]), float(rw[i])) for i in range(len(mv))]
+
+
+def self_play(model, num_games, device, max_moves=None, model_path=None):
+    if model is None and model_path is None:
+        raise ValueError("Either model or model_path must be provided")   # scripts/self_play.py:259-260
+    if model is None:
+        model = _load_model(model_path)
+    sp = SelfPlay(model, int(num_games), device, max_plies=int(max_moves) if max_moves else DEFAULT_PLY_CAP)
+    st = sp.play()
+    logger.info("self-play: %d games, %d plies, W/B/D = %d/%d/%d", num_games, st["plies"], st["white_wins"],
+                st["black_wins"], st["draws"])
+    return sp.records()
+
+
+def generate_self_play_data(model, num_games, device, max_moves=None):
+    data = self_play(model, num_games, device, max_moves)
+    decisive = [s for s in data if abs(s[2]) == 1]   # scripts/self_play.py:304-310
+    if len(decisive) >= 10:
+        return decisive
+    return data

@@ -31,6 +31,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <math.h>
+#include "../include/kv_detmath.h"
 
 #define KVO_API __attribute__((visibility("default")))
 
@@ -646,3 +647,266 @@ KVO_API void kvo_encode(const uint64_t *lines, int n, float *planes) {
 
 /* encode_move ai/ai.py:51-57 */
 KVO_API int kvo_move_index(uint16_t mv) { return (mv & 63) * 64 + ((mv >> 6) & 63); }
+
+
+/* ==========================================================================================================
+ * MCTS oracle — "parity unpinned": the reference has no tree search, so this sequential PUCT
+ * over the pinned rules engine above IS the specification that the GPU tree kernels must match
+ * bit-for-bit (visit counts, W sums, chosen moves), given identical evaluator outputs and seeds.
+ * Evaluator modes: 0 = deterministic hash evaluator (also implemented on the device: whole-pipeline parity,
+ * including softmax / Dirichlet arithmetic), 1 = replay of the values and priors the device engine recorded
+ * for its own network evaluations (tree-logic parity "given identical net outputs").
+ * ========================================================================================================== */
+typedef struct {
+    int32_t sims;        /* simulations per move (the first one expands the root) */
+    int32_t edge_cap;    /* edges per game tree; an expansion that does not fit becomes a terminal draw */
+    int32_t temp_plies;  /* plies < temp_plies sample the move from the visit counts, later plies take the argmax */
+    int32_t max_plies;   /* game is a draw when this many plies were played */
+    float c_puct, dir_alpha, dir_eps;
+    int32_t pad;
+    uint64_t seed;
+} kvo_mcts_cfg;
+
+typedef struct {
+    kvo_state st;
+    int32_t first_edge, n_edges;
+    uint32_t N;
+    int32_t term;
+    float val;           /* terminal value, or the evaluator's value, from the node's side to move */
+} onode;
+typedef struct {
+    float P, W;
+    uint32_t N;
+    int32_t child;
+    uint16_t mv;
+} oedge;
+
+static uint64_t pos_hash(const uint64_t *bb) {
+    uint64_t h = 0x243F6A8885A308D3ull;
+    for (int p = 0; p < 12; p++) h = kvd_mix64(h ^ (bb[p] + (uint64_t)(p + 1) * 0x9E3779B97F4A7C15ull));
+    return h;
+}
+
+/* hash evaluator: logit of move index idx and the white-perspective value */
+static float hash_logit(uint64_t ph, int idx) { return (float)kvd_rand24(ph, (uint64_t)idx, 1, 0) * (4.0f / 16777216.0f) - 2.0f; }
+static float hash_value(uint64_t ph) { return (float)kvd_rand24(ph, 4096, 2, 0) * (2.0f / 16777216.0f) - 1.0f; }
+
+typedef struct {
+    /* replay inputs (device tree dump), NULL in hash mode */
+    const float *rep_node_val;
+    const int32_t *rep_node_first;
+    const float *rep_edge_P;
+} replay_t;
+
+/* Runs one search of cfg->sims simulations from `root`; returns the chosen move word (0xFFFF if the root has no
+ * move).  Outputs: root move list, visit counts, W (bit patterns), number of nodes/edges created. */
+static int mcts_search(const kvo_mcts_cfg *cfg, const kvo_state *root, uint64_t game_id, int ply, const replay_t *rep,
+                       uint16_t *root_moves, uint32_t *root_N, float *root_W, float *root_P, int *n_root,
+                       int *out_nodes, int *out_edges, int *overflow) {
+    const int S = cfg->sims;
+    onode *nodes = (onode *)calloc((size_t)S + 1, sizeof(onode));
+    oedge *edges = (oedge *)calloc((size_t)cfg->edge_cap, sizeof(oedge));
+    int *path_e = (int *)malloc(sizeof(int) * ((size_t)S + 2));
+    int *path_n = (int *)malloc(sizeof(int) * ((size_t)S + 2));
+    int n_nodes = 0, n_edges = 0;
+    *overflow = 0;
+    for (int sim = 0; sim < S; sim++) {
+        int depth = 0, node = 0, leaf = -1;
+        float v = 0.0f;
+        kvo_state child_st;
+        if (n_nodes == 0) {
+            child_st = *root;
+            leaf = 0;
+        } else {
+            for (;;) {
+                onode *nd = &nodes[node];
+                if (nd->term) {
+                    v = nd->val;
+                    nd->N++;
+                    break;
+                }
+                const float sq = KVD_SQRTF((float)nd->N);
+                int best = 0;
+                float bs = 0.0f;
+                for (int k = 0; k < nd->n_edges; k++) {
+                    const oedge *e = &edges[nd->first_edge + k];
+                    float sc = kvd_puct(e->W, e->N, e->P, sq, cfg->c_puct);
+                    if (k == 0 || sc > bs) { bs = sc; best = k; }
+                }
+                const int ei = nd->first_edge + best;
+                path_n[depth] = node;
+                path_e[depth] = ei;
+                depth++;
+                if (edges[ei].child < 0) {
+                    child_st = nd->st;
+                    make_move(&child_st, edges[ei].mv & 63, (edges[ei].mv >> 6) & 63, (edges[ei].mv >> 12) & 7, T_Q);
+                    leaf = n_nodes;
+                    edges[ei].child = leaf;
+                    break;
+                }
+                node = edges[ei].child;
+            }
+        }
+        if (leaf >= 0) {
+            onode *nd = &nodes[leaf];
+            movelist ml;
+            int f;
+            int n = valid_moves(&child_st, &ml, &f);   /* may rewrite child_st (getKingMoves restore quirk) */
+            if (n > 256) n = 256;
+            nd->st = child_st;
+            nd->N = 1;
+            nd->first_edge = -1;
+            nd->n_edges = 0;
+            n_nodes++;
+            if (n == 0) {
+                nd->term = 1;
+                nd->val = (f & RF_CHECKMATE) ? -1.0f : 0.0f;
+            } else if (f & RF_ONLY_KINGS) {
+                nd->term = 1;
+                nd->val = 0.0f;
+            } else if (n_edges + n > cfg->edge_cap) {
+                nd->term = 1;
+                nd->val = 0.0f;
+                *overflow = 1;
+            } else {
+                nd->term = 0;
+                nd->first_edge = n_edges;
+                nd->n_edges = n;
+                oedge *e = &edges[n_edges];
+                n_edges += n;
+                for (int k = 0; k < n; k++) {
+                    e[k].mv = pack_move(&ml.m[k]);
+                    e[k].N = 0;
+                    e[k].W = 0.0f;
+                    e[k].child = -1;
+                }
+                if (rep && rep->rep_node_val) {
+                    nd->val = rep->rep_node_val[leaf];
+                    for (int k = 0; k < n; k++) e[k].P = rep->rep_edge_P[rep->rep_node_first[leaf] + k];
+                } else {
+                    uint64_t w[16];
+                    kvo_pack(&child_st, w);
+                    const uint64_t ph = pos_hash(w);
+                    float mx = 0.0f;
+                    for (int k = 0; k < n; k++) {
+                        e[k].P = hash_logit(ph, kvo_move_index(e[k].mv));
+                        if (k == 0 || e[k].P > mx) mx = e[k].P;
+                    }
+                    float sum = 0.0f;
+                    for (int k = 0; k < n; k++) {
+                        e[k].P = kvd_expf(e[k].P - mx);
+                        sum = sum + e[k].P;
+                    }
+                    for (int k = 0; k < n; k++) e[k].P = e[k].P / sum;
+                    if (leaf == 0 && cfg->dir_eps > 0.0f) {
+                        float gs = 0.0f;
+                        for (int k = 0; k < n; k++) {
+                            e[k].W = kvd_gamma_small(cfg->dir_alpha, cfg->seed, game_id, (uint64_t)ply * 256 + (uint64_t)k);
+                            gs = gs + e[k].W;
+                        }
+                        for (int k = 0; k < n; k++) {
+                            const float eta = e[k].W / gs;
+                            e[k].P = (1.0f - cfg->dir_eps) * e[k].P + cfg->dir_eps * eta;
+                            e[k].W = 0.0f;
+                        }
+                    }
+                    const float vw = hash_value(ph);
+                    nd->val = child_st.white_to_move ? vw : -vw;
+                }
+            }
+            v = nd->val;
+        }
+        for (int i = depth - 1; i >= 0; i--) {
+            v = -v;
+            edges[path_e[i]].W = edges[path_e[i]].W + v;
+            edges[path_e[i]].N++;
+            nodes[path_n[i]].N++;
+        }
+    }
+    int chosen = 0xFFFF;
+    *n_root = 0;
+    if (n_nodes > 0 && !nodes[0].term) {
+        const int n = nodes[0].n_edges;
+        const oedge *e = &edges[nodes[0].first_edge];
+        *n_root = n;
+        uint64_t total = 0;
+        for (int k = 0; k < n; k++) {
+            root_moves[k] = e[k].mv;
+            root_N[k] = e[k].N;
+            root_W[k] = e[k].W;
+            root_P[k] = e[k].P;
+            total += e[k].N;
+        }
+        int pick = 0;
+        if (ply < cfg->temp_plies && total > 0) {
+            const uint64_t r = ((uint64_t)kvd_rand24(cfg->seed, game_id, (uint64_t)ply, 0xC0FFEEull) * total) >> 24;
+            uint64_t cum = 0;
+            for (int k = 0; k < n; k++) {
+                cum += e[k].N;
+                if (cum > r) { pick = k; break; }
+            }
+        } else {
+            for (int k = 1; k < n; k++)
+                if (e[k].N > e[pick].N) pick = k;
+        }
+        chosen = e[pick].mv;
+    }
+    *out_nodes = n_nodes;
+    *out_edges = n_edges;
+    free(nodes);
+    free(edges);
+    free(path_e);
+    free(path_n);
+    return chosen;
+}
+
+/* One search from a packed line.  root_* arrays hold up to 256 entries. */
+KVO_API int kvo_mcts_search(const kvo_mcts_cfg *cfg, const uint64_t *line, uint64_t game_id, int ply,
+                            const float *rep_node_val, const int32_t *rep_node_first, const float *rep_edge_P,
+                            uint16_t *root_moves, uint32_t *root_N, float *root_W, float *root_P, int32_t *info4) {
+    kvo_state s;
+    kvo_unpack(line, &s);
+    replay_t rep = { rep_node_val, rep_node_first, rep_edge_P };
+    int n_root, nn, ne, ov;
+    int mv = mcts_search(cfg, &s, game_id, ply, rep_node_val ? &rep : NULL, root_moves, root_N, root_W, root_P, &n_root,
+                         &nn, &ne, &ov);
+    info4[0] = n_root;
+    info4[1] = nn;
+    info4[2] = ne;
+    info4[3] = ov;
+    return mv;
+}
+
+/* Whole self-play game with the hash evaluator (scripts/self_play.py:111-255 control flow, MCTS choosing the move).
+ * out_moves[ply] = move word; out_lines[ply][16] = position the move was chosen in; returns the number of plies.
+ * *result: +1 white won, -1 black won, 0 draw (self_play.py:211-238). */
+KVO_API int kvo_selfplay_game(const kvo_mcts_cfg *cfg, const uint64_t *start_line, uint64_t game_id, uint16_t *out_moves,
+                              uint64_t *out_lines, int32_t *result) {
+    kvo_state s;
+    kvo_unpack(start_line, &s);
+    uint16_t rm[256];
+    uint32_t rn[256];
+    float rw[256], rp[256];
+    int ply = 0;
+    *result = 0;
+    for (;;) {
+        kvo_state probe = s;
+        movelist ml;
+        int f;
+        int n = valid_moves(&probe, &ml, &f);
+        s = probe;   /* getValidMoves may rewrite the state */
+        if (n == 0) {
+            if (f & RF_CHECKMATE) *result = s.white_to_move ? -1 : 1;
+            break;
+        }
+        if (f & RF_ONLY_KINGS) break;
+        if (ply >= cfg->max_plies) break;
+        int n_root, nn, ne, ov;
+        int mv = mcts_search(cfg, &s, game_id, ply, NULL, rm, rn, rw, rp, &n_root, &nn, &ne, &ov);
+        kvo_pack(&s, out_lines + 16 * (size_t)ply);
+        out_moves[ply] = (uint16_t)mv;
+        make_move(&s, mv & 63, (mv >> 6) & 63, (mv >> 12) & 7, T_Q);
+        ply++;
+    }
+    return ply;
+}

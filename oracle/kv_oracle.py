@@ -93,3 +93,47 @@ def encode(lines: np.ndarray) -> np.ndarray:
     out = np.zeros((n, 12, 8, 8), dtype=np.float32)
     lib().kvo_encode(_p(lines), ctypes.c_int(n), _p(out))
     return out
+
+
+# ---- MCTS oracle (oracle/kv_oracle.c, "parity unpinned": the specification of the new tree search) -----------
+class MctsCfg(ctypes.Structure):
+    _fields_ = [("sims", ctypes.c_int32), ("edge_cap", ctypes.c_int32), ("temp_plies", ctypes.c_int32),
+                ("max_plies", ctypes.c_int32), ("c_puct", ctypes.c_float), ("dir_alpha", ctypes.c_float),
+                ("dir_eps", ctypes.c_float), ("pad", ctypes.c_int32), ("seed", ctypes.c_uint64)]
+
+
+def mcts_cfg(sims, edges_per_node=48, temp_plies=0, max_plies=1 << 20, c_puct=1.5, dir_alpha=0.3, dir_eps=0.25, seed=1):
+    return MctsCfg(sims, max(sims * (edges_per_node or 48), 256), temp_plies, max_plies, c_puct, dir_alpha, dir_eps, 0, seed)
+
+
+def mcts_search(cfg, line, game_id=0, ply=0, replay=None):
+    """One search.  replay = (node_val f32[], node_first i32[], edge_P f32[]) dumps of the device tree, or None for
+    the hash evaluator.  Returns dict(move, moves, N, W, P, nodes, edges, overflow)."""
+    line = np.ascontiguousarray(line, dtype=np.uint64)
+    moves = np.zeros(256, np.uint16); N = np.zeros(256, np.uint32); W = np.zeros(256, np.float32)
+    P = np.zeros(256, np.float32); info = np.zeros(4, np.int32)
+    if replay is None:
+        rv = rf = rp = None
+    else:
+        rv, rf, rp = (np.ascontiguousarray(replay[0], np.float32), np.ascontiguousarray(replay[1], np.int32),
+                      np.ascontiguousarray(replay[2], np.float32))
+    f = lib().kvo_mcts_search
+    f.restype = ctypes.c_int
+    mv = f(ctypes.byref(cfg), _p(line), ctypes.c_uint64(game_id), ctypes.c_int(ply),
+           _p(rv) if rv is not None else None, _p(rf) if rf is not None else None, _p(rp) if rp is not None else None,
+           _p(moves), _p(N), _p(W), _p(P), _p(info))
+    n = int(info[0])
+    return dict(move=mv, moves=moves[:n], N=N[:n], W=W[:n], P=P[:n], nodes=int(info[1]), edges=int(info[2]),
+                overflow=int(info[3]))
+
+
+def selfplay_game(cfg, start_line, game_id=0):
+    start_line = np.ascontiguousarray(start_line, dtype=np.uint64)
+    mp = int(cfg.max_plies)
+    moves = np.zeros(mp, np.uint16)
+    lines = np.zeros((mp, 16), np.uint64)
+    res = ctypes.c_int32(0)
+    f = lib().kvo_selfplay_game
+    f.restype = ctypes.c_int
+    n = f(ctypes.byref(cfg), _p(start_line), ctypes.c_uint64(game_id), _p(moves), _p(lines), ctypes.byref(res))
+    return moves[:n], lines[:n], int(res.value)

@@ -186,3 +186,139 @@ __attribute__((visibility("default"))) void kvemu_perft(const uint64_t* roots, i
 }
 
 }  // extern "C"
+
+// ---- MCTS: the device driver loop of kv_mcts.cu over host memory, hash evaluator ---------------------------------
+struct EmuMcts {
+    kv::MctsCfg cfg;
+    kv::MctsArrays A;
+    int G;
+    std::vector<std::vector<char>> store;
+    template <class T>
+    T* alloc(size_t n) {
+        store.emplace_back(n * sizeof(T), 0);
+        return reinterpret_cast<T*>(store.back().data());
+    }
+};
+
+static EmuMcts* emu_mcts_new(int G, int sims, int edges_per_node, int max_plies, int temp_plies, float c_puct,
+                             float dir_alpha, float dir_eps, uint64_t seed) {
+    EmuMcts* m = new EmuMcts();
+    m->G = G;
+    kv::MctsCfg& c = m->cfg;
+    c.sims = sims;
+    c.node_cap = sims;
+    c.edge_cap = sims * (edges_per_node > 0 ? edges_per_node : 48);
+    if (c.edge_cap < kv::MAX_MOVES) c.edge_cap = kv::MAX_MOVES;
+    c.temp_plies = temp_plies;
+    c.max_plies = max_plies;
+    c.rec_cap = max_plies;
+    c.eval_mode = 0;
+    c.c_puct = c_puct;
+    c.dir_alpha = dir_alpha;
+    c.dir_eps = dir_eps;
+    c.seed = seed;
+    kv::MctsArrays& A = m->A;
+    const size_t g = (size_t)G;
+    A.hdr = m->alloc<kv::GameHdr>(g);
+    A.root_line = m->alloc<uint64_t>(g * 16);
+    A.node_line = m->alloc<uint64_t>(g * c.node_cap * 16);
+    A.node_meta = m->alloc<kv::NodeMeta>(g * c.node_cap);
+    A.eP = m->alloc<float>(g * c.edge_cap);
+    A.eN = m->alloc<uint32_t>(g * c.edge_cap);
+    A.eW = m->alloc<float>(g * c.edge_cap);
+    A.eChild = m->alloc<int>(g * c.edge_cap);
+    A.eMv = m->alloc<uint16_t>(g * c.edge_cap);
+    A.path_edge = m->alloc<int>(g * (c.node_cap + 1));
+    A.path_node = m->alloc<int>(g * (c.node_cap + 1));
+    A.n_eval = m->alloc<uint32_t>(4);
+    A.eval_game = m->alloc<int>(g);
+    A.eval_lines = m->alloc<uint64_t>((g + 1) * 16);
+    A.rec_line = m->alloc<uint64_t>(g * c.rec_cap * 12);
+    A.rec_move = m->alloc<uint16_t>(g * c.rec_cap);
+    return m;
+}
+
+static void emu_mcts_reset(EmuMcts* m, const uint64_t* start, uint64_t id_base) {
+    for (int g = 0; g < m->G; g++) {
+        kv::GameHdr h;
+        memset(&h, 0, sizeof(h));
+        h.pend_node = -1;
+        h.game_id = id_base + (uint64_t)g;
+        m->A.hdr[g] = h;
+        for (int i = 0; i < 16; i++) m->A.root_line[(size_t)g * 16 + i] = i >= 13 ? 0 : start[(size_t)g * 16 + i];
+    }
+}
+
+static void emu_mcts_wave(EmuMcts* m) {
+    uint16_t mv[kv::MAX_MOVES];
+    float scratch[kv::MAX_MOVES];
+    *m->A.n_eval = 0;
+    for (int g = 0; g < m->G; g++)
+        kvemu::run_warp([&](int lane) { kv::mcts_select_warp(g_tables, lane, m->cfg, m->A, g, mv); });
+    const int ne = (int)*m->A.n_eval;
+    for (int slot = 0; slot < ne; slot++)
+        kvemu::run_warp([&](int lane) { kv::mcts_hash_eval_warp(lane, m->cfg, m->A, slot, scratch); });
+}
+
+static void emu_mcts_finish(EmuMcts* m) {
+    uint16_t mv[kv::MAX_MOVES];
+    for (int g = 0; g < m->G; g++)
+        kvemu::run_warp([&](int lane) { kv::mcts_finish_move_warp(g_tables, lane, m->cfg, m->A, g, mv); });
+}
+
+extern "C" {
+
+// One search (sims waves) for G root positions; outputs the root edges of every game ([G][256]) and info [G][4]
+__attribute__((visibility("default"))) void kvemu_mcts_search(int G, const uint64_t* start, uint64_t id_base, int ply0,
+                                                               int sims, int edges_per_node, float c_puct,
+                                                               float dir_alpha, float dir_eps, uint64_t seed,
+                                                               uint16_t* moves, uint32_t* N, float* W, float* P,
+                                                               int32_t* info) {
+    EmuMcts* m = emu_mcts_new(G, sims, edges_per_node, 1 << 20, 0, c_puct, dir_alpha, dir_eps, seed);
+    m->cfg.rec_cap = 1;
+    emu_mcts_reset(m, start, id_base);
+    for (int g = 0; g < G; g++) m->A.hdr[g].ply = ply0;
+    for (int s = 0; s < sims; s++) emu_mcts_wave(m);
+    for (int g = 0; g < G; g++) {
+        const kv::GameHdr& h = m->A.hdr[g];
+        const kv::NodeMeta nm = m->A.node_meta[(size_t)g * m->cfg.node_cap];
+        const int n = (h.n_nodes && !(nm.ne_term >> 16)) ? (nm.ne_term & 0xFFFF) : 0;
+        info[4 * g + 0] = n;
+        info[4 * g + 1] = h.n_nodes;
+        info[4 * g + 2] = h.n_edges;
+        info[4 * g + 3] = h.overflow;
+        const size_t e0 = (size_t)g * m->cfg.edge_cap + (n ? nm.first_edge : 0);
+        for (int k = 0; k < n; k++) {
+            moves[256 * g + k] = m->A.eMv[e0 + k];
+            N[256 * g + k] = m->A.eN[e0 + k];
+            W[256 * g + k] = m->A.eW[e0 + k];
+            P[256 * g + k] = m->A.eP[e0 + k];
+        }
+    }
+    delete m;
+}
+
+// Whole games; out_moves [G][max_plies], out_plies [G], out_result [G]
+__attribute__((visibility("default"))) void kvemu_selfplay(int G, const uint64_t* start, uint64_t id_base, int sims,
+                                                            int edges_per_node, int max_plies, int temp_plies,
+                                                            float c_puct, float dir_alpha, float dir_eps, uint64_t seed,
+                                                            uint16_t* out_moves, int32_t* out_plies, int32_t* out_result) {
+    EmuMcts* m = emu_mcts_new(G, sims, edges_per_node, max_plies, temp_plies, c_puct, dir_alpha, dir_eps, seed);
+    emu_mcts_reset(m, start, id_base);
+    for (int mvno = 0; mvno < max_plies; mvno++) {
+        bool live = false;
+        for (int g = 0; g < G; g++) live |= !m->A.hdr[g].done;
+        if (!live) break;
+        for (int s = 0; s < sims; s++) emu_mcts_wave(m);
+        emu_mcts_finish(m);
+    }
+    for (int g = 0; g < G; g++) {
+        out_plies[g] = m->A.hdr[g].ply;
+        out_result[g] = m->A.hdr[g].result;
+        for (int p = 0; p < m->A.hdr[g].ply && p < max_plies; p++)
+            out_moves[(size_t)g * max_plies + p] = m->A.rec_move[(size_t)g * m->cfg.rec_cap + p];
+    }
+    delete m;
+}
+
+}  // extern "C"

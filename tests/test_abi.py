@@ -45,10 +45,14 @@ def test_no_cpu_fallback(lib):
 
 
 def test_product_never_imports_oracle():
+    """The oracle and the emulator are checkers: nothing under knightvision_b200/ includes, imports or loads them
+    (comments may cite them)."""
     pkg = os.path.join(ROOT, "knightvision_b200")
+    bad = re.compile(r'#\s*include\s*[<"][^">]*(oracle|simt_emu)|^\s*(from|import)\s+(oracle|simt_emu|tests)\b|'
+                     r'libkv_oracle|libkv_emu|kvemu_|kvo_', re.M)
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
-                assert "kv_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
-                assert "simt_emu" not in src or f.endswith((".cuh",)), f
+                m = bad.search(src)
+                assert m is None or (f == "kv_warp.cuh" and "kvemu" in m.group(0)), (f, m.group(0))

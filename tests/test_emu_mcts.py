@@ -1,0 +1,74 @@
+"""The PUCT tree-search kernel SOURCE (kv_mcts.cuh) run on the CPU emulator against the sequential MCTS oracle
+(oracle/kv_oracle.c): visit counts, W sums, priors and whole games must be bit-exact.  CPU only."""
+import numpy as np
+
+import helpers as H
+from knightvision_b200 import layout as L
+from oracle import kv_oracle as O
+from simt_emu import emu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def test_detmath_is_close_to_libm():
+    # the deterministic exp/log are ordinary single-precision approximations (sanity, not parity)
+    import ctypes
+    xs = np.linspace(-20, 5, 101, dtype=np.float32)
+    src = r'''
+    #include "include/kv_detmath.h"
+    float e(float x){return kvd_expf(x);} float l(float x){return kvd_logf(x);}
+    float g(float a, unsigned long long s, unsigned long long i){return kvd_gamma_small(a, s, i, 0);}
+    '''
+    import os, subprocess, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as d:
+        open(d + "/t.c", "w").write(src)
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", root, "-o", d + "/t.so",
+                               d + "/t.c", "-lm"])
+        t = ctypes.CDLL(d + "/t.so")
+        t.e.restype = t.l.restype = t.g.restype = ctypes.c_float
+        t.e.argtypes = t.l.argtypes = [ctypes.c_float]
+        t.g.argtypes = [ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64]
+        for x in xs:
+            assert abs(t.e(float(x)) - np.exp(np.float64(x))) <= 2e-6 * np.exp(np.float64(x)) + 1e-30
+        for x in np.geomspace(1e-6, 1e6, 61):
+            assert abs(t.l(float(x)) - np.log(x)) < 2e-6 * max(1.0, abs(np.log(x)))
+        gs = np.array([t.g(0.3, 11, i) for i in range(4000)])
+        assert abs(gs.mean() - 0.3) < 0.03 and (gs > 0).all()     # Gamma(0.3, 1): mean 0.3
+
+
+def test_emu_search_matches_oracle():
+    lines = H.random_playout_positions(n_games=3, max_plies=60, seed=21)
+    roots = np.concatenate([L.start_line()[None], lines[[7, 40, 90, 130]]])
+    for sims, seed in ((1, 3), (40, 9)):
+        mv, N, W, P, info = emu.mcts_search(roots, sims=sims, id_base=17, ply=2, seed=seed)
+        for g in range(len(roots)):
+            r = O.mcts_search(O.mcts_cfg(sims, seed=seed), roots[g], game_id=17 + g, ply=2)
+            n = int(info[g, 0])
+            assert n == len(r["moves"]) and info[g, 1] == r["nodes"] and info[g, 2] == r["edges"]
+            assert np.array_equal(mv[g, :n], r["moves"]) and np.array_equal(N[g, :n], r["N"])
+            assert np.array_equal(_bits(W[g, :n]), _bits(r["W"])) and np.array_equal(_bits(P[g, :n]), _bits(r["P"]))
+            if sims > 1:
+                assert int(r["N"].sum()) == sims - 1
+
+
+def test_emu_selfplay_games_match_oracle():
+    start = np.stack([L.start_line()] * 2)
+    moves, plies, res = emu.selfplay(start, sims=12, max_plies=24, temp_plies=6, id_base=40, seed=5)
+    for g in range(2):
+        cfg = O.mcts_cfg(12, temp_plies=6, max_plies=24, seed=5)
+        m, lines, r = O.selfplay_game(cfg, start[g], game_id=40 + g)
+        assert len(m) == plies[g] and r == res[g] and np.array_equal(m, moves[g, :plies[g]])
+
+
+def test_edge_pool_overflow_rule_is_shared():
+    # edges_per_node = 1 forces the "expansion does not fit -> terminal draw" rule on both sides
+    roots = L.start_line()[None]
+    mv, N, W, P, info = emu.mcts_search(roots, sims=300, edges_per_node=1, seed=2)
+    cfg = O.mcts_cfg(300, edges_per_node=1, seed=2)
+    r = O.mcts_search(cfg, roots[0])
+    assert r["overflow"] == 1 and info[0, 3] == 1
+    n = int(info[0, 0])
+    assert np.array_equal(N[0, :n], r["N"]) and np.array_equal(_bits(W[0, :n]), _bits(r["W"]))

@@ -1,0 +1,133 @@
+"""GPU tree search vs the sequential MCTS oracle.  Bit-exact visit counts / W / priors / chosen moves:
+ - hash evaluator: the whole pipeline including softmax and Dirichlet arithmetic;
+ - network evaluator: the oracle replays the values and priors the device recorded ("given identical net outputs")."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from knightvision_b200 import layout as L
+from oracle import kv_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from knightvision_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def test_search_hash_evaluator_bit_exact(eng):
+    from knightvision_b200.engine import lines_to_device
+    lines = H.random_playout_positions(n_games=8, max_plies=120, seed=33)
+    roots = lines[np.random.default_rng(1).permutation(len(lines))[:96]]
+    roots[0] = L.start_line()
+    sims = 200
+    eng.mcts_create(len(roots), sims, max_plies=4, temp_plies=0, seed=77, eval_mode=0)
+    eng.mcts_reset(lines_to_device(roots, eng.device), game_id_base=1000)
+    eng.mcts_run_sims(sims)
+    cfg = O.mcts_cfg(sims, seed=77)
+    for g in range(len(roots)):
+        got = eng.mcts_read_root(g)
+        r = O.mcts_search(cfg, roots[g], game_id=1000 + g, ply=0)
+        assert got["nodes"] == r["nodes"] and got["edges"] == r["edges"], g
+        assert np.array_equal(got["moves"], r["moves"]) and np.array_equal(got["N"], r["N"]), g
+        assert np.array_equal(_bits(got["W"]), _bits(r["W"])) and np.array_equal(_bits(got["P"]), _bits(r["P"])), g
+
+
+def test_selfplay_games_hash_evaluator_bit_exact(eng):
+    G, sims, max_plies = 48, 32, 60
+    eng.mcts_create(G, sims, max_plies=max_plies, temp_plies=8, seed=5, eval_mode=0)
+    eng.mcts_reset(None, game_id_base=0)
+    for _ in range(max_plies):
+        eng.mcts_run_move()
+    st = eng.mcts_status()
+    assert st["done"] == G and st["overflow"] == 0
+    lines, move, reward, game = (t.cpu().numpy() for t in eng.mcts_records())
+    lines = lines.view(np.uint64)
+    cfg = O.mcts_cfg(sims, temp_plies=8, max_plies=max_plies, seed=5)
+    total = 0
+    for g in range(G):
+        m, pos, res = O.selfplay_game(cfg, L.start_line(), game_id=g)
+        sel = game == g
+        assert sel.sum() == len(m), g
+        assert np.array_equal(move[sel], [O.lib().kvo_move_index(int(x)) for x in m]), g
+        assert np.array_equal(lines[sel][:, :12], pos[:, :12]), g
+        exp_reward = 1.0 if res > 0 else (-1.0 if res < 0 else 0.2)
+        assert np.allclose(reward[sel], exp_reward), g
+        total += len(m)
+    assert total == len(move) == st["plies"]
+
+
+def test_search_with_network_replayed_by_oracle(eng):
+    """Real tower + heads on the device; the oracle re-runs the search with the recorded values / priors."""
+    from knightvision_b200.model import ChessNet
+    torch.manual_seed(0)
+    net = ChessNet().eval().attach(eng, max_batch=64)
+    G, sims = 24, 160
+    eng.mcts_create(G, sims, max_plies=8, temp_plies=0, seed=9, eval_mode=1)
+    eng.mcts_reset(None, game_id_base=0)
+    eng.mcts_run_sims(sims)
+    cfg = O.mcts_cfg(sims, seed=9)
+    for g in (0, 5, 23):
+        got = eng.mcts_read_root(g)
+        nv, nf, ep, root = eng.mcts_dump_tree(g)
+        r = O.mcts_search(cfg, root, game_id=g, ply=0, replay=(nv, nf, ep))
+        assert got["nodes"] == r["nodes"] and np.array_equal(got["N"], r["N"]), g
+        assert np.array_equal(_bits(got["W"]), _bits(r["W"])), g
+        assert int(got["N"].sum()) == sims - 1
+        # priors are a softmax over the legal moves of the net's logits (masked softmax fused with the heads)
+        pol, val = net.forward_lines(torch.from_numpy(root.view(np.int64)[None]).to(eng.device))
+        idx = [O.lib().kvo_move_index(int(x)) for x in got["moves"]]
+        lg = pol[0, idx].double().cpu().numpy()
+        sm = np.exp(lg - lg.max()); sm /= sm.sum()
+        # root priors carry Dirichlet noise: (1-eps) * softmax + eps * eta, eta >= 0, sum eta = 1
+        eta = (got["P"].astype(np.float64) - 0.75 * sm) / 0.25
+        assert eta.min() > -1e-4 and abs(eta.sum() - 1.0) < 1e-3
+    # and play two moves so finish_move / tree reset are exercised with the net
+    eng.mcts_finish_move()
+    eng.mcts_run_move()
+    st = eng.mcts_status()
+    assert st["plies"] == 2 * G and st["evals"] > 0
+
+
+def test_dropin_self_play_record_format(eng, monkeypatch):
+    from knightvision_b200 import selfplay as SP
+    from knightvision_b200.model import ChessNet
+    monkeypatch.setattr(SP, "DEFAULT_SIMS", 16)
+    monkeypatch.setitem(SP._engines, 0, eng)
+    torch.manual_seed(1)
+    data = SP.self_play(ChessNet().eval(), 3, torch.device("cuda:0"), max_moves=6)
+    assert len(data) == 18
+    s, mv, rw = data[0]
+    assert isinstance(s, np.ndarray) and s.dtype == np.float32 and s.shape == (12, 8, 8)
+    assert np.array_equal(s, O.encode(L.start_line()[None])[0])        # first record = initial position planes
+    assert isinstance(mv, int) and 0 <= mv < 4096 and isinstance(rw, float) and rw == pytest.approx(0.2)
+    assert SP.generate_self_play_data(ChessNet().eval(), 2, torch.device("cuda:0"), max_moves=4) is not None
+    with pytest.raises(ValueError):
+        SP.self_play(None, 1, torch.device("cuda:0"))
+    with pytest.raises(FileNotFoundError):
+        SP.self_play(None, 1, torch.device("cuda:0"), model_path="/nonexistent/model.pth")
+
+
+def test_full_size_wave_4096_games(eng):
+    """BASELINE config 3 size: 4 096 concurrent games; size-independent invariants after 12 waves."""
+    from knightvision_b200.model import ChessNet
+    torch.manual_seed(0)
+    ChessNet().eval().attach(eng, max_batch=4096)
+    eng.mcts_create(4096, 12, max_plies=4, temp_plies=0, seed=3, eval_mode=1)
+    eng.mcts_reset(None, 0)
+    eng.mcts_run_sims(12)
+    st = eng.mcts_status()
+    assert st["sims_in_move"] == 4096 * 12 and st["evals"] == 4096 * 12   # no terminal leaf this early
+    r0, r1 = eng.mcts_read_root(0), eng.mcts_read_root(4095)
+    assert int(r0["N"].sum()) == 11 and int(r1["N"].sum()) == 11 and len(r0["moves"]) == 20
+    eng.mcts_finish_move()
+    assert eng.mcts_status()["plies"] == 4096
