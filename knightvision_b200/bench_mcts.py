@@ -1,0 +1,201 @@
+"""bench.py's self-play workload (BASELINE.json configs[2] / configs[3]): 4 096 concurrent games per GPU, 800 PUCT
+simulations per move, the reference policy/value net (random init, torch.manual_seed(0), BN folded, bf16 tensor-core
+tower), all games from the initial position.  One step = one move for every game = 800 search waves.
+Games shard over ranks by game id (no data-path collective); NCCL only broadcasts the weight blob before the
+generation and gathers the per-rank record counts after it.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+GAMES_PER_GPU = int(os.getenv("KV_BENCH_GAMES", "4096"))
+SIMS = int(os.getenv("KV_BENCH_SIMS", "800"))
+MAX_PLIES = 512
+CONV_FLOPS_PER_EVAL = 2.0 * 64 * 9 * (256 * 512 + 10 * 512 * 512)      # conv2 + 5 residual blocks (tcgen05 kernel)
+NET_FLOPS_PER_EVAL = 2.0 * 1587872256                                   # whole net, SURVEY §8d
+
+
+def _cpu_eval_rate(batch=256, iters=4):
+    """fp32 CPU forward of the reference graph (torch CPU kernels, all threads): evals/s."""
+    import torch
+    from knightvision_b200.model import ChessNet, fp32_reference_forward
+    torch.manual_seed(0)
+    net = ChessNet().eval()
+    x = torch.zeros(batch, 12, 8, 8)
+    x[:, 0, 7, 4] = 1
+    with torch.no_grad():
+        fp32_reference_forward(net, x[:8])
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fp32_reference_forward(net, x)
+        dt = time.perf_counter() - t0
+    return batch * iters / dt, torch.get_num_threads()
+
+
+def _tree_worker(args):
+    from knightvision_b200 import layout as L
+    from oracle import kv_oracle as O
+    gid, sims, n_moves = args
+    cfg = O.mcts_cfg(sims, temp_plies=30, max_plies=n_moves, seed=42)
+    m, lines, res = O.selfplay_game(cfg, L.start_line(), game_id=gid)
+    return len(m) * sims
+
+
+def _cpu_tree_rate(procs, sims, games_per_proc=4, n_moves=10):
+    """Sequential PUCT oracle (oracle/kv_oracle.c) with the hash evaluator on `procs` processes: sims/s."""
+    import multiprocessing as mp
+    from oracle import kv_oracle as O
+    O.build()
+    ctx = mp.get_context("fork")
+    jobs = [(g, sims, n_moves) for g in range(procs * games_per_proc)]
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        tot = sum(pool.map(_tree_worker, jobs))
+    return tot / (time.perf_counter() - t0), len(jobs), n_moves
+
+
+def cpu_baseline(sims):
+    procs = os.cpu_count() or 1
+    tree, n_games, n_moves = _cpu_tree_rate(procs, sims)
+    ev, threads = _cpu_eval_rate()
+    combined = 1.0 / (1.0 / tree + 1.0 / ev)
+    return {"value": combined, "unit": "sims/s", "cores": procs, "kind": "port",
+            "sample": (f"{n_games} games x {n_moves} moves x {sims} sims of the sequential PUCT oracle (oracle/kv_oracle.c, hash "
+                       f"evaluator) on {procs} processes = {tree:.0f} sims/s tree-only; reference net graph fp32 on torch "
+                       f"CPU kernels, batch 256, {threads} threads = {ev:.1f} evals/s; one eval per sim => combined"),
+            "tree_sims_per_s": tree, "net_evals_per_s": ev}
+
+
+def run_reference(args):
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        vals.append(cpu_baseline(SIMS))
+    ms = 1e3 * (time.perf_counter() - t0) / max(1, args.steps)
+    value = float(np.mean([v["value"] for v in vals]))
+    base = vals[-1]
+    base["value"] = value
+    line = {"impl": "reference", "metric": "mcts_sims_per_s", "value": value, "unit": "sims/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"self-play, {SIMS} PUCT sims/move, reference net (random init), initial position",
+                       "sims_per_move": SIMS},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from bench import Clocks, measured_peaks
+    from knightvision_b200 import layout as L
+    from knightvision_b200.engine import Engine, lines_to_device
+    from knightvision_b200.model import ChessNet
+    from knightvision_b200.selfplay import SelfPlay
+
+    G = GAMES_PER_GPU
+    eng = Engine(local_rank)
+    dev = eng.device
+    torch.manual_seed(0)
+    net = ChessNet().eval()
+    sp = SelfPlay(net, G, dev, sims=SIMS, max_plies=MAX_PLIES, seed=42, engine=eng)
+    if world > 1:
+        # generation start: rank 0's fp32 weight blob -> every rank's staging buffer over NCCL, then fold on device
+        blob = eng.net_blob_tensor()
+        if rank == 0:
+            blob.copy_(net.weight_blob().to(dev))
+        dist.broadcast(blob, src=0)
+        eng.net_commit()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.mcts_reset(None, game_id_base=rank * G)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        eng.mcts_run_move()
+    torch.cuda.synchronize()
+    st0 = eng.mcts_status()
+    clocks = Clocks(local_rank)
+    clocks.start()
+    eng.profile(True)
+    eng.profile_read()
+    l0 = eng.launches
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng.mcts_run_move()
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    prof = eng.profile_read()
+    eng.profile(False)
+    launches = eng.launches - l0
+    st1 = eng.mcts_status()
+    live = G - st0["done"]
+    sims_done = live * SIMS * args.steps          # every live game runs SIMS simulations per move
+    evals = st1["evals"] - st0["evals"]
+    positions = st1["plies"] - st0["plies"]
+
+    # e2e: the public API with HOST buffers: start positions from pinned host memory -> one move -> records on the host
+    start_h = torch.from_numpy(np.stack([L.start_line()] * G).view(np.int64)).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 2))
+    rec = 0
+    for _ in range(e2e_steps):
+        d = start_h.to(dev, non_blocking=True)
+        eng.mcts_reset(d, game_id_base=rank * G)
+        eng.mcts_run_move()
+        recs = sp.records()                        # D2H: float planes + move + reward, the reference's tuples
+        rec += len(recs)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(sims_done), float(evals), float(positions), float(rec)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)     # record counts gathered to every rank
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    sims_all, evals_all, pos_all, rec_all = (float(x) for x in cnt)
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    conv_ms, conv_n = prof["net_conv"]
+    achieved = (evals * CONV_FLOPS_PER_EVAL) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    value = sims_all / (dev_ms * 1e-3)
+    e2e_sims = world * G * SIMS * e2e_steps
+    line = {
+        "metric": "mcts_sims_per_s", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": (f"self-play: {G} concurrent games per GPU, {SIMS} PUCT sims/move, reference ChessNet "
+                                "(random init seed 0, BN folded, bf16 tower / fp32 accumulate), all games from the initial "
+                                "position; one step = one move for every game"),
+                   "games_per_gpu": G, "sims_per_move": SIMS, "parallelism": f"games sharded by id over {world} GPU(s)",
+                   "l2": "working set (node/edge pools + activations, > 3 GB) exceeds the 126 MB L2; no flush needed"},
+        "positions_per_s": pos_all / (dev_ms * 1e-3), "net_evals_per_s": evals_all / (dev_ms * 1e-3),
+        "evals_per_sim": evals_all / sims_all if sims_all else None,
+        "clocks": clk, "gpu_launches": launches,
+        "e2e": {"value": e2e_sims / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": G * 128,
+                "d2h_bytes_per_step": G * (12 * 64 * 4 + 8), "records_returned": rec_all,
+                "api": "SelfPlay: host start lines -> kv_mcts_reset -> kv_mcts_run_move -> records() as the reference's tuples"},
+        "roofline": {"kernel": "conv3x3_umma_kernel (tcgen05 implicit GEMM)", "bound": "tensor", "achieved": achieved,
+                     "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
+                     "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 figure",
+                     "kernel_ms_per_step": conv_ms / args.steps, "kernel_share_of_step": conv_ms / dev_ms,
+                     "flops_per_eval_in_kernel": CONV_FLOPS_PER_EVAL, "launches": conv_n},
+        "kernels_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
+        "cpu_baseline": cpu_baseline(SIMS),
+    }
+    print(json.dumps(line), flush=True)
