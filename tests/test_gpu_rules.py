@@ -92,7 +92,9 @@ def test_full_batch_65536_boards(eng):
     moves, counts, flags, after = _movegen(eng, lines)
     em, ec, ef, _ = O.movegen(base.copy())
     assert np.array_equal(counts, ec[np.arange(65536) % len(base)])
-    assert np.array_equal(moves[:7, :64], em[:, :64]) and np.array_equal(moves[-7:, :40], moves[65536 - 14:65536 - 7, :40])
+    for i in list(range(7)) + [65535 - k for k in range(7)]:
+        c = ec[i % len(base)]
+        assert np.array_equal(moves[i, :c], em[i % len(base), :c])
     assert np.array_equal(after, lines)
     # a perft of perfts: sum over the batch equals count * per-position value (depth 2, chunked launches)
     d = lines_to_device(lines, eng.device)
