@@ -146,7 +146,7 @@ def run_reference(args, rank, world):
                 "e2e": {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
-    from knightvision_b200 import bench_mcts
+    import bench_mcts
     bench_mcts.run_reference(args)
 
 
@@ -255,7 +255,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=["mcts", "perft"])
     args, _ = ap.parse_known_args()
     if args.workload is None:
-        args.workload = "mcts" if os.path.exists(os.path.join(ROOT, "knightvision_b200", "bench_mcts.py")) else "perft"
+        args.workload = "mcts" if os.path.exists(os.path.join(ROOT, "bench_mcts.py")) else "perft"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -274,7 +274,7 @@ def main():
         if args.workload == "perft":
             run_perft(args, rank, world, local_rank)
         else:
-            from knightvision_b200 import bench_mcts
+            import bench_mcts
             bench_mcts.run(args, rank, world, local_rank)
     finally:
         if world > 1:

@@ -82,6 +82,10 @@ KV_API int kv_movegen(kv_ctx* ctx, uint64_t* d_lines, int n, uint16_t* d_moves, 
                int32_t* d_flags, void* stream);
 /* in place; d_moves [n] one move word per board, 0xFFFF = leave the board untouched */
 KV_API int kv_make_moves(kv_ctx* ctx, uint64_t* d_lines, int n, const uint16_t* d_moves, void* stream);
+/* squareUnderAttack(r,c) (core/chessEngine.py:400-415) for all 64 squares: bit r*8+c of d_masks[i]; inCheck()
+ * (:388-394) is the bit of the side to move's king location */
+KV_API int kv_attacked(kv_ctx* ctx, const uint64_t* d_lines, int n, uint64_t* d_masks, void* stream);
+KV_API int kv_attacked_host(kv_ctx* ctx, const uint64_t* h_lines, int n, uint64_t* h_masks);
 /* host-buffer forms (copies inside): what a ctypes binding of GameState would call */
 KV_API int kv_movegen_host(kv_ctx* ctx, uint64_t* h_lines, int n, uint16_t* h_moves, int stride, int32_t* h_counts,
                     int32_t* h_flags);

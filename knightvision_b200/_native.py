@@ -26,6 +26,8 @@ SIGNATURES = {
     "kv_make_moves": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "kv_movegen_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "kv_make_moves_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "kv_attacked": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "kv_attacked_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "kv_perft": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "kv_perft_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int]),
     "kv_encode": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

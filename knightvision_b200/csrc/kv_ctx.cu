@@ -156,6 +156,23 @@ int kv_make_moves_host(kv_ctx* ctx, uint64_t* h_lines, int n, const uint16_t* h_
     return 0;
 }
 
+int kv_attacked_host(kv_ctx* ctx, const uint64_t* h_lines, int n, uint64_t* h_masks) {
+    if (!ctx) return -3;
+    if (n <= 0) return 0;
+    KV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t lb = align256((size_t)n * 128), mb = align256((size_t)n * 8);
+    if (int rc = kv_stage_reserve(ctx, lb + mb, lb + mb)) return rc;
+    char* h = (char*)ctx->h_stage;
+    char* d = (char*)ctx->d_stage;
+    memcpy(h, h_lines, (size_t)n * 128);
+    KV_CUDA(ctx, cudaMemcpyAsync(d, h, (size_t)n * 128, cudaMemcpyHostToDevice, 0));
+    if (int rc = kv_attacked(ctx, (const uint64_t*)d, n, (uint64_t*)(d + lb), nullptr)) return rc;
+    KV_CUDA(ctx, cudaMemcpyAsync(h + lb, d + lb, (size_t)n * 8, cudaMemcpyDeviceToHost, 0));
+    KV_CUDA(ctx, cudaStreamSynchronize(0));
+    memcpy(h_masks, h + lb, (size_t)n * 8);
+    return 0;
+}
+
 int kv_perft_host(kv_ctx* ctx, const uint64_t* h_roots, int n, int depth, uint64_t* h_out, int chunk) {
     if (!ctx) return -3;
     if (n <= 0) return 0;

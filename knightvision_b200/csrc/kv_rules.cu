@@ -85,6 +85,20 @@ __global__ void __launch_bounds__(kThreads) make_moves_kernel(uint64_t* __restri
     }
 }
 
+__global__ void __launch_bounds__(kThreads) attacked_kernel(const uint64_t* __restrict__ lines, int n,
+                                                            uint64_t* __restrict__ masks) {
+    __shared__ RulesSmem sm;
+    stage_tables(sm);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int lo, hi;
+    warp_slice(n, blockIdx.x * kWarpsPerCta + wid, gridDim.x * kWarpsPerCta, lo, hi);
+    for (int i = lo; i < hi; i++) {
+        const uint64_t w = ld_line_word(lines + (size_t)i * LINE_WORDS, lane);
+        const uint64_t m = attacked_mask_warp(sm.tab, lane, w);
+        if (lane == 0) masks[i] = m;
+    }
+}
+
 // ---- perft: one frontier level per launch (body: perft_visit_warp, kv_rules.cuh) ---------------------------
 template <bool LEAF>
 __global__ void __launch_bounds__(kThreads) perft_level_kernel(const uint64_t* __restrict__ cur, int m,
@@ -159,6 +173,14 @@ int kv_make_moves(kv_ctx* ctx, uint64_t* d_lines, int n, const uint16_t* d_moves
     if (n <= 0) return 0;
     KvTimed t_(ctx, KVK_MAKE_MOVES, (cudaStream_t)stream);
     make_moves_kernel<<<grid_for(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(d_lines, n, d_moves);
+    KV_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int kv_attacked(kv_ctx* ctx, const uint64_t* d_lines, int n, uint64_t* d_masks, void* stream) {
+    if (!ctx) return -3;
+    if (n <= 0) return 0;
+    attacked_kernel<<<grid_for(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(d_lines, n, d_masks);
     KV_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -541,6 +541,21 @@ KV_DEV uint64_t make_move_warp(int lane, uint64_t w, int mvw, int promo_type) {
     return w;
 }
 
+// squareUnderAttack(r, c) for all 64 squares of one board (core/chessEngine.py:400-415): bit r*8+c of the result.
+KV_DEV uint64_t attacked_mask_warp(const Tables& T, int lane, uint64_t w) {
+    Pos p;
+    load_pos(w, p);
+    Agg g;
+    make_agg(p, g);
+    const bool a0 = attacked(T, g, 2 * lane, p.wtm, p.ep, p.moved, p.akloc);
+    const bool a1 = attacked(T, g, 2 * lane + 1, p.wtm, p.ep, p.moved, p.akloc);
+    const uint32_t b0 = ballot(a0), b1 = ballot(a1);
+    uint64_t m = 0;
+#pragma unroll
+    for (int l = 0; l < 32; l++) m |= ((uint64_t)((b0 >> l) & 1) << (2 * l)) | ((uint64_t)((b1 >> l) & 1) << (2 * l + 1));
+    return m;
+}
+
 // ---- perft (kv_perft): one frontier board per warp -----------------------------------------------------
 KV_DEV uint64_t mix64(uint64_t x) {
     x ^= x >> 30;

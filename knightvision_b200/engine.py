@@ -245,6 +245,13 @@ class Engine:
                 "kv_make_moves_host")
         return out
 
+    def attacked_host(self, lines: np.ndarray) -> np.ndarray:
+        """squareUnderAttack over all 64 squares per board: uint64 masks (bit r*8+c)."""
+        lines = np.ascontiguousarray(lines, dtype=np.uint64)
+        out = np.zeros(lines.shape[0], dtype=np.uint64)
+        N.check(self.ctx, self._lib.kv_attacked_host(self.ctx, _ptr(lines), lines.shape[0], _ptr(out)), "kv_attacked_host")
+        return out
+
     def perft_host(self, roots: np.ndarray, depth: int, chunk: int = 0) -> np.ndarray:
         roots = np.ascontiguousarray(roots, dtype=np.uint64)
         out = np.zeros((roots.shape[0], 8), dtype=np.uint64)

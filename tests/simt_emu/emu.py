@@ -44,6 +44,13 @@ def movegen(lines, stride=256):
     return moves, counts, flags, lines
 
 
+def attacked(lines):
+    lines = np.ascontiguousarray(lines, dtype=np.uint64)
+    out = np.zeros(lines.shape[0], dtype=np.uint64)
+    lib().kvemu_attacked(_p(lines), ctypes.c_int(lines.shape[0]), _p(out))
+    return out
+
+
 def make_moves(lines, mv):
     out = np.ascontiguousarray(lines, dtype=np.uint64).copy()
     mv = np.ascontiguousarray(mv, dtype=np.uint16)

@@ -131,6 +131,17 @@ __attribute__((visibility("default"))) void kvemu_movegen(uint64_t* lines, int n
     }
 }
 
+__attribute__((visibility("default"))) void kvemu_attacked(const uint64_t* lines, int n, uint64_t* masks) {
+    for (int i = 0; i < n; i++) {
+        uint64_t m[32];
+        kvemu::run_warp([&](int lane) {
+            uint64_t w = lane < 16 ? lines[16 * (size_t)i + lane] : 0;
+            m[lane] = kv::attacked_mask_warp(g_tables, lane, w);
+        });
+        masks[i] = m[0];
+    }
+}
+
 __attribute__((visibility("default"))) void kvemu_make_moves(uint64_t* lines, int n, const uint16_t* mv) {
     for (int i = 0; i < n; i++) {
         uint64_t* line = lines + 16 * (size_t)i;

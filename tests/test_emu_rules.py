@@ -26,6 +26,22 @@ def test_emu_make_move_golden(name):
     assert np.array_equal(out[:, :13], rows["line_out"][ok][::2][:, :13])
 
 
+@pytest.mark.parametrize("name", ["playouts", "synthetic"])
+def test_emu_square_under_attack_golden(name):
+    rows = H.load_rows(name)
+    sel = np.arange(0, len(rows["line_in"]), 5)          # the fixtures hold the 64-square mask for every 5th row
+    got = emu.attacked(rows["line_in"][sel])
+    assert np.array_equal(got, rows["sua"][sel])
+    k = L_king_bits(rows["line_in"][sel])
+    assert np.array_equal(((got >> k) & 1).astype(np.uint8), rows["incheck"][sel])
+
+
+def L_king_bits(lines):
+    meta = lines[:, 12]
+    wtm = (meta & 1).astype(bool)
+    return np.where(wtm, (meta >> 16) & 63, (meta >> 24) & 63).astype(np.uint64)
+
+
 def test_emu_movegen_random_playouts_vs_oracle():
     lines = H.random_playout_positions(n_games=12, max_plies=120, seed=5)
     H.check_movegen_against(lines, emu.movegen(lines))

@@ -47,6 +47,17 @@ def test_make_move_golden(eng, name):
     assert np.array_equal(out[:, :13], rows["line_out"][ok][:, :13])
 
 
+@pytest.mark.parametrize("name", ["playouts", "synthetic"])
+def test_square_under_attack_and_in_check_golden(eng, name):
+    rows = H.load_rows(name)
+    sel = np.arange(0, len(rows["line_in"]), 5)
+    got = eng.attacked_host(rows["line_in"][sel])
+    assert np.array_equal(got, rows["sua"][sel])
+    meta = rows["line_in"][sel][:, 12]
+    k = np.where((meta & 1).astype(bool), (meta >> 16) & 63, (meta >> 24) & 63).astype(np.uint64)
+    assert np.array_equal(((got >> k) & 1).astype(np.uint8), rows["incheck"][sel])
+
+
 def test_movegen_random_playouts_vs_oracle(eng):
     lines = H.random_playout_positions(n_games=256, max_plies=200, seed=11)
     assert len(lines) > 20000
