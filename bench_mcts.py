@@ -15,6 +15,7 @@ import numpy as np
 GAMES_PER_GPU = int(os.getenv("KV_BENCH_GAMES", "4096"))
 SIMS = int(os.getenv("KV_BENCH_SIMS", "800"))
 MAX_PLIES = 512
+CACHE_LOG2 = int(os.getenv("KV_BENCH_CACHE_LOG2", "24"))   # evaluation cache: 2^24 x 640 B = 10.7 GB (0 = off)
 CONV_FLOPS_PER_EVAL = 2.0 * 64 * 9 * (256 * 512 + 10 * 512 * 512)      # conv2 + 5 residual blocks (tcgen05 kernel)
 NET_FLOPS_PER_EVAL = 2.0 * 1587872256                                   # whole net, SURVEY §8d
 
@@ -117,6 +118,7 @@ def run(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    eng.mcts_enable_cache(CACHE_LOG2)
     eng.mcts_reset(None, game_id_base=rank * G)
     warm = max(args.warmup, 3)
     for _ in range(warm):
@@ -143,31 +145,50 @@ def run(args, rank, world, local_rank):
     live = G - st0["done"]
     sims_done = live * SIMS * args.steps          # every live game runs SIMS simulations per move
     evals = st1["evals"] - st0["evals"]
+    hits = st1["cache_hits"] - st0["cache_hits"]
     positions = st1["plies"] - st0["plies"]
 
-    # e2e: the public API with HOST buffers: start positions from pinned host memory -> one move -> records on the host
+    # e2e: a fresh generation through the public API with HOST buffers: start positions from pinned host memory,
+    # cold evaluation cache (a new generation means new weights), e2e_steps moves, records back on the host as the
+    # reference's tuples.  Everything, copies included, is inside the timed region.
     start_h = torch.from_numpy(np.stack([L.start_line()] * G).view(np.int64)).pin_memory()
+    e2e_steps = max(1, min(args.steps, 3))
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 2))
-    rec = 0
+    eng._lib.kv_mcts_cache_clear(eng.ctx, None)
+    d = start_h.to(dev, non_blocking=True)
+    eng.mcts_reset(d, game_id_base=rank * G)
     for _ in range(e2e_steps):
-        d = start_h.to(dev, non_blocking=True)
-        eng.mcts_reset(d, game_id_base=rank * G)
         eng.mcts_run_move()
-        recs = sp.records()                        # D2H: float planes + move + reward, the reference's tuples
-        rec += len(recs)
+    recs = sp.records()                            # D2H: float planes + move + reward
+    rec = len(recs)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    ste = eng.mcts_status()
+
+    # the same device-timed measurement with the evaluation cache OFF (one network evaluation per simulation)
+    nocache_ms = None
+    if CACHE_LOG2 and rank == 0 or (CACHE_LOG2 and world > 1):
+        eng.mcts_enable_cache(0)
+        eng.mcts_reset(None, game_id_base=rank * G)
+        eng.mcts_run_move()
+        barrier()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        eng.mcts_run_move()
+        n1.record()
+        barrier()
+        nocache_ms = n0.elapsed_time(n1)
     clk = clocks.stop()
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([float(sims_done), float(evals), float(positions), float(rec)], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(sims_done), float(evals), float(positions), float(rec), float(hits)], dtype=torch.float64,
+                       device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)     # record counts gathered to every rank
     dev_ms, e2e_ms = float(t[0]), float(t[1])
-    sims_all, evals_all, pos_all, rec_all = (float(x) for x in cnt)
+    sims_all, evals_all, pos_all, rec_all, hits_all = (float(x) for x in cnt)
     if rank != 0:
         return
     peaks = measured_peaks()
@@ -186,10 +207,17 @@ def run(args, rank, world, local_rank):
                    "l2": "working set (node/edge pools + activations, > 3 GB) exceeds the 126 MB L2; no flush needed"},
         "positions_per_s": pos_all / (dev_ms * 1e-3), "net_evals_per_s": evals_all / (dev_ms * 1e-3),
         "evals_per_sim": evals_all / sims_all if sims_all else None,
+        "eval_cache": {"log2_slots": CACHE_LOG2, "bytes": (640 << CACHE_LOG2) if CACHE_LOG2 else 0,
+                       "served_per_sim": hits_all / sims_all if sims_all else None,
+                       "note": "keyed by the 12 bitboards (the net's whole input); search results are bit-identical "
+                               "with the cache on or off (tests/test_gpu_mcts.py::test_eval_cache_is_transparent)"},
+        "no_cache": ({"value": world * G * SIMS / (nocache_ms * 1e-3), "unit": "sims/s", "ms_per_step": nocache_ms,
+                      "evals_per_sim": 1.0} if nocache_ms else None),
         "clocks": clk, "gpu_launches": launches,
-        "e2e": {"value": e2e_sims / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": G * 128,
-                "d2h_bytes_per_step": G * (12 * 64 * 4 + 8), "records_returned": rec_all,
-                "api": "SelfPlay: host start lines -> kv_mcts_reset -> kv_mcts_run_move -> records() as the reference's tuples"},
+        "e2e": {"value": e2e_sims / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": G * 128 // e2e_steps,
+                "d2h_bytes_per_step": G * (12 * 64 * 4 + 8), "records_returned": rec_all, "steps": e2e_steps,
+                "api": ("fresh generation through SelfPlay: pinned host start lines -> kv_mcts_reset -> e2e_steps x "
+                        "kv_mcts_run_move -> records() as the reference's (planes, move, reward) tuples; cold cache")},
         "roofline": {"kernel": "conv3x3_umma_kernel (tcgen05 implicit GEMM)", "bound": "tensor", "achieved": achieved,
                      "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
                      "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 figure",

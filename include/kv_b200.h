@@ -135,9 +135,14 @@ KV_API int kv_mcts_reset(kv_ctx* ctx, const uint64_t* d_start, uint64_t game_id_
 KV_API int kv_mcts_run_sims(kv_ctx* ctx, int n_waves, void* stream);   /* n_waves simulations for every live game */
 KV_API int kv_mcts_finish_move(kv_ctx* ctx, void* stream);            /* pick + record + play the move, reset trees */
 KV_API int kv_mcts_run_move(kv_ctx* ctx, void* stream);               /* sims waves + finish_move */
-/* h_out8: games done, sum of sims done in the current move, evaluator calls, plies played, games with edge-pool
- * overflow, white wins, black wins, draws */
-KV_API int kv_mcts_status(kv_ctx* ctx, uint64_t* h_out8, void* stream);
+/* Evaluation cache: 2^log2_slots entries x 640 B keyed by the 12 bitboards (the network's whole input; 0 = off).
+ * A hit skips the tower; priors are re-derived from the cached policy features, so visit counts and games are
+ * bit-identical with the cache on or off.  Cleared automatically by kv_net_commit_weights / kv_net_load. */
+KV_API int kv_mcts_enable_cache(kv_ctx* ctx, int log2_slots);
+KV_API int kv_mcts_cache_clear(kv_ctx* ctx, void* stream);
+/* h_out9: games done, sum of sims done in the current move, tower evaluations, plies played, games with edge-pool
+ * overflow, white wins, black wins, draws, expansions served by the cache (hits + in-wave duplicates) */
+KV_API int kv_mcts_status(kv_ctx* ctx, uint64_t* h_out9, void* stream);
 KV_API int kv_mcts_geometry(kv_ctx* ctx, int32_t* out4);              /* n_games, node_cap, edge_cap, rec_cap */
 /* records of every game in game order; d_lines [cap][16] board lines (kv_encode gives the reference's planes),
  * d_move policy index (ai/ai.py:51-57), d_reward 1.0 / 0.2 / -1.0 (scripts/self_play.py:245-250), d_game index */

@@ -45,6 +45,8 @@ SIGNATURES = {
     "kv_mcts_run_sims": (c_int, [c_void_p, c_int, c_void_p]),
     "kv_mcts_finish_move": (c_int, [c_void_p, c_void_p]),
     "kv_mcts_run_move": (c_int, [c_void_p, c_void_p]),
+    "kv_mcts_enable_cache": (c_int, [c_void_p, c_int]),
+    "kv_mcts_cache_clear": (c_int, [c_void_p, c_void_p]),
     "kv_mcts_status": (c_int, [c_void_p, c_void_p, c_void_p]),
     "kv_mcts_geometry": (c_int, [c_void_p, c_void_p]),
     "kv_mcts_records": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

@@ -31,21 +31,29 @@ __device__ __forceinline__ void stage_tables_m(Tables& dstT) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kMW * 32) mcts_select_kernel(MctsCfg cfg, MctsArrays A, int G) {
+__global__ void __launch_bounds__(kMW * 32) mcts_select_kernel(MctsCfg cfg, MctsArrays A, int G, uint32_t wave) {
     __shared__ MctsSmem sm;
     stage_tables_m(sm.tab);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int g = blockIdx.x * kMW + wid;
     if (g >= G) return;
-    mcts_select_warp(sm.tab, lane, cfg, A, g, sm.mv[wid]);
+    mcts_select_warp(sm.tab, lane, cfg, A, g, sm.mv[wid], wave);
 }
 
-__global__ void __launch_bounds__(kMW * 32) mcts_hash_eval_kernel(MctsCfg cfg, MctsArrays A) {
+__global__ void __launch_bounds__(kMW * 32) mcts_hash_eval_kernel(MctsCfg cfg, MctsArrays A, uint32_t wave) {
     __shared__ float scratch[kMW][MAX_MOVES];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int slot = blockIdx.x * kMW + wid;
     if (slot >= (int)*A.n_eval) return;
-    mcts_hash_eval_warp(lane, cfg, A, slot, scratch[wid]);
+    mcts_hash_eval_warp(lane, cfg, A, slot, scratch[wid], wave);
+}
+
+__global__ void __launch_bounds__(kMW * 32) mcts_hash_late_kernel(MctsCfg cfg, MctsArrays A) {
+    __shared__ float scratch[kMW][MAX_MOVES];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int li = blockIdx.x * kMW + wid;
+    if (li >= (int)*A.n_late) return;
+    mcts_hash_late_warp(lane, cfg, A, li, scratch[wid]);
 }
 
 __global__ void __launch_bounds__(kMW * 32) mcts_finish_move_kernel(MctsCfg cfg, MctsArrays A, int G) {
@@ -62,16 +70,9 @@ struct HeadW {
     int C;
 };
 
-// CTA per queued leaf: heads on the tower output, logits of the legal moves, then the warp-level expand/backup.
-__global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArrays A, const __nv_bfloat16* __restrict__ act,
-                                                            HeadW H) {
-    __shared__ float hp[128], hv[64], red[8], logits[MAX_MOVES];
-    const int slot = blockIdx.x;
-    if (slot >= (int)*A.n_eval) return;
-    const int g = A.eval_game[slot];
-    kvn::head_features(act + (size_t)slot * 64 * H.C, H.C, H.wh, H.bh, hp, hv);
-    __syncthreads();
-    const float v_white = kvn::value_mlp(hv, H.w1, H.b1, H.w2, H.b2, red);
+// logits of the pending leaf's legal moves from the 128 policy features (policy_fc rows of the legal indices only)
+__device__ __forceinline__ void legal_logits(const MctsCfg& cfg, const MctsArrays& A, int g, const HeadW& H, const float* hp,
+                                             float* logits) {
     const GameHdr* h = &A.hdr[g];
     const NodeMeta m = A.node_meta[(size_t)g * cfg.node_cap + h->pend_node];
     const int n = m.ne_term & 0xFFFF;
@@ -87,8 +88,38 @@ __global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArr
         }
         logits[k] = a;
     }
+}
+
+// CTA per queued leaf: heads on the tower output, logits of the legal moves, then the warp-level expand/backup.
+__global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArrays A, const __nv_bfloat16* __restrict__ act,
+                                                            HeadW H, uint32_t wave) {
+    __shared__ float hp[128], hv[64], red[8], logits[MAX_MOVES];
+    const int slot = blockIdx.x;
+    if (slot >= (int)*A.n_eval) return;
+    const int g = A.eval_game[slot];
+    kvn::head_features(act + (size_t)slot * 64 * H.C, H.C, H.wh, H.bh, hp, hv);
     __syncthreads();
-    if (threadIdx.x < 32) mcts_expand_warp((int)threadIdx.x, cfg, A, g, logits, v_white);
+    const float v_white = kvn::value_mlp(hv, H.w1, H.b1, H.w2, H.b2, red);
+    legal_logits(cfg, A, g, H, hp, logits);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        mcts_expand_warp((int)threadIdx.x, cfg, A, g, logits, v_white);
+        if (cfg.cache_mask) cache_fill_warp((int)threadIdx.x, cfg, A, wave, slot, hp, v_white);
+    }
+}
+
+// CTA (128 threads) per late entry: features from the cache (already copied per game) or from this wave's leader
+__global__ void __launch_bounds__(128) mcts_late_net_kernel(MctsCfg cfg, MctsArrays A, HeadW H) {
+    __shared__ float hp[FEAT], logits[MAX_MOVES];
+    const int li = blockIdx.x;
+    if (li >= (int)*A.n_late) return;
+    const int g = A.late_game[li], src = A.late_src[li];
+    const float* f = src < 0 ? A.feat_game + (size_t)g * FEAT : A.feat_slot + (size_t)src * FEAT;
+    for (int i = threadIdx.x; i < FEAT; i += blockDim.x) hp[i] = f[i];
+    __syncthreads();
+    legal_logits(cfg, A, g, H, hp, logits);
+    __syncthreads();
+    if (threadIdx.x < 32) mcts_expand_warp((int)threadIdx.x, cfg, A, g, logits, hp[128], true);
 }
 
 __global__ void mcts_init_kernel(MctsCfg cfg, MctsArrays A, int G, const uint64_t* __restrict__ start, uint64_t id_base) {
@@ -117,6 +148,7 @@ __global__ void mcts_status_kernel(MctsArrays A, int G, unsigned long long* out)
     atomicAdd(out + 2, (unsigned long long)h.n_evals);
     atomicAdd(out + 3, (unsigned long long)h.ply);
     if (h.overflow) atomicAdd(out + 4, 1ull);
+    atomicAdd(out + 8, (unsigned long long)h.cache_hits);
     if (h.done && h.result > 0) atomicAdd(out + 5, 1ull);
     if (h.done && h.result < 0) atomicAdd(out + 6, 1ull);
     if (h.done && h.result == 0) atomicAdd(out + 7, 1ull);
@@ -168,12 +200,16 @@ struct kv_mcts {
     std::vector<void*> allocs;
     unsigned long long* d_status = nullptr;
     int* d_offsets = nullptr;
+    uint32_t wave = 0;
+    void* cache_mem = nullptr;
+    size_t cache_slots = 0;
 };
 
 void kv_mcts_destroy(kv_ctx* ctx) {
     kv_mcts* m = ctx->mcts;
     if (!m) return;
     for (void* p : m->allocs) cudaFree(p);
+    if (m->cache_mem) cudaFree(m->cache_mem);
     delete m;
     ctx->mcts = nullptr;
 }
@@ -230,7 +266,17 @@ int kv_mcts_create(kv_ctx* ctx, int n_games, int sims, int edges_per_node, int m
     if (dalloc(ctx, m, &A.eval_lines, (G + 1) * 16)) return -1;
     if (dalloc(ctx, m, &A.rec_line, G * c.rec_cap * 12)) return -1;
     if (dalloc(ctx, m, &A.rec_move, G * c.rec_cap)) return -1;
-    if (dalloc(ctx, m, &m->d_status, 8)) return -1;
+    if (dalloc(ctx, m, &A.eval_centry, G)) return -1;
+    if (dalloc(ctx, m, &A.eval_hash, G)) return -1;
+    if (dalloc(ctx, m, &A.n_late, 4)) return -1;
+    if (dalloc(ctx, m, &A.late_game, G)) return -1;
+    if (dalloc(ctx, m, &A.late_src, G)) return -1;
+    if (dalloc(ctx, m, &A.feat_game, G * FEAT)) return -1;
+    if (dalloc(ctx, m, &A.feat_slot, G * FEAT)) return -1;
+    A.cache = nullptr;
+    c.cache_mask = 0;
+    KV_CUDA(ctx, cudaMemset(A.n_late, 0, 16));
+    if (dalloc(ctx, m, &m->d_status, 16)) return -1;
     if (dalloc(ctx, m, &m->d_offsets, G + 1)) return -1;
     KV_CUDA(ctx, cudaMemset(A.n_eval, 0, 16));
     return 0;
@@ -269,25 +315,65 @@ static int mcts_wave(kv_ctx* ctx, cudaStream_t st) {
     kv_mcts* m = ctx->mcts;
     const int G = m->G;
     const int grid = (G + kMW - 1) / kMW;
+    const uint32_t wave = ++m->wave;
     KV_CUDA(ctx, cudaMemsetAsync(m->A.n_eval, 0, sizeof(uint32_t), st));
+    if (m->cfg.cache_mask) KV_CUDA(ctx, cudaMemsetAsync(m->A.n_late, 0, sizeof(uint32_t), st));
     {
         KvTimed t_(ctx, KVK_MCTS_SELECT, st);
-        mcts_select_kernel<<<grid, kMW * 32, 0, st>>>(m->cfg, m->A, G);
+        mcts_select_kernel<<<grid, kMW * 32, 0, st>>>(m->cfg, m->A, G, wave);
     }
     KV_LAUNCH_CHECK(ctx);
     if (m->cfg.eval_mode == 0) {
         KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
-        mcts_hash_eval_kernel<<<grid, kMW * 32, 0, st>>>(m->cfg, m->A);
+        mcts_hash_eval_kernel<<<grid, kMW * 32, 0, st>>>(m->cfg, m->A, wave);
         KV_LAUNCH_CHECK(ctx);
+        if (m->cfg.cache_mask) {
+            mcts_hash_late_kernel<<<grid, kMW * 32, 0, st>>>(m->cfg, m->A);
+            KV_LAUNCH_CHECK(ctx);
+        }
     } else {
         int fb = 0;
         if (int rc = kv_net_tower(ctx, m->A.eval_lines, G, st, &fb, -1, reinterpret_cast<const int*>(m->A.n_eval))) return rc;
         kv_net* net = ctx->net;
         HeadW H{net->wh, net->bh, net->wfc, net->bfc, net->w1, net->b1, net->w2, net->b2, net->C};
         KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
-        mcts_eval_net_kernel<<<G, 256, 0, st>>>(m->cfg, m->A, net->act[fb], H);
+        mcts_eval_net_kernel<<<G, 256, 0, st>>>(m->cfg, m->A, net->act[fb], H, wave);
         KV_LAUNCH_CHECK(ctx);
+        if (m->cfg.cache_mask) {
+            mcts_late_net_kernel<<<G, 128, 0, st>>>(m->cfg, m->A, H);
+            KV_LAUNCH_CHECK(ctx);
+        }
     }
+    return 0;
+}
+
+// Evaluation cache of 2^log2_slots entries x 640 B (0 = disable).  Keyed by the 12 bitboards (the network's whole
+// input); search results are bit-identical with the cache on or off, only the number of tower evaluations changes.
+int kv_mcts_enable_cache(kv_ctx* ctx, int log2_slots) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_enable_cache: no search context");
+    kv_mcts* m = ctx->mcts;
+    KV_CUDA(ctx, cudaDeviceSynchronize());
+    if (m->cache_mem) cudaFree(m->cache_mem);
+    m->cache_mem = nullptr;
+    m->A.cache = nullptr;
+    m->cfg.cache_mask = 0;
+    m->cache_slots = 0;
+    if (log2_slots <= 0) return 0;
+    if (log2_slots < 8 || log2_slots > 28) return kv_fail_msg(ctx, "kv_mcts_enable_cache: log2_slots must be in 8..28");
+    const size_t slots = (size_t)1 << log2_slots;
+    KV_CUDA(ctx, cudaMalloc(&m->cache_mem, slots * sizeof(CacheEntry)));
+    KV_CUDA(ctx, cudaMemset(m->cache_mem, 0, slots * sizeof(CacheEntry)));
+    m->A.cache = reinterpret_cast<CacheEntry*>(m->cache_mem);
+    m->cfg.cache_mask = (uint32_t)(slots - 1);
+    m->cache_slots = slots;
+    return 0;
+}
+
+// Must be called when the network weights change (cached features belong to the old weights).
+int kv_mcts_cache_clear(kv_ctx* ctx, void* stream) {
+    if (!ctx || !ctx->mcts) return 0;
+    kv_mcts* m = ctx->mcts;
+    if (m->cache_mem) KV_CUDA(ctx, cudaMemsetAsync(m->cache_mem, 0, m->cache_slots * sizeof(CacheEntry), (cudaStream_t)stream));
     return 0;
 }
 
@@ -318,10 +404,10 @@ int kv_mcts_status(kv_ctx* ctx, uint64_t* h_out8, void* stream) {
     if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_status: no search context");
     kv_mcts* m = ctx->mcts;
     cudaStream_t st = (cudaStream_t)stream;
-    KV_CUDA(ctx, cudaMemsetAsync(m->d_status, 0, 8 * sizeof(unsigned long long), st));
+    KV_CUDA(ctx, cudaMemsetAsync(m->d_status, 0, 16 * sizeof(unsigned long long), st));
     mcts_status_kernel<<<(m->G + 255) / 256, 256, 0, st>>>(m->A, m->G, m->d_status);
     KV_LAUNCH_CHECK(ctx);
-    KV_CUDA(ctx, cudaMemcpyAsync(h_out8, m->d_status, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    KV_CUDA(ctx, cudaMemcpyAsync(h_out8, m->d_status, 9 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     KV_CUDA(ctx, cudaStreamSynchronize(st));
     return 0;
 }

@@ -21,8 +21,26 @@ struct MctsCfg {
     int sims, node_cap, edge_cap, temp_plies, max_plies, eval_mode;   // eval_mode: 0 hash evaluator, 1 network
     float c_puct, dir_alpha, dir_eps;
     int rec_cap;          // records per game (>= max_plies)
+    uint32_t cache_mask;  // evaluation cache slots - 1 (power of two), 0 = cache disabled
     uint64_t seed;
 };
+
+// Evaluation cache entry: the network's input is the 12 bitboards only (ai/ai.py:17-41 has no side/castling/e.p.
+// planes), so the key is the bitboards and the payload is what the heads need to produce ANY legal-move logit:
+// the 128 policy features + the value.  A hit skips the tower; priors are re-derived exactly as on a miss, so
+// search results are bit-identical with the cache on or off.
+struct alignas(128) CacheEntry {   // 640 B
+    uint64_t tag;      // 0 empty, ~0 locked (being rewritten), else position hash
+    uint32_t stamp;    // wave id of the last claim / hit
+    uint32_t pend;     // 0: payload valid; 1 + eval slot: under evaluation in wave `stamp`
+    uint64_t bb[12];
+    float v;           // white-perspective value
+    float pad[3];
+    float hp[128];     // policy-head features (relu(bn(conv1x1)), flatten order)
+};
+constexpr int FEAT = 132;   // hp[128], v, 3 pad
+constexpr uint64_t CACHE_LOCKED = ~0ull;
+constexpr int CACHE_WINDOW = 4;
 
 struct GameHdr {          // 64 B
     int n_nodes, n_edges, ply, done;
@@ -55,6 +73,15 @@ struct MctsArrays {
     uint32_t* n_eval;      // device counter
     int* eval_game;        // [G]
     uint64_t* eval_lines;  // [G][16]
+    // evaluation cache + "late" queue (cache hits and in-wave followers: expanded after the network pass)
+    CacheEntry* cache;     // [cache_mask + 1]
+    int* eval_centry;      // [G] cache entry claimed for the eval slot, -1 none
+    uint64_t* eval_hash;   // [G]
+    uint32_t* n_late;      // device counter
+    int* late_game;        // [G]
+    int* late_src;         // [G] -1: features already in feat_game[g]; else eval slot of the leader
+    float* feat_game;      // [G][FEAT]
+    float* feat_slot;      // [G][FEAT] features of every evaluated slot of this wave
     // game records (scripts/self_play.py:173-174): position bitboards + the move played
     uint64_t* rec_line;    // [G][rec_cap][12]
     uint16_t* rec_move;    // [G][rec_cap]
@@ -86,8 +113,124 @@ KV_DEV void mcts_backup_lane0(const MctsArrays& A, size_t ebase, size_t nbase, s
     }
 }
 
+// ---- evaluation cache ------------------------------------------------------------------------------------------
+KV_DEV uint64_t cache_hash(uint64_t h) { return (h == 0 || h == CACHE_LOCKED) ? 0x9E3779B97F4A7C15ull : h; }
+
+// Probe the cache for the position in w (lanes 0-11 hold the bitboards).  Returns 1 = hit (features copied to
+// feat_game[g]), 2 = the same position is under evaluation in this wave (aux = leader's eval slot), 0 = miss.
+// Readers validate with a seqlock on the tag: writers in the same kernel set tag = LOCKED before touching an entry.
+KV_DEV int cache_lookup_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, uint32_t wave, int g, uint64_t w,
+                             uint64_t h, int& aux) {
+    const uint32_t base = (uint32_t)h & cfg.cache_mask;
+    aux = -1;
+    for (int attempt = 0; attempt < 16; attempt++) {
+        uint64_t t = 0;
+        if (lane < CACHE_WINDOW) t = ld_cg_u64(&A.cache[(base + lane) & cfg.cache_mask].tag);
+        const uint32_t match = ballot(lane < CACHE_WINDOW && t == h);
+        const uint32_t locked = ballot(lane < CACHE_WINDOW && t == CACHE_LOCKED);
+        if (match) {
+            CacheEntry* e = &A.cache[(base + (uint32_t)(ffs32(match) - 1)) & cfg.cache_mask];
+            mem_fence();
+            const uint64_t kb = lane < 12 ? ld_cg_u64(&e->bb[lane]) : 0ull;
+            const bool same = ballot(lane < 12 && kb != w) == 0;
+            const uint32_t stamp = ld_cg_u32(&e->stamp), pend = ld_cg_u32(&e->pend);
+            float f0 = ld_cg_f32(&e->hp[lane * 4]), f1 = ld_cg_f32(&e->hp[lane * 4 + 1]);
+            float f2 = ld_cg_f32(&e->hp[lane * 4 + 2]), f3 = ld_cg_f32(&e->hp[lane * 4 + 3]);
+            const float v = ld_cg_f32(&e->v);
+            mem_fence();
+            const uint64_t t2 = ld_cg_u64(&e->tag);
+            const bool stable = ballot(t2 != h) == 0;
+            if (stable && same) {
+                if (pend == 0) {
+                    float* dst = A.feat_game + (size_t)g * FEAT;
+                    dst[lane * 4] = f0; dst[lane * 4 + 1] = f1; dst[lane * 4 + 2] = f2; dst[lane * 4 + 3] = f3;
+                    if (lane == 0) {
+                        dst[128] = v;
+                        e->stamp = wave;
+                    }
+                    return 1;
+                }
+                if (stamp == wave) {
+                    aux = (int)pend - 1;
+                    return 2;
+                }
+                return 0;   // stale pending entry (its evaluation was never delivered): plain miss
+            }
+            if (stable) return 0;   // 64-bit hash collision with a different position: miss
+            continue;               // entry changed under us: probe again
+        }
+        if (!locked) return 0;
+        // a window slot is being rewritten right now (possibly with this very position): look again
+    }
+    return 0;
+}
+
+// After a miss: try to claim a window slot for this position, marked "under evaluation by eval slot `slot`".
+// Returns the entry index or -1.  Victim = an empty slot, else the least recently stamped one not touched this wave.
+KV_DEV int cache_claim_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, uint32_t wave, uint64_t w, uint64_t h,
+                            int slot) {
+    const uint32_t base = (uint32_t)h & cfg.cache_mask;
+    uint64_t t = 0;
+    uint32_t key = 0xFFFFFFFFu;
+    if (lane < CACHE_WINDOW) {
+        const CacheEntry* e = &A.cache[(base + lane) & cfg.cache_mask];
+        t = ld_cg_u64(&e->tag);
+        const uint32_t stamp = ld_cg_u32(&e->stamp);
+        if (t == 0) key = 0;
+        else if (t != CACHE_LOCKED && stamp != wave) key = 1u + (stamp & 0x7FFFFFFFu);
+    }
+    // min key over lanes 0..3 (ties -> lowest lane)
+    uint32_t bk = key;
+    int bl = lane;
+#pragma unroll
+    for (int d = 2; d >= 1; d >>= 1) {
+        const uint32_t ok = (uint32_t)shfl_xor32((int)bk, d, lane);
+        const int ol = shfl_xor32(bl, d, lane);
+        if (ok < bk || (ok == bk && ol < bl)) {
+            bk = ok;
+            bl = ol;
+        }
+    }
+    bk = (uint32_t)shfl32((int)bk, 0);
+    bl = shfl32(bl, 0);
+    if (bk == 0xFFFFFFFFu) return -1;
+    const uint64_t seen = shfl64(t, bl);
+    const uint32_t idx = (base + (uint32_t)bl) & cfg.cache_mask;
+    CacheEntry* e = &A.cache[idx];
+    int ok = 0;
+    if (lane == 0) ok = atomic_cas_u64(&e->tag, seen, CACHE_LOCKED) == seen;
+    ok = shfl32(ok, 0);
+    if (!ok) return -1;
+    if (lane < 12) e->bb[lane] = w;
+    if (lane == 12) e->stamp = wave;
+    if (lane == 13) e->pend = 1u + (uint32_t)slot;
+    mem_fence();
+    syncwarp();
+    if (lane == 0) atomic_store_u64(&e->tag, h);
+    return (int)idx;
+}
+
+// After the evaluation of eval slot `slot`: publish its features for this wave's followers and, if the claimed
+// cache entry is still ours, fill its payload.  hp may be null (hash evaluator: only the value is meaningful).
+KV_DEV void cache_fill_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, uint32_t wave, int slot, const float* hp,
+                            float v_white) {
+    float* fs = A.feat_slot + (size_t)slot * FEAT;
+    for (int i = lane; i < 128; i += 32) fs[i] = hp ? hp[i] : 0.0f;
+    if (lane == 0) fs[128] = v_white;
+    const int ci = A.eval_centry[slot];
+    if (ci < 0) return;
+    CacheEntry* e = &A.cache[ci];
+    if (e->tag != A.eval_hash[slot] || e->pend != 1u + (uint32_t)slot || e->stamp != wave) return;
+    for (int i = lane; i < 128; i += 32) e->hp[i] = hp ? hp[i] : 0.0f;
+    if (lane == 0) e->v = v_white;
+    mem_fence();
+    syncwarp();
+    if (lane == 0) e->pend = 0;
+}
+
 // One simulation step for game g: descend, create the leaf, queue it for evaluation or back up a terminal value.
-KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, const MctsArrays& A, int g, uint16_t* mv) {
+KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, const MctsArrays& A, int g, uint16_t* mv,
+                             uint32_t wave = 0) {
     GameHdr* h = &A.hdr[g];
     if (h->done) return;
     const size_t nbase = (size_t)g * cfg.node_cap, ebase = (size_t)g * cfg.edge_cap;
@@ -175,12 +318,36 @@ KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, cons
                 A.eP[e] = 0.0f;
                 A.eChild[e] = -1;
             }
-            uint32_t slot = 0;
-            if (lane == 0) slot = atomic_add_u32(A.n_eval, 1u);
-            slot = (uint32_t)shfl32((int)slot, 0);
-            if (lane < LINE_WORDS) A.eval_lines[(size_t)slot * LINE_WORDS + lane] = w;
+            int kind = 0, aux = -1;
+            uint64_t ch = 0;
+            if (cfg.cache_mask) {
+                ch = cache_hash(pos_hash_warp(w, lane));
+                kind = cache_lookup_warp(lane, cfg, A, wave, g, w, ch, aux);
+            }
+            if (kind) {   // cache hit / in-wave follower: no tower pass, expanded by the late kernel
+                uint32_t li = 0;
+                if (lane == 0) li = atomic_add_u32(A.n_late, 1u);
+                li = (uint32_t)shfl32((int)li, 0);
+                if (lane == 0) {
+                    A.late_game[li] = g;
+                    A.late_src[li] = aux;
+                }
+            } else {
+                uint32_t slot = 0;
+                if (lane == 0) slot = atomic_add_u32(A.n_eval, 1u);
+                slot = (uint32_t)shfl32((int)slot, 0);
+                if (lane < LINE_WORDS) A.eval_lines[(size_t)slot * LINE_WORDS + lane] = w;
+                int ci = -1;
+                if (cfg.cache_mask) ci = cache_claim_warp(lane, cfg, A, wave, w, ch, (int)slot);
+                if (lane == 0) {
+                    A.eval_game[slot] = g;
+                    if (cfg.cache_mask) {
+                        A.eval_centry[slot] = ci;
+                        A.eval_hash[slot] = ch;
+                    }
+                }
+            }
             if (lane == 0) {
-                A.eval_game[slot] = g;
                 h->n_edges = n_edges + n;
                 h->pend_node = leaf;
                 h->pend_depth = depth;
@@ -203,7 +370,8 @@ KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, cons
 
 // Finish the pending simulation of game g given the leaf's legal-move logits (n floats, edge order) and the
 // evaluator's white-perspective value: softmax priors (+ root Dirichlet noise), then backup.
-KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int g, const float* logits, float v_white) {
+KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int g, const float* logits, float v_white,
+                             bool from_cache = false) {
     GameHdr* h = &A.hdr[g];
     const size_t nbase = (size_t)g * cfg.node_cap, ebase = (size_t)g * cfg.edge_cap;
     const size_t pbase = (size_t)g * (cfg.node_cap + 1);
@@ -247,7 +415,8 @@ KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, 
         A.node_meta[nbase + c].val = v;
         mcts_backup_lane0(A, ebase, nbase, pbase, depth, v);
         h->sims_done += 1;
-        h->n_evals += 1;
+        if (from_cache) h->cache_hits += 1;
+        else h->n_evals += 1;
         h->pend_node = -1;
     }
     syncwarp();
@@ -255,10 +424,12 @@ KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, 
 
 // Hash evaluator (test evaluator, oracle mode 0): logits and value from a hash of the position.
 // scratch: n floats of per-warp scratch (shared memory on the device).
-KV_DEV void mcts_hash_eval_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int slot, float* scratch) {
+KV_DEV void mcts_hash_eval_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int slot, float* scratch,
+                                uint32_t wave = 0) {
     const int g = A.eval_game[slot];
     const uint64_t w = lane < LINE_WORDS ? A.eval_lines[(size_t)slot * LINE_WORDS + lane] : 0ull;
     const uint64_t ph = pos_hash_warp(w, lane);
+    if (cfg.cache_mask) cache_fill_warp(lane, cfg, A, wave, slot, nullptr, hash_value(ph));
     const GameHdr* h = &A.hdr[g];
     const NodeMeta m = A.node_meta[(size_t)g * cfg.node_cap + h->pend_node];
     const int n = m.ne_term & 0xFFFF;
@@ -266,6 +437,23 @@ KV_DEV void mcts_hash_eval_warp(int lane, const MctsCfg& cfg, const MctsArrays& 
     for (int k = lane; k < n; k += 32) scratch[k] = hash_logit(ph, move_index(A.eMv[e0 + k]));
     syncwarp();
     mcts_expand_warp(lane, cfg, A, g, scratch, hash_value(ph));
+}
+
+// Hash-evaluator counterpart of the late (cache hit / follower) expansion: the value comes from the cached / leader
+// features, the logits are recomputed from the position hash (what a miss would have produced, bit for bit).
+KV_DEV void mcts_hash_late_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int li, float* scratch) {
+    const int g = A.late_game[li], src = A.late_src[li];
+    const GameHdr* h = &A.hdr[g];
+    const size_t nidx = (size_t)g * cfg.node_cap + h->pend_node;
+    const uint64_t w = lane < LINE_WORDS ? A.node_line[nidx * LINE_WORDS + lane] : 0ull;
+    const uint64_t ph = pos_hash_warp(w, lane);
+    const NodeMeta m = A.node_meta[nidx];
+    const int n = m.ne_term & 0xFFFF;
+    const size_t e0 = (size_t)g * cfg.edge_cap + m.first_edge;
+    for (int k = lane; k < n; k += 32) scratch[k] = hash_logit(ph, move_index(A.eMv[e0 + k]));
+    syncwarp();
+    const float v = src < 0 ? A.feat_game[(size_t)g * FEAT + 128] : A.feat_slot[(size_t)src * FEAT + 128];
+    mcts_expand_warp(lane, cfg, A, g, scratch, v, true);
 }
 
 // After cfg.sims simulations: pick the move from the root visit counts, record (position, move), play it,

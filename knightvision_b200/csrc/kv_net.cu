@@ -460,6 +460,8 @@ uint64_t kv_net_blob_floats(kv_ctx* ctx) { return (ctx && ctx->net) ? ctx->net->
 void* kv_net_blob_device_ptr(kv_ctx* ctx) { return (ctx && ctx->net) ? ctx->net->d_blob : nullptr; }
 
 // Fold the fp32 state_dict blob that sits in the net's device staging buffer (kv_net_blob_device_ptr).
+int kv_mcts_cache_clear(kv_ctx* ctx, void* stream);
+
 int kv_net_commit_weights(kv_ctx* ctx, void* stream) {
     if (!ctx || !ctx->net) return kv_fail_msg(ctx, "kv_net_commit_weights: no net");
     kv_net* n = ctx->net;
@@ -508,7 +510,7 @@ int kv_net_commit_weights(kv_ctx* ctx, void* stream) {
     }
     if ((size_t)(p - n->d_blob) != n->blob_floats) return kv_fail_msg(ctx, "kv_net_commit_weights: blob size mismatch");
     n->loaded = true;
-    return 0;
+    return kv_mcts_cache_clear(ctx, stream);   // cached features belong to the old weights
 }
 
 int kv_net_load(kv_ctx* ctx, const float* h_blob, uint64_t n_floats) {

@@ -43,6 +43,12 @@ KV_DEV float shfl_xorf(float v, int m, int lane) { return shflf(v, lane ^ m); }
 KV_DEV uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 KV_DEV void atomic_add_u64(uint64_t* p, uint64_t v) { *p += v; }
 KV_DEV uint64_t ldg64(const uint64_t* p) { return *p; }
+KV_DEV uint64_t atomic_cas_u64(uint64_t* p, uint64_t expect, uint64_t val) { uint64_t o = *p; if (o == expect) *p = val; return o; }
+KV_DEV void atomic_store_u64(uint64_t* p, uint64_t v) { *p = v; }
+KV_DEV uint64_t ld_cg_u64(const uint64_t* p) { return *p; }
+KV_DEV uint32_t ld_cg_u32(const uint32_t* p) { return *p; }
+KV_DEV float ld_cg_f32(const float* p) { return *p; }
+KV_DEV void mem_fence() {}
 }  // namespace kv
 #else
 #define KV_DEV __device__ __forceinline__
@@ -68,6 +74,17 @@ KV_DEV void atomic_add_u64(uint64_t* p, uint64_t v) {
     atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
 }
 KV_DEV uint64_t ldg64(const uint64_t* p) { return __ldg(p); }
+KV_DEV uint64_t atomic_cas_u64(uint64_t* p, uint64_t expect, uint64_t val) {
+    return atomicCAS(reinterpret_cast<unsigned long long*>(p), (unsigned long long)expect, (unsigned long long)val);
+}
+KV_DEV void atomic_store_u64(uint64_t* p, uint64_t v) {
+    atomicExch(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+// L2-coherent loads: data other SMs wrote during the same kernel must not come from this SM's L1
+KV_DEV uint64_t ld_cg_u64(const uint64_t* p) { return __ldcg(p); }
+KV_DEV uint32_t ld_cg_u32(const uint32_t* p) { return __ldcg(p); }
+KV_DEV float ld_cg_f32(const float* p) { return __ldcg(p); }
+KV_DEV void mem_fence() { __threadfence(); }
 }  // namespace kv
 #endif
 

@@ -178,6 +178,10 @@ class Engine:
         self.mcts_games, self.mcts_node_cap, self.mcts_edge_cap, self.mcts_rec_cap = (int(x) for x in g)
         self.mcts_sims = sims
 
+    def mcts_enable_cache(self, log2_slots: int):
+        """Evaluation cache of 2**log2_slots x 640 B entries (0 = off); results are identical with it on or off."""
+        N.check(self.ctx, self._lib.kv_mcts_enable_cache(self.ctx, log2_slots), "kv_mcts_enable_cache")
+
     def mcts_reset(self, start_lines: torch.Tensor | None = None, game_id_base: int = 0):
         N.check(self.ctx, self._lib.kv_mcts_reset(self.ctx, _ptr(start_lines) if start_lines is not None else None,
                                                   game_id_base, self._stream()), "kv_mcts_reset")
@@ -192,9 +196,9 @@ class Engine:
         N.check(self.ctx, self._lib.kv_mcts_run_move(self.ctx, self._stream()), "kv_mcts_run_move")
 
     def mcts_status(self) -> dict:
-        out = np.zeros(8, dtype=np.uint64)
+        out = np.zeros(9, dtype=np.uint64)
         N.check(self.ctx, self._lib.kv_mcts_status(self.ctx, _ptr(out), self._stream()), "kv_mcts_status")
-        keys = ("done", "sims_in_move", "evals", "plies", "overflow", "white_wins", "black_wins", "draws")
+        keys = ("done", "sims_in_move", "evals", "plies", "overflow", "white_wins", "black_wins", "draws", "cache_hits")
         return {k: int(v) for k, v in zip(keys, out)}
 
     def mcts_read_root(self, game: int) -> dict:

@@ -212,7 +212,7 @@ struct EmuMcts {
 };
 
 static EmuMcts* emu_mcts_new(int G, int sims, int edges_per_node, int max_plies, int temp_plies, float c_puct,
-                             float dir_alpha, float dir_eps, uint64_t seed) {
+                             float dir_alpha, float dir_eps, uint64_t seed, int cache_log2 = 0) {
     EmuMcts* m = new EmuMcts();
     m->G = G;
     kv::MctsCfg& c = m->cfg;
@@ -246,6 +246,22 @@ static EmuMcts* emu_mcts_new(int G, int sims, int edges_per_node, int max_plies,
     A.eval_lines = m->alloc<uint64_t>((g + 1) * 16);
     A.rec_line = m->alloc<uint64_t>(g * c.rec_cap * 12);
     A.rec_move = m->alloc<uint16_t>(g * c.rec_cap);
+    A.eval_centry = m->alloc<int>(g);
+    A.eval_hash = m->alloc<uint64_t>(g);
+    A.n_late = m->alloc<uint32_t>(4);
+    A.late_game = m->alloc<int>(g);
+    A.late_src = m->alloc<int>(g);
+    A.feat_game = m->alloc<float>(g * kv::FEAT);
+    A.feat_slot = m->alloc<float>(g * kv::FEAT);
+    A.cache = nullptr;
+    c.cache_mask = 0;
+    if (cache_log2 > 0) {
+        const size_t slots = (size_t)1 << cache_log2;
+        m->store.emplace_back(slots * sizeof(kv::CacheEntry) + 128, 0);
+        uintptr_t p = (reinterpret_cast<uintptr_t>(m->store.back().data()) + 127) & ~(uintptr_t)127;
+        A.cache = reinterpret_cast<kv::CacheEntry*>(p);
+        c.cache_mask = (uint32_t)(slots - 1);
+    }
     return m;
 }
 
@@ -260,15 +276,24 @@ static void emu_mcts_reset(EmuMcts* m, const uint64_t* start, uint64_t id_base) 
     }
 }
 
+static uint32_t g_emu_wave = 0;
+static long g_emu_evals = 0, g_emu_late = 0;
+
 static void emu_mcts_wave(EmuMcts* m) {
     uint16_t mv[kv::MAX_MOVES];
     float scratch[kv::MAX_MOVES];
+    const uint32_t wave = ++g_emu_wave;
     *m->A.n_eval = 0;
+    *m->A.n_late = 0;
     for (int g = 0; g < m->G; g++)
-        kvemu::run_warp([&](int lane) { kv::mcts_select_warp(g_tables, lane, m->cfg, m->A, g, mv); });
-    const int ne = (int)*m->A.n_eval;
+        kvemu::run_warp([&](int lane) { kv::mcts_select_warp(g_tables, lane, m->cfg, m->A, g, mv, wave); });
+    const int ne = (int)*m->A.n_eval, nl = (int)*m->A.n_late;
+    g_emu_evals += ne;
+    g_emu_late += nl;
     for (int slot = 0; slot < ne; slot++)
-        kvemu::run_warp([&](int lane) { kv::mcts_hash_eval_warp(lane, m->cfg, m->A, slot, scratch); });
+        kvemu::run_warp([&](int lane) { kv::mcts_hash_eval_warp(lane, m->cfg, m->A, slot, scratch, wave); });
+    for (int li = 0; li < nl; li++)
+        kvemu::run_warp([&](int lane) { kv::mcts_hash_late_warp(lane, m->cfg, m->A, li, scratch); });
 }
 
 static void emu_mcts_finish(EmuMcts* m) {
@@ -313,8 +338,10 @@ __attribute__((visibility("default"))) void kvemu_mcts_search(int G, const uint6
 __attribute__((visibility("default"))) void kvemu_selfplay(int G, const uint64_t* start, uint64_t id_base, int sims,
                                                             int edges_per_node, int max_plies, int temp_plies,
                                                             float c_puct, float dir_alpha, float dir_eps, uint64_t seed,
-                                                            uint16_t* out_moves, int32_t* out_plies, int32_t* out_result) {
-    EmuMcts* m = emu_mcts_new(G, sims, edges_per_node, max_plies, temp_plies, c_puct, dir_alpha, dir_eps, seed);
+                                                            uint16_t* out_moves, int32_t* out_plies, int32_t* out_result,
+                                                            int cache_log2, int64_t* out_counts2) {
+    EmuMcts* m = emu_mcts_new(G, sims, edges_per_node, max_plies, temp_plies, c_puct, dir_alpha, dir_eps, seed, cache_log2);
+    g_emu_evals = g_emu_late = 0;
     emu_mcts_reset(m, start, id_base);
     for (int mvno = 0; mvno < max_plies; mvno++) {
         bool live = false;
@@ -328,6 +355,10 @@ __attribute__((visibility("default"))) void kvemu_selfplay(int G, const uint64_t
         out_result[g] = m->A.hdr[g].result;
         for (int p = 0; p < m->A.hdr[g].ply && p < max_plies; p++)
             out_moves[(size_t)g * max_plies + p] = m->A.rec_move[(size_t)g * m->cfg.rec_cap + p];
+    }
+    if (out_counts2) {
+        out_counts2[0] = g_emu_evals;
+        out_counts2[1] = g_emu_late;
     }
     delete m;
 }

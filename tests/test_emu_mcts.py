@@ -72,3 +72,16 @@ def test_edge_pool_overflow_rule_is_shared():
     assert r["overflow"] == 1 and info[0, 3] == 1
     n = int(info[0, 0])
     assert np.array_equal(N[0, :n], r["N"]) and np.array_equal(_bits(W[0, :n]), _bits(r["W"]))
+
+
+def test_eval_cache_does_not_change_games():
+    """Cache hits / in-wave followers re-derive the same priors and values: identical games, fewer evaluations."""
+    start = np.stack([L.start_line()] * 6)
+    base = emu.selfplay(start, sims=16, max_plies=10, temp_plies=4, id_base=7, seed=11, return_counts=True)
+    for log2 in (8, 14):    # tiny table (evictions, window pressure) and roomy table
+        got = emu.selfplay(start, sims=16, max_plies=10, temp_plies=4, id_base=7, seed=11, cache_log2=log2,
+                           return_counts=True)
+        assert np.array_equal(base[0], got[0]) and np.array_equal(base[1], got[1]) and np.array_equal(base[2], got[2])
+        evals, late = got[3]
+        assert late > 0 and evals + late == base[3][0]      # every expansion is either a tower eval or a cache serve
+    assert base[3][1] == 0

@@ -131,3 +131,39 @@ def test_full_size_wave_4096_games(eng):
     assert int(r0["N"].sum()) == 11 and int(r1["N"].sum()) == 11 and len(r0["moves"]) == 20
     eng.mcts_finish_move()
     assert eng.mcts_status()["plies"] == 4096
+
+
+def _play_records(eng, G, sims, moves, eval_mode, cache_log2, seed=13):
+    eng.mcts_create(G, sims, max_plies=moves, temp_plies=4, seed=seed, eval_mode=eval_mode)
+    eng.mcts_enable_cache(cache_log2)
+    eng.mcts_reset(None, game_id_base=50)
+    roots = []
+    for i in range(moves):
+        eng.mcts_run_sims(sims)
+        if i == moves - 1:
+            roots = [eng.mcts_read_root(g) for g in (0, G // 2, G - 1)]
+        eng.mcts_finish_move()
+    st = eng.mcts_status()
+    rec = tuple(t.cpu().numpy() for t in eng.mcts_records())
+    return rec, roots, st
+
+
+@pytest.mark.parametrize("eval_mode", [0, 1])
+def test_eval_cache_is_transparent(eng, eval_mode):
+    """Same games, visit counts and W bits with the evaluation cache off, tiny (evictions) and roomy."""
+    if eval_mode == 1:
+        from knightvision_b200.model import ChessNet
+        torch.manual_seed(0)
+        ChessNet().eval().attach(eng, max_batch=256)
+    G, sims, moves = 192, 40, 5
+    base, broots, bst = _play_records(eng, G, sims, moves, eval_mode, 0)
+    assert bst["cache_hits"] == 0 and bst["evals"] > 0
+    for log2 in (10, 18):
+        rec, roots, st = _play_records(eng, G, sims, moves, eval_mode, log2)
+        for a, b in zip(base, rec):
+            assert np.array_equal(a, b)
+        for ra, rb in zip(broots, roots):
+            assert np.array_equal(ra["N"], rb["N"]) and np.array_equal(_bits(ra["W"]), _bits(rb["W"]))
+            assert np.array_equal(_bits(ra["P"]), _bits(rb["P"]))
+        assert st["cache_hits"] > 0 and st["evals"] + st["cache_hits"] == bst["evals"]
+    eng.mcts_enable_cache(0)
