@@ -118,45 +118,50 @@ def run(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_moves(n_moves, profile=False):
+        """n_moves moves for every game; returns (device ms, status before, status after, per-kernel profile, launches)."""
+        s0 = eng.mcts_status()
+        if profile:
+            eng.profile(True)
+            eng.profile_read()
+        l0 = eng.launches
+        barrier()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for _ in range(n_moves):
+            eng.mcts_run_move()
+        b_.record()
+        barrier()
+        prof_ = eng.profile_read() if profile else None
+        if profile:
+            eng.profile(False)
+        return a_.elapsed_time(b_), s0, eng.mcts_status(), prof_, eng.launches - l0
+
+    warm = max(args.warmup, 3)
+    clocks = Clocks(local_rank)
+    # ---- A: BASELINE config 3 — all games from the initial position, evaluation cache on ------------------------
     eng.mcts_enable_cache(CACHE_LOG2)
     eng.mcts_reset(None, game_id_base=rank * G)
-    warm = max(args.warmup, 3)
     for _ in range(warm):
         eng.mcts_run_move()
     torch.cuda.synchronize()
-    st0 = eng.mcts_status()
-    clocks = Clocks(local_rank)
+    snapshot_h = eng.mcts_roots().cpu().pin_memory()      # positions at the start of the timed region (for B and C)
     clocks.start()
-    eng.profile(True)
-    eng.profile_read()
-    l0 = eng.launches
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        eng.mcts_run_move()
-    e1.record()
-    barrier()
-    dev_ms = e0.elapsed_time(e1)
-    prof = eng.profile_read()
-    eng.profile(False)
-    launches = eng.launches - l0
-    st1 = eng.mcts_status()
+    dev_ms, st0, st1, prof, launches = timed_moves(args.steps, profile=True)
     live = G - st0["done"]
     sims_done = live * SIMS * args.steps          # every live game runs SIMS simulations per move
     evals = st1["evals"] - st0["evals"]
     hits = st1["cache_hits"] - st0["cache_hits"]
     positions = st1["plies"] - st0["plies"]
 
-    # e2e: a fresh generation through the public API with HOST buffers: start positions from pinned host memory,
-    # cold evaluation cache (a new generation means new weights), e2e_steps moves, records back on the host as the
+    # ---- B: e2e — the same positions through the public API with HOST buffers: pinned host lines -> device, cold
+    # evaluation cache (a new generation means new weights), the same number of moves, records back on the host as the
     # reference's tuples.  Everything, copies included, is inside the timed region.
-    start_h = torch.from_numpy(np.stack([L.start_line()] * G).view(np.int64)).pin_memory()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = args.steps
     barrier()
     t0 = time.perf_counter()
-    eng._lib.kv_mcts_cache_clear(eng.ctx, None)
-    d = start_h.to(dev, non_blocking=True)
+    eng.mcts_cache_clear()
+    d = snapshot_h.to(dev, non_blocking=True)
     eng.mcts_reset(d, game_id_base=rank * G)
     for _ in range(e2e_steps):
         eng.mcts_run_move()
@@ -164,31 +169,34 @@ def run(args, rank, world, local_rank):
     rec = len(recs)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    ste = eng.mcts_status()
-
-    # the same device-timed measurement with the evaluation cache OFF (one network evaluation per simulation)
-    nocache_ms = None
-    if CACHE_LOG2 and rank == 0 or (CACHE_LOG2 and world > 1):
-        eng.mcts_enable_cache(0)
-        eng.mcts_reset(None, game_id_base=rank * G)
-        eng.mcts_run_move()
-        barrier()
-        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0.record()
-        eng.mcts_run_move()
-        n1.record()
-        barrier()
-        nocache_ms = n0.elapsed_time(n1)
     clk = clocks.stop()
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([float(sims_done), float(evals), float(positions), float(rec), float(hits)], dtype=torch.float64,
-                       device=dev)
+    # ---- C: the same positions with the evaluation cache OFF (one network evaluation per simulation) -----------------
+    nocache_ms = None
+    if CACHE_LOG2:
+        eng.mcts_enable_cache(0)
+        eng.mcts_reset(snapshot_h.to(dev), game_id_base=rank * G)
+        eng.mcts_run_move()
+        nocache_ms = timed_moves(1)[0]
+
+    # ---- D: "random positions" variant: k in [0,40) random legal plies per game, seed 1234, cache on ----
+    eng.mcts_enable_cache(CACHE_LOG2)
+    eng.mcts_reset(eng.random_positions(G, 40, 1234 + rank), game_id_base=rank * G)
+    for _ in range(warm):
+        eng.mcts_run_move()
+    r_ms, r0, r1, _, _ = timed_moves(max(1, min(args.steps, 2)))
+    r_moves = max(1, min(args.steps, 2))
+    r_sims = (G - r0["done"]) * SIMS * r_moves
+    r_evals = r1["evals"] - r0["evals"]
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, nocache_ms or 0.0, r_ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(sims_done), float(evals), float(positions), float(rec), float(hits), float(r_sims),
+                        float(r_evals)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)     # record counts gathered to every rank
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
-    sims_all, evals_all, pos_all, rec_all, hits_all = (float(x) for x in cnt)
+    dev_ms, e2e_ms, nocache_ms, r_ms = float(t[0]), float(t[1]), float(t[2]) or None, float(t[3])
+    sims_all, evals_all, pos_all, rec_all, hits_all, r_sims_all, r_evals_all = (float(x) for x in cnt)
     if rank != 0:
         return
     peaks = measured_peaks()
@@ -212,12 +220,18 @@ def run(args, rank, world, local_rank):
                        "note": "keyed by the 12 bitboards (the net's whole input); search results are bit-identical "
                                "with the cache on or off (tests/test_gpu_mcts.py::test_eval_cache_is_transparent)"},
         "no_cache": ({"value": world * G * SIMS / (nocache_ms * 1e-3), "unit": "sims/s", "ms_per_step": nocache_ms,
-                      "evals_per_sim": 1.0} if nocache_ms else None),
+                      "evals_per_sim": 1.0, "note": "same positions, evaluation cache disabled"} if nocache_ms else None),
+        "random_positions": {"value": r_sims_all / (r_ms * 1e-3), "unit": "sims/s",
+                             "evals_per_sim": r_evals_all / r_sims_all if r_sims_all else None,
+                             "ms_per_step": r_ms / r_moves,
+                             "note": "every game starts after k in [0,40) uniformly random legal plies (seed 1234), "
+                                     "cache on, same warm-up"},
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_sims / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": G * 128 // e2e_steps,
                 "d2h_bytes_per_step": G * (12 * 64 * 4 + 8), "records_returned": rec_all, "steps": e2e_steps,
-                "api": ("fresh generation through SelfPlay: pinned host start lines -> kv_mcts_reset -> e2e_steps x "
-                        "kv_mcts_run_move -> records() as the reference's (planes, move, reward) tuples; cold cache")},
+                "api": ("SelfPlay public API on the timed region's own start positions: pinned host lines -> kv_mcts_reset -> "
+                        "steps x kv_mcts_run_move -> records() as the reference's (planes, move, reward) tuples; "
+                        "evaluation cache cleared first (new generation)")},
         "roofline": {"kernel": "conv3x3_umma_kernel (tcgen05 implicit GEMM)", "bound": "tensor", "achieved": achieved,
                      "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
                      "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 figure",

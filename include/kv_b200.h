@@ -143,6 +143,7 @@ KV_API int kv_mcts_cache_clear(kv_ctx* ctx, void* stream);
 /* h_out9: games done, sum of sims done in the current move, tower evaluations, plies played, games with edge-pool
  * overflow, white wins, black wins, draws, expansions served by the cache (hits + in-wave duplicates) */
 KV_API int kv_mcts_status(kv_ctx* ctx, uint64_t* h_out9, void* stream);
+KV_API int kv_mcts_get_roots(kv_ctx* ctx, uint64_t* d_lines, void* stream); /* current position of every game [n][16] */
 KV_API int kv_mcts_geometry(kv_ctx* ctx, int32_t* out4);              /* n_games, node_cap, edge_cap, rec_cap */
 /* records of every game in game order; d_lines [cap][16] board lines (kv_encode gives the reference's planes),
  * d_move policy index (ai/ai.py:51-57), d_reward 1.0 / 0.2 / -1.0 (scripts/self_play.py:245-250), d_game index */

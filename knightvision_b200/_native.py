@@ -48,6 +48,7 @@ SIGNATURES = {
     "kv_mcts_enable_cache": (c_int, [c_void_p, c_int]),
     "kv_mcts_cache_clear": (c_int, [c_void_p, c_void_p]),
     "kv_mcts_status": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "kv_mcts_get_roots": (c_int, [c_void_p, c_void_p, c_void_p]),
     "kv_mcts_geometry": (c_int, [c_void_p, c_void_p]),
     "kv_mcts_records": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "kv_mcts_read_root": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

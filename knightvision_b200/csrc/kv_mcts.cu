@@ -457,6 +457,14 @@ int kv_mcts_dump_tree(kv_ctx* ctx, int game, float* h_node_val, int32_t* h_node_
     return 0;
 }
 
+// current position of every game: d_lines [n_games][16]
+int kv_mcts_get_roots(kv_ctx* ctx, uint64_t* d_lines, void* stream) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_get_roots: no search context");
+    KV_CUDA(ctx, cudaMemcpyAsync(d_lines, ctx->mcts->A.root_line, (size_t)ctx->mcts->G * 128, cudaMemcpyDeviceToDevice,
+                                 (cudaStream_t)stream));
+    return 0;
+}
+
 int kv_mcts_geometry(kv_ctx* ctx, int32_t* out4) {
     if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_geometry: no search context");
     out4[0] = ctx->mcts->G;

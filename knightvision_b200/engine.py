@@ -201,6 +201,37 @@ class Engine:
         keys = ("done", "sims_in_move", "evals", "plies", "overflow", "white_wins", "black_wins", "draws", "cache_hits")
         return {k: int(v) for k, v in zip(keys, out)}
 
+    def mcts_roots(self) -> torch.Tensor:
+        """Current position of every game, int64 [n_games,16] on the device."""
+        out = torch.empty((self.mcts_games, 16), dtype=torch.int64, device=self.device)
+        N.check(self.ctx, self._lib.kv_mcts_get_roots(self.ctx, _ptr(out), self._stream()), "kv_mcts_get_roots")
+        return out
+
+    def mcts_cache_clear(self):
+        N.check(self.ctx, self._lib.kv_mcts_cache_clear(self.ctx, self._stream()), "kv_mcts_cache_clear")
+
+    def random_positions(self, n: int, max_plies: int = 40, seed: int = 1234) -> torch.Tensor:
+        """n positions after k in [0, max_plies) uniformly random legal plies from the initial position (rules on the
+        device; torch only draws the random numbers).  Positions without a legal move fall back to the initial one."""
+        from . import layout as L
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        start = lines_to_device(np.stack([L.start_line()] * n), self.device)
+        lines = start.clone()
+        k = torch.randint(0, max_plies, (n,), generator=g).to(self.device)
+        for ply in range(max_plies):
+            moves, counts, flags = self.movegen(lines)
+            u = torch.rand(n, generator=g).to(self.device)
+            idx = torch.clamp((u * counts.clamp(min=1)).long(), max=255)
+            pick = moves.gather(1, idx[:, None])[:, 0]
+            skip = (counts == 0) | (k <= ply) | ((flags & 16) != 0)
+            pick = torch.where(skip, torch.full_like(pick, -1), pick)     # 0xFFFF = leave the board untouched
+            self.make_moves(lines, pick.contiguous())
+        moves, counts, flags = self.movegen(lines)
+        bad = (counts == 0) | ((flags & 16) != 0)
+        lines[bad] = start[bad]
+        lines[:, 13:] = 0
+        return lines
+
     def mcts_read_root(self, game: int) -> dict:
         mv = np.zeros(256, np.uint16); n_ = np.zeros(256, np.uint32); w = np.zeros(256, np.float32)
         p = np.zeros(256, np.float32); info = np.zeros(4, np.int32)
