@@ -20,6 +20,21 @@ CONV_FLOPS_PER_EVAL = 2.0 * 64 * 9 * (256 * 512 + 10 * 512 * 512)      # conv2 +
 NET_FLOPS_PER_EVAL = 2.0 * 1587872256                                   # whole net, SURVEY §8d
 
 
+def _ncu_traffic():
+    """Average DRAM bytes (read + write) per launch of the conv kernel from the committed ncu capture, or None."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.abspath(__file__))
+    files = sorted(glob.glob(os.path.join(root, "profiles", "*ncu_conv3x3*.txt")))
+    if not files:
+        return None, None
+    rd = [float(x) for x in re.findall(r"dram__bytes_read\.sum\s+([0-9.]+) Mbyte", open(files[-1]).read())]
+    wr = [float(x) for x in re.findall(r"dram__bytes_write\.sum\s+([0-9.]+) Mbyte", open(files[-1]).read())]
+    if not rd or len(rd) != len(wr):
+        return None, None
+    return 1e6 * (sum(rd) + sum(wr)) / len(rd), os.path.relpath(files[-1], root)
+
+
 def _cpu_eval_rate(batch=256, iters=4):
     """fp32 CPU forward of the reference graph (torch CPU kernels, all threads): evals/s."""
     import torch
@@ -201,6 +216,7 @@ def run(args, rank, world, local_rank):
         return
     peaks = measured_peaks()
     conv_ms, conv_n = prof["net_conv"]
+    traffic, traffic_src = _ncu_traffic()
     achieved = (evals * CONV_FLOPS_PER_EVAL) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     value = sims_all / (dev_ms * 1e-3)
     e2e_sims = world * G * SIMS * e2e_steps
@@ -234,7 +250,11 @@ def run(args, rank, world, local_rank):
                         "evaluation cache cleared first (new generation)")},
         "roofline": {"kernel": "conv3x3_umma_kernel (tcgen05 implicit GEMM)", "bound": "tensor", "achieved": achieved,
                      "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-                     "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 figure",
+                     "traffic": traffic, "traffic_source": (f"{traffic_src}: dram__bytes_read.sum + dram__bytes_write.sum per "
+                                                             "launch at 4096 boards (algorithmic: 268 MB in + 268 MB out "
+                                                             "+ 4.7 MB weights, + 268 MB residual on every second layer)")
+                     if traffic else None,
+                     "peak_source": peaks["source"] + ", sustained bf16 figure",
                      "kernel_ms_per_step": conv_ms / args.steps, "kernel_share_of_step": conv_ms / dev_ms,
                      "flops_per_eval_in_kernel": CONV_FLOPS_PER_EVAL, "launches": conv_n},
         "kernels_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},

@@ -9,36 +9,41 @@
 namespace kvn {
 using bf16 = __nv_bfloat16;
 
-// wh [3][C] fp32 (policy ch0, policy ch1, value; BN folded), bh [3].  One CTA (256 threads) per board.
-// feat out: hp[128] (index c*64 + pixel, torch.flatten order of [2,8,8]) and hv[64], both after relu.
+// wh [3][C] fp32 (policy ch0, policy ch1, value; BN folded), bh [3].  One CTA (>= 256 threads use the first 256)
+// per board.  feat out: hp[128] (index c*64 + pixel, torch.flatten order of [2,8,8]) and hv[64], both after relu.
+// swh: shared-memory staging for wh (3*C floats).  Four consecutive lanes share a pixel and read four consecutive
+// 16 B chunks of its row (64 B contiguous per pixel per request: full sectors).
 __device__ __forceinline__ void head_features(const bf16* __restrict__ act, int C, const float* __restrict__ wh,
-                                              const float* __restrict__ bh, float* hp, float* hv) {
-    const int px = threadIdx.x >> 2, part = threadIdx.x & 3;   // 64 pixels x 4 channel quarters
-    const int cq = C >> 2;
-    const bf16* row = act + (size_t)px * C + part * cq;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int c = 0; c < cq; c += 8) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + c));
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float a0 = __low2float(h[j]), a1 = __high2float(h[j]);
-            const int ci = part * cq + c + 2 * j;
-            s0 += a0 * __ldg(wh + ci) + a1 * __ldg(wh + ci + 1);
-            s1 += a0 * __ldg(wh + C + ci) + a1 * __ldg(wh + C + ci + 1);
-            s2 += a0 * __ldg(wh + 2 * C + ci) + a1 * __ldg(wh + 2 * C + ci + 1);
+                                              const float* __restrict__ bh, float* hp, float* hv, float* swh) {
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) swh[i] = __ldg(wh + i);
+    __syncthreads();
+    if (threadIdx.x < 256) {
+        const int px = threadIdx.x >> 2, part = threadIdx.x & 3;
+        const bf16* row = act + (size_t)px * C;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int c = part * 8; c < C; c += 32) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + c));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+            const float4 w0a = *reinterpret_cast<const float4*>(swh + c), w0b = *reinterpret_cast<const float4*>(swh + c + 4);
+            const float4 w1a = *reinterpret_cast<const float4*>(swh + C + c), w1b = *reinterpret_cast<const float4*>(swh + C + c + 4);
+            const float4 w2a = *reinterpret_cast<const float4*>(swh + 2 * C + c), w2b = *reinterpret_cast<const float4*>(swh + 2 * C + c + 4);
+            const float a0 = __low2float(h[0]), a1 = __high2float(h[0]), a2 = __low2float(h[1]), a3 = __high2float(h[1]);
+            const float a4 = __low2float(h[2]), a5 = __high2float(h[2]), a6 = __low2float(h[3]), a7 = __high2float(h[3]);
+            s0 += a0 * w0a.x + a1 * w0a.y + a2 * w0a.z + a3 * w0a.w + a4 * w0b.x + a5 * w0b.y + a6 * w0b.z + a7 * w0b.w;
+            s1 += a0 * w1a.x + a1 * w1a.y + a2 * w1a.z + a3 * w1a.w + a4 * w1b.x + a5 * w1b.y + a6 * w1b.z + a7 * w1b.w;
+            s2 += a0 * w2a.x + a1 * w2a.y + a2 * w2a.z + a3 * w2a.w + a4 * w2b.x + a5 * w2b.y + a6 * w2b.z + a7 * w2b.w;
         }
-    }
 #pragma unroll
-    for (int m = 1; m <= 2; m <<= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, m);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, m);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, m);
-    }
-    if (part == 0) {
-        hp[px] = fmaxf(s0 + bh[0], 0.f);
-        hp[64 + px] = fmaxf(s1 + bh[1], 0.f);
-        hv[px] = fmaxf(s2 + bh[2], 0.f);
+        for (int m = 1; m <= 2; m <<= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, m);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+        }
+        if (part == 0) {
+            hp[px] = fmaxf(s0 + bh[0], 0.f);
+            hp[64 + px] = fmaxf(s1 + bh[1], 0.f);
+            hv[px] = fmaxf(s2 + bh[2], 0.f);
+        }
     }
 }
 

@@ -94,10 +94,11 @@ __device__ __forceinline__ void legal_logits(const MctsCfg& cfg, const MctsArray
 __global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArrays A, const __nv_bfloat16* __restrict__ act,
                                                             HeadW H, uint32_t wave) {
     __shared__ float hp[128], hv[64], red[8], logits[MAX_MOVES];
+    __shared__ __align__(16) float swh[3 * 512];
     const int slot = blockIdx.x;
     if (slot >= (int)*A.n_eval) return;
     const int g = A.eval_game[slot];
-    kvn::head_features(act + (size_t)slot * 64 * H.C, H.C, H.wh, H.bh, hp, hv);
+    kvn::head_features(act + (size_t)slot * 64 * H.C, H.C, H.wh, H.bh, hp, hv, swh);
     __syncthreads();
     const float v_white = kvn::value_mlp(hv, H.w1, H.b1, H.w2, H.b2, red);
     legal_logits(cfg, A, g, H, hp, logits);

@@ -203,7 +203,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ---- stem: encode + conv1 + bn1 + relu ------------------------------------------------------------------
-// table [9 taps][12 pieces][C1] fp32 (BN scale folded), bias [C1].  One CTA per board, thread = channel.
+// table [9 taps][12 pieces][C1] fp32 (BN scale folded), bias [C1].  One CTA per board.  A warp owns one pixel at a
+// time and its lanes own 8 consecutive channels each: table rows are read as coalesced float4 pairs (L1-resident,
+// 110 KB), the output row is written as one 512 B (C1 = 256) coalesced burst of 16 B stores.
 __global__ void __launch_bounds__(256) stem_kernel(const uint64_t* __restrict__ lines, int n,
                                                    const int* __restrict__ n_ptr,
                                                    const float* __restrict__ table, const float* __restrict__ bias,
@@ -220,20 +222,36 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint64_t* __restrict__ 
         piece[threadIdx.x] = (int8_t)pc;
     }
     __syncthreads();
-    for (int co = threadIdx.x; co < C1; co += blockDim.x) {
-        const float bs = bias[co];
-        for (int px = 0; px < 64; px++) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int c0 = lane * 8; c0 < C1; c0 += 256) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+        for (int px = wid; px < 64; px += 8) {
             const int y = px >> 3, x = px & 7;
-            float acc = bs;
+            float4 a0 = b0, a1 = b1;
 #pragma unroll
             for (int tap = 0; tap < 9; tap++) {
                 const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
                 if (yy >= 0 && yy < 8 && xx >= 0 && xx < 8) {
                     const int pc = piece[yy * 8 + xx];
-                    if (pc >= 0) acc += __ldg(table + ((size_t)tap * 12 + pc) * C1 + co);
+                    if (pc >= 0) {
+                        const float4* t = reinterpret_cast<const float4*>(table + ((size_t)tap * 12 + pc) * C1 + c0);
+                        const float4 t0 = __ldg(t), t1 = __ldg(t + 1);
+                        a0.x += t0.x; a0.y += t0.y; a0.z += t0.z; a0.w += t0.w;
+                        a1.x += t1.x; a1.y += t1.y; a1.z += t1.z; a1.w += t1.w;
+                    }
                 }
             }
-            out[((size_t)b * 64 + px) * C1 + co] = __float2bfloat16(fmaxf(acc, 0.f));
+            const __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(a0.x, 0.f), fmaxf(a0.y, 0.f));
+            const __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(a0.z, 0.f), fmaxf(a0.w, 0.f));
+            const __nv_bfloat162 p2 = __floats2bfloat162_rn(fmaxf(a1.x, 0.f), fmaxf(a1.y, 0.f));
+            const __nv_bfloat162 p3 = __floats2bfloat162_rn(fmaxf(a1.z, 0.f), fmaxf(a1.w, 0.f));
+            uint4 o;
+            o.x = *reinterpret_cast<const uint32_t*>(&p0);
+            o.y = *reinterpret_cast<const uint32_t*>(&p1);
+            o.z = *reinterpret_cast<const uint32_t*>(&p2);
+            o.w = *reinterpret_cast<const uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(out + ((size_t)b * 64 + px) * C1 + c0) = o;
         }
     }
 }
@@ -246,9 +264,10 @@ __global__ void __launch_bounds__(256) head_full_kernel(const bf16* __restrict__
                                                         const float* __restrict__ w2, const float* __restrict__ b2,
                                                         float* __restrict__ policy, float* __restrict__ value) {
     __shared__ float hp[128], hv[64], red[8];
+    __shared__ __align__(16) float swh[3 * 512];
     const int b = blockIdx.x;
     if (b >= n) return;
-    head_features(act + (size_t)b * 64 * C, C, wh, bh, hp, hv);
+    head_features(act + (size_t)b * 64 * C, C, wh, bh, hp, hv, swh);
     __syncthreads();
     const float v = value_mlp(hv, w1, b1, w2, b2, red);
     if (threadIdx.x == 0 && value) value[b] = v;
