@@ -1,0 +1,167 @@
+"""The caller of the hot path: the reference's RL loop (scripts/learn.py:152-209) and training step
+(scripts/train.py:126-196), importable without tensorflow / google.colab / telegram / python-chess.
+
+    train -> self-play -> dataset.extend -> train -> ...
+
+Self-play runs on the B200 engine (knightvision_b200.selfplay); its records stay on the GPU in packed form
+(12 bitboards + move + reward = 104 B per position instead of the reference's 3 080 B float planes) and are expanded
+to planes batch by batch with the encode kernel.  The training step itself is ordinary PyTorch autograd on the
+`ChessNet` parameter container (the reference's trainer is ordinary PyTorch too; it is not part of the hand-written
+hot path): loss = cross-entropy(policy, move) + MSE(value, reward) - 0.01 * entropy (train.py:167-174), gradient
+clipping at 1.0 and accumulation over 2 batches (train.py:183-190), bf16 autocast instead of fp16 + GradScaler.
+With torch.distributed initialised (one process per GPU), gradients are averaged by DistributedDataParallel over
+NCCL and every rank plays its own shard of the games.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from types import SimpleNamespace
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .model import ChessNet
+from .selfplay import SelfPlay, engine_for
+
+logger = logging.getLogger(__name__)
+ENTROPY_COEF = 0.01
+
+
+class TrainGraph(nn.Module):
+    """Autograd graph of ai/model.py:51-77 over a ChessNet's parameters (train-mode BatchNorm)."""
+
+    def __init__(self, net: ChessNet):
+        super().__init__()
+        self.net = net
+
+    def forward(self, x):
+        n = self.net
+        h = F.relu(n.bn1(n.conv1(x)))
+        if n.arch[3]:
+            h = F.relu(n.bn2(n.conv2(h)))
+        for b in n.res_blocks:
+            t = F.relu(b.bn1(b.conv1(h)))
+            h = F.relu(b.bn2(b.conv2(t)) + h)
+        p = n.policy_fc(F.relu(n.policy_bn(n.policy_conv(h))).flatten(1))
+        v = F.relu(n.value_bn(n.value_conv(h))).flatten(1)
+        v = torch.tanh(n.value_fc2(F.relu(n.value_fc1(v))))
+        return p, v
+
+
+class ReplayData:
+    """Packed device-resident training set with the reference's `extend` sink (scripts/train.py:560-561)."""
+
+    def __init__(self, engine):
+        self.eng = engine
+        dev = engine.device
+        self.lines = torch.zeros((0, 16), dtype=torch.int64, device=dev)
+        self.move = torch.zeros(0, dtype=torch.int64, device=dev)
+        self.reward = torch.zeros(0, dtype=torch.float32, device=dev)
+
+    def __len__(self):
+        return self.lines.shape[0]
+
+    def extend_packed(self, lines, move, reward):
+        self.lines = torch.cat([self.lines, lines])
+        self.move = torch.cat([self.move, move.to(torch.int64)])
+        self.reward = torch.cat([self.reward, reward])
+
+    def extend(self, new_records):
+        """Reference-format records [(np.float32 (12,8,8), move_index, reward)]: packed back to bitboards."""
+        import numpy as np
+        if not new_records:
+            return
+        planes = torch.from_numpy(np.stack([r[0] for r in new_records])).to(self.eng.device)
+        w = (planes.reshape(len(new_records), 12, 64) != 0).to(torch.int64)
+        bits = (w << torch.arange(64, device=w.device, dtype=torch.int64)).sum(-1)   # exact in two's complement
+        lines = torch.zeros((len(new_records), 16), dtype=torch.int64, device=self.eng.device)
+        lines[:, :12] = bits
+        self.extend_packed(lines, torch.tensor([r[1] for r in new_records], device=self.eng.device),
+                           torch.tensor([r[2] for r in new_records], dtype=torch.float32, device=self.eng.device))
+
+    def batches(self, batch_size, generator=None):
+        perm = torch.randperm(len(self), device=self.lines.device, generator=generator)
+        for i in range(0, len(self), batch_size):
+            idx = perm[i:i + batch_size]
+            yield self.eng.encode(self.lines[idx].contiguous()), self.move[idx], self.reward[idx]
+
+
+def train_epochs(net: ChessNet, optimizer, data: ReplayData, epochs: int, batch_size: int, accumulate_steps: int = 2):
+    """scripts/train.py:126-196 without the logging side channels.  Returns the mean loss of the last epoch."""
+    graph = TrainGraph(net)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        graph = nn.parallel.DistributedDataParallel(graph, device_ids=[data.eng.index])
+    net.train()
+    last = float("nan")
+    for _ in range(epochs):
+        tot, nb = 0.0, 0
+        optimizer.zero_grad()
+        batches = list(data.batches(batch_size))
+        for i, (boards, moves, outcomes) in enumerate(batches):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                pol, val = graph(boards)
+            pol = pol.float()
+            loss_policy = F.cross_entropy(pol, moves)
+            loss_value = F.mse_loss(val.squeeze(1).float(), outcomes)
+            logp = F.log_softmax(pol, dim=1)
+            entropy = -(logp.exp() * logp).sum(dim=1).mean()
+            loss = loss_policy + loss_value - ENTROPY_COEF * entropy
+            if not torch.isfinite(loss):
+                continue                                   # train.py:176-178
+            (loss / accumulate_steps).backward()
+            if (i + 1) % accumulate_steps == 0 or i == len(batches) - 1:
+                torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=1.0)
+                optimizer.step()
+                optimizer.zero_grad()
+            tot += float(loss.item())
+            nb += 1
+        last = tot / max(nb, 1)
+    net.eval()                                             # train.py:444
+    net.mark_weights_changed()                             # next forward / self-play re-uploads and re-folds the weights
+    return last
+
+
+def build_cfg(**kw):
+    """scripts/learn.py:99-149 without the Google-Drive / Stockfish parts; same environment variables."""
+    cfg = SimpleNamespace(
+        selfplay=SimpleNamespace(num_games=int(os.getenv("NUM_SELFPLAY_GAMES", "5")),
+                                 max_moves=(int(os.environ["SELFPLAY_MAX_MOVES"]) if os.getenv("SELFPLAY_MAX_MOVES") else None),
+                                 sims=int(os.getenv("KV_SIMS", "800"))),
+        train=SimpleNamespace(epochs=int(os.getenv("TRAIN_EPOCHS", "2")), batch_size=int(os.getenv("BATCH_SIZE", "2048")),
+                              lr=float(os.getenv("LR", "1e-3"))),
+        num_iterations=int(os.getenv("NUM_ITERATIONS", "5")),
+        device=torch.device("cuda"), model_path=None, arch={})
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def reinforcement_loop(cfg, net: ChessNet | None = None, data: ReplayData | None = None):
+    """train -> self-play -> extend, cfg.num_iterations times.  Returns (net, data, history)."""
+    eng = engine_for(cfg.device)
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    if net is None:
+        net = ChessNet(**cfg.arch)
+        if cfg.model_path and os.path.exists(cfg.model_path):
+            ck = torch.load(cfg.model_path, map_location="cpu")
+            net.load_state_dict(ck.get("model_state_dict", ck))
+    net = net.to(cfg.device)
+    optimizer = torch.optim.Adam(net.parameters(), lr=cfg.train.lr)
+    data = data or ReplayData(eng)
+    games = max(1, cfg.selfplay.num_games // world)
+    history = []
+    for it in range(1, cfg.num_iterations + 1):
+        loss = train_epochs(net, optimizer, data, cfg.train.epochs, cfg.train.batch_size) if len(data) else float("nan")
+        sp = SelfPlay(net.eval(), games, cfg.device, sims=cfg.selfplay.sims,
+                      max_plies=cfg.selfplay.max_moves or 512, engine=eng)
+        st = sp.play(game_id_base=(it * world + rank) * games)
+        lines, move, reward, _ = sp.records_device()
+        data.extend_packed(lines, move, reward)
+        history.append(dict(iteration=it, loss=loss, records=int(lines.shape[0]), plies=st["plies"],
+                            white=st["white_wins"], black=st["black_wins"], draws=st["draws"]))
+        logger.info("iteration %d: loss %.4f, %d new records", it, loss, lines.shape[0])
+    return net, data, history

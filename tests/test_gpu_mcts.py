@@ -167,3 +167,26 @@ def test_eval_cache_is_transparent(eng, eval_mode):
             assert np.array_equal(_bits(ra["P"]), _bits(rb["P"]))
         assert st["cache_hits"] > 0 and st["evals"] + st["cache_hits"] == bst["evals"]
     eng.mcts_enable_cache(0)
+
+
+def test_learn_loop_small_tower(eng, monkeypatch):
+    """scripts/learn.py loop semantics on a small tower: train -> self-play -> extend; the engine picks up the
+    trained weights (and drops the evaluation cache) between iterations."""
+    from knightvision_b200 import learn as LR
+    from knightvision_b200 import selfplay as SP
+    from knightvision_b200.model import ChessNet
+    monkeypatch.setitem(SP._engines, 0, eng)
+    torch.manual_seed(3)
+    net = ChessNet(stem=64, tower=256, blocks=1, conv2=True, max_batch=32)
+    cfg = LR.build_cfg(num_iterations=2, device=torch.device("cuda:0"))
+    cfg.selfplay.num_games, cfg.selfplay.max_moves, cfg.selfplay.sims = 16, 6, 12
+    cfg.train.epochs, cfg.train.batch_size = 1, 32
+    before = net.weight_blob().clone()
+    net, data, hist = LR.reinforcement_loop(cfg, net=net)
+    assert len(hist) == 2 and hist[0]["records"] == 16 * 6 and len(data) == 2 * 16 * 6
+    assert np.isnan(hist[0]["loss"]) and np.isfinite(hist[1]["loss"])     # nothing to train on before the first games
+    assert not torch.equal(before, net.weight_blob())
+    # reference-format records round-trip through the packed store
+    d2 = LR.ReplayData(eng)
+    d2.extend([(O.encode(L.start_line()[None])[0], 3364, 0.2)])
+    assert int(d2.move[0]) == 3364 and np.array_equal(d2.lines[0, :12].cpu().numpy().view(np.uint64), L.start_line()[:12])
