@@ -168,7 +168,9 @@ def run_perft(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def step():
-        return eng.perft(roots, PERFT_DEPTH)
+        # counts-only mode (negative chunk): nodes + category counts, leaves bulk-counted; the order digest is
+        # exercised by the parity tests (tests/test_gpu_rules.py), not timed here
+        return eng.perft(roots, PERFT_DEPTH, chunk=-PERFT_BOARDS)
 
     for _ in range(max(args.warmup, 3)):
         out = step()
@@ -197,7 +199,7 @@ def run_perft(args, rank, world, local_rank):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = eng.perft_host(roots_h, PERFT_DEPTH)
+        res = eng.perft_host(roots_h, PERFT_DEPTH, chunk=-PERFT_BOARDS)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop()
@@ -217,7 +219,7 @@ def run_perft(args, rank, world, local_rank):
     leaf_boards_per_step = None
     value = world * nodes_per_step * args.steps / (dev_ms * 1e-3)
     # boards the leaf level visits per step = movegen calls - (roots + level-1 boards); derive from perft(d-1)
-    lvl = eng.perft(roots, PERFT_DEPTH - 1)
+    lvl = eng.perft(roots, PERFT_DEPTH - 1, chunk=-PERFT_BOARDS)
     torch.cuda.synchronize()
     leaf_boards_per_step = int(lvl[:, 0].sum().item())
     alg_bytes = leaf_boards_per_step * args.steps * 128.0

@@ -95,7 +95,8 @@ KV_API int kv_make_moves_host(kv_ctx* ctx, uint64_t* h_lines, int n, const uint1
  * counts of SURVEY.md §8c were produced by exactly this driver over the unmodified engine).
  * d_roots [n][16]; out [n][8] u64: nodes, captures, e.p., castles, promotions (of the leaf moves),
  * order digest (order-sensitive hash of every move list visited), movegen calls, 0.
- * chunk = boards per launch (0 = 65536). */
+ * |chunk| = boards per launch (0 = 65536); chunk < 0 = counts only (the digest stays 0; leaves are bulk-counted from
+ * the destination sets without laying the ordered lists out). */
 KV_API int kv_perft(kv_ctx* ctx, const uint64_t* d_roots, int n, int depth, uint64_t* d_out, int chunk, void* stream);
 KV_API int kv_perft_host(kv_ctx* ctx, const uint64_t* h_roots, int n, int depth, uint64_t* h_out, int chunk);
 

@@ -40,7 +40,7 @@ __device__ __forceinline__ uint64_t ld_line_word(const uint64_t* line, int lane)
     return lane < LINE_WORDS ? __ldg(line + lane) : 0ull;
 }
 
-__global__ void __launch_bounds__(kThreads) movegen_kernel(uint64_t* __restrict__ lines, int n,
+__global__ void __launch_bounds__(kThreads, 3) movegen_kernel(uint64_t* __restrict__ lines, int n,
                                                            uint16_t* __restrict__ moves, int stride,
                                                            int32_t* __restrict__ counts, int32_t* __restrict__ flags) {
     __shared__ RulesSmem sm;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kThreads) movegen_kernel(uint64_t* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(kThreads) make_moves_kernel(uint64_t* __restrict__ lines, int n,
+__global__ void __launch_bounds__(kThreads, 3) make_moves_kernel(uint64_t* __restrict__ lines, int n,
                                                               const uint16_t* __restrict__ mvs) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int lo, hi;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kThreads) make_moves_kernel(uint64_t* __restri
     }
 }
 
-__global__ void __launch_bounds__(kThreads) attacked_kernel(const uint64_t* __restrict__ lines, int n,
+__global__ void __launch_bounds__(kThreads, 3) attacked_kernel(const uint64_t* __restrict__ lines, int n,
                                                             uint64_t* __restrict__ masks) {
     __shared__ RulesSmem sm;
     stage_tables(sm);
@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(kThreads) attacked_kernel(const uint64_t* __re
 }
 
 // ---- perft: one frontier level per launch (body: perft_visit_warp, kv_rules.cuh) ---------------------------
-template <bool LEAF>
-__global__ void __launch_bounds__(kThreads) perft_level_kernel(const uint64_t* __restrict__ cur, int m,
+template <bool LEAF, bool DIGEST>
+__global__ void __launch_bounds__(kThreads, 3) perft_level_kernel(const uint64_t* __restrict__ cur, int m,
                                                                uint64_t* __restrict__ next,
                                                                uint32_t* __restrict__ next_count,
                                                                uint64_t* __restrict__ out) {
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kThreads) perft_level_kernel(const uint64_t* _
     int acc_root = -1;
     for (int i = lo; i < hi; i++) {
         const uint64_t w = ld_line_word(cur + (size_t)i * LINE_WORDS, lane);
-        perft_visit_warp<LEAF>(sm.tab, lane, w, sm.mv[wid], accv, acc_root, next, next_count, out);
+        perft_visit_warp<LEAF, DIGEST>(sm.tab, lane, w, sm.mv[wid], accv, acc_root, next, next_count, out);
     }
     perft_acc_flush(accv, acc_root, out, lane);
 }
@@ -197,29 +197,34 @@ int kv_encode(kv_ctx* ctx, const uint64_t* d_lines, int n, float* d_planes, void
 
 // Depth-first over chunks of at most `chunk` boards per launch, breadth-first inside a chunk.
 static int perft_rec(kv_ctx* ctx, const uint64_t* cur, int m, int remaining, int level, uint64_t* d_out, int chunk,
-                     cudaStream_t st) {
+                     cudaStream_t st, bool digest) {
     for (int lo = 0; lo < m; lo += chunk) {
         const int c = (m - lo) < chunk ? (m - lo) : chunk;
         const uint64_t* src = cur + (size_t)lo * LINE_WORDS;
         if (remaining == 1) {
             {
                 KvTimed t_(ctx, KVK_PERFT_LEAF, st);
-                perft_level_kernel<true><<<grid_for(ctx, c), kThreads, 0, st>>>(src, c, nullptr, nullptr, d_out);
+                if (digest) perft_level_kernel<true, true><<<grid_for(ctx, c), kThreads, 0, st>>>(src, c, nullptr, nullptr, d_out);
+                else perft_level_kernel<true, false><<<grid_for(ctx, c), kThreads, 0, st>>>(src, c, nullptr, nullptr, d_out);
             }
             KV_LAUNCH_CHECK(ctx);
         } else {
             KV_CUDA(ctx, cudaMemsetAsync(ctx->perft_counter + level, 0, sizeof(uint32_t), st));
             {
                 KvTimed t_(ctx, KVK_PERFT_EXPAND, st);
-                perft_level_kernel<false><<<grid_for(ctx, c), kThreads, 0, st>>>(src, c, ctx->perft_buf[level],
-                                                                                ctx->perft_counter + level, d_out);
+                if (digest)
+                    perft_level_kernel<false, true><<<grid_for(ctx, c), kThreads, 0, st>>>(
+                        src, c, ctx->perft_buf[level], ctx->perft_counter + level, d_out);
+                else
+                    perft_level_kernel<false, false><<<grid_for(ctx, c), kThreads, 0, st>>>(
+                        src, c, ctx->perft_buf[level], ctx->perft_counter + level, d_out);
             }
             KV_LAUNCH_CHECK(ctx);
             uint32_t cnt = 0;
             KV_CUDA(ctx, cudaMemcpyAsync(&cnt, ctx->perft_counter + level, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             KV_CUDA(ctx, cudaStreamSynchronize(st));
             if (cnt) {
-                int rc = perft_rec(ctx, ctx->perft_buf[level], (int)cnt, remaining - 1, level + 1, d_out, chunk, st);
+                int rc = perft_rec(ctx, ctx->perft_buf[level], (int)cnt, remaining - 1, level + 1, d_out, chunk, st, digest);
                 if (rc) return rc;
             }
         }
@@ -230,6 +235,10 @@ static int perft_rec(kv_ctx* ctx, const uint64_t* cur, int m, int remaining, int
 int kv_perft(kv_ctx* ctx, const uint64_t* d_roots, int n, int depth, uint64_t* d_out, int chunk, void* stream) {
     if (!ctx) return -3;
     if (n <= 0) return 0;
+    // chunk < 0: counts only (nodes, categories, movegen calls) — the order digest stays 0 and leaves are bulk-counted
+    // from the destination sets without laying the move lists out
+    const bool digest = chunk >= 0;
+    if (chunk < 0) chunk = -chunk;
     if (depth < 1 || depth > 8) return kv_fail_msg(ctx, "kv_perft: depth must be in 1..8");
     if (chunk <= 0) chunk = 65536;
     cudaStream_t st = (cudaStream_t)stream;
@@ -254,7 +263,7 @@ int kv_perft(kv_ctx* ctx, const uint64_t* d_roots, int n, int depth, uint64_t* d
     KV_CUDA(ctx, cudaMemsetAsync(d_out, 0, (size_t)n * 8 * sizeof(uint64_t), st));
     perft_seed_kernel<<<(n * LINE_WORDS + 255) / 256, 256, 0, st>>>(d_roots, n, ctx->perft_buf[0]);
     KV_LAUNCH_CHECK(ctx);
-    return perft_rec(ctx, ctx->perft_buf[0], n, depth, 1, d_out, chunk, st);
+    return perft_rec(ctx, ctx->perft_buf[0], n, depth, 1, d_out, chunk, st, digest);
 }
 
 }  // extern "C"

@@ -163,16 +163,20 @@ struct KingOut {
 KV_DEV KingOut king_phase(const Tables& T, int lane, const Pos& p, const Agg& g, int ks, int mode,
                           uint64_t valid, uint64_t pinned) {
     const int home = p.wtm ? 60 : 4;
-    bool ok = false, att = false;
+    // One convergent attacked() evaluation for all 13 work items: lanes 0-7 test a king step on the "king placed"
+    // board (:556-563), lane 8 the king's own square, lanes 9,10 f,g and 11,12 c,d on the unmodified board (:576-599).
+    Agg h = g;
+    int t = 0;
+    bool active = false;
     if (lane < 8) {
         const int dr = (lane < 3) ? -1 : (lane < 5 ? 0 : 1);
         const int dc = (lane == 0 || lane == 3 || lane == 5) ? -1 : ((lane == 1 || lane == 6) ? 0 : 1);
         const int er = (ks >> 3) + dr, ec = (ks & 7) + dc;
         if (er >= 0 && er < 8 && ec >= 0 && ec < 8) {
-            const int t = er * 8 + ec;
+            t = er * 8 + ec;
             const uint64_t tb = bit(t), ksb = bit(ks);
             if (!(g.own & tb)) {
-                Agg h;   // the king placed on t, whatever stood there removed (:556-563)
+                active = true;   // the king placed on t, whatever stood there removed
                 h.occ = (g.occ & ~ksb) | tb;
                 h.own = (g.own & ~ksb) | tb;
                 h.opp = g.opp & ~tb;
@@ -182,14 +186,20 @@ KV_DEV KingOut king_phase(const Tables& T, int lane, const Pos& p, const Agg& g,
                 h.eBQ = g.eBQ & ~tb;
                 h.eP = g.eP & ~tb;
                 h.eR = g.eR & ~tb;
-                ok = !attacked(T, h, t, p.wtm, p.ep, p.moved, p.akloc);
-                if (ok && mode == 1) ok = !attacked(T, g, t, p.wtm, p.ep, p.moved, p.akloc);
             }
         }
     } else if (lane < 13) {
-        // lane 8: the king's own square; 9,10: f,g; 11,12: c,d  — on the unmodified board (:576-599)
-        const int sq = lane == 8 ? ks : (lane == 9 ? home + 1 : (lane == 10 ? home + 2 : (lane == 11 ? home - 2 : home - 1)));
-        att = attacked(T, g, sq, p.wtm, p.ep, p.moved, p.akloc);
+        active = true;
+        t = lane == 8 ? ks : (lane == 9 ? home + 1 : (lane == 10 ? home + 2 : (lane == 11 ? home - 2 : home - 1)));
+    }
+    bool a1 = false;
+    if (active) a1 = attacked(T, h, t, p.wtm, p.ep, p.moved, p.akloc);
+    bool ok = lane < 8 && active && !a1;
+    const bool att = lane >= 8 && lane < 13 && a1;
+    if (mode == 1) {   // getValidMoves :306-309 re-tests king moves on the unmodified board
+        bool a2 = false;
+        if (ok) a2 = attacked(T, g, t, p.wtm, p.ep, p.moved, p.akloc);
+        ok = ok && !a2;
     }
     const uint32_t okb = ballot(ok) & 0xFFu;
     const uint32_t ab = ballot(att) >> 8;
@@ -312,14 +322,23 @@ struct GenOut {
     int flags;   // RF_*
 };
 
-// getValidMoves (core/chessEngine.py:277-321) + checkForEndConditions (:632-651, repetition excluded).
+// Everything getValidMoves decides, before the moves are laid out in order: per-lane slots (squares 2l, 2l+1).
+struct GenState {
+    Pos p;
+    Agg g;
+    Slot sl[2];
+    int mode;    // 0 no check, 1 one check, 2 two or more (king moves only)
+    int flags;
+};
+
+// getValidMoves (core/chessEngine.py:277-321), part 1: pins/checks, king phases, per-piece destination sets.
 //   w       lane i < 16: word i of the board line; updated in place when the getKingMoves restore quirk
 //           (:564, stale king location) rewrites the board (flags & RF_STATE_MUTATED)
-//   mv      this warp's move buffer (shared memory), MAX_MOVES u16: from | to<<6 | ep<<12 | castle<<13 | promo<<14
-KV_DEV GenOut movegen_warp(const Tables& T, int lane, uint64_t& w, uint16_t* mv) {
-    Pos p;
+KV_DEV void movegen_slots_warp(const Tables& T, int lane, uint64_t& w, GenState& S) {
+    Pos& p = S.p;
+    Agg& g = S.g;
+    Slot* sl = S.sl;
     load_pos(w, p);
-    Agg g;
     make_agg(p, g);
     int flags = 0;
 
@@ -383,7 +402,6 @@ KV_DEV GenOut movegen_warp(const Tables& T, int lane, uint64_t& w, uint16_t* mv)
     }
 
     // ---- king phases --------------------------------------------------------------------------------
-    Slot sl[2];
     sl[0].kind = sl[1].kind = K_NONE;
     sl[0].tgt = sl[1].tgt = sl[0].epm = sl[1].epm = 0;
     sl[0].aux = sl[1].aux = 0;
@@ -456,28 +474,66 @@ KV_DEV GenOut movegen_warp(const Tables& T, int lane, uint64_t& w, uint16_t* mv)
             o.epm &= tgt;
         }
     }
+    S.mode = mode;
+    S.flags = flags;
+}
 
-    // ---- ordered emission ------------------------------------------------------------------------------
-    const int c0 = slot_count(sl[0]), c1 = slot_count(sl[1]);
-    const int incl = warp_incl_scan(c0 + c1, lane);
-    const int n = shfl32(incl, 31);
-    int off = incl - (c0 + c1);
-    off = slot_emit(T, p, sl[0], (mode == 2) ? p.kloc : 2 * lane, mv, off);
-    off = slot_emit(T, p, sl[1], (mode == 2) ? p.kloc : 2 * lane + 1, mv, off);
-    syncwarp();
-
-    // ---- checkForEndConditions (:632-651) ---------------------------------------------------------------
+// checkForEndConditions (:632-651, repetition excluded) + isDraw's only-kings clause, given the move count n
+KV_DEV int movegen_end_flags(const Tables& T, const GenState& S, int n) {
+    const Pos& p = S.p;
+    int flags = S.flags;
     if (n == 0) {
-        const bool ic = attacked(T, g, p.kloc, p.wtm, p.ep, p.moved, p.akloc);   // inCheck(), :388-394
+        const bool ic = attacked(T, S.g, p.kloc, p.wtm, p.ep, p.moved, p.akloc);   // inCheck(), :388-394
         flags |= ic ? RF_CHECKMATE : RF_STALEMATE;
     } else if (p.clock >= 100) {
         flags |= RF_DRAW50;
     }
-    if (g.occ == (p.o[T_K] | p.e[T_K])) flags |= RF_ONLY_KINGS;   // isDraw(), :21-33 (the only satisfiable clause)
+    if (S.g.occ == (p.o[T_K] | p.e[T_K])) flags |= RF_ONLY_KINGS;   // isDraw(), :21-33 (the only satisfiable clause)
     if (n > MAX_MOVES) flags |= RF_OVERFLOW;
+    return flags;
+}
+
+// getValidMoves with the ordered move list written to mv (shared memory, MAX_MOVES u16:
+// from | to<<6 | ep<<12 | castle<<13 | promo<<14).
+KV_DEV GenOut movegen_warp(const Tables& T, int lane, uint64_t& w, uint16_t* mv) {
+    GenState S;
+    movegen_slots_warp(T, lane, w, S);
+    const int c0 = slot_count(S.sl[0]), c1 = slot_count(S.sl[1]);
+    const int incl = warp_incl_scan(c0 + c1, lane);
+    const int n = shfl32(incl, 31);
+    int off = incl - (c0 + c1);
+    off = slot_emit(T, S.p, S.sl[0], (S.mode == 2) ? S.p.kloc : 2 * lane, mv, off);
+    off = slot_emit(T, S.p, S.sl[1], (S.mode == 2) ? S.p.kloc : 2 * lane + 1, mv, off);
+    syncwarp();
     GenOut out;
     out.n = n;
-    out.flags = flags;
+    out.flags = movegen_end_flags(T, S, n);
+    return out;
+}
+
+// Bulk count without laying the list out (perft leaves): n plus captures | ep<<16 | castles<<32 | promos<<48
+// (a capture = destination occupied or e.p., Move.pieceCaptured != "--", core/chessEngine.py:699-703).
+KV_DEV GenOut movegen_count_warp(const Tables& T, int lane, uint64_t& w, uint64_t& cats) {
+    GenState S;
+    movegen_slots_warp(T, lane, w, S);
+    const uint64_t last = S.p.wtm ? 0xFFull : 0xFFull << 56;
+    uint64_t c = 0;
+    int n = 0;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const Slot& sl = S.sl[j];
+        if (sl.kind == K_NONE) continue;
+        const int ncast = sl.kind == K_KING ? popc32(sl.aux) : 0;
+        n += popc64(sl.tgt) + ncast;
+        const uint64_t cap = (uint64_t)(popc64(sl.tgt & S.g.opp) + popc64(sl.epm));
+        const uint64_t pro = sl.kind == K_PAWN ? (uint64_t)popc64(sl.tgt & last) : 0;
+        c += cap + ((uint64_t)popc64(sl.epm) << 16) + ((uint64_t)ncast << 32) + (pro << 48);
+    }
+    n = warp_sum32(n, lane);
+    cats = warp_sum64(c, lane);
+    GenOut out;
+    out.n = n;
+    out.flags = movegen_end_flags(T, S, n);
     return out;
 }
 
@@ -583,7 +639,7 @@ KV_DEV void perft_acc_flush(uint64_t& accv, int root, uint64_t* out, int lane) {
 // Visit one frontier board.  LEAF: bulk-count its move list.  Otherwise: write every child board to `next`
 // (slots claimed with one atomic add per parent; the frontier is an unordered multiset and every output is an
 // order-independent sum).  w[13] = root id, w[14] = path hash.
-template <bool LEAF>
+template <bool LEAF, bool DIGEST = true>
 KV_DEV void perft_visit_warp(const Tables& T, int lane, uint64_t w, uint16_t* mv, uint64_t& accv, int& acc_root,
                              uint64_t* next, uint32_t* next_count, uint64_t* out) {
     const int root = (int)(uint32_t)shfl64(w, 13);
@@ -591,6 +647,14 @@ KV_DEV void perft_visit_warp(const Tables& T, int lane, uint64_t w, uint16_t* mv
     if (root != acc_root) {
         perft_acc_flush(accv, acc_root, out, lane);
         acc_root = root;
+    }
+    if (LEAF && !DIGEST) {   // count-only leaves: no ordered list, no digest
+        uint64_t cats = 0;
+        const GenOut g = movegen_count_warp(T, lane, w, cats);
+        if (lane == 0) accv += (unsigned)(g.n < MAX_MOVES ? g.n : MAX_MOVES);
+        if (lane >= 1 && lane <= 4) accv += (cats >> (16 * (lane - 1))) & 0xFFFF;
+        if (lane == 6) accv += 1;
+        return;
     }
     // w reflects the :564 rewrite afterwards, as the reference's makeMove would see it
     const GenOut g = movegen_warp(T, lane, w, mv);
@@ -619,7 +683,7 @@ KV_DEV void perft_visit_warp(const Tables& T, int lane, uint64_t w, uint16_t* mv
             if (lane < LINE_WORDS) next[(size_t)(base + k) * LINE_WORDS + lane] = c;
         }
     }
-    if (lane == 5) accv += dig;
+    if (lane == 5 && DIGEST) accv += dig;
     if (lane == 6) accv += 1;
     syncwarp();
 }

@@ -155,6 +155,7 @@ __attribute__((visibility("default"))) void kvemu_make_moves(uint64_t* lines, in
 }
 
 // kv_perft's level loop over host memory (same chunked depth-first / breadth-first-in-chunk order)
+static bool g_emu_digest = true;
 static void emu_perft_rec(std::vector<uint64_t>& cur, int remaining, uint64_t* out) {
     const int m = (int)(cur.size() / 16);
     uint16_t mv[kv::MAX_MOVES];
@@ -164,7 +165,8 @@ static void emu_perft_rec(std::vector<uint64_t>& cur, int remaining, uint64_t* o
             kvemu::run_warp([&](int lane) {
                 int acc_root = -1;
                 uint64_t w = lane < 16 ? cur[16 * (size_t)i + lane] : 0;
-                kv::perft_visit_warp<true>(g_tables, lane, w, mv, acc[lane], acc_root, nullptr, nullptr, out);
+                if (g_emu_digest) kv::perft_visit_warp<true, true>(g_tables, lane, w, mv, acc[lane], acc_root, nullptr, nullptr, out);
+                else kv::perft_visit_warp<true, false>(g_tables, lane, w, mv, acc[lane], acc_root, nullptr, nullptr, out);
                 kv::perft_acc_flush(acc[lane], acc_root, out, lane);
             });
         }
@@ -177,7 +179,8 @@ static void emu_perft_rec(std::vector<uint64_t>& cur, int remaining, uint64_t* o
         kvemu::run_warp([&](int lane) {
             int acc_root = -1;
             uint64_t w = lane < 16 ? cur[16 * (size_t)i + lane] : 0;
-            kv::perft_visit_warp<false>(g_tables, lane, w, mv, acc[lane], acc_root, next.data(), &cnt, out);
+            if (g_emu_digest) kv::perft_visit_warp<false, true>(g_tables, lane, w, mv, acc[lane], acc_root, next.data(), &cnt, out);
+            else kv::perft_visit_warp<false, false>(g_tables, lane, w, mv, acc[lane], acc_root, next.data(), &cnt, out);
             kv::perft_acc_flush(acc[lane], acc_root, out, lane);
         });
     }
@@ -186,6 +189,8 @@ static void emu_perft_rec(std::vector<uint64_t>& cur, int remaining, uint64_t* o
 }
 
 __attribute__((visibility("default"))) void kvemu_perft(const uint64_t* roots, int n, int depth, uint64_t* out) {
+    g_emu_digest = depth > 0;   // negative depth = counts only
+    if (depth < 0) depth = -depth;
     memset(out, 0, (size_t)n * 8 * sizeof(uint64_t));
     std::vector<uint64_t> cur(roots, roots + (size_t)n * 16);
     for (int i = 0; i < n; i++) {

@@ -57,6 +57,8 @@ def test_emu_perft_vs_oracle():
             assert int(got[i, 0]) == H.PERFT_EXPECT[k][depth - 1], (k, depth)
             assert np.array_equal(got[i], O.perft2(roots[i], depth)), (k, depth)
             assert [int(x) for x in got[i, 1:5]] == gold[k]["depths"][str(depth)]["cats"]
+        cnt = emu.perft(roots, -depth)            # counts-only leaves (no ordered lists, digest 0)
+        assert np.array_equal(cnt[:, :5], got[:, :5]) and np.array_equal(cnt[:, 6], got[:, 6]) and not cnt[:, 5].any()
 
 
 def test_emu_skip_move_and_promotion_choice_default():

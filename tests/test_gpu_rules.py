@@ -76,6 +76,8 @@ def test_perft_golden_all_positions(eng):
             assert [int(x) for x in got[i, 1:5]] == g["cats"], (k, depth)
             if depth <= 3:
                 assert np.array_equal(got[i], O.perft2(roots[i], depth)), (k, depth)
+        cnt = eng.perft_host(roots, depth, chunk=-65536)     # counts-only leaves
+        assert np.array_equal(cnt[:, :5], got[:, :5]) and np.array_equal(cnt[:, 6], got[:, 6]) and not cnt[:, 5].any()
 
 
 def test_perft5_startpos_is_the_custom_count(eng):
