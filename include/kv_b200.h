@@ -111,6 +111,9 @@ KV_API int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int
 /* Weights: the fp32 tensors of ChessNet.state_dict() concatenated in key order (every *.num_batches_tracked
  * skipped): conv w,b then bn weight,bias,running_mean,running_var for each layer; policy_fc / value_fc as stored.
  * BatchNorm is folded (eval mode, eps 1e-5) and the tower weights are converted to bf16 on the device. */
+/* tower kernel variant: 1 = one CTA per 128x256 tile (tcgen05 cta_group::1), 2 = CTA pairs sharing the weight tile
+ * (cta_group::2, 256x256 per pair; default).  Bit-identical outputs. */
+KV_API int kv_net_set_conv_mode(kv_ctx* ctx, int cta_group);
 KV_API uint64_t kv_net_blob_floats(kv_ctx* ctx);
 KV_API int kv_net_load(kv_ctx* ctx, const float* h_blob, uint64_t n_floats);
 /* Device staging buffer of kv_net_blob_floats() floats: write the blob there (e.g. as the target of an NCCL

@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -46,6 +47,42 @@ struct ConvParams {
     int m_tiles, n_tiles, kb_per_tap, cout, m_valid, relu;
     const int* n_ptr;   // optional device-side board count (search waves): overrides m_tiles / m_valid
 };
+
+// epilogue of one 32-column chunk of one output row: +bias (+residual) -> ReLU -> bf16 -> four 16 B stores
+__device__ __forceinline__ void conv_epilogue_store(const ConvParams& P, const uint32_t (&v)[32], size_t rbase, int n_tile,
+                                                    int c) {
+    const float4* bp = reinterpret_cast<const float4*>(P.bias + n_tile * BN + c * 32);
+    uint4 res[4];
+    if (P.residual) {
+        const uint4* rp = reinterpret_cast<const uint4*>(P.residual + rbase + c * 32);
+#pragma unroll
+        for (int j = 0; j < 4; j++) res[j] = __ldg(rp + j);
+    }
+    uint4 o[4];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float4 b = __ldg(bp + j);
+        float x0 = __uint_as_float(v[4 * j + 0]) + b.x, x1 = __uint_as_float(v[4 * j + 1]) + b.y;
+        float x2 = __uint_as_float(v[4 * j + 2]) + b.z, x3 = __uint_as_float(v[4 * j + 3]) + b.w;
+        if (P.residual) {
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&res[j >> 1]) + (j & 1) * 2;
+            const __nv_bfloat162 r01 = *reinterpret_cast<const __nv_bfloat162*>(&rw[0]);
+            const __nv_bfloat162 r23 = *reinterpret_cast<const __nv_bfloat162*>(&rw[1]);
+            x0 += __low2float(r01); x1 += __high2float(r01);
+            x2 += __low2float(r23); x3 += __high2float(r23);
+        }
+        if (P.relu) {
+            x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+        }
+        const __nv_bfloat162 p01 = __floats2bfloat162_rn(x0, x1), p23 = __floats2bfloat162_rn(x2, x3);
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o[j >> 1]) + (j & 1) * 2;
+        ow[0] = *reinterpret_cast<const uint32_t*>(&p01);
+        ow[1] = *reinterpret_cast<const uint32_t*>(&p23);
+    }
+    uint4* op = reinterpret_cast<uint4*>(P.out + rbase + c * 32);
+#pragma unroll
+    for (int j = 0; j < 4; j++) op[j] = o[j];
+}
 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvParams P) {
@@ -157,39 +194,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 uint32_t v[32];
                 kvu::tmem_ld_32x32(tmem_base + (uint32_t)acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
                 kvu::tmem_ld_wait();
-                if (valid) {
-                    const float4* bp = reinterpret_cast<const float4*>(P.bias + n_tile * BN + c * 32);
-                    uint4 res[4];
-                    if (P.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(P.residual + rbase + c * 32);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) res[j] = __ldg(rp + j);
-                    }
-                    uint4 o[4];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float4 b = __ldg(bp + j);
-                        float x0 = __uint_as_float(v[4 * j + 0]) + b.x, x1 = __uint_as_float(v[4 * j + 1]) + b.y;
-                        float x2 = __uint_as_float(v[4 * j + 2]) + b.z, x3 = __uint_as_float(v[4 * j + 3]) + b.w;
-                        if (P.residual) {
-                            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&res[j >> 1]) + (j & 1) * 2;
-                            const __nv_bfloat162 r01 = *reinterpret_cast<const __nv_bfloat162*>(&rw[0]);
-                            const __nv_bfloat162 r23 = *reinterpret_cast<const __nv_bfloat162*>(&rw[1]);
-                            x0 += __low2float(r01); x1 += __high2float(r01);
-                            x2 += __low2float(r23); x3 += __high2float(r23);
-                        }
-                        if (P.relu) {
-                            x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
-                        }
-                        const __nv_bfloat162 p01 = __floats2bfloat162_rn(x0, x1), p23 = __floats2bfloat162_rn(x2, x3);
-                        uint32_t* ow = reinterpret_cast<uint32_t*>(&o[j >> 1]) + (j & 1) * 2;
-                        ow[0] = *reinterpret_cast<const uint32_t*>(&p01);
-                        ow[1] = *reinterpret_cast<const uint32_t*>(&p23);
-                    }
-                    uint4* op = reinterpret_cast<uint4*>(P.out + rbase + c * 32);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) op[j] = o[j];
-                }
+                if (valid) conv_epilogue_store(P, v, rbase, n_tile, c);
             }
             kvu::tc_fence_before();
             kvu::mbar_arrive(&tempty[acc]);
@@ -200,6 +205,143 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     kvu::tc_fence_before();
     __syncthreads();
     if (warp == 2) kvu::tmem_dealloc(tmem_base, 512);
+}
+
+// ---- the same implicit GEMM on CTA pairs (cta_group::2): M = 256 rows (4 boards) x N = 256 per cluster-tile ----------
+// Each CTA TMA-loads its own 128 activation rows and HALF of the weight tile (128 of the 256 output channels); the
+// tensor core of the pair reads both halves, so every SM fetches 32 KB instead of 48 KB per k-step and the same
+// 192 KB of shared memory holds 6 stages instead of 4 (50 % more latency cover for the L2 -> SMEM stream).
+// Leader CTA (rank 0): its `full` barriers collect the bytes of both CTAs, its warp 1 issues the MMAs and commits
+// (multicast) to both CTAs' `empty` / `tfull` barriers; both epilogues arrive on the leader's `tempty`.
+constexpr int STAGES2 = 6;
+constexpr int B2_BYTES = (BN / 2) * BK * 2, STAGE2_BYTES = A_BYTES + B2_BYTES;
+constexpr int CONV2_SMEM = STAGES2 * STAGE2_BYTES + 1024 + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, ConvParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
+    uint64_t* empty = full + STAGES2;
+    uint64_t* tfull = empty + STAGES2;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = kvu::cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    if (warp == 0 && lane == 0) {
+        kvu::prefetch_tmap(&tmA);
+        kvu::prefetch_tmap(&tmBh);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES2; s++) {
+            kvu::mbar_init(&full[s], 1);
+            kvu::mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            kvu::mbar_init(&tfull[a], 1);
+            kvu::mbar_init(&tempty[a], 256);   // 128 epilogue threads of each CTA
+        }
+        kvu::fence_barrier_init();
+    }
+    if (warp == 2) kvu::tmem_alloc2(tmem_slot, 512);
+    kvu::tc_fence_before();
+    __syncthreads();
+    kvu::cluster_sync();
+    kvu::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (P.n_ptr) {
+        const int nb = *P.n_ptr;
+        P.m_tiles = (nb + 3) >> 2;
+        P.m_valid = nb * 64;
+    }
+    const int total = P.m_tiles * P.n_tiles;
+    const int ksteps = 9 * P.kb_per_tap;
+
+    if (warp == 0) {
+        // ---- TMA producer (both CTAs) ---------------------------------------------------------------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = cluster_id; tile < total; tile += n_clusters) {
+            const int m_tile = tile / P.n_tiles, n_tile = tile % P.n_tiles;
+            for (int ks = 0; ks < ksteps; ks++) {
+                const int tap = ks / P.kb_per_tap, kb = ks - tap * P.kb_per_tap;
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                kvu::mbar_wait(&empty[stage], phase ^ 1);
+                if (lane == 0) {
+                    uint8_t* sa = smem + stage * STAGE2_BYTES;
+                    if (rank == 0) kvu::mbar_arrive_expect_tx(&full[stage], 2 * STAGE2_BYTES);
+                    kvu::tma2_load_4d(sa, &tmA, &full[stage], kb * BK, dx, dy, m_tile * 4 + (int)rank * 2);
+                    kvu::tma2_load_2d(sa + A_BYTES, &tmBh, &full[stage], ks * BK, n_tile * BN + (int)rank * (BN / 2));
+                }
+                __syncwarp();
+                if (++stage == STAGES2) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ---- MMA issuer (leader CTA only) -------------------------------------------------------------------
+        constexpr uint32_t idesc = kvu::make_idesc_bf16(2 * BM, BN);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int tile = cluster_id; tile < total; tile += n_clusters) {
+            kvu::mbar_wait(&tempty[acc], acc_phase ^ 1);
+            kvu::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+            for (int ks = 0; ks < ksteps; ks++) {
+                kvu::mbar_wait(&full[stage], phase);
+                kvu::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = kvu::smem_u32(smem + stage * STAGE2_BYTES);
+                    const uint64_t adesc = kvu::make_sw128_kmajor_desc(sa);
+                    const uint64_t bdesc = kvu::make_sw128_kmajor_desc(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++)
+                        kvu::umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+                    kvu::umma2_commit_mc(&empty[stage]);
+                    if (ks == ksteps - 1) kvu::umma2_commit_mc(&tfull[acc]);
+                }
+                __syncwarp();
+                if (++stage == STAGES2) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue (both CTAs, own 128 rows) ------------------------------------------------------------
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = cluster_id; tile < total; tile += n_clusters) {
+            const int m_tile = tile / P.n_tiles, n_tile = tile % P.n_tiles;
+            kvu::mbar_wait(&tfull[acc], acc_phase);
+            kvu::tc_fence_after();
+            const int row = m_tile * 2 * BM + (int)rank * BM + q * 32 + lane;
+            const bool valid = row < P.m_valid;
+            const size_t rbase = (size_t)row * P.cout + (size_t)n_tile * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t v[32];
+                kvu::tmem_ld_32x32(tmem_base + (uint32_t)acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
+                kvu::tmem_ld_wait();
+                if (valid) conv_epilogue_store(P, v, rbase, n_tile, c);
+            }
+            kvu::tc_fence_before();
+            kvu::mbar_arrive_leader(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    kvu::tc_fence_before();
+    __syncthreads();
+    kvu::cluster_sync();   // the peer may still be signalling this CTA's barriers / reading its B half
+    if (warp == 2) kvu::tmem_dealloc2(tmem_base, 512);
 }
 
 // ---- stem: encode + conv1 + bn1 + relu ------------------------------------------------------------------
@@ -382,12 +524,12 @@ static int make_act_map(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boar
     if (r != CUDA_SUCCESS) return kv_fail_msg(ctx, "cuTensorMapEncodeTiled(activations) failed");
     return 0;
 }
-static int make_w_map(kv_ctx* ctx, CUtensorMap* m, void* base, int cout, int K) {
+static int make_w_map(kv_ctx* ctx, CUtensorMap* m, void* base, int cout, int K, int box_rows = 256) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return kv_fail_msg(ctx, "cuTensorMapEncodeTiled unavailable");
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cout};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {64, 256};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -456,6 +598,7 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
         KV_CUDA(ctx, cudaMalloc(&L.w, (size_t)L.cout * 9 * L.cin * sizeof(bf16)));
         KV_CUDA(ctx, cudaMalloc(&L.b, (size_t)L.cout * sizeof(float)));
         if (int rc = make_w_map(ctx, &L.map, L.w, L.cout, 9 * L.cin)) return rc;
+        if (int rc = make_w_map(ctx, &L.map_half, L.w, L.cout, 9 * L.cin, 128)) return rc;
     }
     KV_CUDA(ctx, cudaMalloc(&n->stem_table, (size_t)9 * 12 * n->C1 * sizeof(float)));
     KV_CUDA(ctx, cudaMalloc(&n->stem_bias, (size_t)n->C1 * sizeof(float)));
@@ -472,6 +615,16 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
     n->blob_floats = net_blob_floats(n);
     KV_CUDA(ctx, cudaMalloc(&n->d_blob, n->blob_floats * sizeof(float)));
     KV_CUDA(ctx, cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
+    KV_CUDA(ctx, cudaFuncSetAttribute(conv3x3_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_SMEM));
+    if (const char* e = getenv("KV_CONV_CTA_GROUP")) n->conv_mode = atoi(e) == 1 ? 1 : 2;
+    return 0;
+}
+
+// 1 = one CTA per tile (cta_group::1), 2 = CTA pairs (cta_group::2, default).  Same results bit for bit.
+int kv_net_set_conv_mode(kv_ctx* ctx, int cta_group) {
+    if (!ctx || !ctx->net) return kv_fail_msg(ctx, "kv_net_set_conv_mode: no net");
+    if (cta_group != 1 && cta_group != 2) return kv_fail_msg(ctx, "kv_net_set_conv_mode: 1 or 2");
+    ctx->net->conv_mode = cta_group;
     return 0;
 }
 
@@ -569,12 +722,19 @@ int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, i
         P.m_valid = n * 64;
         P.relu = relu;
         P.n_ptr = n_ptr;
-        const int total = P.m_tiles * P.n_tiles;
-        const int grid = total < ctx->sm_count ? total : ctx->sm_count;
-        {
+        const CUtensorMap& amap = net->map_act[in][L.cin == net->C1 && L.cin != net->C ? 0 : 1];
+        if (net->conv_mode == 2) {
+            P.m_tiles = (n + 3) / 4;   // cluster tiles of 4 boards (M = 256)
+            const int total = P.m_tiles * P.n_tiles;
+            const int pairs = ctx->sm_count / 2;
+            const int grid = 2 * (total < pairs ? total : pairs);
             KvTimed t_(ctx, KVK_NET_CONV, st);
-            conv3x3_umma_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(net->map_act[in][L.cin == net->C1 && L.cin != net->C ? 0 : 1],
-                                                                       L.map, P);
+            conv3x3_umma2_kernel<<<grid, CONV_THREADS, CONV2_SMEM, st>>>(amap, L.map_half, P);
+        } else {
+            const int total = P.m_tiles * P.n_tiles;
+            const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+            KvTimed t_(ctx, KVK_NET_CONV, st);
+            conv3x3_umma_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(amap, L.map, P);
         }
         KV_LAUNCH_CHECK(ctx);
         return 0;

@@ -9,7 +9,8 @@ struct kv_conv {
     __nv_bfloat16* w = nullptr;   // [cout][9][cin], BN scale folded
     float* b = nullptr;           // [cout]
     int cin = 0, cout = 0;
-    CUtensorMap map;
+    CUtensorMap map;        // 2-D boxes {64, 256}: the whole N tile (1-CTA kernel)
+    CUtensorMap map_half;   // 2-D boxes {64, 128}: this CTA's half of the N tile (2-CTA kernel)
 };
 
 struct kv_net {
@@ -26,6 +27,7 @@ struct kv_net {
     float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;   // value_fc1 [512][64], value_fc2 [512]
     float* d_blob = nullptr;               // fp32 state_dict staging (NCCL broadcast target)
     size_t blob_floats = 0;
+    int conv_mode = 2;                     // 1: cta_group::1 kernel, 2: cta_group::2 CTA-pair kernel
     int* d_flag = nullptr;
     uint64_t* d_lines_tmp = nullptr;
 };

@@ -122,6 +122,9 @@ class Engine:
         N.check(self.ctx, self._lib.kv_net_create(self.ctx, stem, tower, blocks, int(conv2), max_boards), "kv_net_create")
         self.net_max_boards = max_boards
 
+    def net_set_conv_mode(self, cta_group: int):
+        N.check(self.ctx, self._lib.kv_net_set_conv_mode(self.ctx, cta_group), "kv_net_set_conv_mode")
+
     def net_load(self, blob: torch.Tensor):
         """blob: fp32 CPU tensor, ChessNet.weight_blob()."""
         blob = blob.detach().to(torch.float32).cpu().contiguous()

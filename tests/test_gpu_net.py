@@ -123,3 +123,18 @@ def test_tower_20x256_variant(eng):
     with torch.no_grad():
         rp, rv = fp32_reference_forward(net.cuda(), torch.from_numpy(O.encode(lines)).cuda())
     assert (pol - rp).abs().max().item() < TOL and (val - rv).abs().max().item() < TOL
+
+
+def test_cta_pair_kernel_matches_single_cta_kernel(eng):
+    """cta_group::2 (CTA pairs, M = 256) and cta_group::1 tower kernels: bit-identical activations and outputs."""
+    from knightvision_b200.engine import lines_to_device
+    net = _net(seed=7, bnrand=True).attach(eng, max_batch=300)
+    lines = _lines(261, seed=12)
+    d = lines_to_device(lines, eng.device)
+    outs = {}
+    for mode in (1, 2):
+        eng.net_set_conv_mode(mode)
+        outs[mode] = (eng.net_forward_partial(d, 1).clone(), eng.net_forward_partial(d, 3).clone(), net.forward_lines(d))
+    eng.net_set_conv_mode(2)
+    assert torch.equal(outs[1][0], outs[2][0]) and torch.equal(outs[1][1], outs[2][1])
+    assert torch.equal(outs[1][2][0], outs[2][2][0]) and torch.equal(outs[1][2][1], outs[2][2][1])
