@@ -480,7 +480,27 @@ KV_DEV void mcts_finish_move_warp(const Tables& T, int lane, const MctsCfg& cfg,
     for (int k = lane; k < n; k += 32) tot += (int)A.eN[e0 + k];
     tot = warp_sum32(tot, lane);
     int pick = 0;
-    if (ply < cfg.temp_plies && tot > 0) {
+    if (tot == 0) {
+        // sims == 1: only the root was expanded.  Sample the move from the (noisy) priors — the reference's own
+        // move rule (scripts/self_play.py:147-167: softmax + Dirichlet, legal renormalise, sample).  Sequential
+        // fp32 prefix sum by lane 0, same order as the oracle.
+        if (lane == 0) {
+            const float u = kvd_u01(kvd_rand24(cfg.seed, h->game_id, (uint64_t)ply, 0xC0FFEEull));
+            float sum = 0.0f;
+            for (int k = 0; k < n; k++) sum = sum + A.eP[e0 + k];
+            const float thr = u * sum;
+            float cum = 0.0f;
+            pick = n - 1;
+            for (int k = 0; k < n; k++) {
+                cum = cum + A.eP[e0 + k];
+                if (cum > thr) {
+                    pick = k;
+                    break;
+                }
+            }
+        }
+        pick = shfl32(pick, 0);
+    } else if (ply < cfg.temp_plies) {
         const uint64_t r = ((uint64_t)kvd_rand24(cfg.seed, h->game_id, (uint64_t)ply, 0xC0FFEEull) * (uint64_t)tot) >> 24;
         int base = 0;
         pick = -1;

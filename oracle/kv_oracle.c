@@ -838,7 +838,19 @@ static int mcts_search(const kvo_mcts_cfg *cfg, const kvo_state *root, uint64_t 
             total += e[k].N;
         }
         int pick = 0;
-        if (ply < cfg->temp_plies && total > 0) {
+        if (total == 0) {
+            /* sims == 1: sample from the (noisy) priors, the reference's own move rule (scripts/self_play.py:147-167) */
+            const float u = kvd_u01(kvd_rand24(cfg->seed, game_id, (uint64_t)ply, 0xC0FFEEull));
+            float sum = 0.0f;
+            for (int k = 0; k < n; k++) sum = sum + e[k].P;
+            const float thr = u * sum;
+            float cum = 0.0f;
+            pick = n - 1;
+            for (int k = 0; k < n; k++) {
+                cum = cum + e[k].P;
+                if (cum > thr) { pick = k; break; }
+            }
+        } else if (ply < cfg->temp_plies) {
             const uint64_t r = ((uint64_t)kvd_rand24(cfg->seed, game_id, (uint64_t)ply, 0xC0FFEEull) * total) >> 24;
             uint64_t cum = 0;
             for (int k = 0; k < n; k++) {

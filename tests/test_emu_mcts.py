@@ -85,3 +85,15 @@ def test_eval_cache_does_not_change_games():
         evals, late = got[3]
         assert late > 0 and evals + late == base[3][0]      # every expansion is either a tower eval or a cache serve
     assert base[3][1] == 0
+
+
+def test_policy_sampling_mode_sims_1():
+    """sims = 1 is the reference's move rule (sample from softmax + Dirichlet over the legal moves, no search)."""
+    start = np.stack([L.start_line()] * 3)
+    moves, plies, res = emu.selfplay(start, sims=1, max_plies=30, temp_plies=30, id_base=3, seed=8)
+    seen = set()
+    for g in range(3):
+        m, lines, r = O.selfplay_game(O.mcts_cfg(1, temp_plies=30, max_plies=30, seed=8), start[g], game_id=3 + g)
+        assert np.array_equal(m, moves[g, :plies[g]]) and r == res[g]
+        seen.add(int(m[0]))
+    assert len(seen) > 1          # not always the first legal move
