@@ -6,7 +6,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libkv_b200.so")
+LIB_PATH = os.environ.get("KV_B200_LIB") or os.path.join(HERE, "libkv_b200.so")   # override: kernel experiments only
 
 _lib = None
 

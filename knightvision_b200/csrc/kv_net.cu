@@ -84,6 +84,36 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvParams& P, const u
     for (int j = 0; j < 4; j++) op[j] = o[j];
 }
 
+// same, with the residual chunk already in registers (prefetched before the accumulator was ready)
+__device__ __forceinline__ void conv_epilogue_store_pf(const ConvParams& P, const uint32_t (&v)[32], const uint4 (&res)[4],
+                                                       size_t rbase, int col0) {
+    const float4* bp = reinterpret_cast<const float4*>(P.bias + col0);
+    uint4 o[4];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float4 b = __ldg(bp + j);
+        float x0 = __uint_as_float(v[4 * j + 0]) + b.x, x1 = __uint_as_float(v[4 * j + 1]) + b.y;
+        float x2 = __uint_as_float(v[4 * j + 2]) + b.z, x3 = __uint_as_float(v[4 * j + 3]) + b.w;
+        if (P.residual) {
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&res[j >> 1]) + (j & 1) * 2;
+            const __nv_bfloat162 r01 = *reinterpret_cast<const __nv_bfloat162*>(&rw[0]);
+            const __nv_bfloat162 r23 = *reinterpret_cast<const __nv_bfloat162*>(&rw[1]);
+            x0 += __low2float(r01); x1 += __high2float(r01);
+            x2 += __low2float(r23); x3 += __high2float(r23);
+        }
+        if (P.relu) {
+            x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+        }
+        const __nv_bfloat162 p01 = __floats2bfloat162_rn(x0, x1), p23 = __floats2bfloat162_rn(x2, x3);
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o[j >> 1]) + (j & 1) * 2;
+        ow[0] = *reinterpret_cast<const uint32_t*>(&p01);
+        ow[1] = *reinterpret_cast<const uint32_t*>(&p23);
+    }
+    uint4* op = reinterpret_cast<uint4*>(P.out + rbase);
+#pragma unroll
+    for (int j = 0; j < 4; j++) op[j] = o[j];
+}
+
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -217,7 +247,9 @@ constexpr int STAGES2 = 6;
 constexpr int B2_BYTES = (BN / 2) * BK * 2, STAGE2_BYTES = A_BYTES + B2_BYTES;
 constexpr int CONV2_SMEM = STAGES2 * STAGE2_BYTES + 1024 + 256;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+constexpr int CONV2_THREADS = 384;   // warps 0-2 producer / MMA / TMEM, warp 3 idle, warps 4-11 epilogue
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV2_THREADS, 1)
 conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, ConvParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -241,7 +273,7 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         for (int a = 0; a < 2; a++) {
             kvu::mbar_init(&tfull[a], 1);
-            kvu::mbar_init(&tempty[a], 256);   // 128 epilogue threads of each CTA
+            kvu::mbar_init(&tempty[a], 512);   // 256 epilogue threads of each CTA
         }
         kvu::fence_barrier_init();
     }
@@ -314,23 +346,33 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (acc == 0) acc_phase ^= 1;
         }
     } else if (warp >= 4) {
-        // ---- epilogue (both CTAs, own 128 rows) ------------------------------------------------------------
-        const int q = warp & 3;
+        // ---- epilogue (both CTAs, own 128 rows): 8 warps = 4 TMEM lane quarters x 2 column halves.  The residual
+        // rows are fetched BEFORE waiting for the accumulator, so their latency hides behind the main loop. ----------
+        const int q = warp & 3, half = (warp - 4) >> 2;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = cluster_id; tile < total; tile += n_clusters) {
             const int m_tile = tile / P.n_tiles, n_tile = tile % P.n_tiles;
-            kvu::mbar_wait(&tfull[acc], acc_phase);
-            kvu::tc_fence_after();
             const int row = m_tile * 2 * BM + (int)rank * BM + q * 32 + lane;
             const bool valid = row < P.m_valid;
-            const size_t rbase = (size_t)row * P.cout + (size_t)n_tile * BN;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
+            const int colb = n_tile * BN + half * (BN / 2);
+            const size_t rbase = (size_t)row * P.cout + (size_t)colb;
+            uint4 res[4][4];
+            if (P.residual && valid) {
+                const uint4* rp = reinterpret_cast<const uint4*>(P.residual + rbase);
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) res[c][j] = __ldg(rp + c * 4 + j);
+            }
+            kvu::mbar_wait(&tfull[acc], acc_phase);
+            kvu::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
                 uint32_t v[32];
-                kvu::tmem_ld_32x32(tmem_base + (uint32_t)acc * BN + c * 32 + ((uint32_t)(q * 32) << 16), v);
+                kvu::tmem_ld_32x32(tmem_base + (uint32_t)acc * BN + half * (BN / 2) + c * 32 + ((uint32_t)(q * 32) << 16), v);
                 kvu::tmem_ld_wait();
-                if (valid) conv_epilogue_store(P, v, rbase, n_tile, c);
+                if (valid) conv_epilogue_store_pf(P, v, res[c], rbase + c * 32, colb + c * 32);
             }
             kvu::tc_fence_before();
             kvu::mbar_arrive_leader(&tempty[acc]);
@@ -729,7 +771,7 @@ int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, i
             const int pairs = ctx->sm_count / 2;
             const int grid = 2 * (total < pairs ? total : pairs);
             KvTimed t_(ctx, KVK_NET_CONV, st);
-            conv3x3_umma2_kernel<<<grid, CONV_THREADS, CONV2_SMEM, st>>>(amap, L.map_half, P);
+            conv3x3_umma2_kernel<<<grid, CONV2_THREADS, CONV2_SMEM, st>>>(amap, L.map_half, P);
         } else {
             const int total = P.m_tiles * P.n_tiles;
             const int grid = total < ctx->sm_count ? total : ctx->sm_count;
