@@ -15,6 +15,7 @@ import numpy as np
 GAMES_PER_GPU = int(os.getenv("KV_BENCH_GAMES", "4096"))
 SIMS = int(os.getenv("KV_BENCH_SIMS", "800"))
 MAX_PLIES = 512
+INFLIGHT = int(os.getenv("KV_BENCH_INFLIGHT", "8"))         # phase E: G/K games x K simulations in flight (0/1 = skip)
 CACHE_LOG2 = int(os.getenv("KV_BENCH_CACHE_LOG2", "24"))   # evaluation cache: 2^24 x 640 B = 10.7 GB (0 = off)
 CONV_FLOPS_PER_EVAL = 2.0 * 64 * 9 * (256 * 512 + 10 * 512 * 512)      # conv2 + 5 residual blocks (tcgen05 kernel)
 NET_FLOPS_PER_EVAL = 2.0 * 1587872256                                   # whole net, SURVEY §8d
@@ -204,6 +205,23 @@ def run(args, rank, world, local_rank):
     r_sims = (G - r0["done"]) * SIMS * r_moves
     r_evals = r1["evals"] - r0["evals"]
 
+    # ---- E: few games, K simulations in flight per game with virtual loss (G/K games x K = the same leaves per wave) ----
+    K = INFLIGHT
+    vl = None
+    if K > 1 and G % K == 0:
+        Gk = G // K
+        eng.mcts_create(Gk, SIMS, MAX_PLIES, seed=42, eval_mode=1, inflight=K)
+        eng.mcts_enable_cache(CACHE_LOG2)
+        eng.mcts_reset(None, game_id_base=rank * Gk)
+        for _ in range(warm):
+            eng.mcts_run_move()
+        w0 = eng.mcts_waves()
+        v_moves = max(1, min(args.steps, 3))
+        v_ms, v0, v1, _, _ = timed_moves(v_moves)
+        vl = {"games_per_gpu": Gk, "inflight": K, "ms_per_step": v_ms / v_moves,
+              "sims": (Gk - v0["done"]) * SIMS * v_moves, "evals": v1["evals"] - v0["evals"],
+              "waves_per_move": (eng.mcts_waves() - w0) / v_moves}
+
     t = torch.tensor([dev_ms, e2e_s * 1e3, nocache_ms or 0.0, r_ms], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(sims_done), float(evals), float(positions), float(rec), float(hits), float(r_sims),
                         float(r_evals)], dtype=torch.float64, device=dev)
@@ -242,13 +260,19 @@ def run(args, rank, world, local_rank):
                              "ms_per_step": r_ms / r_moves,
                              "note": "every game starts after k in [0,40) uniformly random legal plies (seed 1234), "
                                      "cache on, same warm-up"},
+        "virtual_loss": ({"value": world * vl["sims"] / (vl["ms_per_step"] * 1e-3 * max(1, min(args.steps, 3))), "unit": "sims/s",
+                          "games_per_gpu": vl["games_per_gpu"], "inflight": vl["inflight"],
+                          "ms_per_step": vl["ms_per_step"], "evals_per_sim": vl["evals"] / vl["sims"] if vl["sims"] else None,
+                          "waves_per_move": vl["waves_per_move"],
+                          "note": "rank 0's figures x world: G/K games with K simulations in flight per game and wave "
+                                  "(virtual loss), initial position, cache on"} if vl else None),
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_sims / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": G * 128 // e2e_steps,
                 "d2h_bytes_per_step": G * (12 * 64 * 4 + 8), "records_returned": rec_all, "steps": e2e_steps,
                 "api": ("SelfPlay public API on the timed region's own start positions: pinned host lines -> kv_mcts_reset -> "
                         "steps x kv_mcts_run_move -> records() as the reference's (planes, move, reward) tuples; "
                         "evaluation cache cleared first (new generation)")},
-        "roofline": {"kernel": "conv3x3_umma_kernel (tcgen05 implicit GEMM)", "bound": "tensor", "achieved": achieved,
+        "roofline": {"kernel": "conv3x3_umma2_kernel (tcgen05 cta_group::2 implicit GEMM)", "bound": "tensor", "achieved": achieved,
                      "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
                      "traffic": traffic, "traffic_source": (f"{traffic_src}: dram__bytes_read.sum + dram__bytes_write.sum per "
                                                              "launch at 4096 boards (algorithmic: 268 MB in + 268 MB out "

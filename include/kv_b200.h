@@ -134,11 +134,18 @@ KV_API int kv_net_forward_planes(kv_ctx* ctx, const float* d_planes, int n, floa
  * eval_mode 0 = hash test evaluator, 1 = the network of kv_net_create (max_boards >= n_games). */
 KV_API int kv_mcts_create(kv_ctx* ctx, int n_games, int sims, int edges_per_node, int max_plies, int temp_plies,
                           float c_puct, float dir_alpha, float dir_eps, uint64_t seed, int eval_mode);
+/* Same with `inflight` = K simulations in flight per game and wave (kv_mcts_create: K = 1).  K > 1 is for fewer
+ * games than the network batch wants (n_games * K leaves per wave; kv_net_create max_boards >= n_games * K): the K
+ * selections of a wave see each other through VIRTUAL LOSS (an in-flight simulation counts as one visit and one
+ * loss on every edge of its path until it is backed up; north_star item 2 / SURVEY 8a row M3).  Deterministic:
+ * selections and backups of a game run in slot order; oracle/kv_oracle.c emulates the same waves bit for bit. */
+KV_API int kv_mcts_create_k(kv_ctx* ctx, int n_games, int sims, int edges_per_node, int max_plies, int temp_plies,
+                            float c_puct, float dir_alpha, float dir_eps, uint64_t seed, int eval_mode, int inflight);
 /* d_start [n_games][16] start lines or NULL (initial position); game ids = game_id_base + local index (RNG keys) */
 KV_API int kv_mcts_reset(kv_ctx* ctx, const uint64_t* d_start, uint64_t game_id_base, void* stream);
-KV_API int kv_mcts_run_sims(kv_ctx* ctx, int n_waves, void* stream);   /* n_waves simulations for every live game */
+KV_API int kv_mcts_run_sims(kv_ctx* ctx, int n_waves, void* stream);   /* n_waves waves (K = 1: one simulation each) */
 KV_API int kv_mcts_finish_move(kv_ctx* ctx, void* stream);            /* pick + record + play the move, reset trees */
-KV_API int kv_mcts_run_move(kv_ctx* ctx, void* stream);               /* sims waves + finish_move */
+KV_API int kv_mcts_run_move(kv_ctx* ctx, void* stream);               /* waves until `sims` simulations ran + finish_move */
 /* Evaluation cache: 2^log2_slots entries x 640 B keyed by the 12 bitboards (the network's whole input; 0 = off).
  * A hit skips the tower; priors are re-derived from the cached policy features, so visit counts and games are
  * bit-identical with the cache on or off.  Cleared automatically by kv_net_commit_weights / kv_net_load. */
@@ -149,6 +156,7 @@ KV_API int kv_mcts_cache_clear(kv_ctx* ctx, void* stream);
 KV_API int kv_mcts_status(kv_ctx* ctx, uint64_t* h_out9, void* stream);
 KV_API int kv_mcts_get_roots(kv_ctx* ctx, uint64_t* d_lines, void* stream); /* current position of every game [n][16] */
 KV_API int kv_mcts_geometry(kv_ctx* ctx, int32_t* out4);              /* n_games, node_cap, edge_cap, rec_cap */
+KV_API int64_t kv_mcts_waves(kv_ctx* ctx);                            /* search waves launched since create */
 /* records of every game in game order; d_lines [cap][16] board lines (kv_encode gives the reference's planes),
  * d_move policy index (ai/ai.py:51-57), d_reward 1.0 / 0.2 / -1.0 (scripts/self_play.py:245-250), d_game index */
 KV_API int kv_mcts_records(kv_ctx* ctx, uint64_t* d_lines, int32_t* d_move, float* d_reward, int32_t* d_game, int cap,

@@ -56,6 +56,14 @@ __global__ void __launch_bounds__(kMW * 32) mcts_hash_late_kernel(MctsCfg cfg, M
     mcts_hash_late_warp(lane, cfg, A, li, scratch[wid]);
 }
 
+// K > 1 only: warp per game, backs the wave's pending simulations up in slot order (after every expansion)
+__global__ void __launch_bounds__(kMW * 32) mcts_backup_kernel(MctsCfg cfg, MctsArrays A, int G) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * kMW + wid;
+    if (g >= G) return;
+    mcts_backup_game_warp(lane, cfg, A, g);
+}
+
 __global__ void __launch_bounds__(kMW * 32) mcts_finish_move_kernel(MctsCfg cfg, MctsArrays A, int G) {
     __shared__ MctsSmem sm;
     stage_tables_m(sm.tab);
@@ -71,10 +79,10 @@ struct HeadW {
 };
 
 // logits of the pending leaf's legal moves from the 128 policy features (policy_fc rows of the legal indices only)
-__device__ __forceinline__ void legal_logits(const MctsCfg& cfg, const MctsArrays& A, int g, const HeadW& H, const float* hp,
+__device__ __forceinline__ void legal_logits(const MctsCfg& cfg, const MctsArrays& A, int gs, const HeadW& H, const float* hp,
                                              float* logits) {
-    const GameHdr* h = &A.hdr[g];
-    const NodeMeta m = A.node_meta[(size_t)g * cfg.node_cap + h->pend_node];
+    const int g = gs / cfg.inflight;
+    const NodeMeta m = A.node_meta[(size_t)g * cfg.node_cap + A.pend_node[gs]];
     const int n = m.ne_term & 0xFFFF;
     const size_t e0 = (size_t)g * cfg.edge_cap + m.first_edge;
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
@@ -97,14 +105,14 @@ __global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArr
     __shared__ __align__(16) float swh[3 * 512];
     const int slot = blockIdx.x;
     if (slot >= (int)*A.n_eval) return;
-    const int g = A.eval_game[slot];
+    const int gs = A.eval_game[slot];
     kvn::head_features(act + (size_t)slot * 64 * H.C, H.C, H.wh, H.bh, hp, hv, swh);
     __syncthreads();
     const float v_white = kvn::value_mlp(hv, H.w1, H.b1, H.w2, H.b2, red);
-    legal_logits(cfg, A, g, H, hp, logits);
+    legal_logits(cfg, A, gs, H, hp, logits);
     __syncthreads();
     if (threadIdx.x < 32) {
-        mcts_expand_warp((int)threadIdx.x, cfg, A, g, logits, v_white);
+        mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, v_white);
         if (cfg.cache_mask) cache_fill_warp((int)threadIdx.x, cfg, A, wave, slot, hp, v_white);
     }
 }
@@ -114,13 +122,13 @@ __global__ void __launch_bounds__(128) mcts_late_net_kernel(MctsCfg cfg, MctsArr
     __shared__ float hp[FEAT], logits[MAX_MOVES];
     const int li = blockIdx.x;
     if (li >= (int)*A.n_late) return;
-    const int g = A.late_game[li], src = A.late_src[li];
-    const float* f = src < 0 ? A.feat_game + (size_t)g * FEAT : A.feat_slot + (size_t)src * FEAT;
+    const int gs = A.late_game[li], src = A.late_src[li];
+    const float* f = src < 0 ? A.feat_game + (size_t)gs * FEAT : A.feat_slot + (size_t)src * FEAT;
     for (int i = threadIdx.x; i < FEAT; i += blockDim.x) hp[i] = f[i];
     __syncthreads();
-    legal_logits(cfg, A, g, H, hp, logits);
+    legal_logits(cfg, A, gs, H, hp, logits);
     __syncthreads();
-    if (threadIdx.x < 32) mcts_expand_warp((int)threadIdx.x, cfg, A, g, logits, hp[128], true);
+    if (threadIdx.x < 32) mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, hp[128], true);
 }
 
 __global__ void mcts_init_kernel(MctsCfg cfg, MctsArrays A, int G, const uint64_t* __restrict__ start, uint64_t id_base) {
@@ -128,9 +136,9 @@ __global__ void mcts_init_kernel(MctsCfg cfg, MctsArrays A, int G, const uint64_
     if (g >= G) return;
     GameHdr h;
     memset(&h, 0, sizeof(h));
-    h.pend_node = -1;
     h.game_id = id_base + (uint64_t)g;
     A.hdr[g] = h;
+    for (int j = 0; j < cfg.inflight; j++) A.pend_node[(size_t)g * cfg.inflight + j] = -1;
     for (int i = 0; i < LINE_WORDS; i++) {
         uint64_t v = start ? start[(size_t)g * LINE_WORDS + i] : 0ull;
         if (i >= 13) v = 0;
@@ -153,6 +161,14 @@ __global__ void mcts_status_kernel(MctsArrays A, int G, unsigned long long* out)
     if (h.done && h.result > 0) atomicAdd(out + 5, 1ull);
     if (h.done && h.result < 0) atomicAdd(out + 6, 1ull);
     if (h.done && h.result == 0) atomicAdd(out + 7, 1ull);
+}
+
+// number of live games whose current move still has simulations to run (K > 1: waves are not one-per-simulation)
+__global__ void mcts_unfinished_kernel(MctsCfg cfg, MctsArrays A, int G, unsigned int* out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const GameHdr h = A.hdr[g];
+    if (!h.done && h.sims_done < cfg.sims) atomicAdd(out, 1u);
 }
 
 // Records of all games, in game order: lines [N][16] (bitboards, rest 0), move index, reward (self_play.py:245-250:
@@ -202,6 +218,9 @@ struct kv_mcts {
     unsigned long long* d_status = nullptr;
     int* d_offsets = nullptr;
     uint32_t wave = 0;
+    unsigned int* d_unfinished = nullptr;
+    unsigned int* h_unfinished = nullptr;   // pinned
+    long waves_run = 0;
     void* cache_mem = nullptr;
     size_t cache_slots = 0;
 };
@@ -210,6 +229,7 @@ void kv_mcts_destroy(kv_ctx* ctx) {
     kv_mcts* m = ctx->mcts;
     if (!m) return;
     for (void* p : m->allocs) cudaFree(p);
+    if (m->h_unfinished) cudaFreeHost(m->h_unfinished);
     if (m->cache_mem) cudaFree(m->cache_mem);
     delete m;
     ctx->mcts = nullptr;
@@ -226,11 +246,20 @@ extern "C" {
 
 int kv_mcts_create(kv_ctx* ctx, int n_games, int sims, int edges_per_node, int max_plies, int temp_plies, float c_puct,
                    float dir_alpha, float dir_eps, uint64_t seed, int eval_mode) {
+    return kv_mcts_create_k(ctx, n_games, sims, edges_per_node, max_plies, temp_plies, c_puct, dir_alpha, dir_eps, seed,
+                            eval_mode, 1);
+}
+
+int kv_mcts_create_k(kv_ctx* ctx, int n_games, int sims, int edges_per_node, int max_plies, int temp_plies, float c_puct,
+                     float dir_alpha, float dir_eps, uint64_t seed, int eval_mode, int inflight) {
     if (!ctx) return -3;
     KV_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n_games < 1 || sims < 1 || max_plies < 1) return kv_fail_msg(ctx, "kv_mcts_create: bad sizes");
-    if (eval_mode == 1 && (!ctx->net || ctx->net->cap < n_games))
-        return kv_fail_msg(ctx, "kv_mcts_create: network evaluator needs kv_net_create(max_boards >= n_games) first");
+    if (inflight < 1 || inflight > 128) return kv_fail_msg(ctx, "kv_mcts_create: inflight must be in 1..128");
+    if (sims >= (1 << 24)) return kv_fail_msg(ctx, "kv_mcts_create: sims must be < 2^24");
+    if ((long long)n_games * inflight > (1ll << 24)) return kv_fail_msg(ctx, "kv_mcts_create: n_games * inflight too large");
+    if (eval_mode == 1 && (!ctx->net || ctx->net->cap < n_games * inflight))
+        return kv_fail_msg(ctx, "kv_mcts_create: network evaluator needs kv_net_create(max_boards >= n_games * inflight) first");
     kv_mcts_destroy(ctx);
     kv_mcts* m = new kv_mcts();
     ctx->mcts = m;
@@ -249,8 +278,10 @@ int kv_mcts_create(kv_ctx* ctx, int n_games, int sims, int edges_per_node, int m
     c.dir_alpha = dir_alpha;
     c.dir_eps = dir_eps;
     c.seed = seed;
+    c.inflight = inflight;
     MctsArrays& A = m->A;
     const size_t G = (size_t)n_games;
+    const size_t GS = G * (size_t)inflight;   // in-flight slots
     if (dalloc(ctx, m, &A.hdr, G)) return -1;
     if (dalloc(ctx, m, &A.root_line, G * 16)) return -1;
     if (dalloc(ctx, m, &A.node_line, G * c.node_cap * 16)) return -1;
@@ -260,20 +291,25 @@ int kv_mcts_create(kv_ctx* ctx, int n_games, int sims, int edges_per_node, int m
     if (dalloc(ctx, m, &A.eW, G * c.edge_cap)) return -1;
     if (dalloc(ctx, m, &A.eChild, G * c.edge_cap)) return -1;
     if (dalloc(ctx, m, &A.eMv, G * c.edge_cap)) return -1;
-    if (dalloc(ctx, m, &A.path_edge, G * (c.node_cap + 1))) return -1;
-    if (dalloc(ctx, m, &A.path_node, G * (c.node_cap + 1))) return -1;
+    if (dalloc(ctx, m, &A.path_edge, GS * (c.node_cap + 1))) return -1;
+    if (dalloc(ctx, m, &A.path_node, GS * (c.node_cap + 1))) return -1;
+    if (dalloc(ctx, m, &A.pend_node, GS)) return -1;
+    if (dalloc(ctx, m, &A.pend_depth, GS)) return -1;
+    if (dalloc(ctx, m, &A.pend_kind, GS)) return -1;
     if (dalloc(ctx, m, &A.n_eval, 4)) return -1;
-    if (dalloc(ctx, m, &A.eval_game, G)) return -1;
-    if (dalloc(ctx, m, &A.eval_lines, (G + 1) * 16)) return -1;
+    if (dalloc(ctx, m, &A.eval_game, GS)) return -1;
+    if (dalloc(ctx, m, &A.eval_lines, (GS + 1) * 16)) return -1;
     if (dalloc(ctx, m, &A.rec_line, G * c.rec_cap * 12)) return -1;
     if (dalloc(ctx, m, &A.rec_move, G * c.rec_cap)) return -1;
-    if (dalloc(ctx, m, &A.eval_centry, G)) return -1;
-    if (dalloc(ctx, m, &A.eval_hash, G)) return -1;
+    if (dalloc(ctx, m, &A.eval_centry, GS)) return -1;
+    if (dalloc(ctx, m, &A.eval_hash, GS)) return -1;
     if (dalloc(ctx, m, &A.n_late, 4)) return -1;
-    if (dalloc(ctx, m, &A.late_game, G)) return -1;
-    if (dalloc(ctx, m, &A.late_src, G)) return -1;
-    if (dalloc(ctx, m, &A.feat_game, G * FEAT)) return -1;
-    if (dalloc(ctx, m, &A.feat_slot, G * FEAT)) return -1;
+    if (dalloc(ctx, m, &A.late_game, GS)) return -1;
+    if (dalloc(ctx, m, &A.late_src, GS)) return -1;
+    if (dalloc(ctx, m, &A.feat_game, GS * FEAT)) return -1;
+    if (dalloc(ctx, m, &A.feat_slot, GS * FEAT)) return -1;
+    if (dalloc(ctx, m, &m->d_unfinished, 4)) return -1;
+    KV_CUDA(ctx, cudaMallocHost((void**)&m->h_unfinished, 16));
     A.cache = nullptr;
     c.cache_mask = 0;
     KV_CUDA(ctx, cudaMemset(A.n_late, 0, 16));
@@ -314,9 +350,10 @@ int kv_mcts_reset(kv_ctx* ctx, const uint64_t* d_start, uint64_t game_id_base, v
 
 static int mcts_wave(kv_ctx* ctx, cudaStream_t st) {
     kv_mcts* m = ctx->mcts;
-    const int G = m->G;
-    const int grid = (G + kMW - 1) / kMW;
+    const int G = m->G, GS = m->G * m->cfg.inflight;
+    const int grid = (G + kMW - 1) / kMW, grid_s = (GS + kMW - 1) / kMW;
     const uint32_t wave = ++m->wave;
+    m->waves_run++;
     KV_CUDA(ctx, cudaMemsetAsync(m->A.n_eval, 0, sizeof(uint32_t), st));
     if (m->cfg.cache_mask) KV_CUDA(ctx, cudaMemsetAsync(m->A.n_late, 0, sizeof(uint32_t), st));
     {
@@ -326,25 +363,42 @@ static int mcts_wave(kv_ctx* ctx, cudaStream_t st) {
     KV_LAUNCH_CHECK(ctx);
     if (m->cfg.eval_mode == 0) {
         KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
-        mcts_hash_eval_kernel<<<grid, kMW * 32, 0, st>>>(m->cfg, m->A, wave);
+        mcts_hash_eval_kernel<<<grid_s, kMW * 32, 0, st>>>(m->cfg, m->A, wave);
         KV_LAUNCH_CHECK(ctx);
         if (m->cfg.cache_mask) {
-            mcts_hash_late_kernel<<<grid, kMW * 32, 0, st>>>(m->cfg, m->A);
+            mcts_hash_late_kernel<<<grid_s, kMW * 32, 0, st>>>(m->cfg, m->A);
             KV_LAUNCH_CHECK(ctx);
         }
     } else {
         int fb = 0;
-        if (int rc = kv_net_tower(ctx, m->A.eval_lines, G, st, &fb, -1, reinterpret_cast<const int*>(m->A.n_eval))) return rc;
+        if (int rc = kv_net_tower(ctx, m->A.eval_lines, GS, st, &fb, -1, reinterpret_cast<const int*>(m->A.n_eval))) return rc;
         kv_net* net = ctx->net;
         HeadW H{net->wh, net->bh, net->wfc, net->bfc, net->w1, net->b1, net->w2, net->b2, net->C};
         KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
-        mcts_eval_net_kernel<<<G, 256, 0, st>>>(m->cfg, m->A, net->act[fb], H, wave);
+        mcts_eval_net_kernel<<<GS, 256, 0, st>>>(m->cfg, m->A, net->act[fb], H, wave);
         KV_LAUNCH_CHECK(ctx);
         if (m->cfg.cache_mask) {
-            mcts_late_net_kernel<<<G, 128, 0, st>>>(m->cfg, m->A, H);
+            mcts_late_net_kernel<<<GS, 128, 0, st>>>(m->cfg, m->A, H);
             KV_LAUNCH_CHECK(ctx);
         }
     }
+    if (m->cfg.inflight > 1) {
+        KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
+        mcts_backup_kernel<<<grid, kMW * 32, 0, st>>>(m->cfg, m->A, G);
+        KV_LAUNCH_CHECK(ctx);
+    }
+    return 0;
+}
+
+// live games that still owe simulations for the current move (one small kernel + a 4-byte read; synchronises)
+static int mcts_unfinished(kv_ctx* ctx, cudaStream_t st, unsigned int* out) {
+    kv_mcts* m = ctx->mcts;
+    KV_CUDA(ctx, cudaMemsetAsync(m->d_unfinished, 0, sizeof(unsigned int), st));
+    mcts_unfinished_kernel<<<(m->G + 255) / 256, 256, 0, st>>>(m->cfg, m->A, m->G, m->d_unfinished);
+    KV_LAUNCH_CHECK(ctx);
+    KV_CUDA(ctx, cudaMemcpyAsync(m->h_unfinished, m->d_unfinished, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    KV_CUDA(ctx, cudaStreamSynchronize(st));
+    *out = *m->h_unfinished;
     return 0;
 }
 
@@ -397,7 +451,22 @@ int kv_mcts_finish_move(kv_ctx* ctx, void* stream) {
 // one move for every live game: cfg.sims waves, then pick / record / play
 int kv_mcts_run_move(kv_ctx* ctx, void* stream) {
     if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_run_move: no search context");
-    if (int rc = kv_mcts_run_sims(ctx, ctx->mcts->cfg.sims, stream)) return rc;
+    kv_mcts* m = ctx->mcts;
+    const int K = m->cfg.inflight, S = m->cfg.sims;
+    if (K == 1) {
+        if (int rc = kv_mcts_run_sims(ctx, S, stream)) return rc;   // one simulation per game and wave
+    } else {
+        // wave 1 expands the root alone; afterwards at most K simulations per wave, fewer when selections collide
+        // with leaves still under evaluation: run the minimum, then poll until every game has its S simulations
+        int n = 1 + (S - 1 + K - 1) / K;
+        for (int guard = 0; guard < 4 * S + 8; guard++) {
+            if (int rc = kv_mcts_run_sims(ctx, n, stream)) return rc;
+            unsigned int left = 0;
+            if (int rc = mcts_unfinished(ctx, (cudaStream_t)stream, &left)) return rc;
+            if (!left) break;
+            n = 2;
+        }
+    }
     return kv_mcts_finish_move(ctx, stream);
 }
 
@@ -422,7 +491,7 @@ int kv_mcts_read_root(kv_ctx* ctx, int game, uint16_t* h_moves, uint32_t* h_N, f
     KV_CUDA(ctx, cudaMemcpy(&h, m->A.hdr + game, sizeof(h), cudaMemcpyDeviceToHost));
     NodeMeta nm;
     KV_CUDA(ctx, cudaMemcpy(&nm, m->A.node_meta + (size_t)game * m->cfg.node_cap, sizeof(nm), cudaMemcpyDeviceToHost));
-    int n = (h.n_nodes && !(nm.ne_term >> 16)) ? (nm.ne_term & 0xFFFF) : 0;
+    int n = (h.n_nodes && !(nm.ne_term & NODE_TERM)) ? (nm.ne_term & 0xFFFF) : 0;
     h_info4[0] = n;
     h_info4[1] = h.n_nodes;
     h_info4[2] = h.n_edges;
@@ -473,6 +542,11 @@ int kv_mcts_geometry(kv_ctx* ctx, int32_t* out4) {
     out4[2] = ctx->mcts->cfg.edge_cap;
     out4[3] = ctx->mcts->cfg.rec_cap;
     return 0;
+}
+
+/* waves launched since kv_mcts_create (K > 1: a move takes a data-dependent number of waves) */
+int64_t kv_mcts_waves(kv_ctx* ctx) {
+    return (ctx && ctx->mcts) ? (int64_t)ctx->mcts->waves_run : -1;
 }
 
 // Game records in game order (scripts/self_play.py:253 tuple fields, packed): returns the record count in *h_count.

@@ -2,8 +2,13 @@
 //
 // The reference has no tree search; the algorithm is specified in DESIGN.md §MCTS and restated
 // sequentially in oracle/kv_oracle.c (mcts_search), which these functions must match bit-for-bit.
-// One simulation is in flight per game (4 096 concurrent games already fill the network batch), so the search
-// inside a game is sequential and needs no virtual loss; a warp owns a game:
+// cfg.inflight = K simulations are in flight per game and wave.  K = 1 (4 096 concurrent games already fill the
+// network batch) makes the search inside a game sequential; K > 1 (fewer games per GPU) selects K leaves per wave
+// with VIRTUAL LOSS: every edge / node on an in-flight path carries one virtual visit (kept in the top 8 bits of
+// the visit counters, so it never mixes with the fp32 W sums) that counts as a loss in the PUCT score until the
+// simulation is backed up.  The warp that owns the game performs the K selections one after the other and the
+// backups in slot order, so the result is deterministic and bit-exact with the oracle's wave emulation.
+// A warp owns a game:
 //   select   warp-level argmax of the PUCT score over a node's edges (lane k handles edges k, k+32, ...),
 //            ties broken towards the lowest edge index = the reference's move order
 //   expand   make-move + legal move generation for the new leaf (kv_rules.cuh), edges appended to the game's pool
@@ -22,8 +27,15 @@ struct MctsCfg {
     float c_puct, dir_alpha, dir_eps;
     int rec_cap;          // records per game (>= max_plies)
     uint32_t cache_mask;  // evaluation cache slots - 1 (power of two), 0 = cache disabled
+    int inflight;         // K: simulations in flight per game and wave (>= 1); slot index gs = game * K + j
     uint64_t seed;
 };
+
+// visit counters: low 24 bits real visits, top 8 bits virtual visits of in-flight simulations (0 between waves)
+constexpr uint32_t VL_ONE = 1u << 24;
+constexpr uint32_t N_MASK = VL_ONE - 1u;
+constexpr int NODE_TERM = 1 << 16;      // NodeMeta.ne_term: terminal node
+constexpr int NODE_PENDING = 1 << 17;   // expanded this wave, priors not delivered yet
 
 // Evaluation cache entry: the network's input is the 12 bitboards only (ai/ai.py:17-41 has no side/castling/e.p.
 // planes), so the key is the bitboards and the payload is what the heads need to produce ANY legal-move logit:
@@ -44,7 +56,7 @@ constexpr int CACHE_WINDOW = 4;
 
 struct GameHdr {          // 64 B
     int n_nodes, n_edges, ply, done;
-    int result, pend_node, pend_depth, overflow;
+    int result, n_pend, pad2, overflow;   // n_pend: simulations of this wave waiting for their evaluation
     int sims_done, n_evals, cache_hits, pad0;
     uint64_t game_id;
     uint64_t pad1;
@@ -67,21 +79,24 @@ struct MctsArrays {
     float* eW;
     int* eChild;
     uint16_t* eMv;
-    int* path_edge;        // [G][node_cap + 1] (edge index inside the game's pool)
+    int* path_edge;        // [G*K][node_cap + 1] (edge index inside the game's pool), one path per in-flight slot
     int* path_node;
+    int* pend_node;        // [G*K] leaf waiting for its evaluation (-1 none)
+    int* pend_depth;       // [G*K] length of its path
+    int* pend_kind;        // [G*K] 1 evaluated by the tower, 2 served by the cache (set by expand, read by commit)
     // evaluation queue of the current wave
     uint32_t* n_eval;      // device counter
-    int* eval_game;        // [G]
-    uint64_t* eval_lines;  // [G][16]
+    int* eval_game;        // [G*K] slot index gs of the queued leaf
+    uint64_t* eval_lines;  // [G*K][16]
     // evaluation cache + "late" queue (cache hits and in-wave followers: expanded after the network pass)
     CacheEntry* cache;     // [cache_mask + 1]
-    int* eval_centry;      // [G] cache entry claimed for the eval slot, -1 none
-    uint64_t* eval_hash;   // [G]
+    int* eval_centry;      // [G*K] cache entry claimed for the eval slot, -1 none
+    uint64_t* eval_hash;   // [G*K]
     uint32_t* n_late;      // device counter
-    int* late_game;        // [G]
-    int* late_src;         // [G] -1: features already in feat_game[g]; else eval slot of the leader
-    float* feat_game;      // [G][FEAT]
-    float* feat_slot;      // [G][FEAT] features of every evaluated slot of this wave
+    int* late_game;        // [G*K] slot index gs
+    int* late_src;         // [G*K] -1: features already in feat_game[gs]; else eval slot of the leader
+    float* feat_game;      // [G*K][FEAT]
+    float* feat_slot;      // [G*K][FEAT] features of every evaluated slot of this wave
     // game records (scripts/self_play.py:173-174): position bitboards + the move played
     uint64_t* rec_line;    // [G][rec_cap][12]
     uint16_t* rec_move;    // [G][rec_cap]
@@ -102,15 +117,34 @@ KV_DEV float hash_logit(uint64_t ph, int idx) {
 KV_DEV float hash_value(uint64_t ph) { return (float)kvd_rand24(ph, 4096, 2, 0) * (2.0f / 16777216.0f) - 1.0f; }
 KV_DEV int move_index(int mv) { return (mv & 63) * 64 + ((mv >> 6) & 63); }   // encode_move, ai/ai.py:51-57
 
-// lane 0: walk the path, newest edge first
+// lane 0: walk the path, newest edge first; the virtual visit taken at selection becomes the real one
 KV_DEV void mcts_backup_lane0(const MctsArrays& A, size_t ebase, size_t nbase, size_t pbase, int depth, float v) {
     for (int i = depth - 1; i >= 0; i--) {
         v = -v;
         const size_t e = ebase + (size_t)A.path_edge[pbase + i];
         A.eW[e] = A.eW[e] + v;
-        A.eN[e] = A.eN[e] + 1;
-        A.node_meta[nbase + (size_t)A.path_node[pbase + i]].N += 1;
+        A.eN[e] = A.eN[e] + 1u - VL_ONE;
+        A.node_meta[nbase + (size_t)A.path_node[pbase + i]].N += 1u - VL_ONE;
     }
+}
+// lane 0: a selection that ran into a leaf still waiting for its evaluation gives its virtual visits back
+KV_DEV void mcts_unwind_lane0(const MctsArrays& A, size_t ebase, size_t nbase, size_t pbase, int depth) {
+    for (int i = depth - 1; i >= 0; i--) {
+        A.eN[ebase + (size_t)A.path_edge[pbase + i]] -= VL_ONE;
+        A.node_meta[nbase + (size_t)A.path_node[pbase + i]].N -= VL_ONE;
+    }
+}
+// lane 0: finish the pending simulation of slot gs (its leaf's value is in the node): backup + counters
+KV_DEV void mcts_commit_lane0(const MctsCfg& cfg, const MctsArrays& A, int g, int gs) {
+    GameHdr* h = &A.hdr[g];
+    const size_t nbase = (size_t)g * cfg.node_cap, ebase = (size_t)g * cfg.edge_cap;
+    const size_t pbase = (size_t)gs * (cfg.node_cap + 1);
+    const int c = A.pend_node[gs];
+    mcts_backup_lane0(A, ebase, nbase, pbase, A.pend_depth[gs], A.node_meta[nbase + c].val);
+    h->sims_done += 1;
+    if (A.pend_kind[gs] == 2) h->cache_hits += 1;
+    else h->n_evals += 1;
+    A.pend_node[gs] = -1;
 }
 
 // ---- evaluation cache ------------------------------------------------------------------------------------------
@@ -228,15 +262,15 @@ KV_DEV void cache_fill_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, u
     if (lane == 0) e->pend = 0;
 }
 
-// One simulation step for game g: descend, create the leaf, queue it for evaluation or back up a terminal value.
-KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, const MctsArrays& A, int g, uint16_t* mv,
-                             uint32_t wave = 0) {
+// One selection for game g into in-flight slot gs: descend (virtual-loss-aware PUCT), create the leaf, then queue it
+// for evaluation or back up a terminal value at once.
+// Returns 0 = simulation completed (terminal), 1 = leaf queued (pending), 2 = ran into a pending leaf (nothing done).
+KV_DEV int mcts_select_one_warp(const Tables& T, int lane, const MctsCfg& cfg, const MctsArrays& A, int g, int gs,
+                                uint16_t* mv, uint32_t wave) {
     GameHdr* h = &A.hdr[g];
-    if (h->done) return;
     const size_t nbase = (size_t)g * cfg.node_cap, ebase = (size_t)g * cfg.edge_cap;
-    const size_t pbase = (size_t)g * (cfg.node_cap + 1);
+    const size_t pbase = (size_t)gs * (cfg.node_cap + 1);
     const int n_nodes = h->n_nodes;
-    if (n_nodes >= cfg.node_cap) return;   // cannot happen: sims <= node_cap
     int depth = 0, node = 0, leaf = -1;
     float v = 0.0f;
     uint64_t w = 0;
@@ -247,17 +281,25 @@ KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, cons
         for (;;) {
             const NodeMeta m = A.node_meta[nbase + node];
             const int ne = m.ne_term & 0xFFFF;
-            if (m.ne_term >> 16) {
+            if (m.ne_term & NODE_PENDING) {   // only with K > 1: this leaf's priors arrive at the end of the wave
+                syncwarp();
+                if (lane == 0) mcts_unwind_lane0(A, ebase, nbase, pbase, depth);
+                syncwarp();
+                return 2;
+            }
+            if (m.ne_term & NODE_TERM) {
                 v = m.val;
                 if (lane == 0) A.node_meta[nbase + node].N = m.N + 1;
                 break;
             }
-            const float sq = KVD_SQRTF((float)m.N);
+            // visits seen by the score = real + virtual; an in-flight simulation counts as a loss (W - vl)
+            const float sq = KVD_SQRTF((float)((m.N & N_MASK) + (m.N >> 24)));
             float bs = 0.0f;
             int bi = 0x7FFFFFFF;
             for (int k = lane; k < ne; k += 32) {
                 const size_t e = ebase + m.first_edge + k;
-                const float sc = kvd_puct(A.eW[e], A.eN[e], A.eP[e], sq, cfg.c_puct);
+                const uint32_t en = A.eN[e];
+                const float sc = kvd_puct(A.eW[e] - (float)(en >> 24), (en & N_MASK) + (en >> 24), A.eP[e], sq, cfg.c_puct);
                 if (bi == 0x7FFFFFFF || sc > bs) {
                     bs = sc;
                     bi = k;
@@ -276,6 +318,8 @@ KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, cons
             if (lane == 0) {
                 A.path_node[pbase + depth] = node;
                 A.path_edge[pbase + depth] = ei;
+                A.eN[ebase + ei] += VL_ONE;               // virtual visit until the backup
+                A.node_meta[nbase + node].N = m.N + VL_ONE;
             }
             depth++;
             const int child = A.eChild[ebase + ei];
@@ -297,7 +341,7 @@ KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, cons
         NodeMeta nm;
         nm.N = 1;
         nm.first_edge = -1;
-        nm.ne_term = 1 << 16;
+        nm.ne_term = NODE_TERM;
         nm.val = 0.0f;
         const int n_edges = h->n_edges;
         if (n == 0) {
@@ -309,7 +353,7 @@ KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, cons
             if (lane == 0) h->overflow = 1;
         } else {
             nm.first_edge = n_edges;
-            nm.ne_term = n;
+            nm.ne_term = n | NODE_PENDING;
             for (int k = lane; k < n; k += 32) {
                 const size_t e = ebase + n_edges + k;
                 A.eMv[e] = mv[k];
@@ -322,14 +366,14 @@ KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, cons
             uint64_t ch = 0;
             if (cfg.cache_mask) {
                 ch = cache_hash(pos_hash_warp(w, lane));
-                kind = cache_lookup_warp(lane, cfg, A, wave, g, w, ch, aux);
+                kind = cache_lookup_warp(lane, cfg, A, wave, gs, w, ch, aux);
             }
             if (kind) {   // cache hit / in-wave follower: no tower pass, expanded by the late kernel
                 uint32_t li = 0;
                 if (lane == 0) li = atomic_add_u32(A.n_late, 1u);
                 li = (uint32_t)shfl32((int)li, 0);
                 if (lane == 0) {
-                    A.late_game[li] = g;
+                    A.late_game[li] = gs;
                     A.late_src[li] = aux;
                 }
             } else {
@@ -340,7 +384,7 @@ KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, cons
                 int ci = -1;
                 if (cfg.cache_mask) ci = cache_claim_warp(lane, cfg, A, wave, w, ch, (int)slot);
                 if (lane == 0) {
-                    A.eval_game[slot] = g;
+                    A.eval_game[slot] = gs;
                     if (cfg.cache_mask) {
                         A.eval_centry[slot] = ci;
                         A.eval_hash[slot] = ch;
@@ -349,8 +393,8 @@ KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, cons
             }
             if (lane == 0) {
                 h->n_edges = n_edges + n;
-                h->pend_node = leaf;
-                h->pend_depth = depth;
+                A.pend_node[gs] = leaf;
+                A.pend_depth[gs] = depth;
             }
             queued = true;
         }
@@ -366,16 +410,46 @@ KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, cons
         h->sims_done += 1;
     }
     syncwarp();
+    return queued ? 1 : 0;
+}
+
+// One search wave for game g: up to cfg.inflight selections, one after the other (each sees the virtual visits of
+// the earlier ones), as long as the move's simulation budget allows.  A selection that runs into a leaf still
+// waiting for its evaluation ends the wave for this game.
+KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, const MctsArrays& A, int g, uint16_t* mv,
+                             uint32_t wave = 0) {
+    GameHdr* h = &A.hdr[g];
+    if (h->done) return;
+    int n_pend = 0;
+    for (int j = 0; j < cfg.inflight; j++) {
+        if (h->sims_done + n_pend >= cfg.sims) break;
+        const int r = mcts_select_one_warp(T, lane, cfg, A, g, g * cfg.inflight + n_pend, mv, wave);
+        if (r == 2) break;
+        n_pend += r;
+    }
+    if (lane == 0) h->n_pend = n_pend;
+    syncwarp();
+}
+
+// After the wave's expansions (K > 1): back the pending simulations of game g up in slot order.
+KV_DEV void mcts_backup_game_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int g) {
+    GameHdr* h = &A.hdr[g];
+    if (lane == 0) {
+        const int np = h->n_pend;
+        for (int j = 0; j < np; j++) mcts_commit_lane0(cfg, A, g, g * cfg.inflight + j);
+        h->n_pend = 0;
+    }
+    syncwarp();
 }
 
 // Finish the pending simulation of game g given the leaf's legal-move logits (n floats, edge order) and the
 // evaluator's white-perspective value: softmax priors (+ root Dirichlet noise), then backup.
-KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int g, const float* logits, float v_white,
+KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int gs, const float* logits, float v_white,
                              bool from_cache = false) {
+    const int g = gs / cfg.inflight;
     GameHdr* h = &A.hdr[g];
     const size_t nbase = (size_t)g * cfg.node_cap, ebase = (size_t)g * cfg.edge_cap;
-    const size_t pbase = (size_t)g * (cfg.node_cap + 1);
-    const int c = h->pend_node, depth = h->pend_depth;
+    const int c = A.pend_node[gs];
     const NodeMeta m = A.node_meta[nbase + c];
     const int n = m.ne_term & 0xFFFF;
     const size_t e0 = ebase + m.first_edge;
@@ -413,11 +487,14 @@ KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, 
     const float v = wtm ? v_white : -v_white;
     if (lane == 0) {
         A.node_meta[nbase + c].val = v;
-        mcts_backup_lane0(A, ebase, nbase, pbase, depth, v);
-        h->sims_done += 1;
-        if (from_cache) h->cache_hits += 1;
-        else h->n_evals += 1;
-        h->pend_node = -1;
+        A.node_meta[nbase + c].ne_term = n;   // priors delivered: no longer pending
+        A.pend_kind[gs] = from_cache ? 2 : 1;
+        // K == 1: the game's only in-flight simulation, back it up here; K > 1: mcts_backup_game_warp does it in
+        // slot order once every expansion of the wave is in (other CTAs may be expanding this game's other leaves)
+        if (cfg.inflight == 1) {
+            mcts_commit_lane0(cfg, A, g, gs);
+            h->n_pend = 0;
+        }
     }
     syncwarp();
 }
@@ -426,25 +503,23 @@ KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, 
 // scratch: n floats of per-warp scratch (shared memory on the device).
 KV_DEV void mcts_hash_eval_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int slot, float* scratch,
                                 uint32_t wave = 0) {
-    const int g = A.eval_game[slot];
+    const int gs = A.eval_game[slot], g = gs / cfg.inflight;
     const uint64_t w = lane < LINE_WORDS ? A.eval_lines[(size_t)slot * LINE_WORDS + lane] : 0ull;
     const uint64_t ph = pos_hash_warp(w, lane);
     if (cfg.cache_mask) cache_fill_warp(lane, cfg, A, wave, slot, nullptr, hash_value(ph));
-    const GameHdr* h = &A.hdr[g];
-    const NodeMeta m = A.node_meta[(size_t)g * cfg.node_cap + h->pend_node];
+    const NodeMeta m = A.node_meta[(size_t)g * cfg.node_cap + A.pend_node[gs]];
     const int n = m.ne_term & 0xFFFF;
     const size_t e0 = (size_t)g * cfg.edge_cap + m.first_edge;
     for (int k = lane; k < n; k += 32) scratch[k] = hash_logit(ph, move_index(A.eMv[e0 + k]));
     syncwarp();
-    mcts_expand_warp(lane, cfg, A, g, scratch, hash_value(ph));
+    mcts_expand_warp(lane, cfg, A, gs, scratch, hash_value(ph));
 }
 
 // Hash-evaluator counterpart of the late (cache hit / follower) expansion: the value comes from the cached / leader
 // features, the logits are recomputed from the position hash (what a miss would have produced, bit for bit).
 KV_DEV void mcts_hash_late_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int li, float* scratch) {
-    const int g = A.late_game[li], src = A.late_src[li];
-    const GameHdr* h = &A.hdr[g];
-    const size_t nidx = (size_t)g * cfg.node_cap + h->pend_node;
+    const int gs = A.late_game[li], src = A.late_src[li], g = gs / cfg.inflight;
+    const size_t nidx = (size_t)g * cfg.node_cap + A.pend_node[gs];
     const uint64_t w = lane < LINE_WORDS ? A.node_line[nidx * LINE_WORDS + lane] : 0ull;
     const uint64_t ph = pos_hash_warp(w, lane);
     const NodeMeta m = A.node_meta[nidx];
@@ -452,8 +527,8 @@ KV_DEV void mcts_hash_late_warp(int lane, const MctsCfg& cfg, const MctsArrays& 
     const size_t e0 = (size_t)g * cfg.edge_cap + m.first_edge;
     for (int k = lane; k < n; k += 32) scratch[k] = hash_logit(ph, move_index(A.eMv[e0 + k]));
     syncwarp();
-    const float v = src < 0 ? A.feat_game[(size_t)g * FEAT + 128] : A.feat_slot[(size_t)src * FEAT + 128];
-    mcts_expand_warp(lane, cfg, A, g, scratch, v, true);
+    const float v = src < 0 ? A.feat_game[(size_t)gs * FEAT + 128] : A.feat_slot[(size_t)src * FEAT + 128];
+    mcts_expand_warp(lane, cfg, A, gs, scratch, v, true);
 }
 
 // After cfg.sims simulations: pick the move from the root visit counts, record (position, move), play it,
@@ -465,7 +540,7 @@ KV_DEV void mcts_finish_move_warp(const Tables& T, int lane, const MctsCfg& cfg,
     const NodeMeta m = A.node_meta[nbase];
     const int ply = h->ply;
     uint64_t w = lane < LINE_WORDS ? A.root_line[(size_t)g * LINE_WORDS + lane] : 0ull;
-    if (h->n_nodes == 0 || (m.ne_term >> 16)) {   // root had no move at all: the game is over as it stands
+    if (h->n_nodes == 0 || (m.ne_term & NODE_TERM)) {   // root had no move at all: the game is over as it stands
         if (lane == 0) {
             h->done = 1;
             h->result = (h->n_nodes && m.val < 0.0f) ? ((w & 1) ? -1 : 1) : 0;
@@ -547,7 +622,7 @@ KV_DEV void mcts_finish_move_warp(const Tables& T, int lane, const MctsCfg& cfg,
         h->n_nodes = 0;
         h->n_edges = 0;
         h->sims_done = 0;
-        h->pend_node = -1;
+        h->n_pend = 0;
         if (go.n == 0) {
             h->done = 1;
             h->result = (go.flags & RF_CHECKMATE) ? (wtm_new ? -1 : 1) : 0;   // self_play.py:217-220

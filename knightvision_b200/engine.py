@@ -173,9 +173,13 @@ class Engine:
     # ---- self-play search ---------------------------------------------------------------------------
     def mcts_create(self, n_games: int, sims: int, max_plies: int, temp_plies: int = 30, c_puct: float = 1.5,
                     dir_alpha: float = 0.3, dir_eps: float = 0.25, seed: int = 42, eval_mode: int = 1,
-                    edges_per_node: int = 0):
-        N.check(self.ctx, self._lib.kv_mcts_create(self.ctx, n_games, sims, edges_per_node, max_plies, temp_plies,
-                                                   c_puct, dir_alpha, dir_eps, seed, eval_mode), "kv_mcts_create")
+                    edges_per_node: int = 0, inflight: int = 1):
+        """inflight = K simulations in flight per game and wave (virtual loss when K > 1); the network must have been
+        created with max_boards >= n_games * K."""
+        N.check(self.ctx, self._lib.kv_mcts_create_k(self.ctx, n_games, sims, edges_per_node, max_plies, temp_plies,
+                                                     c_puct, dir_alpha, dir_eps, seed, eval_mode, inflight),
+                "kv_mcts_create_k")
+        self.mcts_inflight = inflight
         g = np.zeros(4, dtype=np.int32)
         N.check(self.ctx, self._lib.kv_mcts_geometry(self.ctx, _ptr(g)), "kv_mcts_geometry")
         self.mcts_games, self.mcts_node_cap, self.mcts_edge_cap, self.mcts_rec_cap = (int(x) for x in g)
@@ -197,6 +201,10 @@ class Engine:
 
     def mcts_run_move(self):
         N.check(self.ctx, self._lib.kv_mcts_run_move(self.ctx, self._stream()), "kv_mcts_run_move")
+
+    def mcts_waves(self) -> int:
+        """Search waves launched since mcts_create (with K > 1 a move takes a data-dependent number of waves)."""
+        return int(self._lib.kv_mcts_waves(self.ctx))
 
     def mcts_status(self) -> dict:
         out = np.zeros(9, dtype=np.uint64)

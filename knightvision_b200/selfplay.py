@@ -60,7 +60,8 @@ class SelfPlay:
 
     def __init__(self, model: ChessNet, n_games: int, device, sims: int = DEFAULT_SIMS, max_plies: int = DEFAULT_PLY_CAP,
                  temp_plies: int = TEMP_PLIES, c_puct: float = C_PUCT, dir_alpha: float = DIR_NOISE_ALPHA,
-                 dir_eps: float = DIR_NOISE_EPS, seed: int = SEED, eval_mode: int = 1, engine: Engine | None = None):
+                 dir_eps: float = DIR_NOISE_EPS, seed: int = SEED, eval_mode: int = 1, engine: Engine | None = None,
+                 inflight: int = 1):
         self.eng = engine or engine_for(device)
         self.n_games, self.sims, self.max_plies = n_games, sims, max_plies
         if eval_mode == 1:
@@ -71,9 +72,10 @@ class SelfPlay:
                 net.load_state_dict(inner.state_dict())
                 inner = net
             inner.eval()
-            inner.attach(self.eng, max_batch=max(n_games, 2))
+            inner.attach(self.eng, max_batch=max(n_games * inflight, 2))
             self.model = inner
-        self.eng.mcts_create(n_games, sims, max_plies, temp_plies, c_puct, dir_alpha, dir_eps, seed, eval_mode)
+        self.eng.mcts_create(n_games, sims, max_plies, temp_plies, c_puct, dir_alpha, dir_eps, seed, eval_mode,
+                             inflight=inflight)
 
     def play(self, start_lines: torch.Tensor | None = None, game_id_base: int = 0, progress=None) -> dict:
         eng = self.eng

@@ -663,20 +663,22 @@ typedef struct {
     int32_t temp_plies;  /* plies < temp_plies sample the move from the visit counts, later plies take the argmax */
     int32_t max_plies;   /* game is a draw when this many plies were played */
     float c_puct, dir_alpha, dir_eps;
-    int32_t pad;
+    int32_t inflight;    /* K simulations in flight per wave (0 or 1: sequential search; > 1: virtual loss) */
     uint64_t seed;
 } kvo_mcts_cfg;
 
 typedef struct {
     kvo_state st;
     int32_t first_edge, n_edges;
-    uint32_t N;
+    uint32_t N;          /* 1 + completed simulations through the node */
+    uint32_t VL;         /* virtual visits: simulations of the current wave that went through and are not backed up */
     int32_t term;
+    int32_t pending;     /* created in the current wave, priors not delivered yet */
     float val;           /* terminal value, or the evaluator's value, from the node's side to move */
 } onode;
 typedef struct {
     float P, W;
-    uint32_t N;
+    uint32_t N, VL;
     int32_t child;
     uint16_t mv;
 } oedge;
@@ -698,129 +700,198 @@ typedef struct {
     const float *rep_edge_P;
 } replay_t;
 
+/* priors and value of a freshly expanded (non-terminal) leaf: replayed device outputs, or the hash evaluator with the
+ * softmax / root-noise arithmetic of DESIGN.md 4.3 */
+static void evaluate_leaf(const kvo_mcts_cfg *cfg, onode *nd, oedge *e, int leaf, uint64_t game_id, int ply,
+                          const replay_t *rep) {
+    const int n = nd->n_edges;
+    if (rep && rep->rep_node_val) {
+        nd->val = rep->rep_node_val[leaf];
+        for (int k = 0; k < n; k++) e[k].P = rep->rep_edge_P[rep->rep_node_first[leaf] + k];
+        return;
+    }
+    uint64_t w[16];
+    kvo_pack(&nd->st, w);
+    const uint64_t ph = pos_hash(w);
+    float mx = 0.0f;
+    for (int k = 0; k < n; k++) {
+        e[k].P = hash_logit(ph, kvo_move_index(e[k].mv));
+        if (k == 0 || e[k].P > mx) mx = e[k].P;
+    }
+    float sum = 0.0f;
+    for (int k = 0; k < n; k++) {
+        e[k].P = kvd_expf(e[k].P - mx);
+        sum = sum + e[k].P;
+    }
+    for (int k = 0; k < n; k++) e[k].P = e[k].P / sum;
+    if (leaf == 0 && cfg->dir_eps > 0.0f) {
+        float gs = 0.0f;
+        for (int k = 0; k < n; k++) {
+            e[k].W = kvd_gamma_small(cfg->dir_alpha, cfg->seed, game_id, (uint64_t)ply * 256 + (uint64_t)k);
+            gs = gs + e[k].W;
+        }
+        for (int k = 0; k < n; k++) {
+            const float eta = e[k].W / gs;
+            e[k].P = (1.0f - cfg->dir_eps) * e[k].P + cfg->dir_eps * eta;
+            e[k].W = 0.0f;
+        }
+    }
+    const float vw = hash_value(ph);
+    nd->val = nd->st.white_to_move ? vw : -vw;
+}
+
+/* backup of one simulation: the virtual visit taken at selection becomes the real one */
+static void backup_path(onode *nodes, oedge *edges, const int *path_n, const int *path_e, int depth, float v) {
+    for (int i = depth - 1; i >= 0; i--) {
+        v = -v;
+        edges[path_e[i]].W = edges[path_e[i]].W + v;
+        edges[path_e[i]].N++;
+        edges[path_e[i]].VL--;
+        nodes[path_n[i]].N++;
+        nodes[path_n[i]].VL--;
+    }
+}
+
 /* Runs one search of cfg->sims simulations from `root`; returns the chosen move word (0xFFFF if the root has no
- * move).  Outputs: root move list, visit counts, W (bit patterns), number of nodes/edges created. */
+ * move).  Outputs: root move list, visit counts, W (bit patterns), number of nodes/edges created.
+ *
+ * The search proceeds in WAVES of up to K = cfg->inflight selections.  A selection descends by PUCT over
+ * N + VL visits and W - VL value sums (virtual loss), marks its path with one virtual visit per edge and node, and
+ * ends in (a) a terminal node or a new terminal leaf: backed up at once; (b) a new leaf that needs the evaluator:
+ * it stays in flight until the end of the wave; (c) a leaf that is itself still in flight: the selection is undone
+ * and the wave stops selecting.  At the end of the wave the in-flight leaves get their priors / values and are
+ * backed up in selection order.  With K = 1 this is the plain sequential search (VL is 0 whenever a score is
+ * computed). */
 static int mcts_search(const kvo_mcts_cfg *cfg, const kvo_state *root, uint64_t game_id, int ply, const replay_t *rep,
                        uint16_t *root_moves, uint32_t *root_N, float *root_W, float *root_P, int *n_root,
                        int *out_nodes, int *out_edges, int *overflow) {
     const int S = cfg->sims;
+    const int K = cfg->inflight > 1 ? cfg->inflight : 1;
+    const size_t PL = (size_t)S + 2;   /* path stride */
     onode *nodes = (onode *)calloc((size_t)S + 1, sizeof(onode));
     oedge *edges = (oedge *)calloc((size_t)cfg->edge_cap, sizeof(oedge));
-    int *path_e = (int *)malloc(sizeof(int) * ((size_t)S + 2));
-    int *path_n = (int *)malloc(sizeof(int) * ((size_t)S + 2));
-    int n_nodes = 0, n_edges = 0;
+    int *path_e = (int *)malloc(sizeof(int) * PL * (size_t)K);
+    int *path_n = (int *)malloc(sizeof(int) * PL * (size_t)K);
+    int *pend_leaf = (int *)malloc(sizeof(int) * (size_t)K);
+    int *pend_depth = (int *)malloc(sizeof(int) * (size_t)K);
+    int n_nodes = 0, n_edges = 0, sims_done = 0;
     *overflow = 0;
-    for (int sim = 0; sim < S; sim++) {
-        int depth = 0, node = 0, leaf = -1;
-        float v = 0.0f;
-        kvo_state child_st;
-        if (n_nodes == 0) {
-            child_st = *root;
-            leaf = 0;
-        } else {
-            for (;;) {
-                onode *nd = &nodes[node];
-                if (nd->term) {
-                    v = nd->val;
-                    nd->N++;
-                    break;
-                }
-                const float sq = KVD_SQRTF((float)nd->N);
-                int best = 0;
-                float bs = 0.0f;
-                for (int k = 0; k < nd->n_edges; k++) {
-                    const oedge *e = &edges[nd->first_edge + k];
-                    float sc = kvd_puct(e->W, e->N, e->P, sq, cfg->c_puct);
-                    if (k == 0 || sc > bs) { bs = sc; best = k; }
-                }
-                const int ei = nd->first_edge + best;
-                path_n[depth] = node;
-                path_e[depth] = ei;
-                depth++;
-                if (edges[ei].child < 0) {
-                    child_st = nd->st;
-                    make_move(&child_st, edges[ei].mv & 63, (edges[ei].mv >> 6) & 63, (edges[ei].mv >> 12) & 7, T_Q);
-                    leaf = n_nodes;
-                    edges[ei].child = leaf;
-                    break;
-                }
-                node = edges[ei].child;
-            }
-        }
-        if (leaf >= 0) {
-            onode *nd = &nodes[leaf];
-            movelist ml;
-            int f;
-            int n = valid_moves(&child_st, &ml, &f);   /* may rewrite child_st (getKingMoves restore quirk) */
-            if (n > 256) n = 256;
-            nd->st = child_st;
-            nd->N = 1;
-            nd->first_edge = -1;
-            nd->n_edges = 0;
-            n_nodes++;
-            if (n == 0) {
-                nd->term = 1;
-                nd->val = (f & RF_CHECKMATE) ? -1.0f : 0.0f;
-            } else if (f & RF_ONLY_KINGS) {
-                nd->term = 1;
-                nd->val = 0.0f;
-            } else if (n_edges + n > cfg->edge_cap) {
-                nd->term = 1;
-                nd->val = 0.0f;
-                *overflow = 1;
+    while (sims_done < S) {
+        int n_pend = 0;
+        for (int j = 0; j < K; j++) {
+            if (sims_done + n_pend >= S) break;
+            int *pe = path_e + PL * (size_t)n_pend, *pn = path_n + PL * (size_t)n_pend;
+            int depth = 0, node = 0, leaf = -1, collided = 0;
+            float v = 0.0f;
+            kvo_state child_st;
+            if (n_nodes == 0) {
+                child_st = *root;
+                leaf = 0;
             } else {
-                nd->term = 0;
-                nd->first_edge = n_edges;
-                nd->n_edges = n;
-                oedge *e = &edges[n_edges];
-                n_edges += n;
-                for (int k = 0; k < n; k++) {
-                    e[k].mv = pack_move(&ml.m[k]);
-                    e[k].N = 0;
-                    e[k].W = 0.0f;
-                    e[k].child = -1;
-                }
-                if (rep && rep->rep_node_val) {
-                    nd->val = rep->rep_node_val[leaf];
-                    for (int k = 0; k < n; k++) e[k].P = rep->rep_edge_P[rep->rep_node_first[leaf] + k];
-                } else {
-                    uint64_t w[16];
-                    kvo_pack(&child_st, w);
-                    const uint64_t ph = pos_hash(w);
-                    float mx = 0.0f;
-                    for (int k = 0; k < n; k++) {
-                        e[k].P = hash_logit(ph, kvo_move_index(e[k].mv));
-                        if (k == 0 || e[k].P > mx) mx = e[k].P;
+                for (;;) {
+                    onode *nd = &nodes[node];
+                    if (nd->pending) {
+                        collided = 1;
+                        break;
                     }
-                    float sum = 0.0f;
-                    for (int k = 0; k < n; k++) {
-                        e[k].P = kvd_expf(e[k].P - mx);
-                        sum = sum + e[k].P;
+                    if (nd->term) {
+                        v = nd->val;
+                        nd->N++;
+                        break;
                     }
-                    for (int k = 0; k < n; k++) e[k].P = e[k].P / sum;
-                    if (leaf == 0 && cfg->dir_eps > 0.0f) {
-                        float gs = 0.0f;
-                        for (int k = 0; k < n; k++) {
-                            e[k].W = kvd_gamma_small(cfg->dir_alpha, cfg->seed, game_id, (uint64_t)ply * 256 + (uint64_t)k);
-                            gs = gs + e[k].W;
-                        }
-                        for (int k = 0; k < n; k++) {
-                            const float eta = e[k].W / gs;
-                            e[k].P = (1.0f - cfg->dir_eps) * e[k].P + cfg->dir_eps * eta;
-                            e[k].W = 0.0f;
-                        }
+                    const float sq = KVD_SQRTF((float)(nd->N + nd->VL));
+                    int best = 0;
+                    float bs = 0.0f;
+                    for (int k = 0; k < nd->n_edges; k++) {
+                        const oedge *e = &edges[nd->first_edge + k];
+                        float sc = kvd_puct(e->W - (float)e->VL, e->N + e->VL, e->P, sq, cfg->c_puct);
+                        if (k == 0 || sc > bs) { bs = sc; best = k; }
                     }
-                    const float vw = hash_value(ph);
-                    nd->val = child_st.white_to_move ? vw : -vw;
+                    const int ei = nd->first_edge + best;
+                    pn[depth] = node;
+                    pe[depth] = ei;
+                    depth++;
+                    edges[ei].VL++;
+                    nd->VL++;
+                    if (edges[ei].child < 0) {
+                        child_st = nd->st;
+                        make_move(&child_st, edges[ei].mv & 63, (edges[ei].mv >> 6) & 63, (edges[ei].mv >> 12) & 7, T_Q);
+                        leaf = n_nodes;
+                        edges[ei].child = leaf;
+                        break;
+                    }
+                    node = edges[ei].child;
                 }
             }
-            v = nd->val;
+            if (collided) {
+                for (int i = depth - 1; i >= 0; i--) {
+                    edges[pe[i]].VL--;
+                    nodes[pn[i]].VL--;
+                }
+                break;   /* no more selections in this wave */
+            }
+            int in_flight = 0;
+            if (leaf >= 0) {
+                onode *nd = &nodes[leaf];
+                movelist ml;
+                int f;
+                int n = valid_moves(&child_st, &ml, &f);   /* may rewrite child_st (getKingMoves restore quirk) */
+                if (n > 256) n = 256;
+                nd->st = child_st;
+                nd->N = 1;
+                nd->VL = 0;
+                nd->first_edge = -1;
+                nd->n_edges = 0;
+                nd->pending = 0;
+                n_nodes++;
+                if (n == 0) {
+                    nd->term = 1;
+                    nd->val = (f & RF_CHECKMATE) ? -1.0f : 0.0f;
+                } else if (f & RF_ONLY_KINGS) {
+                    nd->term = 1;
+                    nd->val = 0.0f;
+                } else if (n_edges + n > cfg->edge_cap) {
+                    nd->term = 1;
+                    nd->val = 0.0f;
+                    *overflow = 1;
+                } else {
+                    nd->term = 0;
+                    nd->first_edge = n_edges;
+                    nd->n_edges = n;
+                    nd->pending = 1;
+                    oedge *e = &edges[n_edges];
+                    n_edges += n;
+                    for (int k = 0; k < n; k++) {
+                        e[k].mv = pack_move(&ml.m[k]);
+                        e[k].N = 0;
+                        e[k].VL = 0;
+                        e[k].W = 0.0f;
+                        e[k].P = 0.0f;
+                        e[k].child = -1;
+                    }
+                    pend_leaf[n_pend] = leaf;
+                    pend_depth[n_pend] = depth;
+                    in_flight = 1;
+                }
+                v = nd->val;
+            }
+            if (in_flight) {
+                n_pend++;
+            } else {
+                backup_path(nodes, edges, pn, pe, depth, v);
+                sims_done++;
+            }
         }
-        for (int i = depth - 1; i >= 0; i--) {
-            v = -v;
-            edges[path_e[i]].W = edges[path_e[i]].W + v;
-            edges[path_e[i]].N++;
-            nodes[path_n[i]].N++;
+        /* end of the wave: the evaluator's answers arrive, then the backups in selection order */
+        for (int j = 0; j < n_pend; j++) {
+            onode *nd = &nodes[pend_leaf[j]];
+            evaluate_leaf(cfg, nd, &edges[nd->first_edge], pend_leaf[j], game_id, ply, rep);
+            nd->pending = 0;
+        }
+        for (int j = 0; j < n_pend; j++) {
+            backup_path(nodes, edges, path_n + PL * (size_t)j, path_e + PL * (size_t)j, pend_depth[j],
+                        nodes[pend_leaf[j]].val);
+            sims_done++;
         }
     }
     int chosen = 0xFFFF;
@@ -869,6 +940,8 @@ static int mcts_search(const kvo_mcts_cfg *cfg, const kvo_state *root, uint64_t 
     free(edges);
     free(path_e);
     free(path_n);
+    free(pend_leaf);
+    free(pend_depth);
     return chosen;
 }
 

@@ -99,11 +99,13 @@ def encode(lines: np.ndarray) -> np.ndarray:
 class MctsCfg(ctypes.Structure):
     _fields_ = [("sims", ctypes.c_int32), ("edge_cap", ctypes.c_int32), ("temp_plies", ctypes.c_int32),
                 ("max_plies", ctypes.c_int32), ("c_puct", ctypes.c_float), ("dir_alpha", ctypes.c_float),
-                ("dir_eps", ctypes.c_float), ("pad", ctypes.c_int32), ("seed", ctypes.c_uint64)]
+                ("dir_eps", ctypes.c_float), ("inflight", ctypes.c_int32), ("seed", ctypes.c_uint64)]
 
 
-def mcts_cfg(sims, edges_per_node=48, temp_plies=0, max_plies=1 << 20, c_puct=1.5, dir_alpha=0.3, dir_eps=0.25, seed=1):
-    return MctsCfg(sims, max(sims * (edges_per_node or 48), 256), temp_plies, max_plies, c_puct, dir_alpha, dir_eps, 0, seed)
+def mcts_cfg(sims, edges_per_node=48, temp_plies=0, max_plies=1 << 20, c_puct=1.5, dir_alpha=0.3, dir_eps=0.25, seed=1,
+             inflight=1):
+    return MctsCfg(sims, max(sims * (edges_per_node or 48), 256), temp_plies, max_plies, c_puct, dir_alpha, dir_eps,
+                   inflight, seed)
 
 
 def mcts_search(cfg, line, game_id=0, ply=0, replay=None):

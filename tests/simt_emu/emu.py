@@ -65,19 +65,21 @@ def perft(roots, depth):
     return out
 
 
-def mcts_search(start, sims, id_base=0, ply=0, edges_per_node=48, c_puct=1.5, dir_alpha=0.3, dir_eps=0.25, seed=1):
+def mcts_search(start, sims, id_base=0, ply=0, edges_per_node=48, c_puct=1.5, dir_alpha=0.3, dir_eps=0.25, seed=1,
+                inflight=1):
     start = np.ascontiguousarray(start, dtype=np.uint64)
     G = start.shape[0]
     moves = np.zeros((G, 256), np.uint16); N = np.zeros((G, 256), np.uint32)
     W = np.zeros((G, 256), np.float32); P = np.zeros((G, 256), np.float32); info = np.zeros((G, 4), np.int32)
     lib().kvemu_mcts_search(ctypes.c_int(G), _p(start), ctypes.c_uint64(id_base), ctypes.c_int(ply), ctypes.c_int(sims),
                             ctypes.c_int(edges_per_node), ctypes.c_float(c_puct), ctypes.c_float(dir_alpha),
-                            ctypes.c_float(dir_eps), ctypes.c_uint64(seed), _p(moves), _p(N), _p(W), _p(P), _p(info))
+                            ctypes.c_float(dir_eps), ctypes.c_uint64(seed), _p(moves), _p(N), _p(W), _p(P), _p(info),
+                            ctypes.c_int(inflight))
     return moves, N, W, P, info
 
 
 def selfplay(start, sims, max_plies, temp_plies, id_base=0, edges_per_node=48, c_puct=1.5, dir_alpha=0.3, dir_eps=0.25,
-             seed=1, cache_log2=0, return_counts=False):
+             seed=1, cache_log2=0, return_counts=False, inflight=1):
     start = np.ascontiguousarray(start, dtype=np.uint64)
     G = start.shape[0]
     moves = np.zeros((G, max_plies), np.uint16); plies = np.zeros(G, np.int32); res = np.zeros(G, np.int32)
@@ -85,7 +87,8 @@ def selfplay(start, sims, max_plies, temp_plies, id_base=0, edges_per_node=48, c
     lib().kvemu_selfplay(ctypes.c_int(G), _p(start), ctypes.c_uint64(id_base), ctypes.c_int(sims),
                          ctypes.c_int(edges_per_node), ctypes.c_int(max_plies), ctypes.c_int(temp_plies),
                          ctypes.c_float(c_puct), ctypes.c_float(dir_alpha), ctypes.c_float(dir_eps),
-                         ctypes.c_uint64(seed), _p(moves), _p(plies), _p(res), ctypes.c_int(cache_log2), _p(cnt))
+                         ctypes.c_uint64(seed), _p(moves), _p(plies), _p(res), ctypes.c_int(cache_log2), _p(cnt),
+                         ctypes.c_int(inflight))
     if return_counts:
         return moves, plies, res, (int(cnt[0]), int(cnt[1]))
     return moves, plies, res

@@ -217,9 +217,11 @@ struct EmuMcts {
 };
 
 static EmuMcts* emu_mcts_new(int G, int sims, int edges_per_node, int max_plies, int temp_plies, float c_puct,
-                             float dir_alpha, float dir_eps, uint64_t seed, int cache_log2 = 0) {
+                             float dir_alpha, float dir_eps, uint64_t seed, int cache_log2 = 0, int inflight = 1) {
     EmuMcts* m = new EmuMcts();
     m->G = G;
+    if (inflight < 1) inflight = 1;
+    m->cfg.inflight = inflight;
     kv::MctsCfg& c = m->cfg;
     c.sims = sims;
     c.node_cap = sims;
@@ -234,7 +236,7 @@ static EmuMcts* emu_mcts_new(int G, int sims, int edges_per_node, int max_plies,
     c.dir_eps = dir_eps;
     c.seed = seed;
     kv::MctsArrays& A = m->A;
-    const size_t g = (size_t)G;
+    const size_t g = (size_t)G, gs = g * (size_t)inflight;
     A.hdr = m->alloc<kv::GameHdr>(g);
     A.root_line = m->alloc<uint64_t>(g * 16);
     A.node_line = m->alloc<uint64_t>(g * c.node_cap * 16);
@@ -244,20 +246,23 @@ static EmuMcts* emu_mcts_new(int G, int sims, int edges_per_node, int max_plies,
     A.eW = m->alloc<float>(g * c.edge_cap);
     A.eChild = m->alloc<int>(g * c.edge_cap);
     A.eMv = m->alloc<uint16_t>(g * c.edge_cap);
-    A.path_edge = m->alloc<int>(g * (c.node_cap + 1));
-    A.path_node = m->alloc<int>(g * (c.node_cap + 1));
+    A.path_edge = m->alloc<int>(gs * (c.node_cap + 1));
+    A.path_node = m->alloc<int>(gs * (c.node_cap + 1));
+    A.pend_node = m->alloc<int>(gs);
+    A.pend_depth = m->alloc<int>(gs);
+    A.pend_kind = m->alloc<int>(gs);
     A.n_eval = m->alloc<uint32_t>(4);
-    A.eval_game = m->alloc<int>(g);
-    A.eval_lines = m->alloc<uint64_t>((g + 1) * 16);
+    A.eval_game = m->alloc<int>(gs);
+    A.eval_lines = m->alloc<uint64_t>((gs + 1) * 16);
     A.rec_line = m->alloc<uint64_t>(g * c.rec_cap * 12);
     A.rec_move = m->alloc<uint16_t>(g * c.rec_cap);
-    A.eval_centry = m->alloc<int>(g);
-    A.eval_hash = m->alloc<uint64_t>(g);
+    A.eval_centry = m->alloc<int>(gs);
+    A.eval_hash = m->alloc<uint64_t>(gs);
     A.n_late = m->alloc<uint32_t>(4);
-    A.late_game = m->alloc<int>(g);
-    A.late_src = m->alloc<int>(g);
-    A.feat_game = m->alloc<float>(g * kv::FEAT);
-    A.feat_slot = m->alloc<float>(g * kv::FEAT);
+    A.late_game = m->alloc<int>(gs);
+    A.late_src = m->alloc<int>(gs);
+    A.feat_game = m->alloc<float>(gs * kv::FEAT);
+    A.feat_slot = m->alloc<float>(gs * kv::FEAT);
     A.cache = nullptr;
     c.cache_mask = 0;
     if (cache_log2 > 0) {
@@ -274,9 +279,9 @@ static void emu_mcts_reset(EmuMcts* m, const uint64_t* start, uint64_t id_base) 
     for (int g = 0; g < m->G; g++) {
         kv::GameHdr h;
         memset(&h, 0, sizeof(h));
-        h.pend_node = -1;
         h.game_id = id_base + (uint64_t)g;
         m->A.hdr[g] = h;
+        for (int j = 0; j < m->cfg.inflight; j++) m->A.pend_node[(size_t)g * m->cfg.inflight + j] = -1;
         for (int i = 0; i < 16; i++) m->A.root_line[(size_t)g * 16 + i] = i >= 13 ? 0 : start[(size_t)g * 16 + i];
     }
 }
@@ -299,6 +304,19 @@ static void emu_mcts_wave(EmuMcts* m) {
         kvemu::run_warp([&](int lane) { kv::mcts_hash_eval_warp(lane, m->cfg, m->A, slot, scratch, wave); });
     for (int li = 0; li < nl; li++)
         kvemu::run_warp([&](int lane) { kv::mcts_hash_late_warp(lane, m->cfg, m->A, li, scratch); });
+    if (m->cfg.inflight > 1)
+        for (int g = 0; g < m->G; g++)
+            kvemu::run_warp([&](int lane) { kv::mcts_backup_game_warp(lane, m->cfg, m->A, g); });
+}
+
+// the driver loop of kv_mcts_run_move: waves until every live game has run its simulations
+static void emu_mcts_move_waves(EmuMcts* m) {
+    for (;;) {
+        bool left = false;
+        for (int g = 0; g < m->G; g++) left |= !m->A.hdr[g].done && m->A.hdr[g].sims_done < m->cfg.sims;
+        if (!left) break;
+        emu_mcts_wave(m);
+    }
 }
 
 static void emu_mcts_finish(EmuMcts* m) {
@@ -314,16 +332,16 @@ __attribute__((visibility("default"))) void kvemu_mcts_search(int G, const uint6
                                                                int sims, int edges_per_node, float c_puct,
                                                                float dir_alpha, float dir_eps, uint64_t seed,
                                                                uint16_t* moves, uint32_t* N, float* W, float* P,
-                                                               int32_t* info) {
-    EmuMcts* m = emu_mcts_new(G, sims, edges_per_node, 1 << 20, 0, c_puct, dir_alpha, dir_eps, seed);
+                                                               int32_t* info, int inflight) {
+    EmuMcts* m = emu_mcts_new(G, sims, edges_per_node, 1 << 20, 0, c_puct, dir_alpha, dir_eps, seed, 0, inflight);
     m->cfg.rec_cap = 1;
     emu_mcts_reset(m, start, id_base);
     for (int g = 0; g < G; g++) m->A.hdr[g].ply = ply0;
-    for (int s = 0; s < sims; s++) emu_mcts_wave(m);
+    emu_mcts_move_waves(m);
     for (int g = 0; g < G; g++) {
         const kv::GameHdr& h = m->A.hdr[g];
         const kv::NodeMeta nm = m->A.node_meta[(size_t)g * m->cfg.node_cap];
-        const int n = (h.n_nodes && !(nm.ne_term >> 16)) ? (nm.ne_term & 0xFFFF) : 0;
+        const int n = (h.n_nodes && !(nm.ne_term & kv::NODE_TERM)) ? (nm.ne_term & 0xFFFF) : 0;
         info[4 * g + 0] = n;
         info[4 * g + 1] = h.n_nodes;
         info[4 * g + 2] = h.n_edges;
@@ -344,15 +362,16 @@ __attribute__((visibility("default"))) void kvemu_selfplay(int G, const uint64_t
                                                             int edges_per_node, int max_plies, int temp_plies,
                                                             float c_puct, float dir_alpha, float dir_eps, uint64_t seed,
                                                             uint16_t* out_moves, int32_t* out_plies, int32_t* out_result,
-                                                            int cache_log2, int64_t* out_counts2) {
-    EmuMcts* m = emu_mcts_new(G, sims, edges_per_node, max_plies, temp_plies, c_puct, dir_alpha, dir_eps, seed, cache_log2);
+                                                            int cache_log2, int64_t* out_counts2, int inflight) {
+    EmuMcts* m = emu_mcts_new(G, sims, edges_per_node, max_plies, temp_plies, c_puct, dir_alpha, dir_eps, seed, cache_log2,
+                              inflight);
     g_emu_evals = g_emu_late = 0;
     emu_mcts_reset(m, start, id_base);
     for (int mvno = 0; mvno < max_plies; mvno++) {
         bool live = false;
         for (int g = 0; g < G; g++) live |= !m->A.hdr[g].done;
         if (!live) break;
-        for (int s = 0; s < sims; s++) emu_mcts_wave(m);
+        emu_mcts_move_waves(m);
         emu_mcts_finish(m);
     }
     for (int g = 0; g < G; g++) {

@@ -97,3 +97,38 @@ def test_policy_sampling_mode_sims_1():
         assert np.array_equal(m, moves[g, :plies[g]]) and r == res[g]
         seen.add(int(m[0]))
     assert len(seen) > 1          # not always the first legal move
+
+
+def test_virtual_loss_inflight_search_matches_oracle():
+    """K simulations in flight per game and wave (virtual loss): the kernel source on the emulator
+    against the oracle's wave emulation, bit for bit; K = 1 is the sequential search."""
+    lines = H.random_playout_positions(n_games=3, max_plies=60, seed=33)
+    roots = np.concatenate([L.start_line()[None], lines[[5, 30, 77, 120]]])
+    seq = emu.mcts_search(roots, sims=96, id_base=5, ply=1, seed=4)
+    for K in (1, 2, 4, 8, 16):
+        mv, N, W, P, info = emu.mcts_search(roots, sims=96, id_base=5, ply=1, seed=4, inflight=K)
+        if K == 1:
+            assert np.array_equal(N, seq[1]) and np.array_equal(_bits(W), _bits(seq[2]))
+        differs = False
+        for g in range(len(roots)):
+            r = O.mcts_search(O.mcts_cfg(96, seed=4, inflight=K), roots[g], game_id=5 + g, ply=1)
+            n = int(info[g, 0])
+            assert n == len(r["moves"]) and info[g, 1] == r["nodes"] and info[g, 2] == r["edges"]
+            assert np.array_equal(mv[g, :n], r["moves"]) and np.array_equal(N[g, :n], r["N"])
+            assert np.array_equal(_bits(W[g, :n]), _bits(r["W"])) and np.array_equal(_bits(P[g, :n]), _bits(r["P"]))
+            assert int(r["N"].sum()) == 96 - 1                    # exactly `sims` simulations, whatever the wave shape
+            assert int(N[g, :n].max()) < (1 << 24)                # no virtual visit left behind in the counters
+            differs |= not np.array_equal(N[g, :n], seq[1][g, :n])
+        if K >= 4:
+            assert differs          # virtual loss does change the search (it is not silently sequential)
+
+
+def test_virtual_loss_selfplay_games_match_oracle():
+    start = np.stack([L.start_line()] * 3)
+    for K, cache in ((4, 0), (8, 10)):
+        moves, plies, res = emu.selfplay(start, sims=24, max_plies=16, temp_plies=5, id_base=9, seed=6, inflight=K,
+                                         cache_log2=cache)
+        for g in range(3):
+            cfg = O.mcts_cfg(24, temp_plies=5, max_plies=16, seed=6, inflight=K)
+            m, lines, r = O.selfplay_game(cfg, start[g], game_id=9 + g)
+            assert len(m) == plies[g] and r == res[g] and np.array_equal(m, moves[g, :plies[g]])

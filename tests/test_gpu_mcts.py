@@ -190,3 +190,81 @@ def test_learn_loop_small_tower(eng, monkeypatch):
     d2 = LR.ReplayData(eng)
     d2.extend([(O.encode(L.start_line()[None])[0], 3364, 0.2)])
     assert int(d2.move[0]) == 3364 and np.array_equal(d2.lines[0, :12].cpu().numpy().view(np.uint64), L.start_line()[:12])
+
+
+@pytest.mark.parametrize("K", [4, 16])
+def test_virtual_loss_inflight_hash_evaluator_bit_exact(eng, K):
+    """K simulations in flight per game and wave with virtual loss: whole games, bit-exact with the
+    oracle's wave emulation — visit counts, W bits, priors, chosen moves, records."""
+    from knightvision_b200.engine import lines_to_device
+    lines = H.random_playout_positions(n_games=8, max_plies=120, seed=35)
+    roots = lines[np.random.default_rng(2).permutation(len(lines))[:64]]
+    roots[0] = L.start_line()
+    sims = 200
+    eng.mcts_create(len(roots), sims, max_plies=4, temp_plies=0, seed=78, eval_mode=0, inflight=K)
+    eng.mcts_enable_cache(12 if K == 16 else 0)        # the cache stays transparent with several leaves per game
+    eng.mcts_reset(lines_to_device(roots, eng.device), game_id_base=500)
+    w0 = eng.mcts_waves()
+    eng.mcts_run_sims(1 + (sims - 1 + K - 1) // K)      # the minimum; collisions may leave some simulations to run
+    left = len(roots) * sims - eng.mcts_status()["sims_in_move"]
+    while left:
+        eng.mcts_run_sims(1)
+        left = len(roots) * sims - eng.mcts_status()["sims_in_move"]
+    assert eng.mcts_waves() - w0 < sims                  # far fewer waves than simulations
+    cfg = O.mcts_cfg(sims, seed=78, inflight=K)
+    for g in range(len(roots)):
+        got = eng.mcts_read_root(g)
+        r = O.mcts_search(cfg, roots[g], game_id=500 + g, ply=0)
+        assert got["nodes"] == r["nodes"] and got["edges"] == r["edges"], g
+        assert np.array_equal(got["moves"], r["moves"]) and np.array_equal(got["N"], r["N"]), g
+        assert np.array_equal(_bits(got["W"]), _bits(r["W"])) and np.array_equal(_bits(got["P"]), _bits(r["P"])), g
+        if len(r["N"]):
+            assert int(got["N"].sum()) == sims - 1
+    eng.mcts_enable_cache(0)
+    # whole games through kv_mcts_run_move (its own wave loop)
+    G, sims, max_plies = 32, 48, 40
+    eng.mcts_create(G, sims, max_plies=max_plies, temp_plies=8, seed=6, eval_mode=0, inflight=K)
+    eng.mcts_reset(None, game_id_base=0)
+    for _ in range(max_plies):
+        eng.mcts_run_move()
+    st = eng.mcts_status()
+    assert st["done"] == G and st["overflow"] == 0
+    rl, move, reward, game = (t.cpu().numpy() for t in eng.mcts_records())
+    cfg = O.mcts_cfg(sims, temp_plies=8, max_plies=max_plies, seed=6, inflight=K)
+    for g in range(G):
+        m, pos, res = O.selfplay_game(cfg, L.start_line(), game_id=g)
+        sel = game == g
+        assert sel.sum() == len(m), g
+        assert np.array_equal(move[sel], [O.lib().kvo_move_index(int(x)) for x in m]), g
+        assert np.array_equal(rl.view(np.uint64)[sel][:, :12], pos[:, :12]), g
+
+
+def test_virtual_loss_inflight_with_network_replayed_by_oracle(eng):
+    """512 leaves per wave from 64 games x 8 in flight through the real tower; the oracle replays the recorded values
+    and priors through its own wave emulation."""
+    from knightvision_b200.model import ChessNet
+    torch.manual_seed(0)
+    ChessNet().eval().attach(eng, max_batch=512)
+    G, sims, K = 64, 160, 8
+    eng.mcts_create(G, sims, max_plies=8, temp_plies=0, seed=9, eval_mode=1, inflight=K)
+    for cache in (0, 14):
+        eng.mcts_enable_cache(cache)
+        eng.mcts_reset(None, game_id_base=0)
+        eng.mcts_run_sims(1 + (sims - 1 + K - 1) // K)
+        while eng.mcts_status()["sims_in_move"] < G * sims:
+            eng.mcts_run_sims(1)
+        cfg = O.mcts_cfg(sims, seed=9, inflight=K)
+        for g in (0, 31, 63):
+            got = eng.mcts_read_root(g)
+            nv, nf, ep, root = eng.mcts_dump_tree(g)
+            r = O.mcts_search(cfg, root, game_id=g, ply=0, replay=(nv, nf, ep))
+            assert got["nodes"] == r["nodes"] and np.array_equal(got["N"], r["N"]), g
+            assert np.array_equal(_bits(got["W"]), _bits(r["W"])), g
+            assert int(got["N"].sum()) == sims - 1
+        st = eng.mcts_status()
+        assert st["evals"] + st["cache_hits"] <= G * sims and st["evals"] > 0
+    eng.mcts_enable_cache(0)
+    eng.mcts_reset(None, game_id_base=0)
+    eng.mcts_run_move()
+    eng.mcts_run_move()
+    assert eng.mcts_status()["plies"] == 2 * G
