@@ -21,6 +21,7 @@ __device__ __forceinline__ void head_features(const bf16* __restrict__ act, int 
         const int px = threadIdx.x >> 2, part = threadIdx.x & 3;
         const bf16* row = act + (size_t)px * C;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
         for (int c = part * 8; c < C; c += 32) {
             const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + c));
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);

@@ -78,23 +78,35 @@ struct HeadW {
     int C;
 };
 
-// logits of the pending leaf's legal moves from the 128 policy features (policy_fc rows of the legal indices only)
+// logits of the pending leaf's legal moves from the 128 policy features (policy_fc rows of the legal indices only).
+// Eight consecutive lanes share a move: each takes 16 of the 128 features (four float4 of the weight row), then a
+// fixed-order butterfly over the 8 lanes — the same code serves tower evaluations and cache hits, so a hit
+// reproduces a miss bit for bit.
 __device__ __forceinline__ void legal_logits(const MctsCfg& cfg, const MctsArrays& A, int gs, const HeadW& H, const float* hp,
                                              float* logits) {
     const int g = gs / cfg.inflight;
     const NodeMeta m = A.node_meta[(size_t)g * cfg.node_cap + A.pend_node[gs]];
     const int n = m.ne_term & 0xFFFF;
     const size_t e0 = (size_t)g * cfg.edge_cap + m.first_edge;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        const int idx = move_index(A.eMv[e0 + k]);
-        float a = __ldg(H.bfc + idx);
-        const float4* wr = reinterpret_cast<const float4*>(H.wfc + (size_t)idx * 128);
-#pragma unroll 8
-        for (int i = 0; i < 32; i++) {
-            const float4 w = __ldg(wr + i);
-            a += w.x * hp[4 * i] + w.y * hp[4 * i + 1] + w.z * hp[4 * i + 2] + w.w * hp[4 * i + 3];
+    const int part = threadIdx.x & 7, per = blockDim.x >> 3;
+    for (int k0 = 0; k0 < n; k0 += per) {   // uniform trip count: the shuffles below need whole warps
+        const int k = k0 + (int)(threadIdx.x >> 3);
+        float a = 0.f;
+        int idx = 0;
+        if (k < n) {
+            idx = move_index(A.eMv[e0 + k]);
+            const float4* wr = reinterpret_cast<const float4*>(H.wfc + (size_t)idx * 128 + part * 16);
+            const float* f = hp + part * 16;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float4 w = __ldg(wr + i);
+                a += w.x * f[4 * i] + w.y * f[4 * i + 1] + w.z * f[4 * i + 2] + w.w * f[4 * i + 3];
+            }
         }
-        logits[k] = a;
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (k < n && part == 0) logits[k] = a + __ldg(H.bfc + idx);
     }
 }
 

@@ -117,34 +117,41 @@ KV_DEV float hash_logit(uint64_t ph, int idx) {
 KV_DEV float hash_value(uint64_t ph) { return (float)kvd_rand24(ph, 4096, 2, 0) * (2.0f / 16777216.0f) - 1.0f; }
 KV_DEV int move_index(int mv) { return (mv & 63) * 64 + ((mv >> 6) & 63); }   // encode_move, ai/ai.py:51-57
 
-// lane 0: walk the path, newest edge first; the virtual visit taken at selection becomes the real one
-KV_DEV void mcts_backup_lane0(const MctsArrays& A, size_t ebase, size_t nbase, size_t pbase, int depth, float v) {
-    for (int i = depth - 1; i >= 0; i--) {
-        v = -v;
+// Backup of one simulation, all lanes: lane i owns path level i (i + 32, ...).  The value alternates sign per level
+// (exact), and a path never holds the same edge or node twice, so the levels are independent: W += +/-v, the virtual
+// visit taken at selection becomes the real one.  Same bits as walking the path sequentially.
+KV_DEV void mcts_backup_warp(int lane, const MctsArrays& A, size_t ebase, size_t nbase, size_t pbase, int depth, float v) {
+    for (int i = lane; i < depth; i += 32) {
+        const float vi = ((depth - i) & 1) ? -v : v;
         const size_t e = ebase + (size_t)A.path_edge[pbase + i];
-        A.eW[e] = A.eW[e] + v;
+        A.eW[e] = A.eW[e] + vi;
         A.eN[e] = A.eN[e] + 1u - VL_ONE;
         A.node_meta[nbase + (size_t)A.path_node[pbase + i]].N += 1u - VL_ONE;
     }
+    syncwarp();
 }
-// lane 0: a selection that ran into a leaf still waiting for its evaluation gives its virtual visits back
-KV_DEV void mcts_unwind_lane0(const MctsArrays& A, size_t ebase, size_t nbase, size_t pbase, int depth) {
-    for (int i = depth - 1; i >= 0; i--) {
+// A selection that ran into a leaf still waiting for its evaluation gives its virtual visits back
+KV_DEV void mcts_unwind_warp(int lane, const MctsArrays& A, size_t ebase, size_t nbase, size_t pbase, int depth) {
+    for (int i = lane; i < depth; i += 32) {
         A.eN[ebase + (size_t)A.path_edge[pbase + i]] -= VL_ONE;
         A.node_meta[nbase + (size_t)A.path_node[pbase + i]].N -= VL_ONE;
     }
+    syncwarp();
 }
-// lane 0: finish the pending simulation of slot gs (its leaf's value is in the node): backup + counters
-KV_DEV void mcts_commit_lane0(const MctsCfg& cfg, const MctsArrays& A, int g, int gs) {
+// Finish the pending simulation of slot gs (its leaf's value is in the node): backup + counters.  All lanes.
+KV_DEV void mcts_commit_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int g, int gs) {
     GameHdr* h = &A.hdr[g];
     const size_t nbase = (size_t)g * cfg.node_cap, ebase = (size_t)g * cfg.edge_cap;
     const size_t pbase = (size_t)gs * (cfg.node_cap + 1);
     const int c = A.pend_node[gs];
-    mcts_backup_lane0(A, ebase, nbase, pbase, A.pend_depth[gs], A.node_meta[nbase + c].val);
-    h->sims_done += 1;
-    if (A.pend_kind[gs] == 2) h->cache_hits += 1;
-    else h->n_evals += 1;
-    A.pend_node[gs] = -1;
+    mcts_backup_warp(lane, A, ebase, nbase, pbase, A.pend_depth[gs], A.node_meta[nbase + c].val);
+    if (lane == 0) {
+        h->sims_done += 1;
+        if (A.pend_kind[gs] == 2) h->cache_hits += 1;
+        else h->n_evals += 1;
+        A.pend_node[gs] = -1;
+    }
+    syncwarp();
 }
 
 // ---- evaluation cache ------------------------------------------------------------------------------------------
@@ -283,8 +290,7 @@ KV_DEV int mcts_select_one_warp(const Tables& T, int lane, const MctsCfg& cfg, c
             const int ne = m.ne_term & 0xFFFF;
             if (m.ne_term & NODE_PENDING) {   // only with K > 1: this leaf's priors arrive at the end of the wave
                 syncwarp();
-                if (lane == 0) mcts_unwind_lane0(A, ebase, nbase, pbase, depth);
-                syncwarp();
+                mcts_unwind_warp(lane, A, ebase, nbase, pbase, depth);
                 return 2;
             }
             if (m.ne_term & NODE_TERM) {
@@ -405,9 +411,9 @@ KV_DEV int mcts_select_one_warp(const Tables& T, int lane, const MctsCfg& cfg, c
         }
     }
     syncwarp();
-    if (!queued && lane == 0) {
-        mcts_backup_lane0(A, ebase, nbase, pbase, depth, v);
-        h->sims_done += 1;
+    if (!queued) {
+        mcts_backup_warp(lane, A, ebase, nbase, pbase, depth, v);
+        if (lane == 0) h->sims_done += 1;
     }
     syncwarp();
     return queued ? 1 : 0;
@@ -434,17 +440,16 @@ KV_DEV void mcts_select_warp(const Tables& T, int lane, const MctsCfg& cfg, cons
 // After the wave's expansions (K > 1): back the pending simulations of game g up in slot order.
 KV_DEV void mcts_backup_game_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int g) {
     GameHdr* h = &A.hdr[g];
-    if (lane == 0) {
-        const int np = h->n_pend;
-        for (int j = 0; j < np; j++) mcts_commit_lane0(cfg, A, g, g * cfg.inflight + j);
-        h->n_pend = 0;
-    }
+    const int np = h->n_pend;
+    for (int j = 0; j < np; j++) mcts_commit_warp(lane, cfg, A, g, g * cfg.inflight + j);   // slot order: paths share edges
+    if (lane == 0) h->n_pend = 0;
     syncwarp();
 }
 
 // Finish the pending simulation of game g given the leaf's legal-move logits (n floats, edge order) and the
 // evaluator's white-perspective value: softmax priors (+ root Dirichlet noise), then backup.
-KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int gs, const float* logits, float v_white,
+// `logits` is per-warp scratch (shared memory on the device) and is overwritten.
+KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int gs, float* logits, float v_white,
                              bool from_cache = false) {
     const int g = gs / cfg.inflight;
     GameHdr* h = &A.hdr[g];
@@ -461,24 +466,24 @@ KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, 
         const float o = shfl_xorf(mx, d, lane);
         mx = o > mx ? o : mx;
     }
-    for (int k = lane; k < n; k += 32) A.eP[e0 + k] = kvd_expf(logits[k] - mx);
+    for (int k = lane; k < n; k += 32) logits[k] = kvd_expf(logits[k] - mx);
     syncwarp();
     float s = 0.0f;
     if (lane == 0)
-        for (int k = 0; k < n; k++) s = s + A.eP[e0 + k];
+        for (int k = 0; k < n; k++) s = s + logits[k];   // sequential order = the oracle's
     s = shflf(s, 0);
-    for (int k = lane; k < n; k += 32) A.eP[e0 + k] = A.eP[e0 + k] / s;
+    for (int k = lane; k < n; k += 32) A.eP[e0 + k] = logits[k] / s;
     if (c == 0 && cfg.dir_eps > 0.0f) {
         // root Dirichlet(alpha) noise over the legal moves (scripts/self_play.py:153-154 mixes with eps = 0.25)
         for (int k = lane; k < n; k += 32)
             A.eW[e0 + k] = kvd_gamma_small(cfg.dir_alpha, cfg.seed, h->game_id, (uint64_t)h->ply * 256 + (uint64_t)k);
         syncwarp();
-        float gs = 0.0f;
+        float gsum = 0.0f;
         if (lane == 0)
-            for (int k = 0; k < n; k++) gs = gs + A.eW[e0 + k];
-        gs = shflf(gs, 0);
+            for (int k = 0; k < n; k++) gsum = gsum + A.eW[e0 + k];
+        gsum = shflf(gsum, 0);
         for (int k = lane; k < n; k += 32) {
-            const float eta = A.eW[e0 + k] / gs;
+            const float eta = A.eW[e0 + k] / gsum;
             A.eP[e0 + k] = (1.0f - cfg.dir_eps) * A.eP[e0 + k] + cfg.dir_eps * eta;
             A.eW[e0 + k] = 0.0f;
         }
@@ -489,14 +494,15 @@ KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, 
         A.node_meta[nbase + c].val = v;
         A.node_meta[nbase + c].ne_term = n;   // priors delivered: no longer pending
         A.pend_kind[gs] = from_cache ? 2 : 1;
-        // K == 1: the game's only in-flight simulation, back it up here; K > 1: mcts_backup_game_warp does it in
-        // slot order once every expansion of the wave is in (other CTAs may be expanding this game's other leaves)
-        if (cfg.inflight == 1) {
-            mcts_commit_lane0(cfg, A, g, gs);
-            h->n_pend = 0;
-        }
     }
     syncwarp();
+    // K == 1: the game's only in-flight simulation, back it up here; K > 1: mcts_backup_game_warp does it in
+    // slot order once every expansion of the wave is in (other CTAs may be expanding this game's other leaves)
+    if (cfg.inflight == 1) {
+        mcts_commit_warp(lane, cfg, A, g, gs);
+        if (lane == 0) h->n_pend = 0;
+        syncwarp();
+    }
 }
 
 // Hash evaluator (test evaluator, oracle mode 0): logits and value from a hash of the position.
