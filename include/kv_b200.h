@@ -166,6 +166,23 @@ KV_API int kv_mcts_read_root(kv_ctx* ctx, int game, uint16_t* h_moves, uint32_t*
 KV_API int kv_mcts_dump_tree(kv_ctx* ctx, int game, float* h_node_val, int32_t* h_node_first, float* h_edge_P,
                              uint64_t* h_root_line16);
 
+/* ---- training-side convolution operators (the tower convolutions of ai/model.py:19-25,58-59 as
+ *      scripts/train.py:158-181 runs them forward and backward under autocast; cuDNN in the reference) -------------
+ * All tensors are caller-owned device memory: activations NHWC bf16 [n_boards][8][8][C] (torch channels_last), the
+ * parameter / its gradient fp32 [Cout][Cin][3][3] as PyTorch stores them.  cin % 64 == 0, cout % 256 == 0, <= 512.
+ *   kv_conv3x3_pack   parameter -> the kernels' bf16 [Cout][9][Cin]; flip_transpose = 1 gives the dgrad operand
+ *                     [Cin][9][Cout] with the taps mirrored
+ *   kv_conv3x3_fprop  y = [relu](conv3x3(x, w) + bias [+ residual]) (bias / residual may be NULL).  dgrad is the same
+ *                     call on (dy, flip-transposed pack, cin <-> cout)
+ *   kv_conv3x3_wgrad  dw[co][ci][ky][kx] = sum_{b,y,x} dy[b,y,x,co] * x[b,y+ky-1,x+kx-1,ci], fp32, deterministic
+ *                     (cin % 256 == 0, cout % 128 == 0) */
+KV_API int kv_conv3x3_pack(kv_ctx* ctx, const float* d_w, int cout, int cin, int flip_transpose, void* d_out_bf16,
+                           void* stream);
+KV_API int kv_conv3x3_fprop(kv_ctx* ctx, const void* d_x, const void* d_w_packed, const float* d_bias,
+                            const void* d_residual, void* d_y, int n_boards, int cin, int cout, int relu, void* stream);
+KV_API int kv_conv3x3_wgrad(kv_ctx* ctx, const void* d_x, const void* d_dy, float* d_dw, int n_boards, int cin, int cout,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,10 @@ SIGNATURES = {
     "kv_net_forward_planes": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "kv_mcts_create": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float,
                                ctypes.c_float, c_u64, c_int]),
+    "kv_conv3x3_pack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "kv_conv3x3_fprop": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                 c_void_p]),
+    "kv_conv3x3_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "kv_mcts_create_k": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float,
                                  ctypes.c_float, c_u64, c_int, c_int]),
     "kv_mcts_waves": (ctypes.c_int64, [c_void_p]),

@@ -70,6 +70,8 @@ void kv_destroy(kv_ctx* ctx) {
     if (ctx->perft_counter) cudaFree(ctx->perft_counter);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
+    if (ctx->train_ws) cudaFree(ctx->train_ws);
+    if (ctx->train_zeros) cudaFree(ctx->train_zeros);
     for (auto& p : ctx->ev_live) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto& p : ctx->ev_free) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     delete ctx;

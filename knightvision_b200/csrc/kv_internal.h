@@ -15,7 +15,7 @@ struct kv_mcts;   // kv_mcts.cu
 // kernel categories for the optional per-kernel CUDA-event timing (kv_profile_*)
 enum KvKernel : int {
     KVK_MOVEGEN = 0, KVK_MAKE_MOVES, KVK_PERFT_EXPAND, KVK_PERFT_LEAF, KVK_ENCODE,
-    KVK_NET_STEM, KVK_NET_CONV, KVK_NET_HEAD, KVK_MCTS_SELECT, KVK_MCTS_EXPAND, KVK_MCTS_MISC, KVK_COUNT
+    KVK_NET_STEM, KVK_NET_CONV, KVK_NET_HEAD, KVK_MCTS_SELECT, KVK_MCTS_EXPAND, KVK_MCTS_MISC, KVK_TRAIN_WGRAD, KVK_COUNT
 };
 
 struct KvEventPair {
@@ -45,6 +45,10 @@ struct kv_ctx {
     size_t d_stage_bytes = 0;
     kv_net* net = nullptr;
     kv_mcts* mcts = nullptr;
+    // training operators (kv_train.cu): split-K workspace of the weight-gradient kernel, zero bias
+    float* train_ws = nullptr;
+    size_t train_ws_floats = 0;
+    float* train_zeros = nullptr;
 };
 
 extern std::string g_kv_create_error;

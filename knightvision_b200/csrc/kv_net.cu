@@ -554,17 +554,20 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-static int make_act_map(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boards) {
+int kv_make_act_map(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boards, int box_boards) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return kv_fail_msg(ctx, "cuTensorMapEncodeTiled unavailable");
     cuuint64_t dims[4] = {(cuuint64_t)C, 8, 8, (cuuint64_t)boards};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 16, (cuuint64_t)C * 128};
-    cuuint32_t box[4] = {64, 8, 8, 2};
+    cuuint32_t box[4] = {64, 8, 8, (cuuint32_t)box_boards};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return kv_fail_msg(ctx, "cuTensorMapEncodeTiled(activations) failed");
     return 0;
+}
+static int make_act_map(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boards) {
+    return kv_make_act_map(ctx, m, base, C, boards, 2);
 }
 static int make_w_map(kv_ctx* ctx, CUtensorMap* m, void* base, int cout, int K, int box_rows = 256) {
     PFN_encodeTiled enc = get_encode();
@@ -738,6 +741,39 @@ int kv_net_load(kv_ctx* ctx, const float* h_blob, uint64_t n_floats) {
 }
 
 }  // extern "C"
+
+// One 3x3 convolution on caller-owned NHWC bf16 tensors (the training path, kv_train.cu): the tower's CTA-pair
+// implicit-GEMM kernel with tensor maps built for this call.  y = [relu](conv(x, w) + bias [+ residual]).
+int kv_conv_launch(kv_ctx* ctx, const bf16* x, const bf16* w_packed, const float* bias, const bf16* residual, bf16* y,
+                   int n, int cin, int cout, int relu, cudaStream_t st) {
+    if (cin % 64 || cout % 256 || cin < 64) return kv_fail_msg(ctx, "conv3x3: cin must be a multiple of 64, cout of 256");
+    static bool attr_done = false;
+    if (!attr_done) {
+        KV_CUDA(ctx, cudaFuncSetAttribute(conv3x3_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_SMEM));
+        attr_done = true;
+    }
+    CUtensorMap amap, wmap;
+    if (int rc = kv_make_act_map(ctx, &amap, const_cast<bf16*>(x), cin, n, 2)) return rc;
+    if (int rc = make_w_map(ctx, &wmap, const_cast<bf16*>(w_packed), cout, 9 * cin, 128)) return rc;
+    ConvParams P;
+    P.bias = bias;
+    P.residual = residual;
+    P.out = y;
+    P.m_tiles = (n + 3) / 4;
+    P.n_tiles = cout / BN;
+    P.kb_per_tap = cin / BK;
+    P.cout = cout;
+    P.m_valid = n * 64;
+    P.relu = relu;
+    P.n_ptr = nullptr;
+    const int total = P.m_tiles * P.n_tiles;
+    const int pairs = ctx->sm_count / 2;
+    const int grid = 2 * (total < pairs ? total : pairs);
+    KvTimed t_(ctx, KVK_NET_CONV, st);
+    conv3x3_umma2_kernel<<<grid, CONV2_THREADS, CONV2_SMEM, st>>>(amap, wmap, P);
+    KV_LAUNCH_CHECK(ctx);
+    return 0;
+}
 
 // Runs stem + tower for n boards; returns the buffer index holding the final activations.
 int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, int* final_buf, int max_convs,

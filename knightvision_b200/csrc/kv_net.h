@@ -36,3 +36,9 @@ struct kv_ctx;
 // n = boards (grid sizing / upper bound); n_ptr = optional device-side count that overrides n inside the kernels
 int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, int* final_buf, int max_convs = -1,
                  const int* n_ptr = nullptr);
+
+// training path (kv_train.cu): activation tensor map over a caller-owned NHWC bf16 tensor [boards][8][8][C] with TMA
+// boxes of {64 channels, 8, 8, box_boards}; one 3x3 convolution through the tower kernel on caller-owned tensors
+int kv_make_act_map(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boards, int box_boards);
+int kv_conv_launch(kv_ctx* ctx, const __nv_bfloat16* x, const __nv_bfloat16* w_packed, const float* bias,
+                   const __nv_bfloat16* residual, __nv_bfloat16* y, int n, int cin, int cout, int relu, cudaStream_t st);

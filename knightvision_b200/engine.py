@@ -71,7 +71,7 @@ class Engine:
         return int(self._lib.kv_sm_count(self.ctx))
 
     KERNELS = ("movegen", "make_moves", "perft_expand", "perft_leaf", "encode", "net_stem", "net_conv", "net_head",
-               "mcts_select", "mcts_expand", "mcts_misc")
+               "mcts_select", "mcts_expand", "mcts_misc", "train_wgrad")
 
     def profile(self, on: bool):
         N.check(self.ctx, self._lib.kv_profile_enable(self.ctx, int(on)), "kv_profile_enable")
@@ -169,6 +169,38 @@ class Engine:
         N.check(self.ctx, self._lib.kv_net_forward_planes(self.ctx, _ptr(planes), n, _ptr(pol), _ptr(val),
                                                           self._stream()), "kv_net_forward_planes")
         return pol, val
+
+    # ---- training-side convolution operators (kv_train.cu) ------------------------------------------------------
+    def conv3x3_pack(self, weight: torch.Tensor, flip_transpose: bool = False) -> torch.Tensor:
+        """fp32 [Cout,Cin,3,3] parameter -> bf16 [Cout,9,Cin] (or the dgrad operand [Cin,9,Cout], taps mirrored)."""
+        cout, cin = int(weight.shape[0]), int(weight.shape[1])
+        w = weight.detach().to(torch.float32).contiguous()
+        out = torch.empty((cin, 9, cout) if flip_transpose else (cout, 9, cin), dtype=torch.bfloat16, device=self.device)
+        N.check(self.ctx, self._lib.kv_conv3x3_pack(self.ctx, _ptr(w), cout, cin, int(flip_transpose), _ptr(out),
+                                                    self._stream()), "kv_conv3x3_pack")
+        return out
+
+    def conv3x3_fprop(self, x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor | None = None,
+                      residual: torch.Tensor | None = None, relu: bool = False) -> torch.Tensor:
+        """x: bf16 [n,8,8,Cin] contiguous (NHWC); w_packed [Cout,9,Cin] bf16.  Returns bf16 [n,8,8,Cout]."""
+        n, cin, cout = int(x.shape[0]), int(x.shape[3]), int(w_packed.shape[0])
+        assert x.dtype == torch.bfloat16 and x.is_contiguous() and tuple(x.shape[1:3]) == (8, 8)
+        assert w_packed.dtype == torch.bfloat16 and w_packed.is_contiguous() and int(w_packed.shape[2]) == cin
+        y = torch.empty((n, 8, 8, cout), dtype=torch.bfloat16, device=self.device)
+        N.check(self.ctx, self._lib.kv_conv3x3_fprop(self.ctx, _ptr(x), _ptr(w_packed),
+                                                     _ptr(bias) if bias is not None else None,
+                                                     _ptr(residual) if residual is not None else None, _ptr(y), n, cin, cout,
+                                                     int(relu), self._stream()), "kv_conv3x3_fprop")
+        return y
+
+    def conv3x3_wgrad(self, x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+        """x bf16 [n,8,8,Cin], dy bf16 [n,8,8,Cout] (NHWC contiguous) -> fp32 [Cout,Cin,3,3]."""
+        n, cin, cout = int(x.shape[0]), int(x.shape[3]), int(dy.shape[3])
+        assert x.dtype == dy.dtype == torch.bfloat16 and x.is_contiguous() and dy.is_contiguous()
+        dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=self.device)
+        N.check(self.ctx, self._lib.kv_conv3x3_wgrad(self.ctx, _ptr(x), _ptr(dy), _ptr(dw), n, cin, cout, self._stream()),
+                "kv_conv3x3_wgrad")
+        return dw
 
     # ---- self-play search ---------------------------------------------------------------------------
     def mcts_create(self, n_games: int, sims: int, max_plies: int, temp_plies: int = 30, c_puct: float = 1.5,

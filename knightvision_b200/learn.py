@@ -5,9 +5,9 @@
 
 Self-play runs on the B200 engine (knightvision_b200.selfplay); its records stay on the GPU in packed form
 (12 bitboards + move + reward = 104 B per position instead of the reference's 3 080 B float planes) and are expanded
-to planes batch by batch with the encode kernel.  The training step itself is ordinary PyTorch autograd on the
-`ChessNet` parameter container (the reference's trainer is ordinary PyTorch too; it is not part of the hand-written
-hot path): loss = cross-entropy(policy, move) + MSE(value, reward) - 0.01 * entropy (train.py:167-174), gradient
+to planes batch by batch with the encode kernel.  The training step is PyTorch autograd over the
+`ChessNet` parameter container, with the tower's 3x3 convolutions (99.8 % of the FLOPs) running forward, dgrad and
+wgrad on the hand-written tcgen05 kernels (train_ops.py / csrc/kv_train.cu; KV_TRAIN_NATIVE=0 selects cuDNN): loss = cross-entropy(policy, move) + MSE(value, reward) - 0.01 * entropy (train.py:167-174), gradient
 clipping at 1.0 and accumulation over 2 batches (train.py:183-190), bf16 autocast instead of fp16 + GradScaler.
 With torch.distributed initialised (one process per GPU), gradients are averaged by DistributedDataParallel over
 NCCL and every rank plays its own shard of the games.
@@ -23,6 +23,7 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import train_ops as T
 from .model import ChessNet
 from .selfplay import SelfPlay, engine_for
 
@@ -31,20 +32,31 @@ ENTROPY_COEF = 0.01
 
 
 class TrainGraph(nn.Module):
-    """Autograd graph of ai/model.py:51-77 over a ChessNet's parameters (train-mode BatchNorm)."""
+    """Autograd graph of ai/model.py:51-77 over a ChessNet's parameters (train-mode BatchNorm).
 
-    def __init__(self, net: ChessNet):
+    With `engine` given (the default on CUDA), the tower's 3x3 convolutions run forward, dgrad and wgrad on the
+    tcgen05 kernels (train_ops.conv3x3_b200); otherwise they are torch/cuDNN convolutions (the comparison arm)."""
+
+    def __init__(self, net: ChessNet, engine=None):
         super().__init__()
         self.net = net
+        self.engine = engine
+
+    def _conv(self, m, h):
+        if self.engine is not None and T.supported(m.in_channels, m.out_channels):
+            return T.conv3x3_b200(h, m.weight, m.bias, self.engine)
+        return m(h)
 
     def forward(self, x):
         n = self.net
         h = F.relu(n.bn1(n.conv1(x)))
+        if self.engine is not None:
+            h = h.contiguous(memory_format=torch.channels_last)
         if n.arch[3]:
-            h = F.relu(n.bn2(n.conv2(h)))
+            h = F.relu(n.bn2(self._conv(n.conv2, h)))
         for b in n.res_blocks:
-            t = F.relu(b.bn1(b.conv1(h)))
-            h = F.relu(b.bn2(b.conv2(t)) + h)
+            t = F.relu(b.bn1(self._conv(b.conv1, h)))
+            h = F.relu(b.bn2(self._conv(b.conv2, t)) + h)
         p = n.policy_fc(F.relu(n.policy_bn(n.policy_conv(h))).flatten(1))
         v = F.relu(n.value_bn(n.value_conv(h))).flatten(1)
         v = torch.tanh(n.value_fc2(F.relu(n.value_fc1(v))))
@@ -91,7 +103,7 @@ class ReplayData:
 
 def train_epochs(net: ChessNet, optimizer, data: ReplayData, epochs: int, batch_size: int, accumulate_steps: int = 2):
     """scripts/train.py:126-196 without the logging side channels.  Returns the mean loss of the last epoch."""
-    graph = TrainGraph(net)
+    graph = TrainGraph(net, engine=data.eng if os.getenv("KV_TRAIN_NATIVE", "1") != "0" else None)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         graph = nn.parallel.DistributedDataParallel(graph, device_ids=[data.eng.index])
     net.train()

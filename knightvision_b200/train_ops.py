@@ -1,0 +1,65 @@
+"""Training-side 3x3 convolution of the policy/value tower as an autograd function over the sm_100a kernels.
+
+The reference trains `ai/model.py` under autocast with cuDNN convolutions (scripts/train.py:158-181).  Here the tower
+convolutions (99.8 % of the FLOPs) run on the hand-written tcgen05 kernels in all three directions:
+
+    forward   y  = conv(x, W) + b        kv_conv3x3_fprop  (the self-play tower kernel on caller-owned tensors)
+    dgrad     dx = conv(dy, W')          the same kernel on the flip-transposed weights (kv_conv3x3_pack)
+    wgrad     dW = x (*) dy              kv_conv3x3_wgrad  (MN-major tcgen05 operands straight from NHWC, split-K)
+
+Activations are bf16 in NHWC memory (torch channels_last), accumulation is fp32, the parameter and its gradient stay
+fp32 — the bf16 analogue of the reference's fp16 autocast.  BatchNorm (batch statistics), ReLU, the residual add, the
+12-channel stem and the heads stay ordinary PyTorch: they are memory-bound elementwise / tiny ops.
+There is no CPU path: the function raises without the CUDA library.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def _nhwc(t: torch.Tensor) -> torch.Tensor:
+    """Logical NCHW tensor -> contiguous bf16 [N,8,8,C] view (copying only if it is not channels_last bf16 already)."""
+    t = t.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    v = t.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+class _Conv3x3B200(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, weight, bias, eng):
+        xh = _nhwc(x)
+        y = eng.conv3x3_fprop(xh, eng.conv3x3_pack(weight), bias.detach().float().contiguous() if bias is not None else None)
+        ctx.save_for_backward(xh, weight)
+        ctx.eng = eng
+        ctx.has_bias = bias is not None
+        return y.permute(0, 3, 1, 2)          # logical NCHW, channels_last memory
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_out):
+        xh, weight = ctx.saved_tensors
+        eng = ctx.eng
+        gy = _nhwc(grad_out)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = eng.conv3x3_fprop(gy, eng.conv3x3_pack(weight, flip_transpose=True)).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            dw = eng.conv3x3_wgrad(xh, gy).to(weight.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = gy.float().sum(dim=(0, 1, 2))
+        return dx, dw, db, None
+
+
+def conv3x3_b200(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None, eng) -> torch.Tensor:
+    """3x3 / padding 1 convolution of a [N,C,8,8] CUDA tensor through the B200 kernels, differentiable in x, weight, bias."""
+    if not x.is_cuda:
+        raise RuntimeError("conv3x3_b200 needs CUDA tensors (knightvision_b200 has no CPU fallback)")
+    if tuple(x.shape[2:]) != (8, 8) or tuple(weight.shape[2:]) != (3, 3):
+        raise ValueError("conv3x3_b200: expects [N,C,8,8] inputs and [Cout,Cin,3,3] weights")
+    return _Conv3x3B200.apply(x, weight, bias, eng)
+
+
+def supported(cin: int, cout: int) -> bool:
+    """Channel counts the three kernels accept (the tower layers: 256 / 512 channels)."""
+    return cin % 256 == 0 and cout % 256 == 0 and cin <= 512 and cout <= 512

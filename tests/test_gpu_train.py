@@ -1,0 +1,123 @@
+"""Training-side convolution operators on the B200 against plain PyTorch fp32 of the same op
+(`F.conv2d` and its input / weight gradients): fprop, dgrad and the MN-major tcgen05 wgrad kernel, the autograd
+function built from them, and one optimisation step of the reference's loss (scripts/train.py:158-190) through them.
+Tolerances: outputs are bf16 (rel 2^-8 per element) with fp32 accumulation; wgrad is fp32 end to end."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from knightvision_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _rel(a, r):
+    return ((a.float() - r).abs().max() / r.abs().max()).item()
+
+
+@pytest.mark.parametrize("n,cin,cout", [(1, 256, 256), (6, 256, 512), (101, 512, 512), (300, 512, 256)])
+def test_fprop_dgrad_wgrad_match_torch_fp32(eng, n, cin, cout):
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = (torch.randn(n, 8, 8, cin, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    dy = (torch.randn(n, 8, 8, cout, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * 0.02
+    b = torch.randn(cout, device="cuda", generator=g) * 0.1
+    wb = w.to(torch.bfloat16).float()                       # the kernels see the bf16-rounded parameter
+    xf, dyf = x.float().permute(0, 3, 1, 2), dy.float().permute(0, 3, 1, 2)
+    ref_y = F.conv2d(xf, wb, b, padding=1).permute(0, 2, 3, 1)
+    ref_dx = torch.nn.grad.conv2d_input(xf.shape, wb, dyf, padding=1).permute(0, 2, 3, 1)
+    ref_dw = torch.nn.grad.conv2d_weight(xf, w.shape, dyf, padding=1)
+    y = eng.conv3x3_fprop(x, eng.conv3x3_pack(w), b)
+    dx = eng.conv3x3_fprop(dy, eng.conv3x3_pack(w, flip_transpose=True))
+    dw = eng.conv3x3_wgrad(x, dy)
+    assert y.shape == (n, 8, 8, cout) and dx.shape == (n, 8, 8, cin) and dw.shape == (cout, cin, 3, 3)
+    assert _rel(y, ref_y) < 8e-3 and _rel(dx, ref_dx) < 8e-3        # bf16 output rounding
+    assert _rel(dw, ref_dw) < 1e-4                                   # fp32 accumulate, fp32 out
+    # relu / residual epilogue flags on caller-owned tensors
+    res = (torch.randn(n, 8, 8, cout, device="cuda", generator=g)).to(torch.bfloat16)
+    y2 = eng.conv3x3_fprop(x, eng.conv3x3_pack(w), b, residual=res, relu=True)
+    assert _rel(y2, F.relu(ref_y + res.float())) < 8e-3
+    # deterministic: split-K partials are added in a fixed order
+    assert torch.equal(dw, eng.conv3x3_wgrad(x, dy))
+
+
+def test_wgrad_taps_and_borders_exact(eng):
+    """Integer-valued inputs make every product and partial sum exact in fp32: the nine taps, the zero padding at the
+    board edges and the split-K reduction must then reproduce torch bit for bit."""
+    n, cin, cout = 37, 256, 256
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randint(-2, 3, (n, 8, 8, cin), device="cuda", generator=g).to(torch.bfloat16)
+    dy = torch.randint(-2, 3, (n, 8, 8, cout), device="cuda", generator=g).to(torch.bfloat16)
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, 3, 3), dy.float().permute(0, 3, 1, 2),
+                                      padding=1)
+    assert torch.equal(eng.conv3x3_wgrad(x, dy), ref)
+    w = torch.randint(-1, 2, (cout, cin, 3, 3), device="cuda", generator=g).float()
+    refx = torch.nn.grad.conv2d_input((n, cout, 8, 8)[:1] + (cin, 8, 8), w, dy.float().permute(0, 3, 1, 2), padding=1)
+    dx = eng.conv3x3_fprop(dy, eng.conv3x3_pack(w, flip_transpose=True))
+    # |dx| <= 2 * 9 * 256 = 4608 would not fit bf16 exactly; compare after the same rounding
+    assert torch.equal(dx.float(), refx.permute(0, 2, 3, 1).to(torch.bfloat16).float())
+
+
+def test_autograd_function_matches_torch(eng):
+    from knightvision_b200.train_ops import conv3x3_b200
+    torch.manual_seed(1)
+    n = 48
+    x0 = torch.randn(n, 256, 8, 8, device="cuda")
+    w1 = (torch.randn(512, 256, 3, 3, device="cuda") * 0.02).requires_grad_()
+    b1 = (torch.randn(512, device="cuda") * 0.1).requires_grad_()
+    w2 = (torch.randn(512, 512, 3, 3, device="cuda") * 0.02).requires_grad_()
+    tgt = torch.randn(n, 512, 8, 8, device="cuda")
+
+    def run(conv):
+        x = x0.clone().requires_grad_()
+        h = F.relu(conv(x, w1, b1))
+        y = conv(h, w2, None)
+        loss = ((y.float() - tgt) ** 2).mean()
+        gx, g1, gb, g2 = torch.autograd.grad(loss, (x, w1, b1, w2))
+        return loss.item(), gx, g1, gb, g2
+
+    ref = run(lambda x, w, b: F.conv2d(x, w, b, padding=1))                       # plain fp32
+    def cudnn_bf16(x, w, b):                                                     # what autocast would run
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return F.conv2d(x, w, b, padding=1)
+    lib = run(cudnn_bf16)
+    got = run(lambda x, w, b: conv3x3_b200(x, w, b, eng))
+    assert abs(got[0] - ref[0]) < 5e-3 * abs(ref[0])
+    for a, r, l in zip(got[1:], ref[1:], lib[1:]):
+        assert a.shape == r.shape
+        # two bf16 layers deep with bf16 gradients: no further from fp32 than the library's bf16 path is (x 1.5 + eps)
+        assert _rel(a, r) < max(1.5 * _rel(l, r), 1e-2), (_rel(a, r), _rel(l, r))
+
+
+def test_training_step_native_vs_cudnn(eng, monkeypatch):
+    """One optimisation step of the reference loss on the 20x256-style tower (2 blocks here) with the tower convolutions
+    on the tcgen05 kernels vs on cuDNN: same loss and the same parameter update within bf16 noise."""
+    from knightvision_b200 import learn as LR
+    from knightvision_b200.model import ChessNet
+    from knightvision_b200 import layout as L
+    torch.manual_seed(7)
+    lines = torch.from_numpy(np.stack([L.start_line()] * 96).view(np.int64)).cuda()
+    moves = torch.randint(0, 4096, (96,), device="cuda")
+    rewards = torch.tensor([1.0, 0.2, -1.0] * 32, device="cuda")
+    results = {}
+    for native in ("1", "0"):
+        monkeypatch.setenv("KV_TRAIN_NATIVE", native)
+        torch.manual_seed(3)
+        net = ChessNet(stem=256, tower=256, blocks=2, conv2=False, max_batch=96).cuda()
+        opt = torch.optim.SGD(net.parameters(), lr=0.05)
+        data = LR.ReplayData(eng)
+        data.extend_packed(lines, moves, rewards)
+        l0 = eng.launches
+        loss = LR.train_epochs(net, opt, data, epochs=1, batch_size=96, accumulate_steps=1)
+        results[native] = (loss, net.weight_blob().clone(), eng.launches - l0)
+    assert np.isfinite(results["1"][0]) and abs(results["1"][0] - results["0"][0]) < 2e-2 * abs(results["0"][0])
+    assert results["1"][2] >= 4 * 3 and results["0"][2] == 1          # 4 tower convs x (fprop, dgrad, wgrad) + encode
+    d = (results["1"][1] - results["0"][1]).abs().max().item()
+    assert d < 5e-3, d
