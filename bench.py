@@ -7,8 +7,8 @@ One process per GPU (torchrun for N > 1; RANK/LOCAL_RANK/WORLD_SIZE from the env
 Workloads:
   perft  BASELINE.json configs[1]: perft over 65 536 boards per launch (start position + the reference's six test
          positions, tiled), depth 3.  metric = perft leaf nodes/s.
-  mcts   BASELINE.json configs[2]: 4 096 concurrent games per GPU, PUCT self-play with the reference net
-         (enabled once the net + tree kernels are built; see knightvision_b200/selfplay.py).
+  mcts   BASELINE.json configs[2]: 4 096 concurrent games per GPU, PUCT self-play with the reference net (default).
+  train  BASELINE.json configs[4]: the training step of the learn loop on the 20 x 256 tower (bench_train.py).
 `--impl reference` times the CPU implementation of the same path (the oracle port, all host cores) on a bounded
 sample of the same workload.
 """
@@ -146,6 +146,10 @@ def run_reference(args, rank, world):
                 "e2e": {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
+    if args.workload == "train":
+        import bench_train
+        bench_train.run_reference(args)
+        return
     import bench_mcts
     bench_mcts.run_reference(args)
 
@@ -254,7 +258,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None, choices=["mcts", "perft"])
+    ap.add_argument("--workload", default=None, choices=["mcts", "perft", "train"])
     args, _ = ap.parse_known_args()
     if args.workload is None:
         args.workload = "mcts" if os.path.exists(os.path.join(ROOT, "bench_mcts.py")) else "perft"
@@ -275,6 +279,9 @@ def main():
     try:
         if args.workload == "perft":
             run_perft(args, rank, world, local_rank)
+        elif args.workload == "train":
+            import bench_train
+            bench_train.run(args, rank, world, local_rank)
         else:
             import bench_mcts
             bench_mcts.run(args, rank, world, local_rank)

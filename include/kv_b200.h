@@ -183,6 +183,22 @@ KV_API int kv_conv3x3_fprop(kv_ctx* ctx, const void* d_x, const void* d_w_packed
 KV_API int kv_conv3x3_wgrad(kv_ctx* ctx, const void* d_x, const void* d_dy, float* d_dw, int n_boards, int cin, int cout,
                             void* stream);
 
+/* Train-mode BatchNorm2d + ReLU (+ residual add) on NHWC bf16 [rows = boards * 64][C] (ai/model.py:19-25,58-59 under
+ * scripts/train.py:158-181; torch.nn.BatchNorm2d semantics: batch statistics with biased variance, running statistics
+ * updated with `momentum` and the unbiased variance, eps inside the square root).  C in {64,128,256,512,1024}.
+ *   fwd  y = [relu](gamma * (z - mean) * rstd + beta [+ residual]); writes save_mean / save_rstd [C] for the backward;
+ *        running_mean / running_var may be NULL
+ *   bwd  g = dy * [y > 0]; dgamma = sum g * zhat; dbeta = sum g; dz = gamma * rstd * (g - dbeta/N - zhat * dgamma/N);
+ *        d_dres (nullable) receives g, the gradient of the residual input.  Reductions are deterministic.
+ *   kv_channel_sum  out[c] = sum over rows of x[r][c] (the convolution-bias gradient) */
+KV_API int kv_bn_relu_fwd(kv_ctx* ctx, const void* d_z, const void* d_residual, const float* d_gamma, const float* d_beta,
+                          float* d_running_mean, float* d_running_var, float momentum, float eps, void* d_y,
+                          float* d_save_mean, float* d_save_rstd, int rows, int C, int relu, void* stream);
+KV_API int kv_bn_relu_bwd(kv_ctx* ctx, const void* d_dy, const void* d_y, const void* d_z, const float* d_gamma,
+                          const float* d_save_mean, const float* d_save_rstd, void* d_dz, void* d_dres, float* d_dgamma,
+                          float* d_dbeta, int rows, int C, int relu, void* stream);
+KV_API int kv_channel_sum(kv_ctx* ctx, const void* d_x, float* d_out, int rows, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

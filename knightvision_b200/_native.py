@@ -46,6 +46,11 @@ SIGNATURES = {
     "kv_conv3x3_fprop": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                  c_void_p]),
     "kv_conv3x3_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "kv_bn_relu_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_float,
+                               ctypes.c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "kv_bn_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "kv_channel_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "kv_mcts_create_k": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float,
                                  ctypes.c_float, c_u64, c_int, c_int]),
     "kv_mcts_waves": (ctypes.c_int64, [c_void_p]),

@@ -72,6 +72,7 @@ void kv_destroy(kv_ctx* ctx) {
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->train_ws) cudaFree(ctx->train_ws);
     if (ctx->train_zeros) cudaFree(ctx->train_zeros);
+    if (ctx->bn_ws) cudaFree(ctx->bn_ws);
     for (auto& p : ctx->ev_live) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto& p : ctx->ev_free) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     delete ctx;

@@ -15,7 +15,7 @@ struct kv_mcts;   // kv_mcts.cu
 // kernel categories for the optional per-kernel CUDA-event timing (kv_profile_*)
 enum KvKernel : int {
     KVK_MOVEGEN = 0, KVK_MAKE_MOVES, KVK_PERFT_EXPAND, KVK_PERFT_LEAF, KVK_ENCODE,
-    KVK_NET_STEM, KVK_NET_CONV, KVK_NET_HEAD, KVK_MCTS_SELECT, KVK_MCTS_EXPAND, KVK_MCTS_MISC, KVK_TRAIN_WGRAD, KVK_COUNT
+    KVK_NET_STEM, KVK_NET_CONV, KVK_NET_HEAD, KVK_MCTS_SELECT, KVK_MCTS_EXPAND, KVK_MCTS_MISC, KVK_TRAIN_WGRAD, KVK_TRAIN_BN, KVK_COUNT
 };
 
 struct KvEventPair {
@@ -49,6 +49,8 @@ struct kv_ctx {
     float* train_ws = nullptr;
     size_t train_ws_floats = 0;
     float* train_zeros = nullptr;
+    float* bn_ws = nullptr;          // per-CTA partial sums of the BatchNorm reductions (kv_bn.cu)
+    size_t bn_ws_floats = 0;
 };
 
 extern std::string g_kv_create_error;

@@ -71,7 +71,7 @@ class Engine:
         return int(self._lib.kv_sm_count(self.ctx))
 
     KERNELS = ("movegen", "make_moves", "perft_expand", "perft_leaf", "encode", "net_stem", "net_conv", "net_head",
-               "mcts_select", "mcts_expand", "mcts_misc", "train_wgrad")
+               "mcts_select", "mcts_expand", "mcts_misc", "train_wgrad", "train_bn")
 
     def profile(self, on: bool):
         N.check(self.ctx, self._lib.kv_profile_enable(self.ctx, int(on)), "kv_profile_enable")
@@ -201,6 +201,41 @@ class Engine:
         N.check(self.ctx, self._lib.kv_conv3x3_wgrad(self.ctx, _ptr(x), _ptr(dy), _ptr(dw), n, cin, cout, self._stream()),
                 "kv_conv3x3_wgrad")
         return dw
+
+    def bn_relu_fwd(self, z: torch.Tensor, gamma, beta, running_mean, running_var, momentum: float, eps: float,
+                    residual: torch.Tensor | None = None, relu: bool = True):
+        """Train-mode BatchNorm + ReLU (+ residual) on NHWC bf16 [n,8,8,C]; returns (y, save_mean, save_rstd)."""
+        C = int(z.shape[-1]); rows = z.numel() // C
+        assert z.dtype == torch.bfloat16 and z.is_contiguous()
+        y = torch.empty_like(z)
+        mean = torch.empty(C, dtype=torch.float32, device=self.device)
+        rstd = torch.empty(C, dtype=torch.float32, device=self.device)
+        N.check(self.ctx, self._lib.kv_bn_relu_fwd(
+            self.ctx, _ptr(z), _ptr(residual) if residual is not None else None, _ptr(gamma), _ptr(beta),
+            _ptr(running_mean) if running_mean is not None else None, _ptr(running_var) if running_var is not None else None,
+            momentum, eps, _ptr(y), _ptr(mean), _ptr(rstd), rows, C, int(relu), self._stream()), "kv_bn_relu_fwd")
+        return y, mean, rstd
+
+    def bn_relu_bwd(self, dy, y, z, gamma, mean, rstd, relu: bool = True, want_dres: bool = False):
+        """Returns (dz bf16, dres bf16 or None, dgamma fp32, dbeta fp32)."""
+        C = int(z.shape[-1]); rows = z.numel() // C
+        assert dy.dtype == torch.bfloat16 and dy.is_contiguous() and y.is_contiguous() and z.is_contiguous()
+        dz = torch.empty_like(z)
+        dres = torch.empty_like(z) if want_dres else None
+        dg = torch.empty(C, dtype=torch.float32, device=self.device)
+        db = torch.empty(C, dtype=torch.float32, device=self.device)
+        N.check(self.ctx, self._lib.kv_bn_relu_bwd(self.ctx, _ptr(dy), _ptr(y), _ptr(z), _ptr(gamma), _ptr(mean), _ptr(rstd),
+                                                   _ptr(dz), _ptr(dres) if dres is not None else None, _ptr(dg), _ptr(db),
+                                                   rows, C, int(relu), self._stream()), "kv_bn_relu_bwd")
+        return dz, dres, dg, db
+
+    def channel_sum(self, x: torch.Tensor) -> torch.Tensor:
+        """fp32 [C] column sums of an NHWC bf16 tensor (the convolution-bias gradient)."""
+        C = int(x.shape[-1]); rows = x.numel() // C
+        assert x.dtype == torch.bfloat16 and x.is_contiguous()
+        out = torch.empty(C, dtype=torch.float32, device=self.device)
+        N.check(self.ctx, self._lib.kv_channel_sum(self.ctx, _ptr(x), _ptr(out), rows, C, self._stream()), "kv_channel_sum")
+        return out
 
     # ---- self-play search ---------------------------------------------------------------------------
     def mcts_create(self, n_games: int, sims: int, max_plies: int, temp_plies: int = 30, c_puct: float = 1.5,

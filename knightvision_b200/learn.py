@@ -35,7 +35,8 @@ class TrainGraph(nn.Module):
     """Autograd graph of ai/model.py:51-77 over a ChessNet's parameters (train-mode BatchNorm).
 
     With `engine` given (the default on CUDA), the tower's 3x3 convolutions run forward, dgrad and wgrad on the
-    tcgen05 kernels (train_ops.conv3x3_b200); otherwise they are torch/cuDNN convolutions (the comparison arm)."""
+    tcgen05 kernels (train_ops.conv3x3_b200) and BatchNorm + ReLU (+ residual) on the fused NHWC kernels
+    (train_ops.bn_relu_b200); otherwise everything is torch/cuDNN (the comparison arm)."""
 
     def __init__(self, net: ChessNet, engine=None):
         super().__init__()
@@ -47,16 +48,22 @@ class TrainGraph(nn.Module):
             return T.conv3x3_b200(h, m.weight, m.bias, self.engine)
         return m(h)
 
+    def _bnrelu(self, bn, z, residual=None):
+        if self.engine is not None and bn.training and T.bn_supported(bn.num_features):
+            return T.bn_relu_b200(z, bn, self.engine, residual=residual)
+        return F.relu(bn(z) if residual is None else bn(z) + residual)
+
     def forward(self, x):
         n = self.net
-        h = F.relu(n.bn1(n.conv1(x)))
+        h = n.conv1(x)
         if self.engine is not None:
             h = h.contiguous(memory_format=torch.channels_last)
+        h = self._bnrelu(n.bn1, h)
         if n.arch[3]:
-            h = F.relu(n.bn2(self._conv(n.conv2, h)))
+            h = self._bnrelu(n.bn2, self._conv(n.conv2, h))
         for b in n.res_blocks:
-            t = F.relu(b.bn1(self._conv(b.conv1, h)))
-            h = F.relu(b.bn2(self._conv(b.conv2, t)) + h)
+            t = self._bnrelu(b.bn1, self._conv(b.conv1, h))
+            h = self._bnrelu(b.bn2, self._conv(b.conv2, t), residual=h)
         p = n.policy_fc(F.relu(n.policy_bn(n.policy_conv(h))).flatten(1))
         v = F.relu(n.value_bn(n.value_conv(h))).flatten(1)
         v = torch.tanh(n.value_fc2(F.relu(n.value_fc1(v))))

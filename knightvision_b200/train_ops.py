@@ -8,8 +8,10 @@ convolutions (99.8 % of the FLOPs) run on the hand-written tcgen05 kernels in al
     wgrad     dW = x (*) dy              kv_conv3x3_wgrad  (MN-major tcgen05 operands straight from NHWC, split-K)
 
 Activations are bf16 in NHWC memory (torch channels_last), accumulation is fp32, the parameter and its gradient stay
-fp32 — the bf16 analogue of the reference's fp16 autocast.  BatchNorm (batch statistics), ReLU, the residual add, the
-12-channel stem and the heads stay ordinary PyTorch: they are memory-bound elementwise / tiny ops.
+fp32 — the bf16 analogue of the reference's fp16 autocast.  Train-mode BatchNorm + ReLU (+ the residual add) is one
+fused forward and one fused backward operator over the same NHWC bf16 tensors (csrc/kv_bn.cu: HBM-bound passes,
+deterministic two-stage reductions).  The 12-channel stem convolution, the heads, the loss and the optimizer stay
+ordinary PyTorch (0.2 % of the FLOPs).
 There is no CPU path: the function raises without the CUDA library.
 """
 from __future__ import annotations
@@ -47,7 +49,7 @@ class _Conv3x3B200(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = eng.conv3x3_wgrad(xh, gy).to(weight.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = gy.float().sum(dim=(0, 1, 2))
+            db = eng.channel_sum(gy)
         return dx, dw, db, None
 
 
@@ -58,6 +60,47 @@ def conv3x3_b200(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | Non
     if tuple(x.shape[2:]) != (8, 8) or tuple(weight.shape[2:]) != (3, 3):
         raise ValueError("conv3x3_b200: expects [N,C,8,8] inputs and [Cout,Cin,3,3] weights")
     return _Conv3x3B200.apply(x, weight, bias, eng)
+
+
+class _BNReLUB200(torch.autograd.Function):
+    """Train-mode BatchNorm2d + ReLU (+ residual add), csrc/kv_bn.cu.  Inputs/outputs are logical NCHW tensors in
+    channels_last bf16 memory; gamma/beta and their gradients are fp32."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, z, gamma, beta, residual, eng, running_mean, running_var, momentum, eps, relu):
+        zh = _nhwc(z)
+        rh = _nhwc(residual) if residual is not None else None
+        g = gamma.detach().float().contiguous()
+        y, mean, rstd = eng.bn_relu_fwd(zh, g, beta.detach().float().contiguous(), running_mean, running_var, momentum, eps,
+                                        residual=rh, relu=relu)
+        ctx.save_for_backward(zh, y, g, mean, rstd)
+        ctx.eng, ctx.relu, ctx.has_res = eng, relu, residual is not None
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_out):
+        zh, y, g, mean, rstd = ctx.saved_tensors
+        dz, dres, dgamma, dbeta = ctx.eng.bn_relu_bwd(_nhwc(grad_out), y, zh, g, mean, rstd, relu=ctx.relu,
+                                                      want_dres=ctx.has_res and ctx.needs_input_grad[3])
+        return (dz.permute(0, 3, 1, 2), dgamma, dbeta, dres.permute(0, 3, 1, 2) if dres is not None else None,
+                None, None, None, None, None, None)
+
+
+def bn_relu_b200(z: torch.Tensor, bn: torch.nn.BatchNorm2d, eng, residual: torch.Tensor | None = None, relu: bool = True):
+    """relu(bn(z) [+ residual]) with batch statistics, updating bn.running_mean / running_var / num_batches_tracked as
+    torch.nn.BatchNorm2d does in training mode."""
+    if not bn.training or not bn.track_running_stats or bn.momentum is None:
+        raise RuntimeError("bn_relu_b200 implements training-mode BatchNorm2d with a fixed momentum")
+    with torch.no_grad():
+        bn.num_batches_tracked += 1
+    return _BNReLUB200.apply(z, bn.weight, bn.bias, residual, eng, bn.running_mean, bn.running_var, float(bn.momentum),
+                             float(bn.eps), relu)
+
+
+def bn_supported(C: int) -> bool:
+    return C in (64, 128, 256, 512, 1024)
 
 
 def supported(cin: int, cout: int) -> bool:
