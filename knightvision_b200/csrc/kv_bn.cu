@@ -126,24 +126,35 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(const bf16* __res
     }
 }
 
-// Second reduction stage.  CTA = 32 channels x 8 slices of the partial list; slice p adds partials p, p + 8, ... in
-// fp64, then the 8 slice sums are added in slice order: deterministic, and 8x shorter dependency chains.
+// Second reduction stage.  CTA = 8 channels x 32 slices of the partial list; slice p adds partials p, p + 32, ... in
+// fp64 (all its loads issued first), then the 32 slice sums are added in slice order: deterministic, short dependency
+// chains, and C / 8 CTAs instead of a handful.
 constexpr int FIN_THREADS = 256;
+constexpr int FIN_CH = 8, FIN_SLICES = FIN_THREADS / FIN_CH;   // 32
+constexpr int FIN_MAX_TRIPS = 24;                              // up to 32 * 24 = 768 partials (grid <= 4 * 148 = 592)
 __device__ __forceinline__ void sum_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s, double& q,
-                                             double (*sh)[2][32]) {
-    const int part = threadIdx.x >> 5, cl = threadIdx.x & 31;
+                                             double (*sh)[2][FIN_CH]) {
+    const int part = threadIdx.x / FIN_CH, cl = threadIdx.x % FIN_CH;
+    float va[FIN_MAX_TRIPS], vb[FIN_MAX_TRIPS];
+#pragma unroll
+    for (int u = 0; u < FIN_MAX_TRIPS; u++) {
+        const int k = part + FIN_SLICES * u;
+        const bool ok = c < C && k < nblk;
+        va[u] = ok ? __ldg(partial + ((size_t)k * 2 + 0) * C + c) : 0.f;
+        vb[u] = ok ? __ldg(partial + ((size_t)k * 2 + 1) * C + c) : 0.f;
+    }
     double a = 0.0, b = 0.0;
-    if (c < C)
-        for (int k = part; k < nblk; k += 8) {
-            a += (double)partial[((size_t)k * 2 + 0) * C + c];
-            b += (double)partial[((size_t)k * 2 + 1) * C + c];
-        }
+#pragma unroll
+    for (int u = 0; u < FIN_MAX_TRIPS; u++) {
+        a += (double)va[u];
+        b += (double)vb[u];
+    }
     sh[part][0][cl] = a;
     sh[part][1][cl] = b;
     __syncthreads();
     s = 0.0;
     q = 0.0;
-    for (int p = 0; p < 8; p++) {
+    for (int p = 0; p < FIN_SLICES; p++) {
         s += sh[p][0][cl];
         q += sh[p][1][cl];
     }
@@ -156,11 +167,11 @@ __global__ void __launch_bounds__(FIN_THREADS) bn_fwd_finalize_kernel(const floa
                                                                       float* __restrict__ save_rstd,
                                                                       float* __restrict__ running_mean,
                                                                       float* __restrict__ running_var) {
-    __shared__ double sh[8][2][32];
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    __shared__ double sh[FIN_SLICES][2][FIN_CH];
+    const int c = blockIdx.x * FIN_CH + (threadIdx.x % FIN_CH);
     double s, q;
     sum_partials(partial, nblk, C, c, s, q, sh);
-    if (threadIdx.x >= 32 || c >= C) return;
+    if (threadIdx.x >= FIN_CH || c >= C) return;
     const double n = (double)rows;
     const double m = s / n;
     double var = q / n - m * m;
@@ -177,11 +188,11 @@ __global__ void __launch_bounds__(FIN_THREADS) bn_fwd_finalize_kernel(const floa
 // sums of the partials -> out0 / out1 (either may be null)
 __global__ void __launch_bounds__(FIN_THREADS) bn_sum_partials_kernel(const float* __restrict__ partial, int nblk, int C,
                                                                       float* __restrict__ out0, float* __restrict__ out1) {
-    __shared__ double sh[8][2][32];
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    __shared__ double sh[FIN_SLICES][2][FIN_CH];
+    const int c = blockIdx.x * FIN_CH + (threadIdx.x % FIN_CH);
     double s, q;
     sum_partials(partial, nblk, C, c, s, q, sh);
-    if (threadIdx.x >= 32 || c >= C) return;
+    if (threadIdx.x >= FIN_CH || c >= C) return;
     if (out0) out0[c] = (float)s;
     if (out1) out1[c] = (float)q;
 }
@@ -300,6 +311,7 @@ using namespace kvb;
 static int bn_grid(kv_ctx* ctx, int rows, int C) {
     const int rpi = BN_THREADS / (C >> 3);
     int g = ctx->sm_count * 4;
+    if (g > FIN_SLICES * FIN_MAX_TRIPS) g = FIN_SLICES * FIN_MAX_TRIPS;   // what the second stage reads
     const int need = (rows + rpi - 1) / rpi;
     if (g > need) g = need;
     return g < 1 ? 1 : g;
@@ -337,7 +349,7 @@ int kv_bn_relu_fwd(kv_ctx* ctx, const void* d_z, const void* d_residual, const f
     bn_reduce_kernel<0><<<grid, BN_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(d_z), nullptr, nullptr, nullptr, nullptr,
                                                      rows, C, 0, ctx->bn_ws);
     KV_LAUNCH_CHECK(ctx);
-    bn_fwd_finalize_kernel<<<(C + 31) / 32, FIN_THREADS, 0, st>>>(ctx->bn_ws, grid, C, rows, momentum, eps, d_save_mean, d_save_rstd,
+    bn_fwd_finalize_kernel<<<(C + FIN_CH - 1) / FIN_CH, FIN_THREADS, 0, st>>>(ctx->bn_ws, grid, C, rows, momentum, eps, d_save_mean, d_save_rstd,
                                                             d_running_mean, d_running_var);
     KV_LAUNCH_CHECK(ctx);
     const size_t n8 = (size_t)rows * C / 8;
@@ -364,7 +376,7 @@ int kv_bn_relu_bwd(kv_ctx* ctx, const void* d_dy, const void* d_y, const void* d
                                                      reinterpret_cast<const bf16*>(d_z), d_save_mean, d_save_rstd, rows, C, relu,
                                                      ctx->bn_ws);
     KV_LAUNCH_CHECK(ctx);
-    bn_sum_partials_kernel<<<(C + 31) / 32, FIN_THREADS, 0, st>>>(ctx->bn_ws, grid, C, d_dbeta, d_dgamma);
+    bn_sum_partials_kernel<<<(C + FIN_CH - 1) / FIN_CH, FIN_THREADS, 0, st>>>(ctx->bn_ws, grid, C, d_dbeta, d_dgamma);
     KV_LAUNCH_CHECK(ctx);
     const size_t n8 = (size_t)rows * C / 8;
     size_t ag = (n8 + BN_THREADS - 1) / BN_THREADS;
@@ -388,7 +400,7 @@ int kv_channel_sum(kv_ctx* ctx, const void* d_x, float* d_out, int rows, int C, 
     bn_reduce_kernel<2><<<grid, BN_THREADS, 0, st>>>(reinterpret_cast<const bf16*>(d_x), nullptr, nullptr, nullptr, nullptr, rows,
                                                      C, 0, ctx->bn_ws);
     KV_LAUNCH_CHECK(ctx);
-    bn_sum_partials_kernel<<<(C + 31) / 32, FIN_THREADS, 0, st>>>(ctx->bn_ws, grid, C, d_out, nullptr);
+    bn_sum_partials_kernel<<<(C + FIN_CH - 1) / FIN_CH, FIN_THREADS, 0, st>>>(ctx->bn_ws, grid, C, d_out, nullptr);
     KV_LAUNCH_CHECK(ctx);
     return 0;
 }
