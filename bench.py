@@ -9,6 +9,7 @@ Workloads:
          positions, tiled), depth 3.  metric = perft leaf nodes/s.
   mcts   BASELINE.json configs[2]: 4 096 concurrent games per GPU, PUCT self-play with the reference net (default).
   train  BASELINE.json configs[4]: the training step of the learn loop on the 20 x 256 tower (bench_train.py).
+  learn  BASELINE.json configs[4]: whole loop iterations, self-play feeding training (bench_learn.py).
 `--impl reference` times the CPU implementation of the same path (the oracle port, all host cores) on a bounded
 sample of the same workload.
 """
@@ -258,7 +259,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None, choices=["mcts", "perft", "train"])
+    ap.add_argument("--workload", default=None, choices=["mcts", "perft", "train", "learn"])
     args, _ = ap.parse_known_args()
     if args.workload is None:
         args.workload = "mcts" if os.path.exists(os.path.join(ROOT, "bench_mcts.py")) else "perft"
@@ -282,6 +283,9 @@ def main():
         elif args.workload == "train":
             import bench_train
             bench_train.run(args, rank, world, local_rank)
+        elif args.workload == "learn":
+            import bench_learn
+            bench_learn.run(args, rank, world, local_rank)
         else:
             import bench_mcts
             bench_mcts.run(args, rank, world, local_rank)

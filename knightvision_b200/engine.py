@@ -121,6 +121,7 @@ class Engine:
     def net_create(self, stem: int = 256, tower: int = 512, blocks: int = 5, conv2: bool = True, max_boards: int = 4096):
         N.check(self.ctx, self._lib.kv_net_create(self.ctx, stem, tower, blocks, int(conv2), max_boards), "kv_net_create")
         self.net_max_boards = max_boards
+        self.net_geometry = None          # bookkeeping of ChessNet.attach (re-created only when the shape changes)
 
     def net_set_conv_mode(self, cta_group: int):
         N.check(self.ctx, self._lib.kv_net_set_conv_mode(self.ctx, cta_group), "kv_net_set_conv_mode")
@@ -247,6 +248,8 @@ class Engine:
                                                      c_puct, dir_alpha, dir_eps, seed, eval_mode, inflight),
                 "kv_mcts_create_k")
         self.mcts_inflight = inflight
+        self.mcts_geometry_key = None     # bookkeeping of SelfPlay (pools are kept while the geometry is unchanged)
+        self.mcts_cache_log2 = 0
         g = np.zeros(4, dtype=np.int32)
         N.check(self.ctx, self._lib.kv_mcts_geometry(self.ctx, _ptr(g)), "kv_mcts_geometry")
         self.mcts_games, self.mcts_node_cap, self.mcts_edge_cap, self.mcts_rec_cap = (int(x) for x in g)
@@ -255,6 +258,7 @@ class Engine:
     def mcts_enable_cache(self, log2_slots: int):
         """Evaluation cache of 2**log2_slots x 640 B entries (0 = off); results are identical with it on or off."""
         N.check(self.ctx, self._lib.kv_mcts_enable_cache(self.ctx, log2_slots), "kv_mcts_enable_cache")
+        self.mcts_cache_log2 = log2_slots
 
     def mcts_reset(self, start_lines: torch.Tensor | None = None, game_id_base: int = 0):
         N.check(self.ctx, self._lib.kv_mcts_reset(self.ctx, _ptr(start_lines) if start_lines is not None else None,

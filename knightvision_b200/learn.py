@@ -115,10 +115,17 @@ def train_epochs(net: ChessNet, optimizer, data: ReplayData, epochs: int, batch_
         graph = nn.parallel.DistributedDataParallel(graph, device_ids=[data.eng.index])
     net.train()
     last = float("nan")
+    ddp = isinstance(graph, nn.parallel.DistributedDataParallel)
     for _ in range(epochs):
         tot, nb = 0.0, 0
         optimizer.zero_grad()
         batches = list(data.batches(batch_size))
+        if ddp:
+            # ranks hold different numbers of records (games end at different plies): every rank runs the same number
+            # of steps, or the gradient all-reduce would wait for ever
+            nmin = torch.tensor([len(batches)], device=data.eng.device)
+            dist.all_reduce(nmin, op=dist.ReduceOp.MIN)
+            batches = batches[:int(nmin.item())]
         for i, (boards, moves, outcomes) in enumerate(batches):
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 pol, val = graph(boards)
@@ -173,14 +180,33 @@ def reinforcement_loop(cfg, net: ChessNet | None = None, data: ReplayData | None
     data = data or ReplayData(eng)
     games = max(1, cfg.selfplay.num_games // world)
     history = []
+    import time
+
+    def now():
+        torch.cuda.synchronize()
+        return time.perf_counter()
+
     for it in range(1, cfg.num_iterations + 1):
+        t0 = now()
+        n_train = len(data)
         loss = train_epochs(net, optimizer, data, cfg.train.epochs, cfg.train.batch_size) if len(data) else float("nan")
+        t1 = now()
         sp = SelfPlay(net.eval(), games, cfg.device, sims=cfg.selfplay.sims,
-                      max_plies=cfg.selfplay.max_moves or 512, engine=eng)
-        st = sp.play(game_id_base=(it * world + rank) * games)
+                      max_plies=cfg.selfplay.max_moves or 512, engine=eng,
+                      inflight=getattr(cfg.selfplay, "inflight", 1))
+        if getattr(cfg.selfplay, "cache_log2", 0) and getattr(eng, "mcts_cache_log2", 0) != cfg.selfplay.cache_log2:
+            eng.mcts_enable_cache(cfg.selfplay.cache_log2)       # (cleared by the weight commit above on later iterations)
+        start = None
+        if getattr(cfg.selfplay, "random_start_plies", 0):         # bench variant: diverse start positions
+            start = eng.random_positions(games, cfg.selfplay.random_start_plies, 1234 + it * world + rank)
+        t2 = now()
+        st = sp.play(start, game_id_base=(it * world + rank) * games)
+        t3 = now()
         lines, move, reward, _ = sp.records_device()
         data.extend_packed(lines, move, reward)
         history.append(dict(iteration=it, loss=loss, records=int(lines.shape[0]), plies=st["plies"],
-                            white=st["white_wins"], black=st["black_wins"], draws=st["draws"]))
+                            white=st["white_wins"], black=st["black_wins"], draws=st["draws"], evals=st["evals"],
+                            train_positions=n_train * cfg.train.epochs, train_s=t1 - t0, weights_s=t2 - t1,
+                            selfplay_s=t3 - t2, total_s=now() - t0))
         logger.info("iteration %d: loss %.4f, %d new records", it, loss, lines.shape[0])
     return net, data, history

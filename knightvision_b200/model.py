@@ -76,18 +76,34 @@ class ChessNet(nn.Module):
         self._engine = engine
         if max_batch:
             self.max_batch = max_batch
-        engine.net_create(*self.arch, self.max_batch)
-        engine.net_load(self.weight_blob())
-        self._dirty = False
+        if getattr(engine, "net_geometry", None) != (self.arch, self.max_batch):
+            engine.net_create(*self.arch, self.max_batch)        # (re)allocates activations / weight buffers
+            engine.net_geometry = (self.arch, self.max_batch)
+        self.sync_weights()
         return self
+
+    def sync_weights(self):
+        """Hand the current parameters to the attached engine.  Parameters that live on the engine's GPU go device to
+        device: concatenated straight into the engine's fp32 staging blob (the buffer an NCCL broadcast would target),
+        then folded / converted on the device (kv_net_commit_weights) — no host round trip.  This is the weight bridge
+        between the trainer's fp32 master weights and the self-play engine (ai/model_utils.py:10-29 role)."""
+        eng = self._engine
+        p = next(self.parameters())
+        if p.is_cuda and p.device == eng.device:
+            parts = [v.detach().reshape(-1).to(torch.float32) for k, v in self.state_dict().items()
+                     if not k.endswith("num_batches_tracked")]
+            torch.cat(parts, out=eng.net_blob_tensor())
+            eng.net_commit()
+        else:
+            eng.net_load(self.weight_blob())
+        self._dirty = False
 
     def _ensure(self, device):
         if self._engine is None:
             from .engine import Engine
             self.attach(Engine(device))
         elif self._dirty:
-            self._engine.net_load(self.weight_blob())
-            self._dirty = False
+            self.sync_weights()
         return self._engine
 
     # ---- forward (B200 kernels) ------------------------------------------------------------------------

@@ -74,8 +74,11 @@ class SelfPlay:
             inner.eval()
             inner.attach(self.eng, max_batch=max(n_games * inflight, 2))
             self.model = inner
-        self.eng.mcts_create(n_games, sims, max_plies, temp_plies, c_puct, dir_alpha, dir_eps, seed, eval_mode,
-                             inflight=inflight)
+        geom = (n_games, sims, max_plies, temp_plies, c_puct, dir_alpha, dir_eps, seed, eval_mode, inflight)
+        if getattr(self.eng, "mcts_geometry_key", None) != geom:      # same search context: keep the pools (and the cache)
+            self.eng.mcts_create(n_games, sims, max_plies, temp_plies, c_puct, dir_alpha, dir_eps, seed, eval_mode,
+                                 inflight=inflight)
+            self.eng.mcts_geometry_key = geom
 
     def play(self, start_lines: torch.Tensor | None = None, game_id_base: int = 0, progress=None) -> dict:
         eng = self.eng
