@@ -8,7 +8,7 @@ there is no CPU fallback.
 from . import layout  # noqa: F401
 
 __all__ = ["GameState", "Move", "CastleRights", "ChessNet", "encode_board", "encode_move", "decode_move_index",
-           "self_play", "generate_self_play_data", "Engine"]
+           "self_play", "generate_self_play_data", "Engine", "get_ai_move", "get_mcts_move", "arena"]
 
 
 def __getattr__(name):
@@ -25,6 +25,9 @@ def __getattr__(name):
     if name in ("self_play", "generate_self_play_data", "SelfPlay"):
         from . import selfplay
         return getattr(selfplay, name)
+    if name in ("get_ai_move", "get_mcts_move", "arena"):
+        from . import players
+        return getattr(players, name)
     if name == "Engine":
         from .engine import Engine
         return Engine

@@ -268,3 +268,40 @@ def test_virtual_loss_inflight_with_network_replayed_by_oracle(eng):
     eng.mcts_run_move()
     eng.mcts_run_move()
     assert eng.mcts_status()["plies"] == 2 * G
+
+
+def test_evaluation_players(eng, monkeypatch):
+    """scripts/play_vs_model.py:34-49 greedy player, the single-position search player (virtual loss fills the batch) and
+    the two-network arena."""
+    from knightvision_b200 import chess_engine as CE
+    from knightvision_b200 import players as P
+    from knightvision_b200 import selfplay as SP
+    from knightvision_b200.ai import encode_board, encode_move
+    from knightvision_b200.model import ChessNet
+    monkeypatch.setitem(SP._engines, 0, eng)
+    CE.set_engine(eng)
+    torch.manual_seed(2)
+    net = ChessNet().eval()
+    gs = CE.GameState()
+    mv = P.get_ai_move(gs, net)
+    legal = gs.getValidMoves()
+    assert mv in legal
+    pol, _ = net(torch.from_numpy(encode_board(gs.board)[None]).cuda())
+    idx = [encode_move(m.startRow, m.startCol, m.endRow, m.endCol) for m in legal]
+    assert mv == legal[int(np.argmax(pol[0, idx].cpu().numpy()))]           # masked argmax of the policy
+    # mate in one (several mating moves exist): kings + white queen, white to move
+    gs = CE.GameState()
+    gs.board = [["--"] * 8 for _ in range(8)]
+    gs.board[0][7], gs.board[2][6], gs.board[1][0] = "bK", "wK", "wQ"
+    gs.blackKingLocation, gs.whiteKingLocation = (0, 7), (2, 6)
+    gs.wKingMoved = gs.bKingMoved = True
+    gs.whiteToMove = True
+    m = P.get_mcts_move(gs, net, sims=600, inflight=16, engine=eng)
+    assert m in gs.getValidMoves()
+    gs.makeMove(m)
+    assert gs.getValidMoves() == [] and gs.checkMate
+    # arena: every game is accounted for
+    torch.manual_seed(3)
+    other = ChessNet().eval()
+    r = P.arena(net, other, n_games=8, sims=8, max_plies=6, device="cuda:0")
+    assert r["a_wins"] + r["b_wins"] + r["draws"] == 8 and r["games"] == 8
