@@ -150,6 +150,32 @@ def train_epochs(net: ChessNet, optimizer, data: ReplayData, epochs: int, batch_
     return last
 
 
+def save_checkpoint(path: str, net: ChessNet, optimizer, epoch: int, loss=None):
+    """The reference's checkpoint dictionary (scripts/train.py:207-212, :342-347): readable by
+    ai/model_utils.py:10-29 and scripts/self_play.py:72-76 of an unmodified checkout."""
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    torch.save({"epoch": int(epoch), "model_state_dict": sd, "optimizer_state_dict": optimizer.state_dict(), "loss": loss},
+               path)
+
+
+def load_or_initialize_model(model_path, device, arch=None, lr: float = 1e-3):
+    """ai/model_utils.py:10-29: (model, optimizer, start_epoch); a checkpoint missing the expected keys, or no file,
+    gives a fresh model.  A bare state_dict (scripts/train.py:338-341) is accepted as well, DataParallel prefixes are
+    stripped.  No DataParallel wrapper: multi-GPU runs are one process per GPU."""
+    net = ChessNet(**(arch or {})).to(device)
+    optimizer = torch.optim.Adam(net.parameters(), lr=lr)
+    start_epoch = 0
+    if model_path and os.path.exists(model_path):
+        ck = torch.load(model_path, map_location="cpu")
+        sd = ck.get("model_state_dict", ck) if isinstance(ck, dict) else ck
+        sd = {k[len("module."):] if k.startswith("module.") else k: v for k, v in sd.items()}
+        net.load_state_dict(sd)
+        if isinstance(ck, dict) and "optimizer_state_dict" in ck:
+            optimizer.load_state_dict(ck["optimizer_state_dict"])
+            start_epoch = int(ck.get("epoch", 0))
+    return net, optimizer, start_epoch
+
+
 def build_cfg(**kw):
     """scripts/learn.py:99-149 without the Google-Drive / Stockfish parts; same environment variables."""
     cfg = SimpleNamespace(

@@ -119,3 +119,4 @@ def test_encoders_match_reference_goldens():
     assert encode_move(6, 0, 5, 0) == 3112 and encode_move(6, 4, 4, 4) == 3364 and encode_move(7, 6, 5, 5) == 4013
     for i, sr, sc, er, ec in g["decode"]:
         assert decode_move_index(int(i)) == (sr, sc, er, ec)
+
