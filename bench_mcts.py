@@ -16,6 +16,7 @@ GAMES_PER_GPU = int(os.getenv("KV_BENCH_GAMES", "4096"))
 SIMS = int(os.getenv("KV_BENCH_SIMS", "800"))
 MAX_PLIES = 512
 INFLIGHT = int(os.getenv("KV_BENCH_INFLIGHT", "8"))         # phase E: G/K games x K simulations in flight (0/1 = skip)
+POLICY_MODE_PLIES = int(os.getenv("KV_BENCH_POLICY_PLIES", "40"))   # phase F: plies of reference-rule self-play (0 = skip)
 CACHE_LOG2 = int(os.getenv("KV_BENCH_CACHE_LOG2", "24"))   # evaluation cache: 2^24 x 640 B = 10.7 GB (0 = off)
 CONV_FLOPS_PER_EVAL = 2.0 * 64 * 9 * (256 * 512 + 10 * 512 * 512)      # conv2 + 5 residual blocks (tcgen05 kernel)
 NET_FLOPS_PER_EVAL = 2.0 * 1587872256                                   # whole net, SURVEY §8d
@@ -222,6 +223,19 @@ def run(args, rank, world, local_rank):
               "sims": (Gk - v0["done"]) * SIMS * v_moves, "evals": v1["evals"] - v0["evals"],
               "waves_per_move": (eng.mcts_waves() - w0) / v_moves}
 
+    # ---- F: the reference's own move rule (scripts/self_play.py:147-167): no search, one network evaluation per ply,
+    # the move sampled from softmax(policy) + Dirichlet noise over the legal moves (sims = 1).  positions/s here is
+    # directly comparable with the reference's self-play loop (BASELINE configs[0]).
+    pm = None
+    if POLICY_MODE_PLIES > 0:
+        eng.mcts_create(G, 1, MAX_PLIES, seed=42, eval_mode=1)
+        eng.mcts_enable_cache(0)
+        eng.mcts_reset(None, game_id_base=rank * G)
+        for _ in range(warm):
+            eng.mcts_run_move()
+        p_ms, p0, p1, _, _ = timed_moves(POLICY_MODE_PLIES)
+        pm = {"ms": p_ms, "positions": p1["plies"] - p0["plies"], "evals": p1["evals"] - p0["evals"]}
+
     t = torch.tensor([dev_ms, e2e_s * 1e3, nocache_ms or 0.0, r_ms], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(sims_done), float(evals), float(positions), float(rec), float(hits), float(r_sims),
                         float(r_evals)], dtype=torch.float64, device=dev)
@@ -266,6 +280,11 @@ def run(args, rank, world, local_rank):
                           "waves_per_move": vl["waves_per_move"],
                           "note": "rank 0's figures x world: G/K games with K simulations in flight per game and wave "
                                   "(virtual loss), initial position, cache on"} if vl else None),
+        "policy_mode": ({"value": world * pm["positions"] / (pm["ms"] * 1e-3), "unit": "positions/s", "plies": POLICY_MODE_PLIES,
+                         "evals_per_position": pm["evals"] / pm["positions"] if pm["positions"] else None,
+                         "note": "rank 0's figures x world: KV_SIMS=1, the reference's own rule (no search: one network evaluation per "
+                                 "ply, move sampled from the noisy policy over the legal moves); SURVEY section 6 measured 48.6 "
+                                 "positions/s for the unmodified reference on 8 CPU threads"} if pm else None),
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_sims / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": G * 128 // e2e_steps,
                 "d2h_bytes_per_step": G * (12 * 64 * 4 + 8), "records_returned": rec_all, "steps": e2e_steps,

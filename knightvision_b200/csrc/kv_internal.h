@@ -51,6 +51,8 @@ struct kv_ctx {
     float* train_zeros = nullptr;
     float* bn_ws = nullptr;          // per-CTA partial sums of the BatchNorm reductions (kv_bn.cu)
     size_t bn_ws_floats = 0;
+    bool conv_attr_done = false;     // cudaFuncSetAttribute(max dynamic smem) is per device: once per context
+    bool wgrad_attr_done = false;
 };
 
 extern std::string g_kv_create_error;

@@ -747,10 +747,9 @@ int kv_net_load(kv_ctx* ctx, const float* h_blob, uint64_t n_floats) {
 int kv_conv_launch(kv_ctx* ctx, const bf16* x, const bf16* w_packed, const float* bias, const bf16* residual, bf16* y,
                    int n, int cin, int cout, int relu, cudaStream_t st) {
     if (cin % 64 || cout % 256 || cin < 64) return kv_fail_msg(ctx, "conv3x3: cin must be a multiple of 64, cout of 256");
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!ctx->conv_attr_done) {
         KV_CUDA(ctx, cudaFuncSetAttribute(conv3x3_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_SMEM));
-        attr_done = true;
+        ctx->conv_attr_done = true;
     }
     CUtensorMap amap, wmap;
     if (int rc = kv_make_act_map(ctx, &amap, const_cast<bf16*>(x), cin, n, 2)) return rc;

@@ -238,10 +238,9 @@ int kv_conv3x3_wgrad(kv_ctx* ctx, const void* d_x, const void* d_dy, float* d_dw
     if (n_boards <= 0) return kv_fail_msg(ctx, "kv_conv3x3_wgrad: no boards");
     if (cin % WG_N || cout % WG_M) return kv_fail_msg(ctx, "kv_conv3x3_wgrad: cin must be a multiple of 256, cout of 128");
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!ctx->wgrad_attr_done) {
         KV_CUDA(ctx, cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
-        attr_done = true;
+        ctx->wgrad_attr_done = true;
     }
     WgradParams P;
     P.n_boards = n_boards;
