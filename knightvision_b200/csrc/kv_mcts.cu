@@ -185,17 +185,31 @@ __global__ void mcts_unfinished_kernel(MctsCfg cfg, MctsArrays A, int G, unsigne
 
 // Records of all games, in game order: lines [N][16] (bitboards, rest 0), move index, reward (self_play.py:245-250:
 // white's perspective, win 1.0 / draw 0.2 / loss -1.0, same value on every ply), game id.
-__global__ void mcts_record_offsets_kernel(MctsArrays A, int G, int rec_cap, int* offsets /*[G+1]*/) {
-    // single CTA, sequential scan by thread 0 over <= 32 768 games is fine (once per generation)
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int acc = 0;
-        for (int g = 0; g < G; g++) {
-            offsets[g] = acc;
-            int p = A.hdr[g].ply;
-            acc += p < rec_cap ? p : rec_cap;
-        }
-        offsets[G] = acc;
+__global__ void __launch_bounds__(1024) mcts_record_offsets_kernel(MctsArrays A, int G, int rec_cap, int* offsets /*[G+1]*/) {
+    // one CTA: every thread sums a contiguous chunk of games, a shared-memory scan orders the chunks (game order)
+    __shared__ int part[1024];
+    const int t = threadIdx.x, per = (G + 1023) / 1024;
+    const int lo = t * per, hi = lo + per < G ? lo + per : G;
+    int acc = 0;
+    for (int g = lo; g < hi; g++) {
+        const int p = A.hdr[g].ply;
+        acc += p < rec_cap ? p : rec_cap;
     }
+    part[t] = acc;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {   // inclusive Hillis-Steele scan
+        const int v = t >= d ? part[t - d] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int base = t ? part[t - 1] : 0;
+    for (int g = lo; g < hi; g++) {
+        offsets[g] = base;
+        const int p = A.hdr[g].ply;
+        base += p < rec_cap ? p : rec_cap;
+    }
+    if (t == 1023) offsets[G] = part[1023];
 }
 __global__ void mcts_record_gather_kernel(MctsArrays A, int G, int rec_cap, const int* __restrict__ offsets,
                                           uint64_t* __restrict__ out_lines, int32_t* __restrict__ out_move,
@@ -569,7 +583,7 @@ int kv_mcts_records(kv_ctx* ctx, uint64_t* d_lines, int32_t* d_move, float* d_re
     if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_records: no search context");
     kv_mcts* m = ctx->mcts;
     cudaStream_t st = (cudaStream_t)stream;
-    mcts_record_offsets_kernel<<<1, 32, 0, st>>>(m->A, m->G, m->cfg.rec_cap, m->d_offsets);
+    mcts_record_offsets_kernel<<<1, 1024, 0, st>>>(m->A, m->G, m->cfg.rec_cap, m->d_offsets);
     KV_LAUNCH_CHECK(ctx);
     int total = 0;
     KV_CUDA(ctx, cudaMemcpyAsync(&total, m->d_offsets + m->G, sizeof(int), cudaMemcpyDeviceToHost, st));
