@@ -219,7 +219,7 @@ def reinforcement_loop(cfg, net: ChessNet | None = None, data: ReplayData | None
         t1 = now()
         sp = SelfPlay(net.eval(), games, cfg.device, sims=cfg.selfplay.sims,
                       max_plies=cfg.selfplay.max_moves or 512, engine=eng,
-                      inflight=getattr(cfg.selfplay, "inflight", 1))
+                      inflight=getattr(cfg.selfplay, "inflight", None))
         if getattr(cfg.selfplay, "cache_log2", 0) and getattr(eng, "mcts_cache_log2", 0) != cfg.selfplay.cache_log2:
             eng.mcts_enable_cache(cfg.selfplay.cache_log2)       # (cleared by the weight commit above on later iterations)
         start = None

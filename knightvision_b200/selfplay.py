@@ -61,9 +61,15 @@ class SelfPlay:
     def __init__(self, model: ChessNet, n_games: int, device, sims: int = DEFAULT_SIMS, max_plies: int = DEFAULT_PLY_CAP,
                  temp_plies: int = TEMP_PLIES, c_puct: float = C_PUCT, dir_alpha: float = DIR_NOISE_ALPHA,
                  dir_eps: float = DIR_NOISE_EPS, seed: int = SEED, eval_mode: int = 1, engine: Engine | None = None,
-                 inflight: int = 1):
+                 inflight: int | None = None):
         self.eng = engine or engine_for(device)
         self.n_games, self.sims, self.max_plies = n_games, sims, max_plies
+        if inflight is None:
+            # few games cannot fill a network batch with one simulation per game and wave (the reference's default is 5
+            # games per generation, scripts/learn.py:106): run K simulations per game and wave with virtual loss so that
+            # a wave carries ~2 048 leaves; 2 048 games or more keep the sequential search (K = 1)
+            inflight = int(os.getenv("KV_INFLIGHT", "0")) or max(1, min(32, 2048 // max(n_games, 1), max(sims // 8, 1)))
+        self.inflight = inflight
         if eval_mode == 1:
             inner = model.module if hasattr(model, "module") else model
             if not isinstance(inner, ChessNet):
