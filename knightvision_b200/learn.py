@@ -61,9 +61,14 @@ class TrainGraph(nn.Module):
         h = self._bnrelu(n.bn1, h)
         if n.arch[3]:
             h = self._bnrelu(n.bn2, self._conv(n.conv2, h))
+        fused_block = (self.engine is not None and n.training and T.supported(n.arch[1], n.arch[1])
+                       and T.bn_supported(n.arch[1]) and os.getenv("KV_TRAIN_BLOCK_FUSED", "1") != "0")
         for b in n.res_blocks:
-            t = self._bnrelu(b.bn1, self._conv(b.conv1, h))
-            h = self._bnrelu(b.bn2, self._conv(b.conv2, t), residual=h)
+            if fused_block:
+                h = T.residual_block_b200(h, b, self.engine)       # one autograd node, skip gradient fused into dgrad
+            else:
+                t = self._bnrelu(b.bn1, self._conv(b.conv1, h))
+                h = self._bnrelu(b.bn2, self._conv(b.conv2, t), residual=h)
         p = n.policy_fc(F.relu(n.policy_bn(n.policy_conv(h))).flatten(1))
         v = F.relu(n.value_bn(n.value_conv(h))).flatten(1)
         v = torch.tanh(n.value_fc2(F.relu(n.value_fc1(v))))

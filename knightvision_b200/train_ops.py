@@ -99,6 +99,59 @@ def bn_relu_b200(z: torch.Tensor, bn: torch.nn.BatchNorm2d, eng, residual: torch
                              float(bn.eps), relu)
 
 
+class _ResidualBlockB200(torch.autograd.Function):
+    """ai/model.py:19-25 as ONE autograd node: relu(bn2(conv2(relu(bn1(conv1(x))))) + x) in training mode.
+
+    Same kernels as conv3x3_b200 / bn_relu_b200 chained, but the backward knows the block's shape: the gradient of the
+    skip connection (the ReLU-masked incoming gradient) goes into the `residual` input of the last dgrad launch, so
+    dx = dgrad(dz1) + g is produced by the convolution epilogue instead of a separate elementwise pass, and the
+    block is 1 autograd node instead of 4."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, w1, b1, g1, be1, w2, b2, g2, be2, eng, bn1, bn2):
+        xh = _nhwc(x)
+        f32 = lambda t: t.detach().float().contiguous()
+        z1 = eng.conv3x3_fprop(xh, eng.conv3x3_pack(w1), f32(b1))
+        t, m1, r1 = eng.bn_relu_fwd(z1, f32(g1), f32(be1), bn1.running_mean, bn1.running_var, float(bn1.momentum),
+                                    float(bn1.eps))
+        z2 = eng.conv3x3_fprop(t, eng.conv3x3_pack(w2), f32(b2))
+        y, m2, r2 = eng.bn_relu_fwd(z2, f32(g2), f32(be2), bn2.running_mean, bn2.running_var, float(bn2.momentum),
+                                    float(bn2.eps), residual=xh)
+        ctx.save_for_backward(xh, z1, t, z2, y, w1, w2, f32(g1), f32(g2), m1, r1, m2, r2)
+        ctx.eng = eng
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_out):
+        xh, z1, t, z2, y, w1, w2, g1, g2, m1, r1, m2, r2 = ctx.saved_tensors
+        eng = ctx.eng
+        dy = _nhwc(grad_out)
+        dz2, g, dg2, dbe2 = eng.bn_relu_bwd(dy, y, z2, g2, m2, r2, want_dres=True)
+        dw2 = eng.conv3x3_wgrad(t, dz2)
+        db2 = eng.channel_sum(dz2)
+        dt = eng.conv3x3_fprop(dz2, eng.conv3x3_pack(w2, flip_transpose=True))
+        dz1, _, dg1, dbe1 = eng.bn_relu_bwd(dt, t, z1, g1, m1, r1)
+        dw1 = eng.conv3x3_wgrad(xh, dz1)
+        db1 = eng.channel_sum(dz1)
+        dx = eng.conv3x3_fprop(dz1, eng.conv3x3_pack(w1, flip_transpose=True), residual=g)     # + skip gradient, fused
+        return (dx.permute(0, 3, 1, 2), dw1.to(w1.dtype), db1, dg1, dbe1, dw2.to(w2.dtype), db2, dg2, dbe2, None, None, None)
+
+
+def residual_block_b200(x: torch.Tensor, block, eng) -> torch.Tensor:
+    """One ResidualBlock (conv1, bn1, conv2, bn2 modules with biases) in training mode through the B200 kernels."""
+    for bn in (block.bn1, block.bn2):
+        if not bn.training or not bn.track_running_stats or bn.momentum is None:
+            raise RuntimeError("residual_block_b200 implements training-mode BatchNorm2d with a fixed momentum")
+    with torch.no_grad():
+        block.bn1.num_batches_tracked += 1
+        block.bn2.num_batches_tracked += 1
+    return _ResidualBlockB200.apply(x, block.conv1.weight, block.conv1.bias, block.bn1.weight, block.bn1.bias,
+                                    block.conv2.weight, block.conv2.bias, block.bn2.weight, block.bn2.bias, eng,
+                                    block.bn1, block.bn2)
+
+
 def bn_supported(C: int) -> bool:
     return C in (64, 128, 256, 512, 1024)
 
