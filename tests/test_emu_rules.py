@@ -68,3 +68,12 @@ def test_emu_skip_move_and_promotion_choice_default():
     f = L.unpack_fields(out[0])
     assert f["board"][4][4] == "wp" and f["board"][6][4] == "--" and f["ep"] == (5, 4) and not f["white_to_move"]
     assert f["clock"] == 1   # pawn moves do not reset the clock (core/chessEngine.py:178)
+
+
+def test_emu_synthetic_generator_lines_vs_oracle():
+    """Freshly generated synthetic boards (tame and 'wild': missing / stale kings, back-rank pawns, arbitrary e.p.) through
+    the kernel source on the emulator vs the pinned oracle — the CPU-sized version of the GPU fuzz test."""
+    for wild, seed in ((False, 21), (True, 22)):
+        syn = H.synthetic_lines(1200, seed, wild=wild)
+        H.check_movegen_against(syn, emu.movegen(syn))
+        assert np.array_equal(emu.attacked(syn[:200]), H.oracle_attack_masks(syn[:200]))

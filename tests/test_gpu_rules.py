@@ -64,6 +64,29 @@ def test_movegen_random_playouts_vs_oracle(eng):
     H.check_movegen_against(lines, _movegen(eng, lines))
 
 
+def test_fuzz_large_playouts_and_wild_boards_vs_oracle(eng):
+    """Scale check of the rules kernels against the pinned oracle: ~400 k playout positions (move lists in order, flags,
+    state rewrite, make-move of a random legal move) and 60 000 synthetic boards, half of them 'wild' (missing / stale
+    kings, back-rank pawns, arbitrary e.p. squares — the corners the reference-made synthetic fixtures probe)."""
+    lines = H.random_playout_positions(n_games=2048, max_plies=260, seed=2024)
+    assert len(lines) > 300000
+    got = _movegen(eng, lines)
+    H.check_movegen_against(lines, got)
+    moves, counts = got[0], got[1]
+    rng = np.random.default_rng(3)
+    idx = (rng.random(len(lines)) * np.maximum(counts, 1)).astype(np.int64)
+    pick = np.where(counts > 0, moves[np.arange(len(lines)), idx], 0xFFFF).astype(np.uint16)
+    after = eng.make_moves_host(got[3], pick)
+    live = counts > 0
+    assert np.array_equal(after[live][:, :13], O.make_moves(got[3][live].copy(), pick[live])[:, :13])
+    assert np.array_equal(after[~live], got[3][~live])          # 0xFFFF = leave the board untouched (kv_b200.h)
+    for wild, seed in ((False, 5), (True, 6)):
+        syn = H.synthetic_lines(30000, seed, wild=wild)
+        g2 = _movegen(eng, syn)
+        H.check_movegen_against(syn, g2)
+        assert np.array_equal(eng.attacked_host(syn[:1500]), H.oracle_attack_masks(syn[:1500]))
+
+
 def test_perft_golden_all_positions(eng):
     gold = H.perft_gold()
     names = list(gold)
