@@ -171,6 +171,19 @@ def run(args, rank, world, local_rank):
     hits = st1["cache_hits"] - st0["cache_hits"]
     positions = st1["plies"] - st0["plies"]
 
+    # ---- A2: the same moves on ONE stream (pipelined schedule off): what the two-group overlap is worth -----------------
+    single = None
+    if os.getenv("KV_BENCH_COMPARE", "1") != "0" and G >= 2048:
+        eng.mcts_set_pipeline(0)
+        eng.mcts_cache_clear()
+        eng.mcts_reset(None, game_id_base=rank * G)
+        for _ in range(warm):
+            eng.mcts_run_move()
+        s_ms, s0_, s1_, _, _ = timed_moves(args.steps)
+        single = {"ms_per_step": s_ms / args.steps, "sims": (G - s0_["done"]) * SIMS * args.steps,
+                  "evals": s1_["evals"] - s0_["evals"]}
+        eng.mcts_set_pipeline(-1)
+
     # ---- B: e2e — the same positions through the public API with HOST buffers: pinned host lines -> device, cold
     # evaluation cache (a new generation means new weights), the same number of moves, records back on the host as the
     # reference's tuples.  Everything, copies included, is inside the timed region.
@@ -249,6 +262,7 @@ def run(args, rank, world, local_rank):
     peaks = measured_peaks()
     conv_ms, conv_n = prof["net_conv"]
     traffic, traffic_src = _ncu_traffic()
+    boards_per_launch = G // 2 if G >= 2048 else G     # pipelined schedule: every tower launch covers one game group
     achieved = (evals * CONV_FLOPS_PER_EVAL) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     value = sims_all / (dev_ms * 1e-3)
     e2e_sims = world * G * SIMS * e2e_steps
@@ -267,6 +281,16 @@ def run(args, rank, world, local_rank):
                        "served_per_sim": hits_all / sims_all if sims_all else None,
                        "note": "keyed by the 12 bitboards (the net's whole input); search results are bit-identical "
                                "with the cache on or off (tests/test_gpu_mcts.py::test_eval_cache_is_transparent)"},
+        "schedule": {"pipelined": G >= 2048,
+                     "note": "two game groups of G/2 whose waves alternate on two streams: the tree kernels (select / "
+                             "expand / backup, stem) of one group run on the CUDA cores under the other group's tensor-core "
+                             "tower; results are bit-identical to the single-stream schedule "
+                             "(tests/test_gpu_mcts.py::test_pipelined_groups_are_transparent)",
+                     "single_stream": ({"value": world * single["sims"] / (single["ms_per_step"] * args.steps * 1e-3),
+                                        "unit": "sims/s", "ms_per_step": single["ms_per_step"],
+                                        "evals_per_sim": single["evals"] / single["sims"] if single["sims"] else None,
+                                        "note": "rank 0's figures x world: same moves, same cold cache and warm-up, "
+                                                "pipelined schedule off"} if single else None)},
         "no_cache": ({"value": world * G * SIMS / (nocache_ms * 1e-3), "unit": "sims/s", "ms_per_step": nocache_ms,
                       "evals_per_sim": 1.0, "note": "same positions, evaluation cache disabled"} if nocache_ms else None),
         "random_positions": {"value": r_sims_all / (r_ms * 1e-3), "unit": "sims/s",
@@ -294,8 +318,10 @@ def run(args, rank, world, local_rank):
         "roofline": {"kernel": "conv3x3_umma2_kernel (tcgen05 cta_group::2 implicit GEMM)", "bound": "tensor", "achieved": achieved,
                      "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
                      "traffic": traffic, "traffic_source": (f"{traffic_src}: dram__bytes_read.sum + dram__bytes_write.sum per "
-                                                             "launch at 4096 boards (algorithmic: 268 MB in + 268 MB out "
-                                                             "+ 4.7 MB weights, + 268 MB residual on every second layer)")
+                                                             f"launch of {boards_per_launch} boards (algorithmic per launch: "
+                                                             f"{boards_per_launch * 65536 / 1e6:.0f} MB in + "
+                                                             f"{boards_per_launch * 65536 / 1e6:.0f} MB out + 4.7 MB weights, "
+                                                             "+ as much again for the residual on every second layer)")
                      if traffic else None,
                      "peak_source": peaks["source"] + ", sustained bf16 figure",
                      "kernel_ms_per_step": conv_ms / args.steps, "kernel_share_of_step": conv_ms / dev_ms,

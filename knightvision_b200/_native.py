@@ -54,6 +54,7 @@ SIGNATURES = {
     "kv_mcts_create_k": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float,
                                  ctypes.c_float, c_u64, c_int, c_int]),
     "kv_mcts_waves": (ctypes.c_int64, [c_void_p]),
+    "kv_mcts_set_pipeline": (c_int, [c_void_p, c_int]),
     "kv_mcts_reset": (c_int, [c_void_p, c_void_p, c_u64, c_void_p]),
     "kv_mcts_run_sims": (c_int, [c_void_p, c_int, c_void_p]),
     "kv_mcts_finish_move": (c_int, [c_void_p, c_void_p]),

@@ -19,10 +19,14 @@ namespace kv {
 
 
 constexpr int kMW = 8;   // warps (games) per CTA
-struct __align__(16) MctsSmem {
+constexpr int kMWP = 2;  // ... of the selection kernel in the pipelined search: 64-thread CTAs (8 K registers, 7.5 KB of
+                         // shared memory) fit next to a resident tower CTA
+template <int MW>
+struct __align__(16) MctsSmemT {
     Tables tab;
-    uint16_t mv[kMW][MAX_MOVES];
+    uint16_t mv[MW][MAX_MOVES];
 };
+using MctsSmem = MctsSmemT<kMW>;
 
 __device__ __forceinline__ void stage_tables_m(Tables& dstT) {
     const uint64_t* src = reinterpret_cast<const uint64_t*>(&g_tables);
@@ -31,12 +35,14 @@ __device__ __forceinline__ void stage_tables_m(Tables& dstT) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kMW * 32) mcts_select_kernel(MctsCfg cfg, MctsArrays A, int G, uint32_t wave) {
-    __shared__ MctsSmem sm;
+// games [g0, g1): the whole context, or one of the two groups of the pipelined search
+template <int MW>
+__global__ void __launch_bounds__(MW * 32, 16 / MW) mcts_select_kernel(MctsCfg cfg, MctsArrays A, int g0, int g1, uint32_t wave) {
+    __shared__ MctsSmemT<MW> sm;
     stage_tables_m(sm.tab);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int g = blockIdx.x * kMW + wid;
-    if (g >= G) return;
+    const int g = g0 + blockIdx.x * MW + wid;
+    if (g >= g1) return;
     mcts_select_warp(sm.tab, lane, cfg, A, g, sm.mv[wid], wave);
 }
 
@@ -57,10 +63,10 @@ __global__ void __launch_bounds__(kMW * 32) mcts_hash_late_kernel(MctsCfg cfg, M
 }
 
 // K > 1 only: warp per game, backs the wave's pending simulations up in slot order (after every expansion)
-__global__ void __launch_bounds__(kMW * 32) mcts_backup_kernel(MctsCfg cfg, MctsArrays A, int G) {
+__global__ void __launch_bounds__(kMW * 32) mcts_backup_kernel(MctsCfg cfg, MctsArrays A, int g0, int g1) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int g = blockIdx.x * kMW + wid;
-    if (g >= G) return;
+    const int g = g0 + blockIdx.x * kMW + wid;
+    if (g >= g1) return;
     mcts_backup_game_warp(lane, cfg, A, g);
 }
 
@@ -249,12 +255,32 @@ struct kv_mcts {
     long waves_run = 0;
     void* cache_mem = nullptr;
     size_t cache_slots = 0;
+    // pipelined search: two game groups on two streams (see mcts_wave_group)
+    int pipeline = -1;                 // -1 auto, 0 off, 1 on
+    cudaStream_t side = nullptr;       // group 1's stream (group 0 runs on the caller's)
+    cudaStream_t tower = nullptr;      // the tensor-core kernels of both groups, in issue order (highest priority)
+    cudaEvent_t ev_stem[2] = {nullptr, nullptr};
+    cudaEvent_t ev_tower[2] = {nullptr, nullptr}, ev_eval[2] = {nullptr, nullptr}, ev_late[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool tower_rec[2] = {false, false}, eval_rec[2] = {false, false}, late_rec[2] = {false, false};
+    uint32_t last_wave[2] = {0, 0};
+    bool attrs_done = false;
 };
 
 void kv_mcts_destroy(kv_ctx* ctx) {
     kv_mcts* m = ctx->mcts;
     if (!m) return;
     for (void* p : m->allocs) cudaFree(p);
+    if (m->side) cudaStreamDestroy(m->side);
+    if (m->tower) cudaStreamDestroy(m->tower);
+    for (int i = 0; i < 2; i++) {
+        if (m->ev_stem[i]) cudaEventDestroy(m->ev_stem[i]);
+        if (m->ev_tower[i]) cudaEventDestroy(m->ev_tower[i]);
+        if (m->ev_eval[i]) cudaEventDestroy(m->ev_eval[i]);
+        if (m->ev_late[i]) cudaEventDestroy(m->ev_late[i]);
+    }
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
     if (m->h_unfinished) cudaFreeHost(m->h_unfinished);
     if (m->cache_mem) cudaFree(m->cache_mem);
     delete m;
@@ -374,45 +400,186 @@ int kv_mcts_reset(kv_ctx* ctx, const uint64_t* d_start, uint64_t game_id_base, v
     return 0;
 }
 
-static int mcts_wave(kv_ctx* ctx, cudaStream_t st) {
+// One wave of the games [g0, g1) on stream st.  `grp` < 0: the whole context, one stream (the plain schedule).
+// grp = 0 / 1: one group of the pipelined schedule —
+//
+//   stream A:  select A(w) stem A(w) ............ eval A(w) late A(w) select A(w+1) stem A(w+1) ............ eval A(w+1)
+//   tower   :        ... B(w-1) | tower A(w)        | tower B(w)                         | tower A(w+1)       | ...
+//   stream B:  eval B(w-1) late B(w-1) select B(w) stem B(w) ............ eval B(w) late B(w) select B(w+1) ...
+//
+// the tensor-core kernels of both groups run back to back on one high-priority stream, so the tensor pipe never waits for the tree kernels
+// of the other group, which run on the CUDA cores of the same SMs meanwhile (the tower CTA leaves > 30 KB of shared
+// memory and most of the register file free).  Search results do not depend on the schedule: games are independent,
+// and the evaluation cache — the only state the groups share — is transparent.  Its protocol between the groups:
+// an entry under evaluation by the OTHER group's wave in flight (stamp == peer_wave) is followed like one of the own
+// wave (late kernel after the other group's evaluator: ev_eval) and is never chosen as an eviction victim, so a
+// fill never races with a claim of the same entry; the leader's features stay in feat_slot until the followers of
+// both groups have read them (ev_late).
+static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1) {
     kv_mcts* m = ctx->mcts;
-    const int G = m->G, GS = m->G * m->cfg.inflight;
+    const int K = m->cfg.inflight;
+    const int G = g1 - g0, GS = G * K, s0 = g0 * K;
     const int grid = (G + kMW - 1) / kMW, grid_s = (GS + kMW - 1) / kMW;
     const uint32_t wave = ++m->wave;
-    m->waves_run++;
-    KV_CUDA(ctx, cudaMemsetAsync(m->A.n_eval, 0, sizeof(uint32_t), st));
-    if (m->cfg.cache_mask) KV_CUDA(ctx, cudaMemsetAsync(m->A.n_late, 0, sizeof(uint32_t), st));
+    const int q = grp > 0 ? 1 : 0, peer = 1 - q;
+    const bool piped = grp >= 0;
+    // the group's view of the arrays: own counters and queues, global feat_slot
+    MctsArrays A = m->A;
+    A.n_eval += q;
+    A.n_late += q;
+    A.eval_game += s0;
+    A.eval_lines += (size_t)s0 * LINE_WORDS;
+    A.eval_centry += s0;
+    A.eval_hash += s0;
+    A.late_game += s0;
+    A.late_src += s0;
+    A.slot_base = s0;
+    A.peer_wave = piped ? m->last_wave[peer] : 0;
+    if (piped) m->last_wave[q] = wave;
+    const bool cache = m->cfg.cache_mask != 0;
+    KV_CUDA(ctx, cudaMemsetAsync(A.n_eval, 0, sizeof(uint32_t), st));
+    if (cache) KV_CUDA(ctx, cudaMemsetAsync(A.n_late, 0, sizeof(uint32_t), st));
     {
         KvTimed t_(ctx, KVK_MCTS_SELECT, st);
-        mcts_select_kernel<<<grid, kMW * 32, 0, st>>>(m->cfg, m->A, G, wave);
+        if (piped) mcts_select_kernel<kMWP><<<(G + kMWP - 1) / kMWP, kMWP * 32, 0, st>>>(m->cfg, A, g0, g1, wave);
+        else mcts_select_kernel<kMW><<<grid, kMW * 32, 0, st>>>(m->cfg, A, g0, g1, wave);
     }
     KV_LAUNCH_CHECK(ctx);
+    auto wait_peer = [&](cudaEvent_t* ev, bool* rec) -> int {
+        if (piped && rec[peer]) KV_CUDA(ctx, cudaStreamWaitEvent(st, ev[peer], 0));
+        return 0;
+    };
+    auto mark = [&](cudaEvent_t* ev, bool* rec) -> int {
+        if (piped) {
+            KV_CUDA(ctx, cudaEventRecord(ev[q], st));
+            rec[q] = true;
+        }
+        return 0;
+    };
     if (m->cfg.eval_mode == 0) {
-        KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
-        mcts_hash_eval_kernel<<<grid_s, kMW * 32, 0, st>>>(m->cfg, m->A, wave);
+        // no tower here: ev_tower stands for "selection done", and the evaluator waits for the other group's, which
+        // keeps the order the tower alternation gives the network path (a fill never meets a selection that does not
+        // know its wave as peer_wave)
+        if (int rc = wait_peer(m->ev_tower, m->tower_rec)) return rc;
+        if (int rc = mark(m->ev_tower, m->tower_rec)) return rc;
+        if (cache)
+            if (int rc = wait_peer(m->ev_late, m->late_rec)) return rc;   // feat_slot of this group is rewritten now
+        {
+            KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
+            mcts_hash_eval_kernel<<<grid_s, kMW * 32, 0, st>>>(m->cfg, A, wave);
+        }
         KV_LAUNCH_CHECK(ctx);
-        if (m->cfg.cache_mask) {
-            mcts_hash_late_kernel<<<grid_s, kMW * 32, 0, st>>>(m->cfg, m->A);
+        if (cache) {
+            if (int rc = mark(m->ev_eval, m->eval_rec)) return rc;
+            if (int rc = wait_peer(m->ev_eval, m->eval_rec)) return rc;   // followers of the other group's leaders
+            mcts_hash_late_kernel<<<grid_s, kMW * 32, 0, st>>>(m->cfg, A);
             KV_LAUNCH_CHECK(ctx);
+            if (int rc = mark(m->ev_late, m->late_rec)) return rc;
         }
     } else {
         int fb = 0;
-        if (int rc = kv_net_tower(ctx, m->A.eval_lines, GS, st, &fb, -1, reinterpret_cast<const int*>(m->A.n_eval))) return rc;
         kv_net* net = ctx->net;
+        if (int rc = kv_net_tower(ctx, A.eval_lines, GS, st, &fb, -1, reinterpret_cast<const int*>(A.n_eval), s0,
+                                  piped ? m->tower : nullptr, piped ? m->ev_stem[q] : nullptr))
+            return rc;
+        if (piped) {   // the group's stream continues when its tower is through
+            KV_CUDA(ctx, cudaEventRecord(m->ev_tower[q], m->tower));
+            m->tower_rec[q] = true;
+            KV_CUDA(ctx, cudaStreamWaitEvent(st, m->ev_tower[q], 0));
+        }
+        const int cmax = net->C > net->C1 ? net->C : net->C1;
+        const __nv_bfloat16* act = net->act[fb] + (size_t)s0 * 64 * cmax;
         HeadW H{net->wh, net->bh, net->wfc, net->bfc, net->w1, net->b1, net->w2, net->b2, net->C};
-        KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
-        mcts_eval_net_kernel<<<GS, 256, 0, st>>>(m->cfg, m->A, net->act[fb], H, wave);
+        if (cache)
+            if (int rc = wait_peer(m->ev_late, m->late_rec)) return rc;
+        {
+            KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
+            mcts_eval_net_kernel<<<GS, 256, 0, st>>>(m->cfg, A, act, H, wave);
+        }
         KV_LAUNCH_CHECK(ctx);
-        if (m->cfg.cache_mask) {
-            mcts_late_net_kernel<<<GS, 128, 0, st>>>(m->cfg, m->A, H);
+        if (cache) {
+            if (int rc = mark(m->ev_eval, m->eval_rec)) return rc;
+            if (int rc = wait_peer(m->ev_eval, m->eval_rec)) return rc;
+            {
+                KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
+                mcts_late_net_kernel<<<GS, 128, 0, st>>>(m->cfg, A, H);
+            }
             KV_LAUNCH_CHECK(ctx);
+            if (int rc = mark(m->ev_late, m->late_rec)) return rc;
         }
     }
-    if (m->cfg.inflight > 1) {
+    if (K > 1) {
         KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
-        mcts_backup_kernel<<<grid, kMW * 32, 0, st>>>(m->cfg, m->A, G);
+        mcts_backup_kernel<<<grid, kMW * 32, 0, st>>>(m->cfg, A, g0, g1);
         KV_LAUNCH_CHECK(ctx);
     }
+    return 0;
+}
+
+// Two groups when the evaluator is the network and each half still fills the tensor-core kernel's grid; the split is
+// a multiple of 8 games so that group 1's activations start on a tile boundary.
+static bool mcts_piped(const kv_ctx* ctx) {
+    const kv_mcts* m = ctx->mcts;
+    if (m->G < 16) return false;
+    if (m->pipeline >= 0) return m->pipeline != 0;
+    const kv_net* net = ctx->net;
+    if (m->cfg.eval_mode != 1 || !net) return false;
+    const int cmax = net->C > net->C1 ? net->C : net->C1;
+    if (cmax % net->C || cmax % net->C1) return false;
+    return (long long)m->G * m->cfg.inflight >= 2048;
+}
+
+static int mcts_pipe_setup(kv_ctx* ctx) {
+    kv_mcts* m = ctx->mcts;
+    if (m->side) return 0;
+    int lo = 0, hi = 0;
+    KV_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically lowest = greatest priority
+    KV_CUDA(ctx, cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+    KV_CUDA(ctx, cudaStreamCreateWithPriority(&m->tower, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 2; i++) {
+        KV_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_stem[i], cudaEventDisableTiming));
+        KV_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_tower[i], cudaEventDisableTiming));
+        KV_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_eval[i], cudaEventDisableTiming));
+        KV_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_late[i], cudaEventDisableTiming));
+    }
+    KV_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    KV_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    return 0;
+}
+
+// n_waves waves for every game.  Pipelined: fork the side stream off the caller's, alternate the groups, join.
+static int mcts_run_waves(kv_ctx* ctx, int n_waves, cudaStream_t st) {
+    kv_mcts* m = ctx->mcts;
+    if (n_waves <= 0) return 0;
+    if (!m->attrs_done) {
+        // the tree kernels share SMs with the tower CTAs (227 KB of dynamic shared memory): ask for the same carve-out
+        const int carve = cudaSharedmemCarveoutMaxShared;
+        cudaFuncSetAttribute(mcts_select_kernel<kMW>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(mcts_select_kernel<kMWP>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(mcts_eval_net_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(mcts_late_net_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(mcts_backup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaGetLastError();
+        m->attrs_done = true;
+    }
+    m->waves_run += n_waves;
+    if (!mcts_piped(ctx)) {
+        for (int i = 0; i < n_waves; i++)
+            if (int rc = mcts_wave_group(ctx, st, -1, 0, m->G)) return rc;
+        return 0;
+    }
+    if (int rc = mcts_pipe_setup(ctx)) return rc;
+    const int gh = ((m->G / 2) + 7) & ~7;
+    KV_CUDA(ctx, cudaEventRecord(m->ev_fork, st));
+    KV_CUDA(ctx, cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+    for (int i = 0; i < 2; i++) m->tower_rec[i] = m->eval_rec[i] = m->late_rec[i] = false;
+    m->last_wave[0] = m->last_wave[1] = 0;
+    for (int i = 0; i < n_waves; i++) {
+        if (int rc = mcts_wave_group(ctx, st, 0, 0, gh)) return rc;
+        if (int rc = mcts_wave_group(ctx, m->side, 1, gh, m->G)) return rc;
+    }
+    KV_CUDA(ctx, cudaEventRecord(m->ev_join, m->side));
+    KV_CUDA(ctx, cudaStreamWaitEvent(st, m->ev_join, 0));
     return 0;
 }
 
@@ -460,8 +627,15 @@ int kv_mcts_cache_clear(kv_ctx* ctx, void* stream) {
 
 int kv_mcts_run_sims(kv_ctx* ctx, int n_waves, void* stream) {
     if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_run_sims: no search context");
-    for (int i = 0; i < n_waves; i++)
-        if (int rc = mcts_wave(ctx, (cudaStream_t)stream)) return rc;
+    return mcts_run_waves(ctx, n_waves, (cudaStream_t)stream);
+}
+
+// Pipelined search on two game groups: mode -1 automatic (on for the network evaluator from 2 048 leaves per wave),
+// 0 off, 1 on (any evaluator, at least 16 games).  Search results are identical either way.
+int kv_mcts_set_pipeline(kv_ctx* ctx, int mode) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_set_pipeline: no search context");
+    if (mode < -1 || mode > 1) return kv_fail_msg(ctx, "kv_mcts_set_pipeline: mode must be -1, 0 or 1");
+    ctx->mcts->pipeline = mode;
     return 0;
 }
 

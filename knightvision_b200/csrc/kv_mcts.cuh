@@ -100,6 +100,12 @@ struct MctsArrays {
     // game records (scripts/self_play.py:173-174): position bitboards + the move played
     uint64_t* rec_line;    // [G][rec_cap][12]
     uint16_t* rec_move;    // [G][rec_cap]
+    // Pipelined search (kv_mcts.cu): the games are split into two groups whose waves alternate on two streams.  A
+    // launch gets a VIEW of these arrays: n_eval / n_late / eval_* / late_* point at the group's own queues, while
+    // feat_slot stays global and is indexed by slot_base + (slot inside the group's queue) — the index a cache entry
+    // under evaluation publishes, so that a leaf of one group can follow a leader of the other group.
+    int slot_base = 0;
+    uint32_t peer_wave = 0;   // wave id of the other group's wave still in flight (0 = none)
 };
 
 KV_DEV float f_from_bits(uint32_t u) { return kvd_u2f(u); }
@@ -175,6 +181,7 @@ KV_DEV int cache_lookup_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, 
             const uint64_t kb = lane < 12 ? ld_cg_u64(&e->bb[lane]) : 0ull;
             const bool same = ballot(lane < 12 && kb != w) == 0;
             const uint32_t stamp = ld_cg_u32(&e->stamp), pend = ld_cg_u32(&e->pend);
+            mem_fence();   // the other group's evaluator may be filling this entry right now: payload after pend == 0
             float f0 = ld_cg_f32(&e->hp[lane * 4]), f1 = ld_cg_f32(&e->hp[lane * 4 + 1]);
             float f2 = ld_cg_f32(&e->hp[lane * 4 + 2]), f3 = ld_cg_f32(&e->hp[lane * 4 + 3]);
             const float v = ld_cg_f32(&e->v);
@@ -191,7 +198,7 @@ KV_DEV int cache_lookup_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, 
                     }
                     return 1;
                 }
-                if (stamp == wave) {
+                if (stamp == wave || (A.peer_wave && stamp == A.peer_wave)) {   // leader's slot in feat_slot (global)
                     aux = (int)pend - 1;
                     return 2;
                 }
@@ -218,7 +225,8 @@ KV_DEV int cache_claim_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, u
         t = ld_cg_u64(&e->tag);
         const uint32_t stamp = ld_cg_u32(&e->stamp);
         if (t == 0) key = 0;
-        else if (t != CACHE_LOCKED && stamp != wave) key = 1u + (stamp & 0x7FFFFFFFu);
+        else if (t != CACHE_LOCKED && stamp != wave && !(A.peer_wave && stamp == A.peer_wave))
+            key = 1u + (stamp & 0x7FFFFFFFu);
     }
     // min key over lanes 0..3 (ties -> lowest lane)
     uint32_t bk = key;
@@ -244,7 +252,7 @@ KV_DEV int cache_claim_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, u
     if (!ok) return -1;
     if (lane < 12) e->bb[lane] = w;
     if (lane == 12) e->stamp = wave;
-    if (lane == 13) e->pend = 1u + (uint32_t)slot;
+    if (lane == 13) e->pend = 1u + (uint32_t)(A.slot_base + slot);
     mem_fence();
     syncwarp();
     if (lane == 0) atomic_store_u64(&e->tag, h);
@@ -255,13 +263,13 @@ KV_DEV int cache_claim_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, u
 // cache entry is still ours, fill its payload.  hp may be null (hash evaluator: only the value is meaningful).
 KV_DEV void cache_fill_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, uint32_t wave, int slot, const float* hp,
                             float v_white) {
-    float* fs = A.feat_slot + (size_t)slot * FEAT;
+    float* fs = A.feat_slot + (size_t)(A.slot_base + slot) * FEAT;
     for (int i = lane; i < 128; i += 32) fs[i] = hp ? hp[i] : 0.0f;
     if (lane == 0) fs[128] = v_white;
     const int ci = A.eval_centry[slot];
     if (ci < 0) return;
     CacheEntry* e = &A.cache[ci];
-    if (e->tag != A.eval_hash[slot] || e->pend != 1u + (uint32_t)slot || e->stamp != wave) return;
+    if (e->tag != A.eval_hash[slot] || e->pend != 1u + (uint32_t)(A.slot_base + slot) || e->stamp != wave) return;
     for (int i = lane; i < 128; i += 32) e->hp[i] = hp ? hp[i] : 0.0f;
     if (lane == 0) e->v = v_white;
     mem_fence();

@@ -46,6 +46,7 @@ struct ConvParams {
     bf16* out;
     int m_tiles, n_tiles, kb_per_tap, cout, m_valid, relu;
     const int* n_ptr;   // optional device-side board count (search waves): overrides m_tiles / m_valid
+    int board_base;     // first board of this launch inside the activation buffers (out / residual are already offset)
 };
 
 // epilogue of one 32-column chunk of one output row: +bias (+residual) -> ReLU -> bf16 -> four 16 B stores
@@ -166,7 +167,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (lane == 0) {
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     kvu::mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-                    kvu::tma_load_4d(sa, &tmA, &full[stage], kb * BK, dx, dy, m_tile * 2);
+                    kvu::tma_load_4d(sa, &tmA, &full[stage], kb * BK, dx, dy, P.board_base + m_tile * 2);
                     kvu::tma_load_2d(sa + A_BYTES, &tmB, &full[stage], ks * BK, n_tile * BN);
                 }
                 __syncwarp();
@@ -249,7 +250,9 @@ constexpr int CONV2_SMEM = STAGES2 * STAGE2_BYTES + 1024 + 256;
 
 constexpr int CONV2_THREADS = 384;   // warps 0-2 producer / MMA / TMEM, warp 3 idle, warps 4-11 epilogue
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV2_THREADS, 1)
+// 128 registers (56 B of epilogue spill): 384 threads x 128 leave a quarter of the register file — and ~33 KB of shared
+// memory — to the tree-search kernels that share the SM with this CTA in the pipelined search (kv_mcts.cu)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128)
 conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, ConvParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -304,7 +307,7 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (lane == 0) {
                     uint8_t* sa = smem + stage * STAGE2_BYTES;
                     if (rank == 0) kvu::mbar_arrive_expect_tx(&full[stage], 2 * STAGE2_BYTES);
-                    kvu::tma2_load_4d(sa, &tmA, &full[stage], kb * BK, dx, dy, m_tile * 4 + (int)rank * 2);
+                    kvu::tma2_load_4d(sa, &tmA, &full[stage], kb * BK, dx, dy, P.board_base + m_tile * 4 + (int)rank * 2);
                     kvu::tma2_load_2d(sa + A_BYTES, &tmBh, &full[stage], ks * BK, n_tile * BN + (int)rank * (BN / 2));
                 }
                 __syncwarp();
@@ -631,8 +634,10 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
     for (int i = 0; i < 3; i++) {
         KV_CUDA(ctx, cudaMalloc(&n->act[i], (size_t)n->cap * 64 * cmax * sizeof(bf16)));
         KV_CUDA(ctx, cudaMemset(n->act[i], 0, (size_t)n->cap * 64 * cmax * sizeof(bf16)));
-        if (int rc = make_act_map(ctx, &n->map_act[i][0], n->act[i], n->C1, n->cap)) return rc;
-        if (int rc = make_act_map(ctx, &n->map_act[i][1], n->act[i], n->C, n->cap)) return rc;
+        // each view spans the whole buffer (cap * cmax / C boards of C channels): a launch at board_base > 0 starts at
+        // byte offset board_base * 64 * cmax * 2 in EVERY view, so the regions of two game groups never overlap
+        if (int rc = make_act_map(ctx, &n->map_act[i][0], n->act[i], n->C1, (int)((size_t)n->cap * cmax / n->C1))) return rc;
+        if (int rc = make_act_map(ctx, &n->map_act[i][1], n->act[i], n->C, (int)((size_t)n->cap * cmax / n->C))) return rc;
     }
     const int nconv = (n->has_conv2 ? 1 : 0) + 2 * n->blocks;
     n->convs.resize(nconv);
@@ -765,6 +770,7 @@ int kv_conv_launch(kv_ctx* ctx, const bf16* x, const bf16* w_packed, const float
     P.m_valid = n * 64;
     P.relu = relu;
     P.n_ptr = nullptr;
+    P.board_base = 0;
     const int total = P.m_tiles * P.n_tiles;
     const int pairs = ctx->sm_count / 2;
     const int grid = 2 * (total < pairs ? total : pairs);
@@ -776,22 +782,36 @@ int kv_conv_launch(kv_ctx* ctx, const bf16* x, const bf16* w_packed, const float
 
 // Runs stem + tower for n boards; returns the buffer index holding the final activations.
 int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, int* final_buf, int max_convs,
-                 const int* n_ptr) {
+                 const int* n_ptr, int board_base, cudaStream_t conv_stream, cudaEvent_t handoff) {
     kv_net* net = ctx->net;
     if (!net || !net->loaded) return kv_fail_msg(ctx, "net: weights not loaded");
-    if (n > net->cap) return kv_fail_msg(ctx, "net: batch exceeds max_boards given to kv_net_create");
+    if (board_base < 0 || board_base + n > net->cap)
+        return kv_fail_msg(ctx, "net: batch exceeds max_boards given to kv_net_create");
+    const int cmax = net->C > net->C1 ? net->C : net->C1;
+    if (board_base && (cmax % net->C || cmax % net->C1))
+        return kv_fail_msg(ctx, "net: board_base needs channel counts that divide each other");
+    const size_t off0 = (size_t)board_base * 64 * cmax;   // element offset of this launch in every activation buffer
     {
         KvTimed t_(ctx, KVK_NET_STEM, st);
-        stem_kernel<<<n, 256, 0, st>>>(d_lines, n, n_ptr, net->stem_table, net->stem_bias, net->act[0], net->C1);
+        stem_kernel<<<n, 256, 0, st>>>(d_lines, n, n_ptr, net->stem_table, net->stem_bias, net->act[0] + off0, net->C1);
     }
     KV_LAUNCH_CHECK(ctx);
+    // pipelined search: the tensor-core kernels of both game groups run on one (high-priority) stream, in issue order;
+    // everything up to here ran on the group's own stream and overlaps the other group's tower
+    cudaStream_t cs = st;
+    if (conv_stream && handoff) {
+        KV_CUDA(ctx, cudaEventRecord(handoff, st));
+        KV_CUDA(ctx, cudaStreamWaitEvent(conv_stream, handoff, 0));
+        cs = conv_stream;
+    }
     int x = 0;   // buffer holding the current block input
     auto conv = [&](int layer, int in, int out, int res, int relu) -> int {
         kv_conv& L = net->convs[layer];
         ConvParams P;
         P.bias = L.b;
-        P.residual = res >= 0 ? net->act[res] : nullptr;
-        P.out = net->act[out];
+        P.residual = res >= 0 ? net->act[res] + off0 : nullptr;
+        P.out = net->act[out] + off0;
+        P.board_base = board_base * (cmax / L.cin);   // in boards of the input view
         P.m_tiles = (n + 1) / 2;
         P.n_tiles = L.cout / BN;
         P.kb_per_tap = L.cin / BK;
@@ -805,13 +825,13 @@ int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, i
             const int total = P.m_tiles * P.n_tiles;
             const int pairs = ctx->sm_count / 2;
             const int grid = 2 * (total < pairs ? total : pairs);
-            KvTimed t_(ctx, KVK_NET_CONV, st);
-            conv3x3_umma2_kernel<<<grid, CONV2_THREADS, CONV2_SMEM, st>>>(amap, L.map_half, P);
+            KvTimed t_(ctx, KVK_NET_CONV, cs);
+            conv3x3_umma2_kernel<<<grid, CONV2_THREADS, CONV2_SMEM, cs>>>(amap, L.map_half, P);
         } else {
             const int total = P.m_tiles * P.n_tiles;
             const int grid = total < ctx->sm_count ? total : ctx->sm_count;
-            KvTimed t_(ctx, KVK_NET_CONV, st);
-            conv3x3_umma_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(amap, L.map, P);
+            KvTimed t_(ctx, KVK_NET_CONV, cs);
+            conv3x3_umma_kernel<<<grid, CONV_THREADS, CONV_SMEM, cs>>>(amap, L.map, P);
         }
         KV_LAUNCH_CHECK(ctx);
         return 0;

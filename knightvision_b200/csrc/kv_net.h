@@ -1,6 +1,7 @@
 // kv_net.h — device-resident network state (kv_net.cu), shared with the MCTS translation unit
 #pragma once
 #include <cuda.h>
+#include <cuda_runtime.h>
 #include <cuda_bf16.h>
 
 #include <vector>
@@ -33,9 +34,13 @@ struct kv_net {
 };
 
 struct kv_ctx;
-// n = boards (grid sizing / upper bound); n_ptr = optional device-side count that overrides n inside the kernels
+// n = boards (grid sizing / upper bound); n_ptr = optional device-side count that overrides n inside the kernels;
+// board_base = first board of this launch inside the activation buffers (the result is at act[*final_buf] +
+// board_base * 64 * max(C, C1)); conv_stream + handoff = run the tensor-core kernels on another stream (the stem stays
+// on st; handoff is recorded on st and waited for by conv_stream; the caller orders st after conv_stream again)
 int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, int* final_buf, int max_convs = -1,
-                 const int* n_ptr = nullptr);
+                 const int* n_ptr = nullptr, int board_base = 0, cudaStream_t conv_stream = nullptr,
+                 cudaEvent_t handoff = nullptr);
 
 // training path (kv_train.cu): activation tensor map over a caller-owned NHWC bf16 tensor [boards][8][8][C] with TMA
 // boxes of {64 channels, 8, 8, box_boards}; one 3x3 convolution through the tower kernel on caller-owned tensors

@@ -273,6 +273,11 @@ class Engine:
     def mcts_run_move(self):
         N.check(self.ctx, self._lib.kv_mcts_run_move(self.ctx, self._stream()), "kv_mcts_run_move")
 
+    def mcts_set_pipeline(self, mode: int = -1):
+        """Two game groups whose waves alternate on two streams (tree kernels of one group under the other group's
+        tower): -1 automatic (default), 0 off, 1 on.  Search results are identical either way."""
+        N.check(self.ctx, self._lib.kv_mcts_set_pipeline(self.ctx, mode), "kv_mcts_set_pipeline")
+
     def mcts_waves(self) -> int:
         """Search waves launched since mcts_create (with K > 1 a move takes a data-dependent number of waves)."""
         return int(self._lib.kv_mcts_waves(self.ctx))

@@ -79,7 +79,7 @@ def mcts_search(start, sims, id_base=0, ply=0, edges_per_node=48, c_puct=1.5, di
 
 
 def selfplay(start, sims, max_plies, temp_plies, id_base=0, edges_per_node=48, c_puct=1.5, dir_alpha=0.3, dir_eps=0.25,
-             seed=1, cache_log2=0, return_counts=False, inflight=1):
+             seed=1, cache_log2=0, return_counts=False, inflight=1, pipe_order=0):
     start = np.ascontiguousarray(start, dtype=np.uint64)
     G = start.shape[0]
     moves = np.zeros((G, max_plies), np.uint16); plies = np.zeros(G, np.int32); res = np.zeros(G, np.int32)
@@ -88,7 +88,7 @@ def selfplay(start, sims, max_plies, temp_plies, id_base=0, edges_per_node=48, c
                          ctypes.c_int(edges_per_node), ctypes.c_int(max_plies), ctypes.c_int(temp_plies),
                          ctypes.c_float(c_puct), ctypes.c_float(dir_alpha), ctypes.c_float(dir_eps),
                          ctypes.c_uint64(seed), _p(moves), _p(plies), _p(res), ctypes.c_int(cache_log2), _p(cnt),
-                         ctypes.c_int(inflight))
+                         ctypes.c_int(inflight), ctypes.c_int(pipe_order))
     if return_counts:
         return moves, plies, res, (int(cnt[0]), int(cnt[1]))
     return moves, plies, res

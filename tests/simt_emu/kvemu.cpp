@@ -289,33 +289,131 @@ static void emu_mcts_reset(EmuMcts* m, const uint64_t* start, uint64_t id_base) 
 static uint32_t g_emu_wave = 0;
 static long g_emu_evals = 0, g_emu_late = 0;
 
-static void emu_mcts_wave(EmuMcts* m) {
+static int g_emu_pipe = 0;   // 0: one group; 1..3: two groups, one of the interleavings kv_mcts.cu's events allow
+
+// the view of the arrays a group's launches get (mirrors mcts_wave_group in kv_mcts.cu)
+static kv::MctsArrays emu_view(EmuMcts* m, int q, int s0, uint32_t peer_wave) {
+    kv::MctsArrays A = m->A;
+    A.n_eval += q;
+    A.n_late += q;
+    A.eval_game += s0;
+    A.eval_lines += (size_t)s0 * 16;
+    A.eval_centry += s0;
+    A.eval_hash += s0;
+    A.late_game += s0;
+    A.late_src += s0;
+    A.slot_base = s0;
+    A.peer_wave = peer_wave;
+    return A;
+}
+
+struct EmuGroup {
+    int g0 = 0, g1 = 0;
+    kv::MctsArrays A;
+    uint32_t wave = 0;
+};
+
+static void emu_select(EmuMcts* m, EmuGroup& G) {
     uint16_t mv[kv::MAX_MOVES];
+    *G.A.n_eval = 0;
+    *G.A.n_late = 0;
+    for (int g = G.g0; g < G.g1; g++)
+        kvemu::run_warp([&](int lane) { kv::mcts_select_warp(g_tables, lane, m->cfg, G.A, g, mv, G.wave); });
+}
+static void emu_eval(EmuMcts* m, EmuGroup& G) {
     float scratch[kv::MAX_MOVES];
-    const uint32_t wave = ++g_emu_wave;
-    *m->A.n_eval = 0;
-    *m->A.n_late = 0;
-    for (int g = 0; g < m->G; g++)
-        kvemu::run_warp([&](int lane) { kv::mcts_select_warp(g_tables, lane, m->cfg, m->A, g, mv, wave); });
-    const int ne = (int)*m->A.n_eval, nl = (int)*m->A.n_late;
+    const int ne = (int)*G.A.n_eval;
     g_emu_evals += ne;
-    g_emu_late += nl;
     for (int slot = 0; slot < ne; slot++)
-        kvemu::run_warp([&](int lane) { kv::mcts_hash_eval_warp(lane, m->cfg, m->A, slot, scratch, wave); });
+        kvemu::run_warp([&](int lane) { kv::mcts_hash_eval_warp(lane, m->cfg, G.A, slot, scratch, G.wave); });
+}
+static void emu_late(EmuMcts* m, EmuGroup& G) {
+    float scratch[kv::MAX_MOVES];
+    const int nl = (int)*G.A.n_late;
+    g_emu_late += nl;
     for (int li = 0; li < nl; li++)
-        kvemu::run_warp([&](int lane) { kv::mcts_hash_late_warp(lane, m->cfg, m->A, li, scratch); });
+        kvemu::run_warp([&](int lane) { kv::mcts_hash_late_warp(lane, m->cfg, G.A, li, scratch); });
     if (m->cfg.inflight > 1)
-        for (int g = 0; g < m->G; g++)
-            kvemu::run_warp([&](int lane) { kv::mcts_backup_game_warp(lane, m->cfg, m->A, g); });
+        for (int g = G.g0; g < G.g1; g++)
+            kvemu::run_warp([&](int lane) { kv::mcts_backup_game_warp(lane, m->cfg, G.A, g); });
+}
+
+static void emu_mcts_wave(EmuMcts* m) {
+    EmuGroup G;
+    G.g1 = m->G;
+    G.wave = ++g_emu_wave;
+    G.A = emu_view(m, 0, 0, 0);
+    emu_select(m, G);
+    emu_eval(m, G);
+    emu_late(m, G);
+}
+
+// n waves for both groups in one of the orders the device's stream/event graph admits (kv_mcts.cu mcts_run_waves):
+//   1: A and B strictly one after the other          selA evA ltA | selB evB ltB
+//   2: both selections first                          selA selB | evA ltA evB ltB      (B follows A's pending leaders)
+//   3: A runs one selection ahead                     ... selB(w) evA(w) ltA(w) selA(w+1) evB(w) ltB(w)
+//                                                     (A(w+1) follows B(w)'s pending leaders as well)
+static void emu_mcts_waves_piped(EmuMcts* m, int n, int order) {
+    const int K = m->cfg.inflight;
+    const int gh = ((m->G / 2) + 7) & ~7;
+    EmuGroup A, B;
+    A.g0 = 0; A.g1 = gh;
+    B.g0 = gh; B.g1 = m->G;
+    uint32_t lastA = 0, lastB = 0;
+    auto begin = [&](EmuGroup& X, int q, uint32_t peer) {
+        X.wave = ++g_emu_wave;
+        X.A = emu_view(m, q, X.g0 * K, peer);
+    };
+    if (order == 3) {
+        begin(A, 0, 0);
+        lastA = A.wave;
+        emu_select(m, A);
+    }
+    for (int w = 0; w < n; w++) {
+        if (order == 1) {
+            begin(A, 0, lastB); lastA = A.wave;
+            emu_select(m, A); emu_eval(m, A); emu_late(m, A);
+            begin(B, 1, lastA); lastB = B.wave;
+            emu_select(m, B); emu_eval(m, B); emu_late(m, B);
+        } else if (order == 2) {
+            begin(A, 0, lastB); lastA = A.wave;
+            emu_select(m, A);
+            begin(B, 1, lastA); lastB = B.wave;
+            emu_select(m, B);
+            emu_eval(m, A); emu_late(m, A);
+            emu_eval(m, B); emu_late(m, B);
+        } else {
+            begin(B, 1, lastA); lastB = B.wave;
+            emu_select(m, B);
+            emu_eval(m, A); emu_late(m, A);
+            if (w + 1 < n) {
+                EmuGroup A2 = A;
+                begin(A2, 0, lastB); lastA = A2.wave;
+                emu_select(m, A2);
+                emu_eval(m, B); emu_late(m, B);
+                A = A2;
+            } else {
+                emu_eval(m, B); emu_late(m, B);
+            }
+        }
+    }
 }
 
 // the driver loop of kv_mcts_run_move: waves until every live game has run its simulations
 static void emu_mcts_move_waves(EmuMcts* m) {
+    const bool piped = g_emu_pipe > 0 && m->G >= 16;
+    const int K = m->cfg.inflight, S = m->cfg.sims;
+    int n = K == 1 ? S : 1 + (S - 1 + K - 1) / K;
     for (;;) {
         bool left = false;
         for (int g = 0; g < m->G; g++) left |= !m->A.hdr[g].done && m->A.hdr[g].sims_done < m->cfg.sims;
         if (!left) break;
-        emu_mcts_wave(m);
+        if (piped) {
+            emu_mcts_waves_piped(m, n, g_emu_pipe);
+            n = 2;
+        } else {
+            emu_mcts_wave(m);
+        }
     }
 }
 
@@ -362,9 +460,11 @@ __attribute__((visibility("default"))) void kvemu_selfplay(int G, const uint64_t
                                                             int edges_per_node, int max_plies, int temp_plies,
                                                             float c_puct, float dir_alpha, float dir_eps, uint64_t seed,
                                                             uint16_t* out_moves, int32_t* out_plies, int32_t* out_result,
-                                                            int cache_log2, int64_t* out_counts2, int inflight) {
+                                                            int cache_log2, int64_t* out_counts2, int inflight,
+                                                            int pipe_order) {
     EmuMcts* m = emu_mcts_new(G, sims, edges_per_node, max_plies, temp_plies, c_puct, dir_alpha, dir_eps, seed, cache_log2,
                               inflight);
+    g_emu_pipe = pipe_order;
     g_emu_evals = g_emu_late = 0;
     emu_mcts_reset(m, start, id_base);
     for (int mvno = 0; mvno < max_plies; mvno++) {
@@ -384,6 +484,7 @@ __attribute__((visibility("default"))) void kvemu_selfplay(int G, const uint64_t
         out_counts2[0] = g_emu_evals;
         out_counts2[1] = g_emu_late;
     }
+    g_emu_pipe = 0;
     delete m;
 }
 

@@ -87,6 +87,26 @@ def test_eval_cache_does_not_change_games():
     assert base[3][1] == 0
 
 
+def test_pipelined_groups_do_not_change_games():
+    """Two game groups with alternating waves (kv_mcts.cu mcts_run_waves): every interleaving the stream/event graph
+    admits gives the games of the plain schedule, with and without the shared evaluation cache (cross-group followers
+    included), for K = 1 and with virtual loss."""
+    lines = H.random_playout_positions(n_games=2, max_plies=40, seed=12)
+    # 20 games = groups of 16 + 4; the initial position is in both groups, so leaves of one group follow leaders of the other
+    start = np.concatenate([np.stack([L.start_line()] * 8), lines[[3, 9, 17, 25, 31, 38]], np.stack([L.start_line()] * 6)])
+    for K, sims, cases in ((1, 12, ((0, 2), (7, 1), (7, 2), (7, 3), (13, 3))), (4, 16, ((7, 2), (13, 3)))):
+        base = emu.selfplay(start, sims=sims, max_plies=4, temp_plies=2, id_base=21, seed=13, inflight=K,
+                            return_counts=True)
+        for log2, order in cases:
+            got = emu.selfplay(start, sims=sims, max_plies=4, temp_plies=2, id_base=21, seed=13, inflight=K,
+                               cache_log2=log2, return_counts=True, pipe_order=order)
+            assert np.array_equal(base[0], got[0]) and np.array_equal(base[1], got[1])
+            assert np.array_equal(base[2], got[2])
+            evals, late = got[3]
+            assert evals + late == base[3][0]
+            assert (late > 0) == (log2 > 0)
+
+
 def test_policy_sampling_mode_sims_1():
     """sims = 1 is the reference's move rule (sample from softmax + Dirichlet over the legal moves, no search)."""
     start = np.stack([L.start_line()] * 3)

@@ -133,13 +133,22 @@ def test_full_size_wave_4096_games(eng):
     assert eng.mcts_status()["plies"] == 4096
 
 
-def _play_records(eng, G, sims, moves, eval_mode, cache_log2, seed=13):
-    eng.mcts_create(G, sims, max_plies=moves, temp_plies=4, seed=seed, eval_mode=eval_mode)
+def _play_records(eng, G, sims, moves, eval_mode, cache_log2, seed=13, pipeline=0, inflight=1):
+    eng.mcts_create(G, sims, max_plies=moves, temp_plies=4, seed=seed, eval_mode=eval_mode, inflight=inflight)
+    eng.mcts_set_pipeline(pipeline)
     eng.mcts_enable_cache(cache_log2)
     eng.mcts_reset(None, game_id_base=50)
     roots = []
     for i in range(moves):
-        eng.mcts_run_sims(sims)
+        if inflight == 1:
+            eng.mcts_run_sims(sims)
+        else:
+            eng.mcts_run_sims(1 + (sims - 2 + inflight) // inflight)
+            while True:
+                st = eng.mcts_status()
+                if st["sims_in_move"] >= (G - st["done"]) * sims:
+                    break
+                eng.mcts_run_sims(1)
         if i == moves - 1:
             roots = [eng.mcts_read_root(g) for g in (0, G // 2, G - 1)]
         eng.mcts_finish_move()
@@ -166,6 +175,50 @@ def test_eval_cache_is_transparent(eng, eval_mode):
             assert np.array_equal(ra["N"], rb["N"]) and np.array_equal(_bits(ra["W"]), _bits(rb["W"]))
             assert np.array_equal(_bits(ra["P"]), _bits(rb["P"]))
         assert st["cache_hits"] > 0 and st["evals"] + st["cache_hits"] == bst["evals"]
+    eng.mcts_enable_cache(0)
+
+
+@pytest.mark.parametrize("eval_mode,K", [(0, 1), (1, 1), (1, 4)])
+def test_pipelined_groups_are_transparent(eng, eval_mode, K):
+    """Two game groups whose waves alternate on two streams (kv_mcts_set_pipeline): the same games, visit counts, W and
+    prior bits as the single-stream schedule, with the shared evaluation cache off, tiny (evictions while the other
+    group's evaluator is filling) and roomy (leaves of one group following leaders of the other)."""
+    if eval_mode == 1:
+        from knightvision_b200.model import ChessNet
+        torch.manual_seed(0)
+        ChessNet().eval().attach(eng, max_batch=200 * K)
+    G, sims, moves = 200, 40, 5          # groups of 104 + 96 games
+    base, broots, bst = _play_records(eng, G, sims, moves, eval_mode, 0, pipeline=0, inflight=K)
+    for log2 in (0, 10, 18):
+        rec, roots, st = _play_records(eng, G, sims, moves, eval_mode, log2, pipeline=1, inflight=K)
+        for a, b in zip(base, rec):
+            assert np.array_equal(a, b)
+        for ra, rb in zip(broots, roots):
+            assert np.array_equal(ra["N"], rb["N"]) and np.array_equal(_bits(ra["W"]), _bits(rb["W"]))
+            assert np.array_equal(_bits(ra["P"]), _bits(rb["P"]))
+        assert st["evals"] + st["cache_hits"] == bst["evals"] and (st["cache_hits"] > 0) == (log2 > 0)
+    eng.mcts_enable_cache(0)
+
+
+def test_pipelined_selfplay_hash_evaluator_matches_oracle(eng):
+    """Whole games through kv_mcts_run_move with the pipelined schedule, against the sequential oracle."""
+    G, sims, max_plies = 40, 24, 30
+    eng.mcts_create(G, sims, max_plies=max_plies, temp_plies=8, seed=15, eval_mode=0)
+    eng.mcts_set_pipeline(1)
+    eng.mcts_enable_cache(12)
+    eng.mcts_reset(None, game_id_base=0)
+    for _ in range(max_plies):
+        eng.mcts_run_move()
+    st = eng.mcts_status()
+    assert st["done"] == G and st["cache_hits"] > 0
+    rl, move, reward, game = (t.cpu().numpy() for t in eng.mcts_records())
+    cfg = O.mcts_cfg(sims, temp_plies=8, max_plies=max_plies, seed=15)
+    for g in range(G):
+        m, pos, res = O.selfplay_game(cfg, L.start_line(), game_id=g)
+        sel = game == g
+        assert sel.sum() == len(m), g
+        assert np.array_equal(move[sel], [O.lib().kvo_move_index(int(x)) for x in m]), g
+        assert np.array_equal(rl.view(np.uint64)[sel][:, :12], pos[:, :12]), g
     eng.mcts_enable_cache(0)
 
 
