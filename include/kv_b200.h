@@ -114,6 +114,10 @@ KV_API int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int
 /* tower kernel variant: 1 = one CTA per 128x256 tile (tcgen05 cta_group::1), 2 = CTA pairs sharing the weight tile
  * (cta_group::2, 256x256 per pair; default).  Bit-identical outputs. */
 KV_API int kv_net_set_conv_mode(kv_ctx* ctx, int cta_group);
+/* 1 (default) = the tower convolutions of a forward pass run as ONE launch scheduled by tile dependencies (a 3x3
+ * convolution is board-local: no grid-wide barrier between layers, no per-layer tail); 0 = one launch per layer.
+ * CTA-pair kernel only.  Bit-identical outputs. */
+KV_API int kv_net_set_tower_fused(kv_ctx* ctx, int on);
 KV_API uint64_t kv_net_blob_floats(kv_ctx* ctx);
 KV_API int kv_net_load(kv_ctx* ctx, const float* h_blob, uint64_t n_floats);
 /* Device staging buffer of kv_net_blob_floats() floats: write the blob there (e.g. as the target of an NCCL

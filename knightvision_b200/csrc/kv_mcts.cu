@@ -41,9 +41,10 @@ __global__ void __launch_bounds__(MW * 32, 16 / MW) mcts_select_kernel(MctsCfg c
     __shared__ MctsSmemT<MW> sm;
     stage_tables_m(sm.tab);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int g = g0 + blockIdx.x * MW + wid;
-    if (g >= g1) return;
-    mcts_select_warp(sm.tab, lane, cfg, A, g, sm.mv[wid], wave);
+    // grid-stride over the games: the pipelined search launches only as many CTAs as fit NEXT TO the resident tower
+    // CTAs (so they never keep the next tower layer waiting for an SM); otherwise one game per warp, one pass
+    for (int g = g0 + blockIdx.x * MW + wid; g < g1; g += gridDim.x * MW)
+        mcts_select_warp(sm.tab, lane, cfg, A, g, sm.mv[wid], wave);
 }
 
 __global__ void __launch_bounds__(kMW * 32) mcts_hash_eval_kernel(MctsCfg cfg, MctsArrays A, uint32_t wave) {
@@ -65,9 +66,7 @@ __global__ void __launch_bounds__(kMW * 32) mcts_hash_late_kernel(MctsCfg cfg, M
 // K > 1 only: warp per game, backs the wave's pending simulations up in slot order (after every expansion)
 __global__ void __launch_bounds__(kMW * 32) mcts_backup_kernel(MctsCfg cfg, MctsArrays A, int g0, int g1) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int g = g0 + blockIdx.x * kMW + wid;
-    if (g >= g1) return;
-    mcts_backup_game_warp(lane, cfg, A, g);
+    for (int g = g0 + blockIdx.x * kMW + wid; g < g1; g += gridDim.x * kMW) mcts_backup_game_warp(lane, cfg, A, g);
 }
 
 __global__ void __launch_bounds__(kMW * 32) mcts_finish_move_kernel(MctsCfg cfg, MctsArrays A, int G) {
@@ -121,32 +120,36 @@ __global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArr
                                                             HeadW H, uint32_t wave) {
     __shared__ float hp[128], hv[64], red[8], logits[MAX_MOVES];
     __shared__ __align__(16) float swh[3 * 512];
-    const int slot = blockIdx.x;
-    if (slot >= (int)*A.n_eval) return;
-    const int gs = A.eval_game[slot];
-    kvn::head_features(act + (size_t)slot * 64 * H.C, H.C, H.wh, H.bh, hp, hv, swh);
-    __syncthreads();
-    const float v_white = kvn::value_mlp(hv, H.w1, H.b1, H.w2, H.b2, red);
-    legal_logits(cfg, A, gs, H, hp, logits);
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, v_white);
-        if (cfg.cache_mask) cache_fill_warp((int)threadIdx.x, cfg, A, wave, slot, hp, v_white);
+    const int n_eval = (int)*A.n_eval;
+    for (int slot = blockIdx.x; slot < n_eval; slot += gridDim.x) {   // grid-stride: see mcts_select_kernel
+        const int gs = A.eval_game[slot];
+        kvn::head_features(act + (size_t)slot * 64 * H.C, H.C, H.wh, H.bh, hp, hv, swh);
+        __syncthreads();
+        const float v_white = kvn::value_mlp(hv, H.w1, H.b1, H.w2, H.b2, red);
+        legal_logits(cfg, A, gs, H, hp, logits);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, v_white);
+            if (cfg.cache_mask) cache_fill_warp((int)threadIdx.x, cfg, A, wave, slot, hp, v_white);
+        }
+        __syncthreads();   // hp / hv / red / logits are reused by the next leaf
     }
 }
 
 // CTA (128 threads) per late entry: features from the cache (already copied per game) or from this wave's leader
 __global__ void __launch_bounds__(128) mcts_late_net_kernel(MctsCfg cfg, MctsArrays A, HeadW H) {
     __shared__ float hp[FEAT], logits[MAX_MOVES];
-    const int li = blockIdx.x;
-    if (li >= (int)*A.n_late) return;
-    const int gs = A.late_game[li], src = A.late_src[li];
-    const float* f = src < 0 ? A.feat_game + (size_t)gs * FEAT : A.feat_slot + (size_t)src * FEAT;
-    for (int i = threadIdx.x; i < FEAT; i += blockDim.x) hp[i] = f[i];
-    __syncthreads();
-    legal_logits(cfg, A, gs, H, hp, logits);
-    __syncthreads();
-    if (threadIdx.x < 32) mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, hp[128], true);
+    const int n_late = (int)*A.n_late;
+    for (int li = blockIdx.x; li < n_late; li += gridDim.x) {
+        const int gs = A.late_game[li], src = A.late_src[li];
+        const float* f = src < 0 ? A.feat_game + (size_t)gs * FEAT : A.feat_slot + (size_t)src * FEAT;
+        for (int i = threadIdx.x; i < FEAT; i += blockDim.x) hp[i] = f[i];
+        __syncthreads();
+        legal_logits(cfg, A, gs, H, hp, logits);
+        __syncthreads();
+        if (threadIdx.x < 32) mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, hp[128], true);
+        __syncthreads();
+    }
 }
 
 __global__ void mcts_init_kernel(MctsCfg cfg, MctsArrays A, int G, const uint64_t* __restrict__ start, uint64_t id_base) {
@@ -423,6 +426,10 @@ static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1
     const uint32_t wave = ++m->wave;
     const int q = grp > 0 ? 1 : 0, peer = 1 - q;
     const bool piped = grp >= 0;
+    // pipelined: grids sized to what fits beside one tower CTA per SM (16 K registers, ~33 KB of shared memory free):
+    // 2 selection CTAs (64 threads x 128 registers), 1 evaluator CTA (256 x 40), 3 late CTAs (128 x 40), 2 backup CTAs
+    const int sms = ctx->sm_count;
+    auto imin = [](int a, int b) { return a < b ? a : b; };
     // the group's view of the arrays: own counters and queues, global feat_slot
     MctsArrays A = m->A;
     A.n_eval += q;
@@ -441,7 +448,7 @@ static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1
     if (cache) KV_CUDA(ctx, cudaMemsetAsync(A.n_late, 0, sizeof(uint32_t), st));
     {
         KvTimed t_(ctx, KVK_MCTS_SELECT, st);
-        if (piped) mcts_select_kernel<kMWP><<<(G + kMWP - 1) / kMWP, kMWP * 32, 0, st>>>(m->cfg, A, g0, g1, wave);
+        if (piped) mcts_select_kernel<kMWP><<<imin((G + kMWP - 1) / kMWP, 2 * sms), kMWP * 32, 0, st>>>(m->cfg, A, g0, g1, wave);
         else mcts_select_kernel<kMW><<<grid, kMW * 32, 0, st>>>(m->cfg, A, g0, g1, wave);
     }
     KV_LAUNCH_CHECK(ctx);
@@ -480,7 +487,7 @@ static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1
         int fb = 0;
         kv_net* net = ctx->net;
         if (int rc = kv_net_tower(ctx, A.eval_lines, GS, st, &fb, -1, reinterpret_cast<const int*>(A.n_eval), s0,
-                                  piped ? m->tower : nullptr, piped ? m->ev_stem[q] : nullptr))
+                                  piped ? m->tower : nullptr, piped ? m->ev_stem[q] : nullptr, piped ? sms : 0))
             return rc;
         if (piped) {   // the group's stream continues when its tower is through
             KV_CUDA(ctx, cudaEventRecord(m->ev_tower[q], m->tower));
@@ -494,7 +501,7 @@ static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1
             if (int rc = wait_peer(m->ev_late, m->late_rec)) return rc;
         {
             KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
-            mcts_eval_net_kernel<<<GS, 256, 0, st>>>(m->cfg, A, act, H, wave);
+            mcts_eval_net_kernel<<<piped ? imin(GS, sms) : GS, 256, 0, st>>>(m->cfg, A, act, H, wave);
         }
         KV_LAUNCH_CHECK(ctx);
         if (cache) {
@@ -502,7 +509,7 @@ static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1
             if (int rc = wait_peer(m->ev_eval, m->eval_rec)) return rc;
             {
                 KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
-                mcts_late_net_kernel<<<GS, 128, 0, st>>>(m->cfg, A, H);
+                mcts_late_net_kernel<<<piped ? imin(GS, 3 * sms) : GS, 128, 0, st>>>(m->cfg, A, H);
             }
             KV_LAUNCH_CHECK(ctx);
             if (int rc = mark(m->ev_late, m->late_rec)) return rc;
@@ -510,7 +517,7 @@ static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1
     }
     if (K > 1) {
         KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
-        mcts_backup_kernel<<<grid, kMW * 32, 0, st>>>(m->cfg, A, g0, g1);
+        mcts_backup_kernel<<<piped ? imin(grid, 2 * sms) : grid, kMW * 32, 0, st>>>(m->cfg, A, g0, g1);
         KV_LAUNCH_CHECK(ctx);
     }
     return 0;

@@ -389,6 +389,219 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (warp == 2) kvu::tmem_dealloc2(tmem_base, 512);
 }
 
+// ---- the whole tower as ONE launch: a dependency-driven schedule over (layer, board tile, channel tile) tasks ------
+// A 3x3 convolution is board-local, so tile (l, m, n) — layer l, boards [4m, 4m+4), output channels [256n, 256n+256) —
+// needs exactly the two tiles (l-1, m, 0..1).  Tasks are numbered layer-major, t = (l * M + m) * NT + n, and CTA pair
+// c runs t = c, c + pairs, ... in order: with >= 74 tiles per layer a task's inputs were finished about a layer's worth
+// of time ago, so the waits below almost never spin, there is NO grid-wide barrier and no per-layer tail (the eleven
+// tile-granular tails of the per-layer launches — half a round each on average, 3 % of a 2 500-board tower — shrink
+// to one).  done[l][m] counts the epilogue warps that have stored their part of (l, m, .): 2 channel tiles x 2 CTAs x
+// 8 warps = 32.  Writers: st.global -> fence.proxy.async (the readers are TMA loads, the async proxy) -> __threadfence
+// -> red.release; readers: ld.acquire -> fence.proxy.async -> TMA.  Deadlock-free: a task waits only for tasks with a
+// smaller number, every pair runs its tasks in increasing order, and all pairs are resident (grid <= 148 CTAs, 1 / SM).
+// The spin is bounded and traps (a protocol bug must not hang the GPU box).
+struct alignas(128) TowerLayerDev {
+    CUtensorMap wmap;        // this layer's weights, {64, 128} boxes (one CTA's half of the N tile)
+    const float* bias;
+    int in_buf, in_view;     // activation buffer 0..2 and view (0: C1 channels, 1: C channels) of the input
+    int out_buf, res_buf;    // res_buf < 0: no residual
+    int kb_per_tap, relu;
+    int pad_[24];
+};
+static_assert(sizeof(TowerLayerDev) == 256, "TowerLayerDev layout");
+
+struct TowerActMaps {
+    CUtensorMap m[3][2];
+};
+
+struct TowerArgs {
+    bf16* act[3];            // activation buffers, already offset to this launch's first board
+    const TowerLayerDev* layers;
+    uint32_t* done;          // [n_layers][m_stride], zeroed before the launch
+    const int* n_ptr;        // optional device-side board count
+    int n_layers, m_stride, n_boards, cout;
+    int board_base[2];       // first board of this launch in the C1 / C view of the buffers
+};
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u32(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr uint32_t TOWER_TILE_DONE = 32;
+// one lane polls, the warp follows
+__device__ __forceinline__ void tower_wait_tile(const uint32_t* flag, int lane) {
+    if (lane == 0) {
+        uint32_t it = 0;
+        while (ld_acquire_u32(flag) < TOWER_TILE_DONE) {
+            __nanosleep(64);
+            if (++it > (1u << 24)) __trap();
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128)
+tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
+    uint64_t* empty = full + STAGES2;
+    uint64_t* tfull = empty + STAGES2;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = kvu::cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES2; s++) {
+            kvu::mbar_init(&full[s], 1);
+            kvu::mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            kvu::mbar_init(&tfull[a], 1);
+            kvu::mbar_init(&tempty[a], 512);   // 256 epilogue threads of each CTA
+        }
+        kvu::fence_barrier_init();
+    }
+    if (warp == 2) kvu::tmem_alloc2(tmem_slot, 512);
+    kvu::tc_fence_before();
+    __syncthreads();
+    kvu::cluster_sync();
+    kvu::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nb = T.n_ptr ? *T.n_ptr : T.n_boards;
+    const int M = (nb + 3) >> 2, NT = T.cout / BN;
+    const int m_valid = nb * 64;
+    const int per_layer = M * NT, total = T.n_layers * per_layer;
+
+    if (warp == 0) {
+        // ---- TMA producer (both CTAs) ---------------------------------------------------------------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = cluster_id; t < total; t += n_clusters) {
+            const int l = t / per_layer, r = t - l * per_layer;
+            const int m_tile = r / NT, n_tile = r - m_tile * NT;
+            const TowerLayerDev* L = T.layers + l;
+            const int kb_per_tap = L->kb_per_tap, ksteps = 9 * kb_per_tap;
+            const CUtensorMap* tmA = &maps.m[L->in_buf][L->in_view];
+            const int b0 = T.board_base[L->in_view] + m_tile * 4 + (int)rank * 2;
+            if (l > 0) {   // the input tile must be complete (all channels of these four boards)
+                tower_wait_tile(T.done + (size_t)(l - 1) * T.m_stride + m_tile, lane);
+                fence_proxy_async();
+            }
+            for (int ks = 0; ks < ksteps; ks++) {
+                const int tap = ks / kb_per_tap, kb = ks - tap * kb_per_tap;
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                kvu::mbar_wait(&empty[stage], phase ^ 1);
+                if (lane == 0) {
+                    uint8_t* sa = smem + stage * STAGE2_BYTES;
+                    if (rank == 0) kvu::mbar_arrive_expect_tx(&full[stage], 2 * STAGE2_BYTES);
+                    kvu::tma2_load_4d(sa, tmA, &full[stage], kb * BK, dx, dy, b0);
+                    kvu::tma2_load_2d(sa + A_BYTES, &L->wmap, &full[stage], ks * BK, n_tile * BN + (int)rank * (BN / 2));
+                }
+                __syncwarp();
+                if (++stage == STAGES2) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ---- MMA issuer (leader CTA only) -------------------------------------------------------------------
+        constexpr uint32_t idesc = kvu::make_idesc_bf16(2 * BM, BN);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int t = cluster_id; t < total; t += n_clusters) {
+            const int l = t / per_layer;
+            const int ksteps = 9 * T.layers[l].kb_per_tap;
+            kvu::mbar_wait(&tempty[acc], acc_phase ^ 1);
+            kvu::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+            for (int ks = 0; ks < ksteps; ks++) {
+                kvu::mbar_wait(&full[stage], phase);
+                kvu::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = kvu::smem_u32(smem + stage * STAGE2_BYTES);
+                    const uint64_t adesc = kvu::make_sw128_kmajor_desc(sa);
+                    const uint64_t bdesc = kvu::make_sw128_kmajor_desc(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++)
+                        kvu::umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+                    kvu::umma2_commit_mc(&empty[stage]);
+                    if (ks == ksteps - 1) kvu::umma2_commit_mc(&tfull[acc]);
+                }
+                __syncwarp();
+                if (++stage == STAGES2) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue (both CTAs, own 128 rows): 8 warps = 4 TMEM lane quarters x 2 column halves -------------------
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = cluster_id; t < total; t += n_clusters) {
+            const int l = t / per_layer, r = t - l * per_layer;
+            const int m_tile = r / NT, n_tile = r - m_tile * NT;
+            const TowerLayerDev* L = T.layers + l;
+            ConvParams P;
+            P.bias = L->bias;
+            P.out = T.act[L->out_buf];
+            P.residual = L->res_buf >= 0 ? T.act[L->res_buf] : nullptr;
+            P.relu = L->relu;
+            const int row = m_tile * 2 * BM + (int)rank * BM + q * 32 + lane;
+            const bool valid = row < m_valid;
+            const int colb = n_tile * BN + half * (BN / 2);
+            const size_t rbase = (size_t)row * T.cout + (size_t)colb;
+            uint4 res[4][4];
+            if (P.residual) {
+                // the residual is the output of layer l-2 for these boards: complete once (l-1, m, .) is, which the
+                // accumulator below cannot precede anyway
+                if (l > 0) tower_wait_tile(T.done + (size_t)(l - 1) * T.m_stride + m_tile, lane);
+                if (valid) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(P.residual + rbase);
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) res[c][j] = __ldcg(rp + c * 4 + j);
+                }
+            }
+            kvu::mbar_wait(&tfull[acc], acc_phase);
+            kvu::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t v[32];
+                kvu::tmem_ld_32x32(tmem_base + (uint32_t)acc * BN + half * (BN / 2) + c * 32 + ((uint32_t)(q * 32) << 16), v);
+                kvu::tmem_ld_wait();
+                if (valid) conv_epilogue_store_pf(P, v, res[c], rbase + c * 32, colb + c * 32);
+            }
+            kvu::tc_fence_before();
+            kvu::mbar_arrive_leader(&tempty[acc]);
+            // publish this warp's part of the tile to the TMA loads of the next layer
+            fence_proxy_async();
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) red_release_add_u32(T.done + (size_t)l * T.m_stride + m_tile, 1u);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    kvu::tc_fence_before();
+    __syncthreads();
+    kvu::cluster_sync();   // the peer may still be signalling this CTA's barriers / reading its B half
+    if (warp == 2) kvu::tmem_dealloc2(tmem_base, 512);
+}
+
 // ---- stem: encode + conv1 + bn1 + relu ------------------------------------------------------------------
 // table [9 taps][12 pieces][C1] fp32 (BN scale folded), bias [C1].  One CTA per board.  A warp owns one pixel at a
 // time and its lanes own 8 consecutive channels each: table rows are read as coalesced float4 pairs (L1-resident,
@@ -398,9 +611,9 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint64_t* __restrict__ 
                                                    const float* __restrict__ table, const float* __restrict__ bias,
                                                    bf16* __restrict__ out, int C1) {
     __shared__ int8_t piece[64];
-    const int b = blockIdx.x;
     if (n_ptr) n = *n_ptr;
-    if (b >= n) return;
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {   // grid-stride (the pipelined search launches one CTA per SM)
+    __syncthreads();                                    // piece[] of the previous board is no longer read
     if (threadIdx.x < 64) {
         int pc = -1;
 #pragma unroll
@@ -440,6 +653,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint64_t* __restrict__ 
             o.w = *reinterpret_cast<const uint32_t*>(&p3);
             *reinterpret_cast<uint4*>(out + ((size_t)b * 64 + px) * C1 + c0) = o;
         }
+    }
     }
 }
 
@@ -595,6 +809,26 @@ static size_t net_blob_floats(const kv_net* n) {
     return t;
 }
 
+// buffer rotation of the tower: conv2 (0 -> 1), then per residual block x -> t -> o (+ x), x = o
+struct TowerStep {
+    int in, out, res;
+};
+static std::vector<TowerStep> tower_plan(const kv_net* n) {
+    std::vector<TowerStep> p;
+    int x = 0;
+    if (n->has_conv2) {
+        p.push_back({0, 1, -1});
+        x = 1;
+    }
+    for (int b = 0; b < n->blocks; b++) {
+        const int t = (x + 1) % 3, o = (x + 2) % 3;
+        p.push_back({x, t, -1});
+        p.push_back({t, o, x});
+        x = o;
+    }
+    return p;
+}
+
 void kv_net_destroy(kv_ctx* ctx) {
     kv_net* n = ctx->net;
     if (!n) return;
@@ -605,7 +839,7 @@ void kv_net_destroy(kv_ctx* ctx) {
     for (int i = 0; i < 3; i++)
         if (n->act[i]) cudaFree(n->act[i]);
     void* ptrs[] = {n->stem_table, n->stem_bias, n->wh, n->bh, n->wfc, n->bfc, n->w1, n->b1, n->w2, n->b2, n->d_blob,
-                    n->d_flag, n->d_lines_tmp};
+                    n->d_flag, n->d_lines_tmp, n->d_layers, n->d_done[0], n->d_done[1]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete n;
@@ -667,6 +901,36 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
     KV_CUDA(ctx, cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
     KV_CUDA(ctx, cudaFuncSetAttribute(conv3x3_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_SMEM));
     if (const char* e = getenv("KV_CONV_CTA_GROUP")) n->conv_mode = atoi(e) == 1 ? 1 : 2;
+    // the whole-tower launch: per-layer table (weight map, bias, buffer rotation) and the tile-completion counters
+    KV_CUDA(ctx, cudaFuncSetAttribute(tower_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_SMEM));
+    if (nconv > 0) {
+        std::vector<TowerLayerDev> tab(nconv);
+        std::vector<TowerStep> plan = tower_plan(n);
+        for (int l = 0; l < nconv; l++) {
+            memset(&tab[l], 0, sizeof(TowerLayerDev));
+            tab[l].wmap = n->convs[l].map_half;
+            tab[l].bias = n->convs[l].b;
+            tab[l].in_buf = plan[l].in;
+            tab[l].in_view = (n->convs[l].cin == n->C1 && n->convs[l].cin != n->C) ? 0 : 1;
+            tab[l].out_buf = plan[l].out;
+            tab[l].res_buf = plan[l].res;
+            tab[l].kb_per_tap = n->convs[l].cin / BK;
+            tab[l].relu = 1;
+        }
+        KV_CUDA(ctx, cudaMalloc(&n->d_layers, nconv * sizeof(TowerLayerDev)));
+        KV_CUDA(ctx, cudaMemcpy(n->d_layers, tab.data(), nconv * sizeof(TowerLayerDev), cudaMemcpyHostToDevice));
+        n->m_stride = (n->cap + 3) / 4;
+        for (int i = 0; i < 2; i++) KV_CUDA(ctx, cudaMalloc(&n->d_done[i], (size_t)nconv * n->m_stride * sizeof(uint32_t)));
+    }
+    if (const char* e = getenv("KV_TOWER_FUSED")) n->tower_fused = atoi(e) != 0;
+    return 0;
+}
+
+// 1 (default) = the tower convolutions of a forward pass run as ONE dependency-scheduled launch (tower_umma2_kernel),
+// 0 = one launch per layer.  Same tiles, same arithmetic: bit-identical outputs.
+int kv_net_set_tower_fused(kv_ctx* ctx, int on) {
+    if (!ctx || !ctx->net) return kv_fail_msg(ctx, "kv_net_set_tower_fused: no net");
+    ctx->net->tower_fused = on != 0;
     return 0;
 }
 
@@ -782,7 +1046,7 @@ int kv_conv_launch(kv_ctx* ctx, const bf16* x, const bf16* w_packed, const float
 
 // Runs stem + tower for n boards; returns the buffer index holding the final activations.
 int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, int* final_buf, int max_convs,
-                 const int* n_ptr, int board_base, cudaStream_t conv_stream, cudaEvent_t handoff) {
+                 const int* n_ptr, int board_base, cudaStream_t conv_stream, cudaEvent_t handoff, int stem_grid) {
     kv_net* net = ctx->net;
     if (!net || !net->loaded) return kv_fail_msg(ctx, "net: weights not loaded");
     if (board_base < 0 || board_base + n > net->cap)
@@ -793,7 +1057,8 @@ int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, i
     const size_t off0 = (size_t)board_base * 64 * cmax;   // element offset of this launch in every activation buffer
     {
         KvTimed t_(ctx, KVK_NET_STEM, st);
-        stem_kernel<<<n, 256, 0, st>>>(d_lines, n, n_ptr, net->stem_table, net->stem_bias, net->act[0] + off0, net->C1);
+        stem_kernel<<<(stem_grid > 0 && stem_grid < n) ? stem_grid : n, 256, 0, st>>>(d_lines, n, n_ptr, net->stem_table,
+                                                                                      net->stem_bias, net->act[0] + off0, net->C1);
     }
     KV_LAUNCH_CHECK(ctx);
     // pipelined search: the tensor-core kernels of both game groups run on one (high-priority) stream, in issue order;
@@ -839,6 +1104,36 @@ int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, i
     int layer = 0;
     *final_buf = 0;
     if (max_convs == 0) return 0;
+    if (net->conv_mode == 2 && net->tower_fused && !net->convs.empty()) {
+        const std::vector<TowerStep> plan = tower_plan(net);
+        const int nl = (max_convs < 0 || max_convs > (int)plan.size()) ? (int)plan.size() : max_convs;
+        *final_buf = plan[nl - 1].out;
+        uint32_t* done = net->d_done[board_base ? 1 : 0];
+        KV_CUDA(ctx, cudaMemsetAsync(done, 0, (size_t)nl * net->m_stride * sizeof(uint32_t), cs));
+        TowerActMaps maps;
+        for (int i = 0; i < 3; i++)
+            for (int v = 0; v < 2; v++) maps.m[i][v] = net->map_act[i][v];
+        TowerArgs T;
+        for (int i = 0; i < 3; i++) T.act[i] = net->act[i] + off0;
+        T.layers = reinterpret_cast<const TowerLayerDev*>(net->d_layers);
+        T.done = done;
+        T.n_ptr = n_ptr;
+        T.n_layers = nl;
+        T.m_stride = net->m_stride;
+        T.n_boards = n;
+        T.cout = net->C;
+        T.board_base[0] = board_base * (cmax / net->C1);
+        T.board_base[1] = board_base * (cmax / net->C);
+        const int total = nl * ((n + 3) / 4) * (net->C / BN);
+        const int pairs = ctx->sm_count / 2;
+        const int grid = 2 * (total < pairs ? total : pairs);
+        {
+            KvTimed t_(ctx, KVK_NET_CONV, cs);
+            tower_umma2_kernel<<<grid, CONV2_THREADS, CONV2_SMEM, cs>>>(maps, T);
+        }
+        KV_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     if (net->has_conv2) {
         if (int rc = conv(layer++, 0, 1, -1, 1)) return rc;
         x = 1;

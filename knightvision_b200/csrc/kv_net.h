@@ -29,6 +29,10 @@ struct kv_net {
     float* d_blob = nullptr;               // fp32 state_dict staging (NCCL broadcast target)
     size_t blob_floats = 0;
     int conv_mode = 2;                     // 1: cta_group::1 kernel, 2: cta_group::2 CTA-pair kernel
+    int tower_fused = 1;                   // conv_mode 2 only: the whole tower as one dependency-scheduled launch
+    void* d_layers = nullptr;              // TowerLayerDev[convs.size()] (kv_net.cu)
+    uint32_t* d_done[2] = {nullptr, nullptr};   // tile-completion counters [layers][m_stride], one set per game group
+    int m_stride = 0;
     int* d_flag = nullptr;
     uint64_t* d_lines_tmp = nullptr;
 };
@@ -40,7 +44,7 @@ struct kv_ctx;
 // on st; handoff is recorded on st and waited for by conv_stream; the caller orders st after conv_stream again)
 int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, int* final_buf, int max_convs = -1,
                  const int* n_ptr = nullptr, int board_base = 0, cudaStream_t conv_stream = nullptr,
-                 cudaEvent_t handoff = nullptr);
+                 cudaEvent_t handoff = nullptr, int stem_grid = 0);   // stem_grid > 0: CTAs of the (grid-stride) stem
 
 // training path (kv_train.cu): activation tensor map over a caller-owned NHWC bf16 tensor [boards][8][8][C] with TMA
 // boxes of {64 channels, 8, 8, box_boards}; one 3x3 convolution through the tower kernel on caller-owned tensors

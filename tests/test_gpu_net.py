@@ -138,3 +138,23 @@ def test_cta_pair_kernel_matches_single_cta_kernel(eng):
     eng.net_set_conv_mode(2)
     assert torch.equal(outs[1][0], outs[2][0]) and torch.equal(outs[1][1], outs[2][1])
     assert torch.equal(outs[1][2][0], outs[2][2][0]) and torch.equal(outs[1][2][1], outs[2][2][1])
+
+
+@pytest.mark.parametrize("arch,n", [("ref", 1237), ("ref", 9), ("20x256", 333)])
+def test_whole_tower_launch_matches_per_layer_launches(eng, arch, n):
+    """tower_umma2_kernel (all layers in one launch, tiles scheduled by their dependencies) against one launch per
+    layer: same tiles, same arithmetic -> bit-identical activations and outputs; repeated runs agree (a missed
+    dependency would show up as run-to-run differences)."""
+    from knightvision_b200.engine import lines_to_device
+    kw = {} if arch == "ref" else dict(stem=256, tower=256, blocks=20, conv2=False)
+    net = _net(seed=11, bnrand=True, **kw).attach(eng, max_batch=n + 3)
+    lines = _lines(n, seed=21)
+    d = lines_to_device(lines, eng.device)
+    eng.net_set_tower_fused(False)
+    ref_mid = eng.net_forward_partial(d, 4).clone()
+    ref_pol, ref_val = (t.clone() for t in net.forward_lines(d))
+    eng.net_set_tower_fused(True)
+    for _ in range(4):
+        assert torch.equal(eng.net_forward_partial(d, 4), ref_mid)
+        pol, val = net.forward_lines(d)
+        assert torch.equal(pol, ref_pol) and torch.equal(val, ref_val)
