@@ -23,18 +23,20 @@ NET_FLOPS_PER_EVAL = 2.0 * 1587872256                                   # whole 
 
 
 def _ncu_traffic():
-    """Average DRAM bytes (read + write) per launch of the conv kernel from the committed ncu capture, or None."""
+    """Average DRAM bytes (read + write) per launch of the tower kernel from the committed ncu capture, or None."""
     import glob
     import re
     root = os.path.dirname(os.path.abspath(__file__))
-    files = sorted(glob.glob(os.path.join(root, "profiles", "*ncu_conv3x3*.txt")))
+    files = sorted(glob.glob(os.path.join(root, "profiles", "*ncu_tower_umma2*.txt")))
     if not files:
         return None, None
-    rd = [float(x) for x in re.findall(r"dram__bytes_read\.sum\s+([0-9.]+) Mbyte", open(files[-1]).read())]
-    wr = [float(x) for x in re.findall(r"dram__bytes_write\.sum\s+([0-9.]+) Mbyte", open(files[-1]).read())]
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    txt = open(files[-1]).read()
+    rd = [float(v) * unit[u] for v, u in re.findall(r"dram__bytes_read\.sum\s+([0-9.]+) (\w*byte)", txt)]
+    wr = [float(v) * unit[u] for v, u in re.findall(r"dram__bytes_write\.sum\s+([0-9.]+) (\w*byte)", txt)]
     if not rd or len(rd) != len(wr):
         return None, None
-    return 1e6 * (sum(rd) + sum(wr)) / len(rd), os.path.relpath(files[-1], root)
+    return (sum(rd) + sum(wr)) / len(rd), os.path.relpath(files[-1], root)
 
 
 def _cpu_eval_rate(batch=256, iters=4):
@@ -171,17 +173,17 @@ def run(args, rank, world, local_rank):
     hits = st1["cache_hits"] - st0["cache_hits"]
     positions = st1["plies"] - st0["plies"]
 
-    # ---- A2: the same moves on ONE stream (pipelined schedule off): what the two-group overlap is worth -----------------
-    single = None
+    # ---- A2: the same moves with the pipelined schedule (two game groups on two streams, opt-in) ---------------------------
+    alt = None
     if os.getenv("KV_BENCH_COMPARE", "1") != "0" and G >= 2048:
-        eng.mcts_set_pipeline(0)
+        eng.mcts_set_pipeline(1)
         eng.mcts_cache_clear()
         eng.mcts_reset(None, game_id_base=rank * G)
         for _ in range(warm):
             eng.mcts_run_move()
         s_ms, s0_, s1_, _, _ = timed_moves(args.steps)
-        single = {"ms_per_step": s_ms / args.steps, "sims": (G - s0_["done"]) * SIMS * args.steps,
-                  "evals": s1_["evals"] - s0_["evals"]}
+        alt = {"ms_per_step": s_ms / args.steps, "sims": (G - s0_["done"]) * SIMS * args.steps,
+               "evals": s1_["evals"] - s0_["evals"]}
         eng.mcts_set_pipeline(-1)
 
     # ---- B: e2e — the same positions through the public API with HOST buffers: pinned host lines -> device, cold
@@ -262,7 +264,7 @@ def run(args, rank, world, local_rank):
     peaks = measured_peaks()
     conv_ms, conv_n = prof["net_conv"]
     traffic, traffic_src = _ncu_traffic()
-    boards_per_launch = G // 2 if G >= 2048 else G     # pipelined schedule: every tower launch covers one game group
+    boards_per_launch = G
     achieved = (evals * CONV_FLOPS_PER_EVAL) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     value = sims_all / (dev_ms * 1e-3)
     e2e_sims = world * G * SIMS * e2e_steps
@@ -281,16 +283,16 @@ def run(args, rank, world, local_rank):
                        "served_per_sim": hits_all / sims_all if sims_all else None,
                        "note": "keyed by the 12 bitboards (the net's whole input); search results are bit-identical "
                                "with the cache on or off (tests/test_gpu_mcts.py::test_eval_cache_is_transparent)"},
-        "schedule": {"pipelined": G >= 2048,
-                     "note": "two game groups of G/2 whose waves alternate on two streams: the tree kernels (select / "
-                             "expand / backup, stem) of one group run on the CUDA cores under the other group's tensor-core "
-                             "tower; results are bit-identical to the single-stream schedule "
-                             "(tests/test_gpu_mcts.py::test_pipelined_groups_are_transparent)",
-                     "single_stream": ({"value": world * single["sims"] / (single["ms_per_step"] * args.steps * 1e-3),
-                                        "unit": "sims/s", "ms_per_step": single["ms_per_step"],
-                                        "evals_per_sim": single["evals"] / single["sims"] if single["sims"] else None,
-                                        "note": "rank 0's figures x world: same moves, same cold cache and warm-up, "
-                                                "pipelined schedule off"} if single else None)},
+        "schedule": {"tower": "one dependency-scheduled launch per evaluation batch (tower_umma2_kernel, depth-first chunks)",
+                     "pipelined": False,
+                     "pipelined_alt": ({"value": world * alt["sims"] / (alt["ms_per_step"] * args.steps * 1e-3),
+                                        "unit": "sims/s", "ms_per_step": alt["ms_per_step"],
+                                        "evals_per_sim": alt["evals"] / alt["sims"] if alt["sims"] else None,
+                                        "note": "rank 0's figures x world: same moves, same cold cache and warm-up, with "
+                                                "kv_mcts_set_pipeline(1): two game groups whose waves alternate on two "
+                                                "streams (tree kernels of one group under the other group's tower); "
+                                                "bit-identical results, opt-in because the step is power-bound"}
+                                       if alt else None)},
         "no_cache": ({"value": world * G * SIMS / (nocache_ms * 1e-3), "unit": "sims/s", "ms_per_step": nocache_ms,
                       "evals_per_sim": 1.0, "note": "same positions, evaluation cache disabled"} if nocache_ms else None),
         "random_positions": {"value": r_sims_all / (r_ms * 1e-3), "unit": "sims/s",
@@ -315,13 +317,14 @@ def run(args, rank, world, local_rank):
                 "api": ("SelfPlay public API on the timed region's own start positions: pinned host lines -> kv_mcts_reset -> "
                         "steps x kv_mcts_run_move -> records() as the reference's (planes, move, reward) tuples; "
                         "evaluation cache cleared first (new generation)")},
-        "roofline": {"kernel": "conv3x3_umma2_kernel (tcgen05 cta_group::2 implicit GEMM)", "bound": "tensor", "achieved": achieved,
+        "roofline": {"kernel": ("tower_umma2_kernel (tcgen05 cta_group::2 implicit GEMM, the 11 tower convolutions of one "
+                                "evaluation batch in one dependency-scheduled launch)"), "bound": "tensor", "achieved": achieved,
                      "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-                     "traffic": traffic, "traffic_source": (f"{traffic_src}: dram__bytes_read.sum + dram__bytes_write.sum per "
-                                                             f"launch of {boards_per_launch} boards (algorithmic per launch: "
-                                                             f"{boards_per_launch * 65536 / 1e6:.0f} MB in + "
-                                                             f"{boards_per_launch * 65536 / 1e6:.0f} MB out + 4.7 MB weights, "
-                                                             "+ as much again for the residual on every second layer)")
+                     "traffic": traffic, "traffic_source": (f"{traffic_src}: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                                             f"launch over {boards_per_launch} boards (a wave of the search "
+                                                             "evaluates fewer: evals_per_sim x games).  If every layer went through "
+                                                             "HBM the launch would move 7.1 GB (2.8 in + 2.95 out + 1.34 residual + "
+                                                             "0.05 weights); depth-first chunks keep a chunk's activations in L2")
                      if traffic else None,
                      "peak_source": peaks["source"] + ", sustained bf16 figure",
                      "kernel_ms_per_step": conv_ms / args.steps, "kernel_share_of_step": conv_ms / dev_ms,

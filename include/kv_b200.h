@@ -161,11 +161,12 @@ KV_API int kv_mcts_status(kv_ctx* ctx, uint64_t* h_out9, void* stream);
 KV_API int kv_mcts_get_roots(kv_ctx* ctx, uint64_t* d_lines, void* stream); /* current position of every game [n][16] */
 KV_API int kv_mcts_geometry(kv_ctx* ctx, int32_t* out4);              /* n_games, node_cap, edge_cap, rec_cap */
 KV_API int64_t kv_mcts_waves(kv_ctx* ctx);                            /* search waves launched since create */
-/* Pipelined search: the games are split into two groups whose waves alternate on two CUDA streams (the caller's and
- * an internal one, forked and joined inside every kv_mcts_run_* call), so that the tree kernels of one group run on
- * the CUDA cores while the tensor-core tower of the other group runs.  mode -1 = automatic (on with the network
- * evaluator from 2 048 leaves per wave; the default), 0 = off, 1 = on.  Search results are bit-identical either way
- * (games are independent; the shared evaluation cache is transparent). */
+/* Pipelined search (opt-in): the games are split into two groups whose waves alternate on two CUDA streams (the
+ * caller's and an internal one, forked and joined inside every kv_mcts_run_* call) plus a high-priority stream for the
+ * tensor-core kernels, so that the tree kernels of one group run on the CUDA cores while the tower of the other group
+ * runs.  mode -1 = default (off, unless the environment sets KV_MCTS_PIPELINE=1), 0 = off, 1 = on.  Search results are
+ * bit-identical either way (games are independent; the shared evaluation cache is transparent).  Measured gain on
+ * B200: about 1 % — the step is bound by the power cap, not by idle SMs. */
 KV_API int kv_mcts_set_pipeline(kv_ctx* ctx, int mode);
 /* records of every game in game order; d_lines [cap][16] board lines (kv_encode gives the reference's planes),
  * d_move policy index (ai/ai.py:51-57), d_reward 1.0 / 0.2 / -1.0 (scripts/self_play.py:245-250), d_game index */

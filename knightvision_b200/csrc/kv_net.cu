@@ -395,8 +395,8 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // c runs t = c, c + pairs, ... in order: with >= 74 tiles per layer a task's inputs were finished about a layer's worth
 // of time ago, so the waits below almost never spin, there is NO grid-wide barrier and no per-layer tail (the eleven
 // tile-granular tails of the per-layer launches — half a round each on average, 3 % of a 2 500-board tower — shrink
-// to one).  done[l][m] counts the epilogue warps that have stored their part of (l, m, .): 2 channel tiles x 2 CTAs x
-// 8 warps = 32.  Writers: st.global -> fence.proxy.async (the readers are TMA loads, the async proxy) -> __threadfence
+// to one).  done[l][m] counts the epilogue warps that have stored their part of (l, m, .): channel tiles x 2 CTAs x
+// 8 warps (32 for the 512-channel tower).  Writers: st.global -> fence.proxy.async (the readers are TMA loads, the async proxy) -> __threadfence
 // -> red.release; readers: ld.acquire -> fence.proxy.async -> TMA.  Deadlock-free: a task waits only for tasks with a
 // smaller number, every pair runs its tasks in increasing order, and all pairs are resident (grid <= 148 CTAs, 1 / SM).
 // The spin is bounded and traps (a protocol bug must not hang the GPU box).
@@ -421,6 +421,39 @@ struct TowerArgs {
     const int* n_ptr;        // optional device-side board count
     int n_layers, m_stride, n_boards, cout;
     int board_base[2];       // first board of this launch in the C1 / C view of the buffers
+    int chunk_tiles;         // depth-first order: board tiles per chunk (0 = layer-major over all boards)
+};
+
+// Task order.  Layer-major over ALL boards streams every layer's activations through HBM (a layer of 4 096 boards is
+// 268 MB, twice the L2).  Depth-first in chunks of Mc board tiles — all layers of chunk 0, then chunk 1, ... — keeps the
+// three ping-pong buffers of a chunk (Mc x 768 KB) in the 126 MB L2: a layer's output is read back from L2 and is
+// overwritten there before it is ever evicted.  Inside a chunk the order is layer-major, so a task's inputs were
+// finished Mc * NT tasks (>= 2 rounds of the 74 CTA pairs) ago.  The chunks are equal up to one tile (no small last
+// chunk whose layers would wait for each other).
+struct TowerOrder {
+    int M, NT, n_layers, n_chunks, Mc, big;   // the first `big` chunks have Mc tiles, the others Mc - 1
+    int total;
+    __device__ void init(int M_, int NT_, int n_layers_, int chunk_tiles) {
+        M = M_; NT = NT_; n_layers = n_layers_;
+        n_chunks = (chunk_tiles > 0 && M > 0) ? (M / chunk_tiles > 1 ? M / chunk_tiles : 1) : 1;
+        Mc = (M + n_chunks - 1) / n_chunks;
+        big = M - (Mc - 1) * n_chunks;
+        total = n_layers * M * NT;
+    }
+    __device__ void decode(int t, int& l, int& m_tile, int& n_tile) const {
+        const int full = n_layers * Mc * NT, tb = big * full;
+        int c, mc, m0;
+        if (t < tb) {
+            c = t / full; t -= c * full; mc = Mc; m0 = c * Mc;
+        } else {
+            const int small = n_layers * (Mc - 1) * NT;
+            t -= tb; c = t / small; t -= c * small; mc = Mc - 1; m0 = big * Mc + c * (Mc - 1);
+        }
+        l = t / (mc * NT);
+        const int r = t - l * mc * NT;
+        m_tile = m0 + r / NT;
+        n_tile = r - (r / NT) * NT;
+    }
 };
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -432,12 +465,11 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 __device__ __forceinline__ void red_release_add_u32(uint32_t* p, uint32_t v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-constexpr uint32_t TOWER_TILE_DONE = 32;
-// one lane polls, the warp follows
-__device__ __forceinline__ void tower_wait_tile(const uint32_t* flag, int lane) {
+// one lane polls, the warp follows; `need` = epilogue warps per board tile = channel tiles x 2 CTAs x 8 warps
+__device__ __forceinline__ void tower_wait_tile(const uint32_t* flag, uint32_t need, int lane) {
     if (lane == 0) {
         uint32_t it = 0;
-        while (ld_acquire_u32(flag) < TOWER_TILE_DONE) {
+        while (ld_acquire_u32(flag) < need) {
             __nanosleep(64);
             if (++it > (1u << 24)) __trap();
         }
@@ -478,21 +510,24 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
     const int nb = T.n_ptr ? *T.n_ptr : T.n_boards;
     const int M = (nb + 3) >> 2, NT = T.cout / BN;
     const int m_valid = nb * 64;
-    const int per_layer = M * NT, total = T.n_layers * per_layer;
+    TowerOrder ord;
+    ord.init(M, NT, T.n_layers, T.chunk_tiles);
+    const int total = ord.total;
+    const uint32_t need = 16u * (uint32_t)NT;
 
     if (warp == 0) {
         // ---- TMA producer (both CTAs) ---------------------------------------------------------------------
         int stage = 0;
         uint32_t phase = 0;
         for (int t = cluster_id; t < total; t += n_clusters) {
-            const int l = t / per_layer, r = t - l * per_layer;
-            const int m_tile = r / NT, n_tile = r - m_tile * NT;
+            int l, m_tile, n_tile;
+            ord.decode(t, l, m_tile, n_tile);
             const TowerLayerDev* L = T.layers + l;
             const int kb_per_tap = L->kb_per_tap, ksteps = 9 * kb_per_tap;
             const CUtensorMap* tmA = &maps.m[L->in_buf][L->in_view];
             const int b0 = T.board_base[L->in_view] + m_tile * 4 + (int)rank * 2;
             if (l > 0) {   // the input tile must be complete (all channels of these four boards)
-                tower_wait_tile(T.done + (size_t)(l - 1) * T.m_stride + m_tile, lane);
+                tower_wait_tile(T.done + (size_t)(l - 1) * T.m_stride + m_tile, need, lane);
                 fence_proxy_async();
             }
             for (int ks = 0; ks < ksteps; ks++) {
@@ -518,7 +553,8 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         for (int t = cluster_id; t < total; t += n_clusters) {
-            const int l = t / per_layer;
+            int l, m_tile, n_tile;
+            ord.decode(t, l, m_tile, n_tile);
             const int ksteps = 9 * T.layers[l].kb_per_tap;
             kvu::mbar_wait(&tempty[acc], acc_phase ^ 1);
             kvu::tc_fence_after();
@@ -551,8 +587,8 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = cluster_id; t < total; t += n_clusters) {
-            const int l = t / per_layer, r = t - l * per_layer;
-            const int m_tile = r / NT, n_tile = r - m_tile * NT;
+            int l, m_tile, n_tile;
+            ord.decode(t, l, m_tile, n_tile);
             const TowerLayerDev* L = T.layers + l;
             ConvParams P;
             P.bias = L->bias;
@@ -567,7 +603,7 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
             if (P.residual) {
                 // the residual is the output of layer l-2 for these boards: complete once (l-1, m, .) is, which the
                 // accumulator below cannot precede anyway
-                if (l > 0) tower_wait_tile(T.done + (size_t)(l - 1) * T.m_stride + m_tile, lane);
+                if (l > 0) tower_wait_tile(T.done + (size_t)(l - 1) * T.m_stride + m_tile, need, lane);
                 if (valid) {
                     const uint4* rp = reinterpret_cast<const uint4*>(P.residual + rbase);
 #pragma unroll
@@ -609,7 +645,7 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
 __global__ void __launch_bounds__(256) stem_kernel(const uint64_t* __restrict__ lines, int n,
                                                    const int* __restrict__ n_ptr,
                                                    const float* __restrict__ table, const float* __restrict__ bias,
-                                                   bf16* __restrict__ out, int C1) {
+                                                   bf16* __restrict__ out, int C1, int pitch) {
     __shared__ int8_t piece[64];
     if (n_ptr) n = *n_ptr;
     for (int b = blockIdx.x; b < n; b += gridDim.x) {   // grid-stride (the pipelined search launches one CTA per SM)
@@ -651,7 +687,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint64_t* __restrict__ 
             o.y = *reinterpret_cast<const uint32_t*>(&p1);
             o.z = *reinterpret_cast<const uint32_t*>(&p2);
             o.w = *reinterpret_cast<const uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>(out + ((size_t)b * 64 + px) * C1 + c0) = o;
+            *reinterpret_cast<uint4*>(out + ((size_t)b * 64 + px) * pitch + c0) = o;   // pixel pitch of the tower
         }
     }
     }
@@ -771,11 +807,13 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-int kv_make_act_map(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boards, int box_boards) {
+// pitch = elements between consecutive pixels (0: dense, = C)
+int kv_make_act_map(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boards, int box_boards, int pitch) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return kv_fail_msg(ctx, "cuTensorMapEncodeTiled unavailable");
+    if (pitch <= 0) pitch = C;
     cuuint64_t dims[4] = {(cuuint64_t)C, 8, 8, (cuuint64_t)boards};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 16, (cuuint64_t)C * 128};
+    cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * 16, (cuuint64_t)pitch * 128};
     cuuint32_t box[4] = {64, 8, 8, (cuuint32_t)box_boards};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -783,8 +821,8 @@ int kv_make_act_map(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boards, 
     if (r != CUDA_SUCCESS) return kv_fail_msg(ctx, "cuTensorMapEncodeTiled(activations) failed");
     return 0;
 }
-static int make_act_map(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boards) {
-    return kv_make_act_map(ctx, m, base, C, boards, 2);
+static int make_act_map(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boards, int pitch) {
+    return kv_make_act_map(ctx, m, base, C, boards, 2, pitch);
 }
 static int make_w_map(kv_ctx* ctx, CUtensorMap* m, void* base, int cout, int K, int box_rows = 256) {
     PFN_encodeTiled enc = get_encode();
@@ -854,6 +892,8 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
     if (stem_channels % 64 || tower_channels % 256 || stem_channels > 512 || tower_channels > 512 || n_blocks < 0 ||
         max_boards < 1)
         return kv_fail_msg(ctx, "kv_net_create: channels must be multiples of 64 (stem) / 256 (tower), <= 512");
+    if (stem_channels > tower_channels)
+        return kv_fail_msg(ctx, "kv_net_create: the stem must not be wider than the tower");
     if (!has_conv2 && stem_channels != tower_channels)
         return kv_fail_msg(ctx, "kv_net_create: without conv2 the stem must produce the tower width");
     kv_net_destroy(ctx);
@@ -868,10 +908,11 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
     for (int i = 0; i < 3; i++) {
         KV_CUDA(ctx, cudaMalloc(&n->act[i], (size_t)n->cap * 64 * cmax * sizeof(bf16)));
         KV_CUDA(ctx, cudaMemset(n->act[i], 0, (size_t)n->cap * 64 * cmax * sizeof(bf16)));
-        // each view spans the whole buffer (cap * cmax / C boards of C channels): a launch at board_base > 0 starts at
-        // byte offset board_base * 64 * cmax * 2 in EVERY view, so the regions of two game groups never overlap
-        if (int rc = make_act_map(ctx, &n->map_act[i][0], n->act[i], n->C1, (int)((size_t)n->cap * cmax / n->C1))) return rc;
-        if (int rc = make_act_map(ctx, &n->map_act[i][1], n->act[i], n->C, (int)((size_t)n->cap * cmax / n->C))) return rc;
+        // every view has the pixel pitch of the widest layer (cmax channels): board b lives at byte b * 64 * cmax * 2 in
+        // every view, so a narrower tensor (the stem output) aliases only the SAME board of a wider one — the
+        // dependency-scheduled tower relies on that (a tile's output may only overwrite data of its own boards)
+        if (int rc = make_act_map(ctx, &n->map_act[i][0], n->act[i], n->C1, n->cap, cmax)) return rc;
+        if (int rc = make_act_map(ctx, &n->map_act[i][1], n->act[i], n->C, n->cap, cmax)) return rc;
     }
     const int nconv = (n->has_conv2 ? 1 : 0) + 2 * n->blocks;
     n->convs.resize(nconv);
@@ -923,6 +964,10 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
         for (int i = 0; i < 2; i++) KV_CUDA(ctx, cudaMalloc(&n->d_done[i], (size_t)nconv * n->m_stride * sizeof(uint32_t)));
     }
     if (const char* e = getenv("KV_TOWER_FUSED")) n->tower_fused = atoi(e) != 0;
+    // depth-first chunks: one round of the CTA pairs per layer and channel tile, 57-85 MB of activations per chunk at
+    // 512 channels (more tiles for a narrower tower: same bytes)
+    n->tower_chunk = (ctx->sm_count / 2) * (512 / n->C);
+    if (const char* e = getenv("KV_TOWER_CHUNK")) n->tower_chunk = atoi(e);
     return 0;
 }
 
@@ -1051,14 +1096,12 @@ int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, i
     if (!net || !net->loaded) return kv_fail_msg(ctx, "net: weights not loaded");
     if (board_base < 0 || board_base + n > net->cap)
         return kv_fail_msg(ctx, "net: batch exceeds max_boards given to kv_net_create");
-    const int cmax = net->C > net->C1 ? net->C : net->C1;
-    if (board_base && (cmax % net->C || cmax % net->C1))
-        return kv_fail_msg(ctx, "net: board_base needs channel counts that divide each other");
+    const int cmax = net->C;   // C1 <= C (kv_net_create): every activation row has the tower's pixel pitch
     const size_t off0 = (size_t)board_base * 64 * cmax;   // element offset of this launch in every activation buffer
     {
         KvTimed t_(ctx, KVK_NET_STEM, st);
         stem_kernel<<<(stem_grid > 0 && stem_grid < n) ? stem_grid : n, 256, 0, st>>>(d_lines, n, n_ptr, net->stem_table,
-                                                                                      net->stem_bias, net->act[0] + off0, net->C1);
+                                                                                      net->stem_bias, net->act[0] + off0, net->C1, cmax);
     }
     KV_LAUNCH_CHECK(ctx);
     // pipelined search: the tensor-core kernels of both game groups run on one (high-priority) stream, in issue order;
@@ -1076,7 +1119,7 @@ int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, i
         P.bias = L.b;
         P.residual = res >= 0 ? net->act[res] + off0 : nullptr;
         P.out = net->act[out] + off0;
-        P.board_base = board_base * (cmax / L.cin);   // in boards of the input view
+        P.board_base = board_base;
         P.m_tiles = (n + 1) / 2;
         P.n_tiles = L.cout / BN;
         P.kb_per_tap = L.cin / BK;
@@ -1122,8 +1165,8 @@ int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, i
         T.m_stride = net->m_stride;
         T.n_boards = n;
         T.cout = net->C;
-        T.board_base[0] = board_base * (cmax / net->C1);
-        T.board_base[1] = board_base * (cmax / net->C);
+        T.board_base[0] = T.board_base[1] = board_base;
+        T.chunk_tiles = net->tower_chunk;
         const int total = nl * ((n + 3) / 4) * (net->C / BN);
         const int pairs = ctx->sm_count / 2;
         const int grid = 2 * (total < pairs ? total : pairs);
@@ -1180,7 +1223,9 @@ int kv_net_forward_partial(kv_ctx* ctx, const uint64_t* d_lines, int n, int n_co
     if (int rc = kv_net_tower(ctx, d_lines, n, nullptr, &fb, n_convs)) return rc;
     const int C = n_convs == 0 ? ctx->net->C1 : ctx->net->C;
     if (channels) *channels = C;
-    KV_CUDA(ctx, cudaMemcpyAsync(d_act_out, ctx->net->act[fb], (size_t)n * 64 * C * 2, cudaMemcpyDeviceToDevice, nullptr));
+    // rows of C channels at the tower's pixel pitch -> dense [n*64][C]
+    KV_CUDA(ctx, cudaMemcpy2DAsync(d_act_out, (size_t)C * 2, ctx->net->act[fb], (size_t)ctx->net->C * 2, (size_t)C * 2,
+                                   (size_t)n * 64, cudaMemcpyDeviceToDevice, nullptr));
     KV_CUDA(ctx, cudaStreamSynchronize(nullptr));
     return 0;
 }

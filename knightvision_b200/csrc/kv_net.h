@@ -33,6 +33,7 @@ struct kv_net {
     void* d_layers = nullptr;              // TowerLayerDev[convs.size()] (kv_net.cu)
     uint32_t* d_done[2] = {nullptr, nullptr};   // tile-completion counters [layers][m_stride], one set per game group
     int m_stride = 0;
+    int tower_chunk = 74;                  // board tiles per depth-first chunk of the whole-tower launch (0: layer-major)
     int* d_flag = nullptr;
     uint64_t* d_lines_tmp = nullptr;
 };
@@ -48,6 +49,6 @@ int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, i
 
 // training path (kv_train.cu): activation tensor map over a caller-owned NHWC bf16 tensor [boards][8][8][C] with TMA
 // boxes of {64 channels, 8, 8, box_boards}; one 3x3 convolution through the tower kernel on caller-owned tensors
-int kv_make_act_map(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boards, int box_boards);
+int kv_make_act_map(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boards, int box_boards, int pitch = 0);
 int kv_conv_launch(kv_ctx* ctx, const __nv_bfloat16* x, const __nv_bfloat16* w_packed, const float* bias,
                    const __nv_bfloat16* residual, __nv_bfloat16* y, int n, int cin, int cout, int relu, cudaStream_t st);

@@ -279,7 +279,7 @@ class Engine:
 
     def mcts_set_pipeline(self, mode: int = -1):
         """Two game groups whose waves alternate on two streams (tree kernels of one group under the other group's
-        tower): -1 automatic (default), 0 off, 1 on.  Search results are identical either way."""
+        tower): -1 default (off unless KV_MCTS_PIPELINE=1), 0 off, 1 on.  Search results are identical either way."""
         N.check(self.ctx, self._lib.kv_mcts_set_pipeline(self.ctx, mode), "kv_mcts_set_pipeline")
 
     def mcts_waves(self) -> int:
