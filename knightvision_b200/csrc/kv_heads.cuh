@@ -50,15 +50,17 @@ __device__ __forceinline__ void head_features(const bf16* __restrict__ act, int 
 
 __device__ __forceinline__ float value_mlp(const float* hv, const float* __restrict__ w1, const float* __restrict__ b1,
                                            const float* __restrict__ w2, const float* __restrict__ b2, float* red) {
-    // value_fc1 64->512 + relu, value_fc2 512->1, tanh (ai/model.py:70-73)
+    // value_fc1 64->512 + relu, value_fc2 512->1, tanh (ai/model.py:70-73).  w1 is TRANSPOSED here: w1[i * 512 + j] is
+    // value_fc1.weight[j][i], so the 32 lanes of a warp read 128 contiguous bytes per input i.  The sum keeps the
+    // association of the row-major version (four products added left to right, then added to the accumulator).
     float part = 0.f;
     for (int j = threadIdx.x; j < 512; j += blockDim.x) {
         float a = __ldg(b1 + j);
-        const float4* wr = reinterpret_cast<const float4*>(w1 + (size_t)j * 64);
 #pragma unroll
         for (int i = 0; i < 16; i++) {
-            const float4 w = __ldg(wr + i);
-            a += w.x * hv[4 * i] + w.y * hv[4 * i + 1] + w.z * hv[4 * i + 2] + w.w * hv[4 * i + 3];
+            const float wx = __ldg(w1 + (4 * i + 0) * 512 + j), wy = __ldg(w1 + (4 * i + 1) * 512 + j);
+            const float wz = __ldg(w1 + (4 * i + 2) * 512 + j), ww = __ldg(w1 + (4 * i + 3) * 512 + j);
+            a += wx * hv[4 * i] + wy * hv[4 * i + 1] + wz * hv[4 * i + 2] + ww * hv[4 * i + 3];
         }
         part += fmaxf(a, 0.f) * __ldg(w2 + j);
     }

@@ -268,7 +268,6 @@ struct kv_mcts {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool tower_rec[2] = {false, false}, eval_rec[2] = {false, false}, late_rec[2] = {false, false};
     uint32_t last_wave[2] = {0, 0};
-    bool attrs_done = false;
 };
 
 void kv_mcts_destroy(kv_ctx* ctx) {
@@ -528,6 +527,8 @@ static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1
 // +1 % at most (4 096 games x 800 simulations: 3 985 ms against 4 029 ms per move) — the step is bound by the power cap,
 // not by SM idle time, so hiding the tree kernels under the tower buys almost nothing.
 // The split is a multiple of 8 games so that group 1's activations start on a tile boundary.
+static int g_attrs_state = -1;   // carve-out preference last applied to the tree kernels (per process): 0 default, 1 max shared
+
 static bool mcts_piped(const kv_ctx* ctx) {
     const kv_mcts* m = ctx->mcts;
     if (m->G < 16) return false;
@@ -561,16 +562,20 @@ static int mcts_pipe_setup(kv_ctx* ctx) {
 static int mcts_run_waves(kv_ctx* ctx, int n_waves, cudaStream_t st) {
     kv_mcts* m = ctx->mcts;
     if (n_waves <= 0) return 0;
-    if (!m->attrs_done) {
-        // the tree kernels share SMs with the tower CTAs (227 KB of dynamic shared memory): ask for the same carve-out
-        const int carve = cudaSharedmemCarveoutMaxShared;
-        cudaFuncSetAttribute(mcts_select_kernel<kMW>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        cudaFuncSetAttribute(mcts_select_kernel<kMWP>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        cudaFuncSetAttribute(mcts_eval_net_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        cudaFuncSetAttribute(mcts_late_net_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        cudaFuncSetAttribute(mcts_backup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        cudaGetLastError();
-        m->attrs_done = true;
+    {
+        // pipelined: the tree kernels share SMs with the tower CTAs (198 KB of dynamic shared memory), so they ask for the
+        // same carve-out; otherwise the default (a large L1 keeps value_fc1's 131 KB resident for the evaluator CTAs)
+        const int want = mcts_piped(ctx) ? 1 : 0;
+        if (g_attrs_state != want) {
+            const int carve = want ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault;
+            cudaFuncSetAttribute(mcts_select_kernel<kMW>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(mcts_select_kernel<kMWP>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(mcts_eval_net_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(mcts_late_net_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(mcts_backup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaGetLastError();
+            g_attrs_state = want;
+        }
     }
     m->waves_run += n_waves;
     if (!mcts_piped(ctx)) {

@@ -740,6 +740,11 @@ __global__ void fold_conv3x3_kernel(const float* __restrict__ w, const float* __
         bout[i] = (cb[i] - mu[i]) * s + be[i];
     }
 }
+// value_fc1.weight [512][64] -> [64][512]
+__global__ void transpose_w1_kernel(const float* __restrict__ w, float* __restrict__ wt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 512 * 64) wt[(i & 63) * 512 + (i >> 6)] = w[i];
+}
 // stem: [C1][12][3][3] -> table [9][12][C1] fp32
 __global__ void fold_stem_kernel(const float* __restrict__ w, const float* __restrict__ cb, const float* __restrict__ g,
                                  const float* __restrict__ be, const float* __restrict__ mu,
@@ -1034,7 +1039,10 @@ int kv_net_commit_weights(kv_ctx* ctx, void* stream) {
         const float *g = take(1), *be = take(1), *mu = take(1), *var = take(1);
         fold_head_kernel<<<(n->C + 255) / 256, 256, 0, st>>>(w, cb, g, be, mu, var, 1, n->C, n->wh + 2 * n->C, n->bh + 2);
         KV_LAUNCH_CHECK(ctx);
-        KV_CUDA(ctx, cudaMemcpyAsync(n->w1, take(512 * 64), 512 * 64 * 4, cudaMemcpyDeviceToDevice, st));
+        // value_fc1 is kept TRANSPOSED ([64 inputs][512 units]): consecutive threads own consecutive units, so every
+        // weight load of the value MLP is one coalesced 128 B request instead of 32 scattered 16 B ones
+        transpose_w1_kernel<<<(512 * 64 + 255) / 256, 256, 0, st>>>(take(512 * 64), n->w1);
+        KV_LAUNCH_CHECK(ctx);
         KV_CUDA(ctx, cudaMemcpyAsync(n->b1, take(512), 512 * 4, cudaMemcpyDeviceToDevice, st));
         KV_CUDA(ctx, cudaMemcpyAsync(n->w2, take(512), 512 * 4, cudaMemcpyDeviceToDevice, st));
         KV_CUDA(ctx, cudaMemcpyAsync(n->b2, take(1), 4, cudaMemcpyDeviceToDevice, st));

@@ -1,8 +1,10 @@
 cd $GRAFT_REPO_ROOT
-rm -f gpurun_out/sched4.jsonl
-for ch in 56 64; do KV_TOWER_CHUNK=$ch KV_SCHED_CONFIGS=1:0 timeout 200 python tools/bench_sched.py 2>> gpurun_out/sched4.err | sed "s/^/chunk=$ch /" >> gpurun_out/sched4.jsonl; done
-cat gpurun_out/sched4.jsonl
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:tower_umma2 -s 3 -c 1 -f -o gpurun_out/prof_tower python tools/bench_net.py --iters 2 > gpurun_out/ncu_tower_full.log 2>&1; echo "ncu full rc=$?"
-KV_BENCH_SIMS=8 KV_BENCH_POLICY_PLIES=2 KV_BENCH_COMPARE=0 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_mcts.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
-timeout 700 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_mcts.json 2> gpurun_out/bench_mcts.err; echo "bench rc=$?"
-tail -2 gpurun_out/bench_mcts.err; cat gpurun_out/bench_mcts.json
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/t7.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t7.log
+tail -4 gpurun_out/t7.log
+KV_BENCH_POLICY_PLIES=0 KV_BENCH_INFLIGHT=0 KV_BENCH_COMPARE=0 timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/b7.json 2> gpurun_out/b7.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/b7.json'))
+print({k:d[k] for k in ('value','ms_per_step','evals_per_sim','kernels_ms_per_step','clocks')})
+print(d['no_cache'], d['random_positions']['value'], d['roofline']['achieved'], d['roofline']['traffic'], d['e2e']['value'])
+PY
