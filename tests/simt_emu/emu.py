@@ -92,3 +92,12 @@ def selfplay(start, sims, max_plies, temp_plies, id_base=0, edges_per_node=48, c
     if return_counts:
         return moves, plies, res, (int(cnt[0]), int(cnt[1]))
     return moves, plies, res
+
+
+def tower_order(M, NT, n_layers, chunk_tiles):
+    """(layer, board tile, channel tile) of every task of the whole-tower launch, in task order (kv_tower_order.h)."""
+    args = (ctypes.c_int(M), ctypes.c_int(NT), ctypes.c_int(n_layers), ctypes.c_int(chunk_tiles))
+    total = lib().kvemu_tower_order(*args, None)
+    out = np.zeros((total, 3), np.int32)
+    lib().kvemu_tower_order(*args, _p(out))
+    return out

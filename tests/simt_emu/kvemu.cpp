@@ -100,6 +100,7 @@ void run_warp(std::function<void(int)> body) {
 #define KV_HOST_EMU 1
 #include "../../knightvision_b200/csrc/kv_rules.cuh"
 #include "../../knightvision_b200/csrc/kv_mcts.cuh"
+#include "../../knightvision_b200/csrc/kv_tower_order.h"
 
 static const kv::Tables g_tables = kv::make_tables();
 
@@ -486,6 +487,18 @@ __attribute__((visibility("default"))) void kvemu_selfplay(int G, const uint64_t
     }
     g_emu_pipe = 0;
     delete m;
+}
+
+// task order of the whole-tower launch: out [total][3] = (layer, board tile, channel tile) of task t; returns total
+__attribute__((visibility("default"))) int kvemu_tower_order(int M, int NT, int n_layers, int chunk_tiles, int32_t* out) {
+    kvn::TowerOrder o;
+    o.init(M, NT, n_layers, chunk_tiles);
+    for (int t = 0; out && t < o.total; t++) {
+        int l, m, n;
+        o.decode(t, l, m, n);
+        out[3 * t] = l; out[3 * t + 1] = m; out[3 * t + 2] = n;
+    }
+    return o.total;
 }
 
 }  // extern "C"

@@ -24,3 +24,34 @@ def test_checkpoint_format_round_trip(tmp_path):
     _, _, ep4 = LR.load_or_initialize_model(str(tmp_path / "missing.pth"), "cpu")
     assert ep4 == 0
 
+
+
+def test_whole_tower_task_order():
+    """kv_tower_order.h (the schedule of tower_umma2_kernel): every (layer, board tile, channel tile) exactly once; a tile
+    comes after the tiles it reads — (l-1, m, *) — by at least a round of the 74 CTA pairs whenever a chunk is large enough,
+    so the dependency waits of the kernel do not spin; chunks are contiguous and differ by at most one board tile."""
+    import numpy as np
+    from simt_emu import emu
+    for M, NT, nl, ct in [(1024, 2, 11, 74), (508, 2, 11, 74), (1, 2, 11, 74), (75, 2, 3, 74), (149, 1, 40, 148),
+                          (300, 1, 40, 148), (7, 2, 11, 1), (1024, 2, 11, 0), (223, 2, 11, 74), (625, 2, 11, 74)]:
+        o = emu.tower_order(M, NT, nl, ct)
+        assert len(o) == nl * M * NT
+        key = (o[:, 0].astype(np.int64) * M + o[:, 1]) * NT + o[:, 2]
+        assert len(np.unique(key)) == len(key) and key.min() == 0 and key.max() == len(key) - 1
+        pos = np.empty(len(key), np.int64)
+        pos[key] = np.arange(len(key))
+        m = np.arange(M)
+        dmin = None
+        for l in range(1, nl):
+            for n in range(NT):
+                for n2 in range(NT):
+                    d = (pos[(l * M + m) * NT + n] - pos[((l - 1) * M + m) * NT + n2]).min()
+                    dmin = d if dmin is None else min(dmin, d)
+        assert dmin is None or dmin > 0
+        if dmin is not None and ct * NT >= 74 and M >= ct:
+            assert dmin >= 74             # inputs finished at least one full round of the CTA pairs earlier
+        if ct > 0 and M >= 2 * ct:        # depth-first: the layer-0 tasks of a chunk are contiguous, chunks are balanced
+            idx = np.flatnonzero(o[:, 0] == 0)
+            cuts = np.flatnonzero(np.diff(idx) > 1)
+            sizes = np.diff(np.concatenate([[0], cuts + 1, [len(idx)]])) // NT
+            assert sizes.max() - sizes.min() <= 1 and sizes.min() >= ct and sizes.sum() == M
