@@ -283,7 +283,8 @@ def run(args, rank, world, local_rank):
                        "served_per_sim": hits_all / sims_all if sims_all else None,
                        "note": "keyed by the 12 bitboards (the net's whole input); search results are bit-identical "
                                "with the cache on or off (tests/test_gpu_mcts.py::test_eval_cache_is_transparent)"},
-        "schedule": {"tower": "one dependency-scheduled launch per evaluation batch (tower_umma2_kernel, depth-first chunks)",
+        "schedule": {"tower": ("one dependency-scheduled launch per evaluation batch (tower_umma2_kernel<halo>: depth-first "
+                               "chunks, activation tiles fetched 3x instead of 9x per channel block)"),
                      "pipelined": False,
                      "pipelined_alt": ({"value": world * alt["sims"] / (alt["ms_per_step"] * args.steps * 1e-3),
                                         "unit": "sims/s", "ms_per_step": alt["ms_per_step"],

@@ -114,9 +114,12 @@ KV_API int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int
 /* tower kernel variant: 1 = one CTA per 128x256 tile (tcgen05 cta_group::1), 2 = CTA pairs sharing the weight tile
  * (cta_group::2, 256x256 per pair; default).  Bit-identical outputs. */
 KV_API int kv_net_set_conv_mode(kv_ctx* ctx, int cta_group);
-/* 1 (default) = the tower convolutions of a forward pass run as ONE launch scheduled by tile dependencies (a 3x3
- * convolution is board-local: no grid-wide barrier between layers, no per-layer tail); 0 = one launch per layer.
- * CTA-pair kernel only.  Bit-identical outputs. */
+/* Tower schedule (CTA-pair kernel only).  0 = one launch per layer.  1 = the tower convolutions of a forward pass as ONE
+ * launch scheduled by tile dependencies (a 3x3 convolution is board-local: no grid-wide barrier between layers, no
+ * per-layer tail); bit-identical to 0.  2 (default) = the whole-tower launch with the halo activation operand: each
+ * activation tile is fetched 3 times per 64-channel block instead of 9 (row shifts are descriptor offsets), 11 % faster;
+ * the taps are accumulated in another order, so it equals 0 / 1 to fp32 rounding (same 2e-2 tolerance against the fp32
+ * reference). */
 KV_API int kv_net_set_tower_fused(kv_ctx* ctx, int on);
 KV_API uint64_t kv_net_blob_floats(kv_ctx* ctx);
 KV_API int kv_net_load(kv_ctx* ctx, const float* h_blob, uint64_t n_floats);

@@ -412,7 +412,8 @@ struct alignas(128) TowerLayerDev {
 static_assert(sizeof(TowerLayerDev) == 256, "TowerLayerDev layout");
 
 struct TowerActMaps {
-    CUtensorMap m[3][2];
+    CUtensorMap m[3][2];   // boxes {64 ch, 8 x, 8 y, 2 boards}
+    CUtensorMap h[3][2];   // boxes {64 ch, 8 x, 2 boards, 10 y} (halo variant)
 };
 
 struct TowerArgs {
@@ -446,13 +447,29 @@ __device__ __forceinline__ void tower_wait_tile(const uint32_t* flag, uint32_t n
     __syncwarp();
 }
 
+// HALO = true: the activation tile is fetched THREE times per 64-channel block instead of nine.  One TMA box per column
+// shift dx, `{64 ch, 8 x, 2 boards, 10 y}` from (c0, dx, b0, -1), lands as rows ordered [y = -1..8][board][x] (20 groups of
+// 8 rows x 128 B, the groups y = -1 and y = 8 zero-filled by the TMA unit like the out-of-board columns).  A row shift dy is
+// then a 2 KB offset of the operand's start address — two whole 8-row swizzle atoms, so the SWIZZLE_128B pattern is
+// preserved — and the three taps (dy = -1, 0, 1; dx) read the same 20 KB through descriptors at +0 / +2 KB / +4 KB.
+// A stage = that box + the three weight tiles of the taps: 68 KB, three stages.  Per 64-channel block and CTA the
+// L2 -> shared-memory stream is 60 + 144 KB instead of 144 + 144 KB.  TMEM lane r of a CTA is (y, board, x) =
+// (r / 16, (r / 8) % 2, r % 8); the taps are accumulated in the order (dx, dy) instead of (dy, dx), so results agree
+// with the other kernels to fp32 rounding, not bit for bit.
+constexpr int STAGES_H = 3;
+constexpr int AH_BYTES = 20 * 1024, STAGE_H_BYTES = AH_BYTES + 3 * B2_BYTES;
+constexpr int TOWER_H_SMEM = STAGES_H * STAGE_H_BYTES + 1024 + 256;
+
+template <bool HALO>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128)
 tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
+    constexpr int NSTAGE = HALO ? STAGES_H : STAGES2;
+    constexpr int SBYTES = HALO ? STAGE_H_BYTES : STAGE2_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
-    uint64_t* empty = full + STAGES2;
-    uint64_t* tfull = empty + STAGES2;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * SBYTES);
+    uint64_t* empty = full + NSTAGE;
+    uint64_t* tfull = empty + NSTAGE;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -460,7 +477,7 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
     const uint32_t rank = kvu::cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES2; s++) {
+        for (int s = 0; s < NSTAGE; s++) {
             kvu::mbar_init(&full[s], 1);
             kvu::mbar_init(&empty[s], 1);
         }
@@ -499,21 +516,43 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
                 tower_wait_tile(T.done + (size_t)(l - 1) * T.m_stride + m_tile, need, lane);
                 fence_proxy_async();
             }
+            if constexpr (HALO) {
+                const CUtensorMap* tmH = &maps.h[L->in_buf][L->in_view];
+                for (int st3 = 0; st3 < 3 * kb_per_tap; st3++) {   // (channel block, dx)
+                    const int kb = st3 / 3, dxi = st3 - kb * 3;
+                    kvu::mbar_wait(&empty[stage], phase ^ 1);
+                    if (lane == 0) {
+                        uint8_t* sa = smem + stage * SBYTES;
+                        if (rank == 0) kvu::mbar_arrive_expect_tx(&full[stage], 2 * SBYTES);
+                        kvu::tma2_load_4d(sa, tmH, &full[stage], kb * BK, dxi - 1, b0, -1);
+#pragma unroll
+                        for (int dyi = 0; dyi < 3; dyi++)
+                            kvu::tma2_load_2d(sa + AH_BYTES + dyi * B2_BYTES, &L->wmap, &full[stage],
+                                              ((dyi * 3 + dxi) * kb_per_tap + kb) * BK, n_tile * BN + (int)rank * (BN / 2));
+                    }
+                    __syncwarp();
+                    if (++stage == NSTAGE) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            } else {
             for (int ks = 0; ks < ksteps; ks++) {
                 const int tap = ks / kb_per_tap, kb = ks - tap * kb_per_tap;
                 const int dy = tap / 3 - 1, dx = tap % 3 - 1;
                 kvu::mbar_wait(&empty[stage], phase ^ 1);
                 if (lane == 0) {
-                    uint8_t* sa = smem + stage * STAGE2_BYTES;
-                    if (rank == 0) kvu::mbar_arrive_expect_tx(&full[stage], 2 * STAGE2_BYTES);
+                    uint8_t* sa = smem + stage * SBYTES;
+                    if (rank == 0) kvu::mbar_arrive_expect_tx(&full[stage], 2 * SBYTES);
                     kvu::tma2_load_4d(sa, tmA, &full[stage], kb * BK, dx, dy, b0);
                     kvu::tma2_load_2d(sa + A_BYTES, &L->wmap, &full[stage], ks * BK, n_tile * BN + (int)rank * (BN / 2));
                 }
                 __syncwarp();
-                if (++stage == STAGES2) {
+                if (++stage == NSTAGE) {
                     stage = 0;
                     phase ^= 1;
                 }
+            }
             }
         }
     } else if (warp == 1 && rank == 0) {
@@ -528,11 +567,36 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
             kvu::mbar_wait(&tempty[acc], acc_phase ^ 1);
             kvu::tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+            if constexpr (HALO) {
+                const int nst = ksteps / 3;   // stages of this tile: (channel block, dx)
+                for (int s3 = 0; s3 < nst; s3++) {
+                    kvu::mbar_wait(&full[stage], phase);
+                    kvu::tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = kvu::smem_u32(smem + stage * SBYTES);
+#pragma unroll
+                        for (int dyi = 0; dyi < 3; dyi++) {
+                            const uint64_t adesc = kvu::make_sw128_kmajor_desc(sa + dyi * 2048);
+                            const uint64_t bdesc = kvu::make_sw128_kmajor_desc(sa + AH_BYTES + dyi * B2_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; k++)
+                                kvu::umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (s3 | dyi | k) != 0);
+                        }
+                        kvu::umma2_commit_mc(&empty[stage]);
+                        if (s3 == nst - 1) kvu::umma2_commit_mc(&tfull[acc]);
+                    }
+                    __syncwarp();
+                    if (++stage == NSTAGE) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            } else {
             for (int ks = 0; ks < ksteps; ks++) {
                 kvu::mbar_wait(&full[stage], phase);
                 kvu::tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t sa = kvu::smem_u32(smem + stage * STAGE2_BYTES);
+                    const uint32_t sa = kvu::smem_u32(smem + stage * SBYTES);
                     const uint64_t adesc = kvu::make_sw128_kmajor_desc(sa);
                     const uint64_t bdesc = kvu::make_sw128_kmajor_desc(sa + A_BYTES);
 #pragma unroll
@@ -542,10 +606,11 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
                     if (ks == ksteps - 1) kvu::umma2_commit_mc(&tfull[acc]);
                 }
                 __syncwarp();
-                if (++stage == STAGES2) {
+                if (++stage == NSTAGE) {
                     stage = 0;
                     phase ^= 1;
                 }
+            }
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -564,7 +629,11 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
             P.out = T.act[L->out_buf];
             P.residual = L->res_buf >= 0 ? T.act[L->res_buf] : nullptr;
             P.relu = L->relu;
-            const int row = m_tile * 2 * BM + (int)rank * BM + q * 32 + lane;
+            int row = m_tile * 2 * BM + (int)rank * BM + q * 32 + lane;
+            if constexpr (HALO) {   // TMEM lane r = (y, board, x): r / 16, (r / 8) % 2, r % 8
+                const int r = q * 32 + lane;
+                row = m_tile * 2 * BM + (int)rank * BM + ((r >> 3) & 1) * 64 + (r >> 4) * 8 + (r & 7);
+            }
             const bool valid = row < m_valid;
             const int colb = n_tile * BN + half * (BN / 2);
             const size_t rbase = (size_t)row * T.cout + (size_t)colb;
@@ -795,6 +864,19 @@ int kv_make_act_map(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boards, 
     if (r != CUDA_SUCCESS) return kv_fail_msg(ctx, "cuTensorMapEncodeTiled(activations) failed");
     return 0;
 }
+// halo variant: dims (channel, x, board, y) so that a box {64, 8, 2, 10} lands as rows [y][board][x]
+static int make_act_map_h(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boards, int pitch) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return kv_fail_msg(ctx, "cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[4] = {(cuuint64_t)C, 8, (cuuint64_t)boards, 8};
+    cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * 128, (cuuint64_t)pitch * 16};
+    cuuint32_t box[4] = {64, 8, 2, 10};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return kv_fail_msg(ctx, "cuTensorMapEncodeTiled(activations, halo layout) failed");
+    return 0;
+}
 static int make_act_map(kv_ctx* ctx, CUtensorMap* m, void* base, int C, int boards, int pitch) {
     return kv_make_act_map(ctx, m, base, C, boards, 2, pitch);
 }
@@ -887,6 +969,8 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
         // dependency-scheduled tower relies on that (a tile's output may only overwrite data of its own boards)
         if (int rc = make_act_map(ctx, &n->map_act[i][0], n->act[i], n->C1, n->cap, cmax)) return rc;
         if (int rc = make_act_map(ctx, &n->map_act[i][1], n->act[i], n->C, n->cap, cmax)) return rc;
+        n->halo_ok = n->halo_ok && make_act_map_h(ctx, &n->map_act_h[i][0], n->act[i], n->C1, n->cap, cmax) == 0 &&
+                     make_act_map_h(ctx, &n->map_act_h[i][1], n->act[i], n->C, n->cap, cmax) == 0;
     }
     const int nconv = (n->has_conv2 ? 1 : 0) + 2 * n->blocks;
     n->convs.resize(nconv);
@@ -917,7 +1001,8 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
     KV_CUDA(ctx, cudaFuncSetAttribute(conv3x3_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_SMEM));
     if (const char* e = getenv("KV_CONV_CTA_GROUP")) n->conv_mode = atoi(e) == 1 ? 1 : 2;
     // the whole-tower launch: per-layer table (weight map, bias, buffer rotation) and the tile-completion counters
-    KV_CUDA(ctx, cudaFuncSetAttribute(tower_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_SMEM));
+    KV_CUDA(ctx, cudaFuncSetAttribute(tower_umma2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_SMEM));
+    KV_CUDA(ctx, cudaFuncSetAttribute(tower_umma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_H_SMEM));
     if (nconv > 0) {
         std::vector<TowerLayerDev> tab(nconv);
         std::vector<TowerStep> plan = tower_plan(n);
@@ -937,7 +1022,8 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
         n->m_stride = (n->cap + 3) / 4;
         for (int i = 0; i < 2; i++) KV_CUDA(ctx, cudaMalloc(&n->d_done[i], (size_t)nconv * n->m_stride * sizeof(uint32_t)));
     }
-    if (const char* e = getenv("KV_TOWER_FUSED")) n->tower_fused = atoi(e) != 0;
+    if (const char* e = getenv("KV_TOWER_FUSED")) n->tower_fused = atoi(e);
+    if (n->tower_fused < 0 || n->tower_fused > 2 || (n->tower_fused == 2 && !n->halo_ok)) n->tower_fused = 1;
     // depth-first chunks: one round of the CTA pairs per layer and channel tile, 57-85 MB of activations per chunk at
     // 512 channels (more tiles for a narrower tower: same bytes)
     n->tower_chunk = (ctx->sm_count / 2) * (512 / n->C);
@@ -949,7 +1035,9 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
 // 0 = one launch per layer.  Same tiles, same arithmetic: bit-identical outputs.
 int kv_net_set_tower_fused(kv_ctx* ctx, int on) {
     if (!ctx || !ctx->net) return kv_fail_msg(ctx, "kv_net_set_tower_fused: no net");
-    ctx->net->tower_fused = on != 0;
+    if (on < 0 || on > 2) return kv_fail_msg(ctx, "kv_net_set_tower_fused: 0, 1 or 2");
+    if (on == 2 && !ctx->net->halo_ok) return kv_fail_msg(ctx, "kv_net_set_tower_fused: halo tensor maps unavailable");
+    ctx->net->tower_fused = on;
     return 0;
 }
 
@@ -1132,7 +1220,10 @@ int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, i
         KV_CUDA(ctx, cudaMemsetAsync(done, 0, (size_t)nl * net->m_stride * sizeof(uint32_t), cs));
         TowerActMaps maps;
         for (int i = 0; i < 3; i++)
-            for (int v = 0; v < 2; v++) maps.m[i][v] = net->map_act[i][v];
+            for (int v = 0; v < 2; v++) {
+                maps.m[i][v] = net->map_act[i][v];
+                maps.h[i][v] = net->map_act_h[i][v];
+            }
         TowerArgs T;
         for (int i = 0; i < 3; i++) T.act[i] = net->act[i] + off0;
         T.layers = reinterpret_cast<const TowerLayerDev*>(net->d_layers);
@@ -1149,7 +1240,8 @@ int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, i
         const int grid = 2 * (total < pairs ? total : pairs);
         {
             KvTimed t_(ctx, KVK_NET_CONV, cs);
-            tower_umma2_kernel<<<grid, CONV2_THREADS, CONV2_SMEM, cs>>>(maps, T);
+            if (net->tower_fused == 2) tower_umma2_kernel<true><<<grid, CONV2_THREADS, TOWER_H_SMEM, cs>>>(maps, T);
+            else tower_umma2_kernel<false><<<grid, CONV2_THREADS, CONV2_SMEM, cs>>>(maps, T);
         }
         KV_LAUNCH_CHECK(ctx);
         return 0;

@@ -22,6 +22,7 @@ struct kv_net {
     std::vector<kv_conv> convs;
     __nv_bfloat16* act[3] = {nullptr, nullptr, nullptr};   // NHWC bf16 [cap*64][max(C1,C)]
     CUtensorMap map_act[3][2];             // [buffer][0: C1-channel view, 1: C-channel view]
+    CUtensorMap map_act_h[3][2];           // same views, dims (c, x, board, y) and boxes {64, 8, 2, 10}: the halo variant
     float *stem_table = nullptr, *stem_bias = nullptr;
     float *wh = nullptr, *bh = nullptr;    // head 1x1 convs [3][C], [3]
     float *wfc = nullptr, *bfc = nullptr;  // policy_fc [4096][128], [4096]
@@ -29,10 +30,12 @@ struct kv_net {
     float* d_blob = nullptr;               // fp32 state_dict staging (NCCL broadcast target)
     size_t blob_floats = 0;
     int conv_mode = 2;                     // 1: cta_group::1 kernel, 2: cta_group::2 CTA-pair kernel
-    int tower_fused = 1;                   // conv_mode 2 only: the whole tower as one dependency-scheduled launch
+    int tower_fused = 2;                   // conv_mode 2 only: 1 = the whole tower as one dependency-scheduled launch,
+                                           // 2 (default) = the same with the halo A-operand (3 instead of 9 fetches)
     void* d_layers = nullptr;              // TowerLayerDev[convs.size()] (kv_net.cu)
     uint32_t* d_done[2] = {nullptr, nullptr};   // tile-completion counters [layers][m_stride], one set per game group
     int m_stride = 0;
+    bool halo_ok = true;                   // the halo tensor maps could be encoded
     int tower_chunk = 74;                  // board tiles per depth-first chunk of the whole-tower launch (0: layer-major)
     int* d_flag = nullptr;
     uint64_t* d_lines_tmp = nullptr;

@@ -123,9 +123,10 @@ class Engine:
         self.net_max_boards = max_boards
         self.net_geometry = None          # bookkeeping of ChessNet.attach (re-created only when the shape changes)
 
-    def net_set_tower_fused(self, on: bool):
-        """Whole tower as one dependency-scheduled launch (default) or one launch per layer; same bits."""
-        N.check(self.ctx, self._lib.kv_net_set_tower_fused(self.ctx, int(on)), "kv_net_set_tower_fused")
+    def net_set_tower_fused(self, mode):
+        """0 = one launch per tower layer, 1 / True = whole tower as one dependency-scheduled launch (default, same bits),
+        2 = whole-tower launch with the halo activation operand (3 instead of 9 fetches per tile; fp32-rounding equal)."""
+        N.check(self.ctx, self._lib.kv_net_set_tower_fused(self.ctx, int(mode)), "kv_net_set_tower_fused")
 
     def net_set_conv_mode(self, cta_group: int):
         N.check(self.ctx, self._lib.kv_net_set_conv_mode(self.ctx, cta_group), "kv_net_set_conv_mode")

@@ -35,7 +35,7 @@ def timed(n):
 for fused, piped in CONFIGS:
     fused, piped = int(fused), int(piped)
     eng.mcts_create(G, SIMS, 512, seed=42, eval_mode=1)
-    eng.net_set_tower_fused(bool(fused))
+    eng.net_set_tower_fused(int(fused))
     eng.mcts_set_pipeline(piped)
     eng.mcts_enable_cache(24)
     eng.mcts_reset(None, 0)
