@@ -401,15 +401,14 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // -> red.release; readers: ld.acquire -> fence.proxy.async -> TMA.  Deadlock-free: a task waits only for tasks with a
 // smaller number, every pair runs its tasks in increasing order, and all pairs are resident (grid <= 148 CTAs, 1 / SM).
 // The spin is bounded and traps (a protocol bug must not hang the GPU box).
-struct alignas(128) TowerLayerDev {
+struct TowerLayerDev {
     CUtensorMap wmap;        // this layer's weights, {64, 128} boxes (one CTA's half of the N tile)
     const float* bias;
     int in_buf, in_view;     // activation buffer 0..2 and view (0: C1 channels, 1: C channels) of the input
     int out_buf, res_buf;    // res_buf < 0: no residual
     int kb_per_tap, relu;
-    int pad_[24];
 };
-static_assert(sizeof(TowerLayerDev) == 256, "TowerLayerDev layout");
+static_assert(sizeof(TowerLayerDev) % 64 == 0, "TowerLayerDev: the tensor map of every array element must stay 64 B aligned");
 
 struct TowerActMaps {
     CUtensorMap m[3][2];   // boxes {64 ch, 8 x, 8 y, 2 boards}
@@ -424,6 +423,7 @@ struct TowerArgs {
     int n_layers, m_stride, n_boards, cout;
     int board_base[2];       // first board of this launch in the C1 / C view of the buffers
     int chunk_tiles;         // depth-first order: board tiles per chunk (0 = layer-major over all boards)
+    TowerLayerDev single;    // layers == nullptr: the one layer of this launch (a convolution on caller-owned tensors)
 };
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -462,7 +462,7 @@ constexpr int TOWER_H_SMEM = STAGES_H * STAGE_H_BYTES + 1024 + 256;
 
 template <bool HALO>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128)
-tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
+tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, const __grid_constant__ TowerArgs T) {
     constexpr int NSTAGE = HALO ? STAGES_H : STAGES2;
     constexpr int SBYTES = HALO ? STAGE_H_BYTES : STAGE2_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -508,7 +508,7 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
         for (int t = cluster_id; t < total; t += n_clusters) {
             int l, m_tile, n_tile;
             ord.decode(t, l, m_tile, n_tile);
-            const TowerLayerDev* L = T.layers + l;
+            const TowerLayerDev* L = T.layers ? T.layers + l : &T.single;
             const int kb_per_tap = L->kb_per_tap, ksteps = 9 * kb_per_tap;
             const CUtensorMap* tmA = &maps.m[L->in_buf][L->in_view];
             const int b0 = T.board_base[L->in_view] + m_tile * 4 + (int)rank * 2;
@@ -563,7 +563,7 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
         for (int t = cluster_id; t < total; t += n_clusters) {
             int l, m_tile, n_tile;
             ord.decode(t, l, m_tile, n_tile);
-            const int ksteps = 9 * T.layers[l].kb_per_tap;
+            const int ksteps = 9 * (T.layers ? T.layers[l].kb_per_tap : T.single.kb_per_tap);
             kvu::mbar_wait(&tempty[acc], acc_phase ^ 1);
             kvu::tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
@@ -623,7 +623,7 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
         for (int t = cluster_id; t < total; t += n_clusters) {
             int l, m_tile, n_tile;
             ord.decode(t, l, m_tile, n_tile);
-            const TowerLayerDev* L = T.layers + l;
+            const TowerLayerDev* L = T.layers ? T.layers + l : &T.single;
             ConvParams P;
             P.bias = L->bias;
             P.out = T.act[L->out_buf];
@@ -665,7 +665,7 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, TowerArgs T) {
             fence_proxy_async();
             __threadfence();
             __syncwarp();
-            if (lane == 0) red_release_add_u32(T.done + (size_t)l * T.m_stride + m_tile, 1u);
+            if (lane == 0 && T.done) red_release_add_u32(T.done + (size_t)l * T.m_stride + m_tile, 1u);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -1007,7 +1007,7 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
         std::vector<TowerLayerDev> tab(nconv);
         std::vector<TowerStep> plan = tower_plan(n);
         for (int l = 0; l < nconv; l++) {
-            memset(&tab[l], 0, sizeof(TowerLayerDev));
+            memset(static_cast<void*>(&tab[l]), 0, sizeof(TowerLayerDev));
             tab[l].wmap = n->convs[l].map_half;
             tab[l].bias = n->convs[l].b;
             tab[l].in_buf = plan[l].in;
@@ -1126,13 +1126,46 @@ int kv_net_load(kv_ctx* ctx, const float* h_blob, uint64_t n_floats) {
 int kv_conv_launch(kv_ctx* ctx, const bf16* x, const bf16* w_packed, const float* bias, const bf16* residual, bf16* y,
                    int n, int cin, int cout, int relu, cudaStream_t st) {
     if (cin % 64 || cout % 256 || cin < 64) return kv_fail_msg(ctx, "conv3x3: cin must be a multiple of 64, cout of 256");
-    if (!ctx->conv_attr_done) {
-        KV_CUDA(ctx, cudaFuncSetAttribute(conv3x3_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_SMEM));
-        ctx->conv_attr_done = true;
-    }
     CUtensorMap amap, wmap;
-    if (int rc = kv_make_act_map(ctx, &amap, const_cast<bf16*>(x), cin, n, 2)) return rc;
     if (int rc = make_w_map(ctx, &wmap, const_cast<bf16*>(w_packed), cout, 9 * cin, 128)) return rc;
+    const int pairs = ctx->sm_count / 2;
+    static const bool no_halo = [] {
+        const char* e = getenv("KV_CONV_HALO");
+        return e && atoi(e) == 0;
+    }();
+    if (!no_halo) {
+        // the halo-operand kernel as a one-layer launch: x is buffer 0, y buffer 1, the residual buffer 2
+        TowerActMaps maps;          // only h[0][1] is read
+        memset(static_cast<void*>(&maps), 0, sizeof(maps));
+        if (int rc = make_act_map_h(ctx, &maps.h[0][1], const_cast<bf16*>(x), cin, n, cin)) return rc;
+        TowerArgs T;
+        memset(static_cast<void*>(&T), 0, sizeof(T));
+        T.act[0] = const_cast<bf16*>(x);
+        T.act[1] = y;
+        T.act[2] = const_cast<bf16*>(residual);
+        T.n_layers = 1;
+        T.n_boards = n;
+        T.cout = cout;
+        T.single.wmap = wmap;
+        T.single.bias = bias;
+        T.single.in_buf = 0;
+        T.single.in_view = 1;
+        T.single.out_buf = 1;
+        T.single.res_buf = residual ? 2 : -1;
+        T.single.kb_per_tap = cin / BK;
+        T.single.relu = relu;
+        if (!ctx->conv_attr_done) {
+            KV_CUDA(ctx, cudaFuncSetAttribute(tower_umma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_H_SMEM));
+            ctx->conv_attr_done = true;
+        }
+        const int total = ((n + 3) / 4) * (cout / BN);
+        const int grid = 2 * (total < pairs ? total : pairs);
+        KvTimed t_(ctx, KVK_NET_CONV, st);
+        tower_umma2_kernel<true><<<grid, CONV2_THREADS, TOWER_H_SMEM, st>>>(maps, T);
+        KV_LAUNCH_CHECK(ctx);
+        return 0;
+    }
+    if (int rc = kv_make_act_map(ctx, &amap, const_cast<bf16*>(x), cin, n, 2)) return rc;
     ConvParams P;
     P.bias = bias;
     P.residual = residual;
@@ -1146,8 +1179,8 @@ int kv_conv_launch(kv_ctx* ctx, const bf16* x, const bf16* w_packed, const float
     P.n_ptr = nullptr;
     P.board_base = 0;
     const int total = P.m_tiles * P.n_tiles;
-    const int pairs = ctx->sm_count / 2;
     const int grid = 2 * (total < pairs ? total : pairs);
+    KV_CUDA(ctx, cudaFuncSetAttribute(conv3x3_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_SMEM));
     KvTimed t_(ctx, KVK_NET_CONV, st);
     conv3x3_umma2_kernel<<<grid, CONV2_THREADS, CONV2_SMEM, st>>>(amap, wmap, P);
     KV_LAUNCH_CHECK(ctx);
