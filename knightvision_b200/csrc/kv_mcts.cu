@@ -411,7 +411,7 @@ int kv_mcts_reset(kv_ctx* ctx, const uint64_t* d_start, uint64_t game_id_base, v
 //   stream B:  eval B(w-1) late B(w-1) select B(w) stem B(w) ............ eval B(w) late B(w) select B(w+1) ...
 //
 // the tensor-core kernels of both groups run back to back on one high-priority stream, so the tensor pipe never waits for the tree kernels
-// of the other group, which run on the CUDA cores of the same SMs meanwhile (the tower CTA leaves > 30 KB of shared
+// of the other group, which run on the CUDA cores of the same SMs meanwhile (the tower CTA leaves 18-33 KB of shared
 // memory and most of the register file free).  Search results do not depend on the schedule: games are independent,
 // and the evaluation cache — the only state the groups share — is transparent.  Its protocol between the groups:
 // an entry under evaluation by the OTHER group's wave in flight (stamp == peer_wave) is followed like one of the own
@@ -426,7 +426,8 @@ static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1
     const uint32_t wave = ++m->wave;
     const int q = grp > 0 ? 1 : 0, peer = 1 - q;
     const bool piped = grp >= 0;
-    // pipelined: grids sized to what fits beside one tower CTA per SM (16 K registers, ~33 KB of shared memory free):
+    // pipelined: grids sized to what fits beside one tower CTA per SM (16 K registers; 18 KB of shared memory next to the
+    // halo-operand tower, 33 KB next to the 9-fetch one):
     // 2 selection CTAs (64 threads x 128 registers), 1 evaluator CTA (256 x 40), 3 late CTAs (128 x 40), 2 backup CTAs
     const int sms = ctx->sm_count;
     auto imin = [](int a, int b) { return a < b ? a : b; };
@@ -563,7 +564,7 @@ static int mcts_run_waves(kv_ctx* ctx, int n_waves, cudaStream_t st) {
     kv_mcts* m = ctx->mcts;
     if (n_waves <= 0) return 0;
     {
-        // pipelined: the tree kernels share SMs with the tower CTAs (198 KB of dynamic shared memory), so they ask for the
+        // pipelined: the tree kernels share SMs with the tower CTAs (198-210 KB of dynamic shared memory), so they ask for the
         // same carve-out; otherwise the default (a large L1 keeps value_fc1's 131 KB resident for the evaluator CTAs)
         const int want = mcts_piped(ctx) ? 1 : 0;
         if (g_attrs_state != want) {

@@ -251,7 +251,7 @@ constexpr int CONV2_SMEM = STAGES2 * STAGE2_BYTES + 1024 + 256;
 
 constexpr int CONV2_THREADS = 384;   // warps 0-2 producer / MMA / TMEM, warp 3 idle, warps 4-11 epilogue
 
-// 128 registers (56 B of epilogue spill): 384 threads x 128 leave a quarter of the register file — and ~33 KB of shared
+// 128 registers (56 B of epilogue spill): 384 threads x 128 leave a quarter of the register file — and 18-33 KB of shared
 // memory — to the tree-search kernels that share the SM with this CTA in the pipelined search (kv_mcts.cu)
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128)
 conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, ConvParams P) {
