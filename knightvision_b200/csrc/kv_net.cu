@@ -510,7 +510,7 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, const __grid_const
             ord.decode(t, l, m_tile, n_tile);
             const TowerLayerDev* L = T.layers ? T.layers + l : &T.single;
             const int kb_per_tap = L->kb_per_tap, ksteps = 9 * kb_per_tap;
-            const CUtensorMap* tmA = &maps.m[L->in_buf][L->in_view];
+            [[maybe_unused]] const CUtensorMap* tmA = &maps.m[L->in_buf][L->in_view];
             const int b0 = T.board_base[L->in_view] + m_tile * 4 + (int)rank * 2;
             if (l > 0) {   // the input tile must be complete (all channels of these four boards)
                 tower_wait_tile(T.done + (size_t)(l - 1) * T.m_stride + m_tile, need, lane);
