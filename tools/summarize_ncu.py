@@ -12,7 +12,9 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed.sum", "smsp__inst_executed.avg.per_cycle_active", "sm__cycles_active.avg",
         "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "l1tex__t_sector_hit_rate.pct",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__occupancy_limit_registers",
-        "sm__maximum_warps_per_active_cycle_pct", "launch__shared_mem_per_block_dynamic"]
+        "sm__maximum_warps_per_active_cycle_pct", "launch__shared_mem_per_block_dynamic",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 
 def launches(src, dst):
