@@ -235,7 +235,7 @@ def run(args, rank, world, local_rank):
                      "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 figure",
                      "kernel_ms_per_step": wg_ms / args.steps, "kernel_share_of_step": wg_ms / r["dev_ms"],
                      "launches": wg_n,
-                     "fprop_dgrad": {"kernel": "conv3x3_umma2_kernel", "achieved": cv_tf, "unit": "TFLOP/s",
+                     "fprop_dgrad": {"kernel": "tower_umma2_kernel<halo> (one-layer launches)", "achieved": cv_tf, "unit": "TFLOP/s",
                                      "kernel_ms_per_step": cv_ms / args.steps, "launches": cv_n}},
         "kernels_ms_per_step": {k: v[0] / args.steps for k, v in r["prof"].items() if v[1]},
         "loss": r["loss"], "loss_cudnn_arm": results["cudnn"]["loss"] if "cudnn" in results else None,

@@ -251,145 +251,6 @@ constexpr int CONV2_SMEM = STAGES2 * STAGE2_BYTES + 1024 + 256;
 
 constexpr int CONV2_THREADS = 384;   // warps 0-2 producer / MMA / TMEM, warp 3 idle, warps 4-11 epilogue
 
-// 128 registers (56 B of epilogue spill): 384 threads x 128 leave a quarter of the register file — and 18-33 KB of shared
-// memory — to the tree-search kernels that share the SM with this CTA in the pipelined search (kv_mcts.cu)
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128)
-conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, ConvParams P) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
-    uint64_t* empty = full + STAGES2;
-    uint64_t* tfull = empty + STAGES2;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = kvu::cluster_ctarank();
-    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-    if (warp == 0 && lane == 0) {
-        kvu::prefetch_tmap(&tmA);
-        kvu::prefetch_tmap(&tmBh);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES2; s++) {
-            kvu::mbar_init(&full[s], 1);
-            kvu::mbar_init(&empty[s], 1);
-        }
-        for (int a = 0; a < 2; a++) {
-            kvu::mbar_init(&tfull[a], 1);
-            kvu::mbar_init(&tempty[a], 512);   // 256 epilogue threads of each CTA
-        }
-        kvu::fence_barrier_init();
-    }
-    if (warp == 2) kvu::tmem_alloc2(tmem_slot, 512);
-    kvu::tc_fence_before();
-    __syncthreads();
-    kvu::cluster_sync();
-    kvu::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    if (P.n_ptr) {
-        const int nb = *P.n_ptr;
-        P.m_tiles = (nb + 3) >> 2;
-        P.m_valid = nb * 64;
-    }
-    const int total = P.m_tiles * P.n_tiles;
-    const int ksteps = 9 * P.kb_per_tap;
-
-    if (warp == 0) {
-        // ---- TMA producer (both CTAs) ---------------------------------------------------------------------
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = cluster_id; tile < total; tile += n_clusters) {
-            const int m_tile = tile / P.n_tiles, n_tile = tile % P.n_tiles;
-            for (int ks = 0; ks < ksteps; ks++) {
-                const int tap = ks / P.kb_per_tap, kb = ks - tap * P.kb_per_tap;
-                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                kvu::mbar_wait(&empty[stage], phase ^ 1);
-                if (lane == 0) {
-                    uint8_t* sa = smem + stage * STAGE2_BYTES;
-                    if (rank == 0) kvu::mbar_arrive_expect_tx(&full[stage], 2 * STAGE2_BYTES);
-                    kvu::tma2_load_4d(sa, &tmA, &full[stage], kb * BK, dx, dy, P.board_base + m_tile * 4 + (int)rank * 2);
-                    kvu::tma2_load_2d(sa + A_BYTES, &tmBh, &full[stage], ks * BK, n_tile * BN + (int)rank * (BN / 2));
-                }
-                __syncwarp();
-                if (++stage == STAGES2) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            }
-        }
-    } else if (warp == 1 && rank == 0) {
-        // ---- MMA issuer (leader CTA only) -------------------------------------------------------------------
-        constexpr uint32_t idesc = kvu::make_idesc_bf16(2 * BM, BN);
-        int stage = 0, acc = 0;
-        uint32_t phase = 0, acc_phase = 0;
-        for (int tile = cluster_id; tile < total; tile += n_clusters) {
-            kvu::mbar_wait(&tempty[acc], acc_phase ^ 1);
-            kvu::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
-            for (int ks = 0; ks < ksteps; ks++) {
-                kvu::mbar_wait(&full[stage], phase);
-                kvu::tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sa = kvu::smem_u32(smem + stage * STAGE2_BYTES);
-                    const uint64_t adesc = kvu::make_sw128_kmajor_desc(sa);
-                    const uint64_t bdesc = kvu::make_sw128_kmajor_desc(sa + A_BYTES);
-#pragma unroll
-                    for (int k = 0; k < BK / 16; k++)
-                        kvu::umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
-                    kvu::umma2_commit_mc(&empty[stage]);
-                    if (ks == ksteps - 1) kvu::umma2_commit_mc(&tfull[acc]);
-                }
-                __syncwarp();
-                if (++stage == STAGES2) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
-        }
-    } else if (warp >= 4) {
-        // ---- epilogue (both CTAs, own 128 rows): 8 warps = 4 TMEM lane quarters x 2 column halves.  The residual
-        // rows are fetched BEFORE waiting for the accumulator, so their latency hides behind the main loop. ----------
-        const int q = warp & 3, half = (warp - 4) >> 2;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = cluster_id; tile < total; tile += n_clusters) {
-            const int m_tile = tile / P.n_tiles, n_tile = tile % P.n_tiles;
-            const int row = m_tile * 2 * BM + (int)rank * BM + q * 32 + lane;
-            const bool valid = row < P.m_valid;
-            const int colb = n_tile * BN + half * (BN / 2);
-            const size_t rbase = (size_t)row * P.cout + (size_t)colb;
-            uint4 res[4][4];
-            if (P.residual && valid) {
-                const uint4* rp = reinterpret_cast<const uint4*>(P.residual + rbase);
-#pragma unroll
-                for (int c = 0; c < 4; c++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) res[c][j] = __ldg(rp + c * 4 + j);
-            }
-            kvu::mbar_wait(&tfull[acc], acc_phase);
-            kvu::tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                uint32_t v[32];
-                kvu::tmem_ld_32x32(tmem_base + (uint32_t)acc * BN + half * (BN / 2) + c * 32 + ((uint32_t)(q * 32) << 16), v);
-                kvu::tmem_ld_wait();
-                if (valid) conv_epilogue_store_pf(P, v, res[c], rbase + c * 32, colb + c * 32);
-            }
-            kvu::tc_fence_before();
-            kvu::mbar_arrive_leader(&tempty[acc]);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
-        }
-    }
-    kvu::tc_fence_before();
-    __syncthreads();
-    kvu::cluster_sync();   // the peer may still be signalling this CTA's barriers / reading its B half
-    if (warp == 2) kvu::tmem_dealloc2(tmem_base, 512);
-}
-
 // ---- the whole tower as ONE launch: a dependency-driven schedule over (layer, board tile, channel tile) tasks ------
 // A 3x3 convolution is board-local, so tile (l, m, n) — layer l, boards [4m, 4m+4), output channels [256n, 256n+256) —
 // needs exactly the two tiles (l-1, m, 0..1).  Tasks are numbered layer-major, t = (l * M + m) * NT + n, and CTA pair
@@ -460,6 +321,10 @@ constexpr int STAGES_H = 3;
 constexpr int AH_BYTES = 20 * 1024, STAGE_H_BYTES = AH_BYTES + 3 * B2_BYTES;
 constexpr int TOWER_H_SMEM = STAGES_H * STAGE_H_BYTES + 1024 + 256;
 
+// 128 registers (a few dozen bytes of epilogue spill): 384 threads x 128 leave a quarter of the register file — and 18-33 KB
+// of shared memory — to the tree-search kernels that share the SM with this CTA in the pipelined search (kv_mcts.cu).
+// With T.layers == nullptr the launch is ONE convolution described by T.single (the per-layer mode of the tower and the
+// training-side convolutions on caller-owned tensors).
 template <bool HALO>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(128)
 tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, const __grid_constant__ TowerArgs T) {
@@ -998,7 +863,6 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
     n->blob_floats = net_blob_floats(n);
     KV_CUDA(ctx, cudaMalloc(&n->d_blob, n->blob_floats * sizeof(float)));
     KV_CUDA(ctx, cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
-    KV_CUDA(ctx, cudaFuncSetAttribute(conv3x3_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_SMEM));
     if (const char* e = getenv("KV_CONV_CTA_GROUP")) n->conv_mode = atoi(e) == 1 ? 1 : 2;
     // the whole-tower launch: per-layer table (weight map, bias, buffer rotation) and the tile-completion counters
     KV_CUDA(ctx, cudaFuncSetAttribute(tower_umma2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_SMEM));
@@ -1126,63 +990,47 @@ int kv_net_load(kv_ctx* ctx, const float* h_blob, uint64_t n_floats) {
 int kv_conv_launch(kv_ctx* ctx, const bf16* x, const bf16* w_packed, const float* bias, const bf16* residual, bf16* y,
                    int n, int cin, int cout, int relu, cudaStream_t st) {
     if (cin % 64 || cout % 256 || cin < 64) return kv_fail_msg(ctx, "conv3x3: cin must be a multiple of 64, cout of 256");
-    CUtensorMap amap, wmap;
+    CUtensorMap wmap;
     if (int rc = make_w_map(ctx, &wmap, const_cast<bf16*>(w_packed), cout, 9 * cin, 128)) return rc;
-    const int pairs = ctx->sm_count / 2;
-    static const bool no_halo = [] {
+    static const bool halo = [] {
         const char* e = getenv("KV_CONV_HALO");
-        return e && atoi(e) == 0;
+        return !(e && atoi(e) == 0);
     }();
-    if (!no_halo) {
-        // the halo-operand kernel as a one-layer launch: x is buffer 0, y buffer 1, the residual buffer 2
-        TowerActMaps maps;          // only h[0][1] is read
-        memset(static_cast<void*>(&maps), 0, sizeof(maps));
+    // a one-layer launch of the tower kernel: x is buffer 0, y buffer 1, the residual buffer 2
+    TowerActMaps maps;              // only [0][1] of the variant's map set is read
+    memset(static_cast<void*>(&maps), 0, sizeof(maps));
+    if (halo) {
         if (int rc = make_act_map_h(ctx, &maps.h[0][1], const_cast<bf16*>(x), cin, n, cin)) return rc;
-        TowerArgs T;
-        memset(static_cast<void*>(&T), 0, sizeof(T));
-        T.act[0] = const_cast<bf16*>(x);
-        T.act[1] = y;
-        T.act[2] = const_cast<bf16*>(residual);
-        T.n_layers = 1;
-        T.n_boards = n;
-        T.cout = cout;
-        T.single.wmap = wmap;
-        T.single.bias = bias;
-        T.single.in_buf = 0;
-        T.single.in_view = 1;
-        T.single.out_buf = 1;
-        T.single.res_buf = residual ? 2 : -1;
-        T.single.kb_per_tap = cin / BK;
-        T.single.relu = relu;
-        if (!ctx->conv_attr_done) {
-            KV_CUDA(ctx, cudaFuncSetAttribute(tower_umma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_H_SMEM));
-            ctx->conv_attr_done = true;
-        }
-        const int total = ((n + 3) / 4) * (cout / BN);
-        const int grid = 2 * (total < pairs ? total : pairs);
-        KvTimed t_(ctx, KVK_NET_CONV, st);
-        tower_umma2_kernel<true><<<grid, CONV2_THREADS, TOWER_H_SMEM, st>>>(maps, T);
-        KV_LAUNCH_CHECK(ctx);
-        return 0;
+    } else {
+        if (int rc = kv_make_act_map(ctx, &maps.m[0][1], const_cast<bf16*>(x), cin, n, 2)) return rc;
     }
-    if (int rc = kv_make_act_map(ctx, &amap, const_cast<bf16*>(x), cin, n, 2)) return rc;
-    ConvParams P;
-    P.bias = bias;
-    P.residual = residual;
-    P.out = y;
-    P.m_tiles = (n + 3) / 4;
-    P.n_tiles = cout / BN;
-    P.kb_per_tap = cin / BK;
-    P.cout = cout;
-    P.m_valid = n * 64;
-    P.relu = relu;
-    P.n_ptr = nullptr;
-    P.board_base = 0;
-    const int total = P.m_tiles * P.n_tiles;
+    TowerArgs T;
+    memset(static_cast<void*>(&T), 0, sizeof(T));
+    T.act[0] = const_cast<bf16*>(x);
+    T.act[1] = y;
+    T.act[2] = const_cast<bf16*>(residual);
+    T.n_layers = 1;
+    T.n_boards = n;
+    T.cout = cout;
+    T.single.wmap = wmap;
+    T.single.bias = bias;
+    T.single.in_buf = 0;
+    T.single.in_view = 1;
+    T.single.out_buf = 1;
+    T.single.res_buf = residual ? 2 : -1;
+    T.single.kb_per_tap = cin / BK;
+    T.single.relu = relu;
+    if (!ctx->conv_attr_done) {
+        KV_CUDA(ctx, cudaFuncSetAttribute(tower_umma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_H_SMEM));
+        KV_CUDA(ctx, cudaFuncSetAttribute(tower_umma2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_SMEM));
+        ctx->conv_attr_done = true;
+    }
+    const int pairs = ctx->sm_count / 2;
+    const int total = ((n + 3) / 4) * (cout / BN);
     const int grid = 2 * (total < pairs ? total : pairs);
-    KV_CUDA(ctx, cudaFuncSetAttribute(conv3x3_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_SMEM));
     KvTimed t_(ctx, KVK_NET_CONV, st);
-    conv3x3_umma2_kernel<<<grid, CONV2_THREADS, CONV2_SMEM, st>>>(amap, wmap, P);
+    if (halo) tower_umma2_kernel<true><<<grid, CONV2_THREADS, TOWER_H_SMEM, st>>>(maps, T);
+    else tower_umma2_kernel<false><<<grid, CONV2_THREADS, CONV2_SMEM, st>>>(maps, T);
     KV_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -1226,13 +1074,34 @@ int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, i
         P.relu = relu;
         P.n_ptr = n_ptr;
         const CUtensorMap& amap = net->map_act[in][L.cin == net->C1 && L.cin != net->C ? 0 : 1];
-        if (net->conv_mode == 2) {
-            P.m_tiles = (n + 3) / 4;   // cluster tiles of 4 boards (M = 256)
-            const int total = P.m_tiles * P.n_tiles;
+        if (net->conv_mode == 2) {   // one-layer launch of the CTA-pair kernel (9-fetch variant)
+            TowerActMaps maps;
+            for (int i = 0; i < 3; i++)
+                for (int v = 0; v < 2; v++) {
+                    maps.m[i][v] = net->map_act[i][v];
+                    maps.h[i][v] = net->map_act_h[i][v];
+                }
+            TowerArgs T;
+            memset(static_cast<void*>(&T), 0, sizeof(T));
+            for (int i = 0; i < 3; i++) T.act[i] = net->act[i] + off0;
+            T.n_ptr = n_ptr;
+            T.n_layers = 1;
+            T.n_boards = n;
+            T.cout = L.cout;
+            T.board_base[0] = T.board_base[1] = board_base;
+            T.single.wmap = L.map_half;
+            T.single.bias = L.b;
+            T.single.in_buf = in;
+            T.single.in_view = (L.cin == net->C1 && L.cin != net->C) ? 0 : 1;
+            T.single.out_buf = out;
+            T.single.res_buf = res;
+            T.single.kb_per_tap = L.cin / BK;
+            T.single.relu = relu;
+            const int total = ((n + 3) / 4) * P.n_tiles;
             const int pairs = ctx->sm_count / 2;
             const int grid = 2 * (total < pairs ? total : pairs);
             KvTimed t_(ctx, KVK_NET_CONV, cs);
-            conv3x3_umma2_kernel<<<grid, CONV2_THREADS, CONV2_SMEM, cs>>>(amap, L.map_half, P);
+            tower_umma2_kernel<false><<<grid, CONV2_THREADS, CONV2_SMEM, cs>>>(maps, T);
         } else {
             const int total = P.m_tiles * P.n_tiles;
             const int grid = total < ctx->sm_count ? total : ctx->sm_count;
