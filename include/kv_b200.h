@@ -121,6 +121,11 @@ KV_API int kv_net_set_conv_mode(kv_ctx* ctx, int cta_group);
  * the taps are accumulated in another order, so it equals 0 / 1 to fp32 rounding (same 2e-2 tolerance against the fp32
  * reference). */
 KV_API int kv_net_set_tower_fused(kv_ctx* ctx, int on);
+/* modes 3 / 4 (opt-in): mode 2 on clusters of four CTAs — two CTA pairs on neighbouring board tiles share every weight
+ * tile by TMA multicast; bit-identical to mode 2.  Mode 3 uses only the SMs such clusters can cover (132 of 148 on B200:
+ * slower); mode 4 also runs the CTA-pair kernel on the remaining SMs, concurrently (+1 % over mode 2).
+ * kv_net_tower_clusters4 = how many 4-CTA clusters are co-resident on this GPU (< 8: modes 3 / 4 unavailable). */
+KV_API int kv_net_tower_clusters4(kv_ctx* ctx);
 KV_API uint64_t kv_net_blob_floats(kv_ctx* ctx);
 KV_API int kv_net_load(kv_ctx* ctx, const float* h_blob, uint64_t n_floats);
 /* Device staging buffer of kv_net_blob_floats() floats: write the blob there (e.g. as the target of an NCCL

@@ -34,6 +34,7 @@ SIGNATURES = {
     "kv_net_create": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
     "kv_net_set_conv_mode": (c_int, [c_void_p, c_int]),
     "kv_net_set_tower_fused": (c_int, [c_void_p, c_int]),
+    "kv_net_tower_clusters4": (c_int, [c_void_p]),
     "kv_net_blob_floats": (c_u64, [c_void_p]),
     "kv_net_load": (c_int, [c_void_p, c_void_p, c_u64]),
     "kv_net_blob_device_ptr": (c_void_p, [c_void_p]),

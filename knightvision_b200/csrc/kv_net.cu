@@ -264,6 +264,7 @@ constexpr int CONV2_THREADS = 384;   // warps 0-2 producer / MMA / TMEM, warp 3 
 // The spin is bounded and traps (a protocol bug must not hang the GPU box).
 struct TowerLayerDev {
     CUtensorMap wmap;        // this layer's weights, {64, 128} boxes (one CTA's half of the N tile)
+    CUtensorMap wmap_q;      // {64, 64} boxes: a quarter of the N tile (4-CTA clusters: two CTAs multicast a half each)
     const float* bias;
     int in_buf, in_view;     // activation buffer 0..2 and view (0: C1 channels, 1: C channels) of the input
     int out_buf, res_buf;    // res_buf < 0: no residual
@@ -285,7 +286,19 @@ struct TowerArgs {
     int board_base[2];       // first board of this launch in the C1 / C view of the buffers
     int chunk_tiles;         // depth-first order: board tiles per chunk (0 = layer-major over all boards)
     TowerLayerDev single;    // layers == nullptr: the one layer of this launch (a convolution on caller-owned tensors)
+    // hybrid launch: this kernel computes only a slice of the board tiles — part 1: tiles [0, Ma), part 2: [Ma, M), with
+    // Ma = M * split_num / split_den rounded down to even (M may be a device-side count); part 0: everything
+    int part, split_num, split_den;
 };
+__device__ __forceinline__ void tower_slice(const TowerArgs& T, int M, int& m_off, int& m_cnt) {
+    m_off = 0;
+    m_cnt = M;
+    if (T.part) {
+        const int Ma = (int)(((long long)M * T.split_num / T.split_den) & ~1ll);
+        if (T.part == 1) m_cnt = Ma;
+        else { m_off = Ma; m_cnt = M - Ma; }
+    }
+}
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
@@ -359,7 +372,9 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, const __grid_const
     kvu::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int nb = T.n_ptr ? *T.n_ptr : T.n_boards;
-    const int M = (nb + 3) >> 2, NT = T.cout / BN;
+    const int NT = T.cout / BN;
+    int m_off, M;
+    tower_slice(T, (nb + 3) >> 2, m_off, M);
     const int m_valid = nb * 64;
     TowerOrder ord;
     ord.init(M, NT, T.n_layers, T.chunk_tiles);
@@ -373,6 +388,7 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, const __grid_const
         for (int t = cluster_id; t < total; t += n_clusters) {
             int l, m_tile, n_tile;
             ord.decode(t, l, m_tile, n_tile);
+            m_tile += m_off;
             const TowerLayerDev* L = T.layers ? T.layers + l : &T.single;
             const int kb_per_tap = L->kb_per_tap, ksteps = 9 * kb_per_tap;
             [[maybe_unused]] const CUtensorMap* tmA = &maps.m[L->in_buf][L->in_view];
@@ -428,6 +444,7 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, const __grid_const
         for (int t = cluster_id; t < total; t += n_clusters) {
             int l, m_tile, n_tile;
             ord.decode(t, l, m_tile, n_tile);
+            m_tile += m_off;
             const int ksteps = 9 * (T.layers ? T.layers[l].kb_per_tap : T.single.kb_per_tap);
             kvu::mbar_wait(&tempty[acc], acc_phase ^ 1);
             kvu::tc_fence_after();
@@ -488,6 +505,7 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, const __grid_const
         for (int t = cluster_id; t < total; t += n_clusters) {
             int l, m_tile, n_tile;
             ord.decode(t, l, m_tile, n_tile);
+            m_tile += m_off;
             const TowerLayerDev* L = T.layers ? T.layers + l : &T.single;
             ConvParams P;
             P.bias = L->bias;
@@ -538,6 +556,190 @@ tower_umma2_kernel(const __grid_constant__ TowerActMaps maps, const __grid_const
     kvu::tc_fence_before();
     __syncthreads();
     kvu::cluster_sync();   // the peer may still be signalling this CTA's barriers / reading its B half
+    if (warp == 2) kvu::tmem_dealloc2(tmem_base, 512);
+}
+
+// ---- 4-CTA clusters: two CTA pairs on neighbouring board tiles share every weight tile ---------------------------------
+// After the halo operand 70 % of the L2 -> shared-memory stream is weights, fetched once per board tile.  Here a cluster
+// is two pairs (CTAs 0,1 and 2,3) working on board tiles 2s and 2s+1 of the same layer and channel tile; the half of the
+// weight tile that CTA r needs is the one CTA r^2 needs too, so each of the two loads a QUARTER ({64 k, 64 rows} box)
+// and multicasts it to both: every CTA still receives 48 KB of weights per stage but only 24 KB per CTA cross L2 -> SM
+// (132 instead of 204 KB per channel block and CTA).  A stage slot is now written by loads of the other pair, so the
+// `empty` barriers collect the commits of BOTH pairs' MMA issuers (count 2, commit multicast to all four CTAs); the
+// `full` / `tfull` / `tempty` barriers stay per pair.  Tasks are (layer, pair of board tiles, channel tile).
+template <int UNUSED = 0>
+__global__ void __cluster_dims__(4, 1, 1) __maxnreg__(128)
+tower_umma4_kernel(const __grid_constant__ TowerActMaps maps, const __grid_constant__ TowerArgs T) {
+    constexpr int NSTAGE = STAGES_H;
+    constexpr int SBYTES = STAGE_H_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * SBYTES);
+    uint64_t* empty = full + NSTAGE;
+    uint64_t* tfull = empty + NSTAGE;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank4 = kvu::cluster_ctarank();
+    const int pair = (int)(rank4 >> 1), rank = (int)(rank4 & 1);   // pair inside the cluster, CTA inside the pair
+    const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));
+    const int cluster_id = blockIdx.x >> 2, n_clusters = gridDim.x >> 2;
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NSTAGE; s++) {
+            kvu::mbar_init(&full[s], 1);
+            kvu::mbar_init(&empty[s], 2);      // both pairs' MMA issuers
+        }
+        for (int a = 0; a < 2; a++) {
+            kvu::mbar_init(&tfull[a], 1);
+            kvu::mbar_init(&tempty[a], 512);   // 256 epilogue threads of each CTA of the pair
+        }
+        kvu::fence_barrier_init();
+    }
+    if (warp == 2) kvu::tmem_alloc2(tmem_slot, 512);
+    kvu::tc_fence_before();
+    __syncthreads();
+    kvu::cluster_sync();
+    kvu::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nb = T.n_ptr ? *T.n_ptr : T.n_boards;
+    const int NT = T.cout / BN;
+    int m_off, M;                                   // this launch's slice of the board tiles: [m_off, m_off + M)
+    tower_slice(T, (nb + 3) >> 2, m_off, M);
+    const int Ms = (M + 1) >> 1;
+    const int m_valid = nb * 64;
+    TowerOrder ord;
+    ord.init(Ms, NT, T.n_layers, T.chunk_tiles > 1 ? T.chunk_tiles / 2 : T.chunk_tiles);
+    const int total = ord.total;
+    const uint32_t need = 16u * (uint32_t)NT;
+
+    if (warp == 0) {
+        // ---- TMA producer (all four CTAs) ---------------------------------------------------------------------
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint16_t bmask = (uint16_t)((1u << rank) | (1u << (rank + 2)));   // the CTAs that hold this half
+        for (int t = cluster_id; t < total; t += n_clusters) {
+            int l, ms, n_tile;
+            ord.decode(t, l, ms, n_tile);
+            const int m_tile = m_off + 2 * ms + pair;
+            const TowerLayerDev* L = T.layers ? T.layers + l : &T.single;
+            const int kb_per_tap = L->kb_per_tap;
+            const CUtensorMap* tmH = &maps.h[L->in_buf][L->in_view];
+            const int b0 = T.board_base[L->in_view] + m_tile * 4 + rank * 2;
+            if (l > 0 && m_tile < m_off + M) {
+                tower_wait_tile(T.done + (size_t)(l - 1) * T.m_stride + m_tile, need, lane);
+                fence_proxy_async();
+            }
+            for (int st3 = 0; st3 < 3 * kb_per_tap; st3++) {   // (channel block, dx)
+                const int kb = st3 / 3, dxi = st3 - kb * 3;
+                kvu::mbar_wait(&empty[stage], phase ^ 1);
+                if (lane == 0) {
+                    uint8_t* sa = smem + stage * SBYTES;
+                    if (rank == 0) kvu::mbar_arrive_expect_tx(&full[stage], 2 * SBYTES);
+                    kvu::tma2_load_4d(sa, tmH, &full[stage], kb * BK, dxi - 1, b0, -1);
+#pragma unroll
+                    for (int dyi = 0; dyi < 3; dyi++)
+                        kvu::tma2_load_2d_mc(sa + AH_BYTES + dyi * B2_BYTES + pair * (B2_BYTES / 2), &L->wmap_q, &full[stage],
+                                             ((dyi * 3 + dxi) * kb_per_tap + kb) * BK,
+                                             n_tile * BN + rank * (BN / 2) + pair * (BN / 4), bmask);
+                }
+                __syncwarp();
+                if (++stage == NSTAGE) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ---- MMA issuer (the leader CTA of each pair) ------------------------------------------------------------
+        constexpr uint32_t idesc = kvu::make_idesc_bf16(2 * BM, BN);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int t = cluster_id; t < total; t += n_clusters) {
+            int l, ms, n_tile;
+            ord.decode(t, l, ms, n_tile);
+            const int nst = 3 * (T.layers ? T.layers[l].kb_per_tap : T.single.kb_per_tap);
+            kvu::mbar_wait(&tempty[acc], acc_phase ^ 1);
+            kvu::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+            for (int s3 = 0; s3 < nst; s3++) {
+                kvu::mbar_wait(&full[stage], phase);
+                kvu::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = kvu::smem_u32(smem + stage * SBYTES);
+#pragma unroll
+                    for (int dyi = 0; dyi < 3; dyi++) {
+                        const uint64_t adesc = kvu::make_sw128_kmajor_desc(sa + dyi * 2048);
+                        const uint64_t bdesc = kvu::make_sw128_kmajor_desc(sa + AH_BYTES + dyi * B2_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; k++)
+                            kvu::umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (s3 | dyi | k) != 0);
+                    }
+                    kvu::umma2_commit_mask(&empty[stage], 0xF);          // the slot is free once BOTH pairs have read it
+                    if (s3 == nst - 1) kvu::umma2_commit_mask(&tfull[acc], pair_mask);
+                }
+                __syncwarp();
+                if (++stage == NSTAGE) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue (all four CTAs, own 128 rows) -----------------------------------------------------------------
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = cluster_id; t < total; t += n_clusters) {
+            int l, ms, n_tile;
+            ord.decode(t, l, ms, n_tile);
+            const int m_tile = m_off + 2 * ms + pair;
+            const TowerLayerDev* L = T.layers ? T.layers + l : &T.single;
+            ConvParams P;
+            P.bias = L->bias;
+            P.out = T.act[L->out_buf];
+            P.residual = L->res_buf >= 0 ? T.act[L->res_buf] : nullptr;
+            P.relu = L->relu;
+            const int r = q * 32 + lane;   // TMEM lane r = (y, board, x): r / 16, (r / 8) % 2, r % 8
+            const int row = m_tile * 2 * BM + rank * BM + ((r >> 3) & 1) * 64 + (r >> 4) * 8 + (r & 7);
+            const bool valid = row < m_valid;
+            const int colb = n_tile * BN + half * (BN / 2);
+            const size_t rbase = (size_t)row * T.cout + (size_t)colb;
+            uint4 res[4][4];
+            if (P.residual) {
+                if (l > 0 && m_tile < m_off + M) tower_wait_tile(T.done + (size_t)(l - 1) * T.m_stride + m_tile, need, lane);
+                if (valid) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(P.residual + rbase);
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) res[c][j] = __ldcg(rp + c * 4 + j);
+                }
+            }
+            kvu::mbar_wait(&tfull[acc], acc_phase);
+            kvu::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t v[32];
+                kvu::tmem_ld_32x32(tmem_base + (uint32_t)acc * BN + half * (BN / 2) + c * 32 + ((uint32_t)(q * 32) << 16), v);
+                kvu::tmem_ld_wait();
+                if (valid) conv_epilogue_store_pf(P, v, res[c], rbase + c * 32, colb + c * 32);
+            }
+            kvu::tc_fence_before();
+            kvu::mbar_arrive_leader(&tempty[acc]);
+            fence_proxy_async();
+            __threadfence();
+            __syncwarp();
+            if (lane == 0 && T.done && m_tile < m_off + M) red_release_add_u32(T.done + (size_t)l * T.m_stride + m_tile, 1u);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    kvu::tc_fence_before();
+    __syncthreads();
+    kvu::cluster_sync();   // CTAs of the cluster may still be signalling this CTA's barriers / multicasting into it
     if (warp == 2) kvu::tmem_dealloc2(tmem_base, 512);
 }
 
@@ -801,6 +1003,9 @@ void kv_net_destroy(kv_ctx* ctx) {
                     n->d_flag, n->d_lines_tmp, n->d_layers, n->d_done[0], n->d_done[1]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    if (n->side) cudaStreamDestroy(n->side);
+    if (n->ev_fork) cudaEventDestroy(n->ev_fork);
+    if (n->ev_join) cudaEventDestroy(n->ev_join);
     delete n;
     ctx->net = nullptr;
 }
@@ -847,6 +1052,7 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
         KV_CUDA(ctx, cudaMalloc(&L.b, (size_t)L.cout * sizeof(float)));
         if (int rc = make_w_map(ctx, &L.map, L.w, L.cout, 9 * L.cin)) return rc;
         if (int rc = make_w_map(ctx, &L.map_half, L.w, L.cout, 9 * L.cin, 128)) return rc;
+        if (int rc = make_w_map(ctx, &L.map_q, L.w, L.cout, 9 * L.cin, 64)) return rc;
     }
     KV_CUDA(ctx, cudaMalloc(&n->stem_table, (size_t)9 * 12 * n->C1 * sizeof(float)));
     KV_CUDA(ctx, cudaMalloc(&n->stem_bias, (size_t)n->C1 * sizeof(float)));
@@ -873,6 +1079,7 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
         for (int l = 0; l < nconv; l++) {
             memset(static_cast<void*>(&tab[l]), 0, sizeof(TowerLayerDev));
             tab[l].wmap = n->convs[l].map_half;
+            tab[l].wmap_q = n->convs[l].map_q;
             tab[l].bias = n->convs[l].b;
             tab[l].in_buf = plan[l].in;
             tab[l].in_view = (n->convs[l].cin == n->C1 && n->convs[l].cin != n->C) ? 0 : 1;
@@ -886,8 +1093,30 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
         n->m_stride = (n->cap + 3) / 4;
         for (int i = 0; i < 2; i++) KV_CUDA(ctx, cudaMalloc(&n->d_done[i], (size_t)nconv * n->m_stride * sizeof(uint32_t)));
     }
+    {   // 4-CTA clusters: how many are co-resident (the dependency schedule needs every cluster of the grid resident)
+        cudaError_t e = cudaFuncSetAttribute(tower_umma4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOWER_H_SMEM);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(ctx->sm_count / 4 * 4));
+        cfg.blockDim = dim3(CONV2_THREADS);
+        cfg.dynamicSmemBytes = TOWER_H_SMEM;
+        cudaLaunchAttribute at;
+        memset(&at, 0, sizeof(at));
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 4;
+        at.val.clusterDim.y = 1;
+        at.val.clusterDim.z = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = 1;
+        int nc = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&nc, tower_umma4_kernel<0>, &cfg);
+        n->clusters4 = (e == cudaSuccess && n->halo_ok) ? nc : 0;
+        cudaGetLastError();
+    }
     if (const char* e = getenv("KV_TOWER_FUSED")) n->tower_fused = atoi(e);
-    if (n->tower_fused < 0 || n->tower_fused > 2 || (n->tower_fused == 2 && !n->halo_ok)) n->tower_fused = 1;
+    if (n->tower_fused < 0 || n->tower_fused > 4 || (n->tower_fused == 2 && !n->halo_ok) ||
+        (n->tower_fused >= 3 && n->clusters4 < 8))
+        n->tower_fused = 1;
     // depth-first chunks: one round of the CTA pairs per layer and channel tile, 57-85 MB of activations per chunk at
     // 512 channels (more tiles for a narrower tower: same bytes)
     n->tower_chunk = (ctx->sm_count / 2) * (512 / n->C);
@@ -899,7 +1128,8 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
 // 0 = one launch per layer.  Same tiles, same arithmetic: bit-identical outputs.
 int kv_net_set_tower_fused(kv_ctx* ctx, int on) {
     if (!ctx || !ctx->net) return kv_fail_msg(ctx, "kv_net_set_tower_fused: no net");
-    if (on < 0 || on > 2) return kv_fail_msg(ctx, "kv_net_set_tower_fused: 0, 1 or 2");
+    if (on < 0 || on > 4) return kv_fail_msg(ctx, "kv_net_set_tower_fused: 0 .. 4");
+    if (on >= 3 && ctx->net->clusters4 < 8) return kv_fail_msg(ctx, "kv_net_set_tower_fused: 4-CTA clusters unavailable");
     if (on == 2 && !ctx->net->halo_ok) return kv_fail_msg(ctx, "kv_net_set_tower_fused: halo tensor maps unavailable");
     ctx->net->tower_fused = on;
     return 0;
@@ -912,6 +1142,9 @@ int kv_net_set_conv_mode(kv_ctx* ctx, int cta_group) {
     ctx->net->conv_mode = cta_group;
     return 0;
 }
+
+// co-resident 4-CTA clusters of the multicast tower kernel (0: kv_net_set_tower_fused(3) is unavailable)
+int kv_net_tower_clusters4(kv_ctx* ctx) { return (ctx && ctx->net) ? ctx->net->clusters4 : 0; }
 
 uint64_t kv_net_blob_floats(kv_ctx* ctx) { return (ctx && ctx->net) ? ctx->net->blob_floats : 0; }
 void* kv_net_blob_device_ptr(kv_ctx* ctx) { return (ctx && ctx->net) ? ctx->net->d_blob : nullptr; }
@@ -1127,6 +1360,7 @@ int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, i
                 maps.h[i][v] = net->map_act_h[i][v];
             }
         TowerArgs T;
+        memset(static_cast<void*>(&T), 0, sizeof(T));
         for (int i = 0; i < 3; i++) T.act[i] = net->act[i] + off0;
         T.layers = reinterpret_cast<const TowerLayerDev*>(net->d_layers);
         T.done = done;
@@ -1142,7 +1376,31 @@ int kv_net_tower(kv_ctx* ctx, const uint64_t* d_lines, int n, cudaStream_t st, i
         const int grid = 2 * (total < pairs ? total : pairs);
         {
             KvTimed t_(ctx, KVK_NET_CONV, cs);
-            if (net->tower_fused == 2) tower_umma2_kernel<true><<<grid, CONV2_THREADS, TOWER_H_SMEM, cs>>>(maps, T);
+            if (net->tower_fused == 4 && (n + 3) / 4 >= 4 * net->clusters4) {
+                // hybrid: the 4-CTA clusters cannot cover every SM (33 clusters = 132 of 148 SMs on B200: GPCs whose SM
+                // count is not a multiple of four), so the multicast kernel takes the share of the board tiles that matches
+                // its SMs and the CTA-pair kernel runs the rest on the remaining TPCs, concurrently on a second stream
+                if (!net->side) {
+                    KV_CUDA(ctx, cudaStreamCreateWithFlags(&net->side, cudaStreamNonBlocking));
+                    KV_CUDA(ctx, cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming));
+                    KV_CUDA(ctx, cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming));
+                }
+                const int sm4 = 4 * net->clusters4, rest = ctx->sm_count - sm4;
+                T.split_num = sm4;
+                T.split_den = sm4 + rest;
+                KV_CUDA(ctx, cudaEventRecord(net->ev_fork, cs));
+                KV_CUDA(ctx, cudaStreamWaitEvent(net->side, net->ev_fork, 0));
+                T.part = 1;
+                tower_umma4_kernel<0><<<sm4, CONV2_THREADS, TOWER_H_SMEM, cs>>>(maps, T);
+                T.part = 2;
+                tower_umma2_kernel<true><<<rest & ~1, CONV2_THREADS, TOWER_H_SMEM, net->side>>>(maps, T);
+                KV_CUDA(ctx, cudaEventRecord(net->ev_join, net->side));
+                KV_CUDA(ctx, cudaStreamWaitEvent(cs, net->ev_join, 0));
+            } else if (net->tower_fused == 3 || net->tower_fused == 4) {
+                const int total4 = nl * (((n + 3) / 4 + 1) / 2) * (net->C / BN);
+                const int nc = total4 < net->clusters4 ? total4 : net->clusters4;
+                tower_umma4_kernel<0><<<4 * nc, CONV2_THREADS, TOWER_H_SMEM, cs>>>(maps, T);
+            } else if (net->tower_fused == 2) tower_umma2_kernel<true><<<grid, CONV2_THREADS, TOWER_H_SMEM, cs>>>(maps, T);
             else tower_umma2_kernel<false><<<grid, CONV2_THREADS, CONV2_SMEM, cs>>>(maps, T);
         }
         KV_LAUNCH_CHECK(ctx);

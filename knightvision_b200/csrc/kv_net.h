@@ -12,6 +12,7 @@ struct kv_conv {
     int cin = 0, cout = 0;
     CUtensorMap map;        // 2-D boxes {64, 256}: the whole N tile (1-CTA kernel)
     CUtensorMap map_half;   // 2-D boxes {64, 128}: this CTA's half of the N tile (2-CTA kernel)
+    CUtensorMap map_q;      // 2-D boxes {64, 64}: a quarter of the N tile (4-CTA clusters, multicast)
 };
 
 struct kv_net {
@@ -31,11 +32,15 @@ struct kv_net {
     size_t blob_floats = 0;
     int conv_mode = 2;                     // 1: cta_group::1 kernel, 2: cta_group::2 CTA-pair kernel
     int tower_fused = 2;                   // conv_mode 2 only: 1 = the whole tower as one dependency-scheduled launch,
-                                           // 2 (default) = the same with the halo A-operand (3 instead of 9 fetches)
+                                           // 2 (default) = the same with the halo A-operand (3 instead of 9 fetches),
+                                           // 3 = halo operand + 4-CTA clusters sharing the weight tiles by multicast
     void* d_layers = nullptr;              // TowerLayerDev[convs.size()] (kv_net.cu)
     uint32_t* d_done[2] = {nullptr, nullptr};   // tile-completion counters [layers][m_stride], one set per game group
     int m_stride = 0;
     bool halo_ok = true;                   // the halo tensor maps could be encoded
+    cudaStream_t side = nullptr;           // hybrid tower launch: the CTA-pair kernel's stream, forked / joined per launch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int clusters4 = 0;                     // co-resident 4-CTA clusters of tower_umma4_kernel (0: variant unavailable)
     int tower_chunk = 74;                  // board tiles per depth-first chunk of the whole-tower launch (0: layer-major)
     int* d_flag = nullptr;
     uint64_t* d_lines_tmp = nullptr;

@@ -177,6 +177,23 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
                  ::"r"(smem_u32(bar)), "h"(mask)
                  : "memory");
 }
+// 2-D TMA load multicast to the CTAs in `mask` (same shared-memory offset in each); the completion bytes are credited,
+// in every destination CTA, to the barrier at this offset in that CTA's PAIR LEADER (rank bit cleared)
+__device__ __forceinline__ void tma2_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "h"(mask), "r"(c0),
+        "r"(c1)
+        : "memory");
+}
+// commit with an explicit CTA mask (clusters of more than one CTA pair)
+__device__ __forceinline__ void umma2_commit_mask(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
 // arrive on the LEADER CTA's copy of a barrier (works from either CTA)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");

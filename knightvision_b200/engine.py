@@ -125,8 +125,14 @@ class Engine:
 
     def net_set_tower_fused(self, mode):
         """0 = one launch per tower layer, 1 / True = whole tower as one dependency-scheduled launch (default, same bits),
-        2 = whole-tower launch with the halo activation operand (3 instead of 9 fetches per tile; fp32-rounding equal)."""
+        2 = whole-tower launch with the halo activation operand (default; 3 instead of 9 fetches per tile; fp32-rounding
+        equal), 3 / 4 = mode 2 on 4-CTA clusters sharing the weight tiles by multicast (4: plus CTA pairs on the SMs the
+        clusters cannot cover; same bits as 2)."""
         N.check(self.ctx, self._lib.kv_net_set_tower_fused(self.ctx, int(mode)), "kv_net_set_tower_fused")
+
+    def net_tower_clusters4(self) -> int:
+        """Co-resident 4-CTA clusters of the weight-multicast tower kernel (0: net_set_tower_fused(3) unavailable)."""
+        return int(self._lib.kv_net_tower_clusters4(self.ctx))
 
     def net_set_conv_mode(self, cta_group: int):
         N.check(self.ctx, self._lib.kv_net_set_conv_mode(self.ctx, cta_group), "kv_net_set_conv_mode")

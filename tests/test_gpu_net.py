@@ -186,3 +186,26 @@ def test_halo_operand_tower(eng, arch, n):
     with torch.no_grad():
         rp, rv = fp32_reference_forward(net.cuda(), torch.from_numpy(O.encode(lines)).cuda())
     assert (pol2 - rp).abs().max().item() < TOL and (val2 - rv).abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("arch,n", [("ref", 1237), ("ref", 5), ("ref", 24), ("20x256", 333)])
+def test_weight_multicast_clusters_match_pairs(eng, arch, n):
+    """Mode 3 (4-CTA clusters, weight tiles multicast to two CTA pairs) computes every tile exactly like mode 2:
+    bit-identical activations and outputs, odd numbers of board tiles included; repeated runs agree."""
+    from knightvision_b200.engine import lines_to_device
+    kw = {} if arch == "ref" else dict(stem=256, tower=256, blocks=20, conv2=False)
+    net = _net(seed=17, bnrand=True, **kw).attach(eng, max_batch=n + 2)
+    if eng.net_tower_clusters4() < 8:
+        pytest.skip("4-CTA clusters of the tower kernel are not co-resident on this GPU")
+    lines = _lines(n, seed=29)
+    d = lines_to_device(lines, eng.device)
+    eng.net_set_tower_fused(2)
+    mid2 = eng.net_forward_partial(d, 3).clone()
+    pol2, val2 = (t.clone() for t in net.forward_lines(d))
+    for mode in (3, 4):      # 4 = hybrid: the clusters on the SMs they can cover, CTA pairs on the rest, concurrently
+        eng.net_set_tower_fused(mode)
+        for _ in range(3):
+            assert torch.equal(eng.net_forward_partial(d, 3), mid2)
+            pol3, val3 = net.forward_lines(d)
+            assert torch.equal(pol3, pol2) and torch.equal(val3, val2)
+    eng.net_set_tower_fused(2)

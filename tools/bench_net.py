@@ -13,6 +13,7 @@ eng = Engine(0)
 torch.manual_seed(0)
 net = ChessNet(tower=a.tower, blocks=a.blocks, conv2=not a.no_conv2, stem=256).eval().attach(eng, max_batch=a.batch)
 eng.net_set_conv_mode(a.cta_group)
+clusters4 = eng.net_tower_clusters4()
 lines = lines_to_device(np.stack([L.start_line()] * a.batch), eng.device)
 for _ in range(3):
     eng.net_forward(lines, want_policy=False)
@@ -27,7 +28,7 @@ ms = e0.elapsed_time(e1) / a.iters
 prof = eng.profile_read()
 macs = {(512, 5, True): 1587872256}.get((a.tower, a.blocks, not a.no_conv2), None)
 flops = 2 * macs if macs else None
-out = {"cta_group": a.cta_group, "batch": a.batch, "ms_per_forward": ms, "evals_per_s": a.batch / ms * 1e3,
+out = {"clusters4": clusters4, "cta_group": a.cta_group, "batch": a.batch, "ms_per_forward": ms, "evals_per_s": a.batch / ms * 1e3,
        "tflops": (a.batch * flops / ms / 1e9) if flops else None,
        "kernels_ms": {k: v[0] / a.iters for k, v in prof.items() if v[1]}}
 print(json.dumps(out))
