@@ -291,13 +291,7 @@ struct TowerArgs {
     int part, split_num, split_den;
 };
 __device__ __forceinline__ void tower_slice(const TowerArgs& T, int M, int& m_off, int& m_cnt) {
-    m_off = 0;
-    m_cnt = M;
-    if (T.part) {
-        const int Ma = (int)(((long long)M * T.split_num / T.split_den) & ~1ll);
-        if (T.part == 1) m_cnt = Ma;
-        else { m_off = Ma; m_cnt = M - Ma; }
-    }
+    tower_slice_tiles(T.part, T.split_num, T.split_den, M, m_off, m_cnt);
 }
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }

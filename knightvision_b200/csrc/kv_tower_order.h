@@ -42,4 +42,19 @@ struct TowerOrder {
     }
 };
 
+// Hybrid launch (4-CTA clusters + CTA pairs, kv_net.cu): the slice of the M board tiles a kernel computes.  part 0: all;
+// part 1: [0, Ma); part 2: [Ma, M); Ma = M * num / den rounded down to even (the clusters take board tiles in pairs).
+KV_TO_HD inline void tower_slice_tiles(int part, int num, int den, int M, int& m_off, int& m_cnt) {
+    m_off = 0;
+    m_cnt = M;
+    if (part) {
+        const int Ma = (int)(((long long)M * num / den) & ~1ll);
+        if (part == 1) m_cnt = Ma;
+        else {
+            m_off = Ma;
+            m_cnt = M - Ma;
+        }
+    }
+}
+
 }  // namespace kvn

@@ -101,3 +101,10 @@ def tower_order(M, NT, n_layers, chunk_tiles):
     out = np.zeros((total, 3), np.int32)
     lib().kvemu_tower_order(*args, _p(out))
     return out
+
+
+def tower_slice(part, num, den, M):
+    """(first board tile, count) of a kernel's slice in the hybrid tower launch (kv_tower_order.h)."""
+    out = np.zeros(2, np.int32)
+    lib().kvemu_tower_slice(ctypes.c_int(part), ctypes.c_int(num), ctypes.c_int(den), ctypes.c_int(M), _p(out))
+    return int(out[0]), int(out[1])

@@ -501,4 +501,11 @@ __attribute__((visibility("default"))) int kvemu_tower_order(int M, int NT, int 
     return o.total;
 }
 
+__attribute__((visibility("default"))) void kvemu_tower_slice(int part, int num, int den, int M, int32_t* out2) {
+    int off, cnt;
+    kvn::tower_slice_tiles(part, num, den, M, off, cnt);
+    out2[0] = off;
+    out2[1] = cnt;
+}
+
 }  // extern "C"

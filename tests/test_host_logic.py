@@ -55,3 +55,15 @@ def test_whole_tower_task_order():
             cuts = np.flatnonzero(np.diff(idx) > 1)
             sizes = np.diff(np.concatenate([[0], cuts + 1, [len(idx)]])) // NT
             assert sizes.max() - sizes.min() <= 1 and sizes.min() >= ct and sizes.sum() == M
+
+
+def test_hybrid_tower_slices_partition_the_board_tiles():
+    """The two kernels of the hybrid tower launch split the board tiles without gap or overlap; the cluster kernel's share
+    is even (it takes tiles in pairs) and proportional to its SMs."""
+    from simt_emu import emu
+    for M in (0, 1, 2, 3, 37, 132, 133, 625, 1024, 4097):
+        assert emu.tower_slice(0, 132, 148, M) == (0, M)
+        o1, c1 = emu.tower_slice(1, 132, 148, M)
+        o2, c2 = emu.tower_slice(2, 132, 148, M)
+        assert o1 == 0 and c1 % 2 == 0 and o2 == c1 and c1 + c2 == M
+        assert abs(c1 - M * 132 / 148) < 2
