@@ -163,9 +163,26 @@ KV_API int kv_mcts_run_move(kv_ctx* ctx, void* stream);               /* waves u
  * bit-identical with the cache on or off.  Cleared automatically by kv_net_commit_weights / kv_net_load. */
 KV_API int kv_mcts_enable_cache(kv_ctx* ctx, int log2_slots);
 KV_API int kv_mcts_cache_clear(kv_ctx* ctx, void* stream);
-/* h_out9: games done, sum of sims done in the current move, tower evaluations, plies played, games with edge-pool
- * overflow, white wins, black wins, draws, expansions served by the cache (hits + in-wave duplicates) */
-KV_API int kv_mcts_status(kv_ctx* ctx, uint64_t* h_out9, void* stream);
+/* h_out10: games done, sum of sims done in the current move, tower evaluations, plies played, games with edge-pool
+ * overflow, white wins, black wins, draws, expansions served by the cache (hits + in-wave duplicates), games stopped
+ * by an illegal scripted move */
+KV_API int kv_mcts_status(kv_ctx* ctx, uint64_t* h_out10, void* stream);
+/* Game-loop rules of scripts/self_play.py:180-199 applied after every move, in the reference's order: only-kings
+ * draw (:180), resignation (:185-189: more than min_plies plies played and the network's value of the position the
+ * move was chosen in < threshold => -1 if white is to move, else +1), ply cap (:196), then no-moves at the loop head
+ * (:125: checkmate :217 / stalemate :221).  Defaults are the reference's: threshold -0.7, min_plies 15;
+ * min_plies < 0 switches resignation off. */
+KV_API int kv_mcts_set_resign(kv_ctx* ctx, float threshold, int min_plies);
+/* Root priors.  0: softmax over the legal moves' logits, Dirichlet noise over the legal moves (tree search).
+ * 1: the reference's rule (scripts/self_play.py:150-167) — softmax over ALL 4096 logits, Dirichlet(alpha) noise over
+ * all 4096 indices, (1-eps) p + eps noise, then the legal entries renormalised.  -1 = default: 1 when sims == 1 (no
+ * search: the move is sampled from these priors exactly as the reference samples it), else 0. */
+KV_API int kv_mcts_set_root_mix(kv_ctx* ctx, int mode);
+/* Scripted play (replay of recorded games through the game loop): d_moves [n_games][stride] u16 move words matched on
+ * (from, to) against the legal moves (0xFFFF = choose as usual; an illegal one stops the game and is counted in
+ * kv_mcts_status), d_values [n_games][stride] the value the resign rule sees at that ply (NaN = the evaluator's).
+ * Either may be NULL; caller-owned device memory; (NULL, NULL, 0) clears. */
+KV_API int kv_mcts_set_script(kv_ctx* ctx, const uint16_t* d_moves, const float* d_values, int stride);
 KV_API int kv_mcts_get_roots(kv_ctx* ctx, uint64_t* d_lines, void* stream); /* current position of every game [n][16] */
 KV_API int kv_mcts_geometry(kv_ctx* ctx, int32_t* out4);              /* n_games, node_cap, edge_cap, rec_cap */
 KV_API int64_t kv_mcts_waves(kv_ctx* ctx);                            /* search waves launched since create */

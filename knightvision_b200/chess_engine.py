@@ -33,8 +33,8 @@ def set_engine(engine):
 
 
 class CastleRights:
-    def __init__(self, wks, bks, wqs, bqs):
-        self.wks, self.bks, self.wqs, self.bqs = wks, bks, wqs, bqs
+    def __init__(self, wks, wqs, bks, bqs):          # argument order of core/chessEngine.py:13-18
+        self.wks, self.wqs, self.bks, self.bqs = wks, wqs, bks, bqs
 
 
 class Move:
@@ -110,7 +110,7 @@ class GameState:
             if getattr(self, a):
                 moved |= bit
         return L.pack_fields(self.board, self.whiteToMove, self.whiteKingLocation, self.blackKingLocation, moved,
-                             self.enPassantPossible, self.halfMoveClock)
+                             self.enPassantPossible, self.halfMoveClock, fen_pawns=True)
 
     def _adopt(self, line, board_only=False):
         f = L.unpack_fields(line)
@@ -233,7 +233,11 @@ class GameState:
         return str(self.board) + str(self.whiteToMove)
 
     def loadFEN(self, fen):
-        """:85-122 — sets board, side, e.p. and an unused castleRights; NOT the king locations, moved-flags or clock."""
+        """:85-122 — sets board, side, e.p. and an unused castleRights; NOT the king locations, moved-flags or clock.
+        Like the reference it writes pawns as 'wP' / 'bP' (`char.upper()`, :100), so `board` and getFEN() agree with
+        it; the rules kernels treat those as ordinary pawns (the reference treats them as a separate kind that moves
+        like a pawn but never promotes, captures e.p. or gives a pawn check — an accident no reference caller relies
+        on: nothing calls loadFEN).  Documented in INTEGRATION.md."""
         parts = fen.split()
         for r, txt in enumerate(parts[0].split("/")[:8]):
             row = []

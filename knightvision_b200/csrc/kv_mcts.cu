@@ -116,11 +116,36 @@ __device__ __forceinline__ void legal_logits(const MctsCfg& cfg, const MctsArray
     }
 }
 
+// All 4096 policy logits of one position into shared memory (cfg.root_mix roots only: the reference's softmax runs
+// over every index, scripts/self_play.py:150).  Same per-row arithmetic as legal_logits (8 lanes x 16 features, fixed
+// butterfly), so a legal move's entry equals its legal_logits value bit for bit.
+__device__ __forceinline__ void all_logits(const HeadW& H, const float* hp, float* out) {
+    const int part = threadIdx.x & 7, per = blockDim.x >> 3;
+    const float* f = hp + part * 16;
+    for (int r0 = 0; r0 < POLICY_N; r0 += per) {
+        const int idx = r0 + (int)(threadIdx.x >> 3);
+        const float4* wr = reinterpret_cast<const float4*>(H.wfc + (size_t)idx * 128 + part * 16);
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float4 w = __ldg(wr + i);
+            a += w.x * f[4 * i] + w.y * f[4 * i + 1] + w.z * f[4 * i + 2] + w.w * f[4 * i + 3];
+        }
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (part == 0) out[idx] = a + __ldg(H.bfc + idx);
+    }
+}
+
 // CTA per queued leaf: heads on the tower output, logits of the legal moves, then the warp-level expand/backup.
+// ROOTMIX (cfg.root_mix): a root additionally gets all 4096 logits (16 KB of shared memory) for the full softmax.
+template <bool ROOTMIX>
 __global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArrays A, const __nv_bfloat16* __restrict__ act,
                                                             HeadW H, uint32_t wave) {
     __shared__ float hp[128], hv[64], red[8], logits[MAX_MOVES];
     __shared__ __align__(16) float swh[3 * 512];
+    __shared__ float lall[ROOTMIX ? POLICY_N : 1];
     const int n_eval = (int)*A.n_eval;
     for (int slot = blockIdx.x; slot < n_eval; slot += gridDim.x) {   // grid-stride: see mcts_select_kernel
         const int gs = A.eval_game[slot];
@@ -128,9 +153,13 @@ __global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArr
         __syncthreads();
         const float v_white = kvn::value_mlp(hv, H.w1, H.b1, H.w2, H.b2, red);
         legal_logits(cfg, A, gs, H, hp, logits);
+        const bool mix = ROOTMIX && A.pend_node[gs] == 0;
+        if (mix) all_logits(H, hp, lall);
         __syncthreads();
         if (threadIdx.x < 32) {
-            mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, v_white);
+            float mx_all = 0.f, z_all = 0.f;
+            if (mix) full_softmax_stats_warp((int)threadIdx.x, [&](int i) { return lall[i]; }, mx_all, z_all);
+            mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, v_white, false, mx_all, z_all);
             if (cfg.cache_mask) cache_fill_warp((int)threadIdx.x, cfg, A, wave, slot, hp, v_white);
         }
         __syncthreads();   // hp / hv / red / logits are reused by the next leaf
@@ -138,8 +167,10 @@ __global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArr
 }
 
 // CTA (128 threads) per late entry: features from the cache (already copied per game) or from this wave's leader
+template <bool ROOTMIX>
 __global__ void __launch_bounds__(128) mcts_late_net_kernel(MctsCfg cfg, MctsArrays A, HeadW H) {
     __shared__ float hp[FEAT], logits[MAX_MOVES];
+    __shared__ float lall[ROOTMIX ? POLICY_N : 1];
     const int n_late = (int)*A.n_late;
     for (int li = blockIdx.x; li < n_late; li += gridDim.x) {
         const int gs = A.late_game[li], src = A.late_src[li];
@@ -147,8 +178,14 @@ __global__ void __launch_bounds__(128) mcts_late_net_kernel(MctsCfg cfg, MctsArr
         for (int i = threadIdx.x; i < FEAT; i += blockDim.x) hp[i] = f[i];
         __syncthreads();
         legal_logits(cfg, A, gs, H, hp, logits);
+        const bool mix = ROOTMIX && A.pend_node[gs] == 0;
+        if (mix) all_logits(H, hp, lall);
         __syncthreads();
-        if (threadIdx.x < 32) mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, hp[128], true);
+        if (threadIdx.x < 32) {
+            float mx_all = 0.f, z_all = 0.f;
+            if (mix) full_softmax_stats_warp((int)threadIdx.x, [&](int i) { return lall[i]; }, mx_all, z_all);
+            mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, hp[128], true, mx_all, z_all);
+        }
         __syncthreads();
     }
 }
@@ -169,7 +206,7 @@ __global__ void mcts_init_kernel(MctsCfg cfg, MctsArrays A, int G, const uint64_
 }
 
 // status: [0] games done, [1] sum sims_done, [2] sum evals, [3] sum plies, [4] overflow count, [5] white wins,
-// [6] black wins, [7] draws (among done)
+// [6] black wins, [7] draws (among done), [8] expansions served by the cache, [9] games stopped by an illegal scripted move
 __global__ void mcts_status_kernel(MctsArrays A, int G, unsigned long long* out) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
@@ -178,7 +215,8 @@ __global__ void mcts_status_kernel(MctsArrays A, int G, unsigned long long* out)
     atomicAdd(out + 1, (unsigned long long)h.sims_done);
     atomicAdd(out + 2, (unsigned long long)h.n_evals);
     atomicAdd(out + 3, (unsigned long long)h.ply);
-    if (h.overflow) atomicAdd(out + 4, 1ull);
+    if (h.overflow & HDR_OVERFLOW) atomicAdd(out + 4, 1ull);
+    if (h.overflow & HDR_SCRIPT_MISS) atomicAdd(out + 9, 1ull);
     atomicAdd(out + 8, (unsigned long long)h.cache_hits);
     if (h.done && h.result > 0) atomicAdd(out + 5, 1ull);
     if (h.done && h.result < 0) atomicAdd(out + 6, 1ull);
@@ -334,6 +372,10 @@ int kv_mcts_create_k(kv_ctx* ctx, int n_games, int sims, int edges_per_node, int
     c.dir_eps = dir_eps;
     c.seed = seed;
     c.inflight = inflight;
+    c.resign_thr = -0.7f;        // scripts/self_play.py:185
+    c.resign_min_plies = 15;
+    c.root_mix = sims == 1;      // no search: the move is sampled from the root priors, so they follow the reference's rule
+    c.script_stride = 0;
     MctsArrays& A = m->A;
     const size_t G = (size_t)n_games;
     const size_t GS = G * (size_t)inflight;   // in-flight slots
@@ -502,7 +544,8 @@ static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1
             if (int rc = wait_peer(m->ev_late, m->late_rec)) return rc;
         {
             KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
-            mcts_eval_net_kernel<<<piped ? imin(GS, sms) : GS, 256, 0, st>>>(m->cfg, A, act, H, wave);
+            if (m->cfg.root_mix) mcts_eval_net_kernel<true><<<piped ? imin(GS, sms) : GS, 256, 0, st>>>(m->cfg, A, act, H, wave);
+            else mcts_eval_net_kernel<false><<<piped ? imin(GS, sms) : GS, 256, 0, st>>>(m->cfg, A, act, H, wave);
         }
         KV_LAUNCH_CHECK(ctx);
         if (cache) {
@@ -510,7 +553,8 @@ static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1
             if (int rc = wait_peer(m->ev_eval, m->eval_rec)) return rc;
             {
                 KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
-                mcts_late_net_kernel<<<piped ? imin(GS, 3 * sms) : GS, 128, 0, st>>>(m->cfg, A, H);
+                if (m->cfg.root_mix) mcts_late_net_kernel<true><<<piped ? imin(GS, 3 * sms) : GS, 128, 0, st>>>(m->cfg, A, H);
+                else mcts_late_net_kernel<false><<<piped ? imin(GS, 3 * sms) : GS, 128, 0, st>>>(m->cfg, A, H);
             }
             KV_LAUNCH_CHECK(ctx);
             if (int rc = mark(m->ev_late, m->late_rec)) return rc;
@@ -571,8 +615,8 @@ static int mcts_run_waves(kv_ctx* ctx, int n_waves, cudaStream_t st) {
             const int carve = want ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault;
             cudaFuncSetAttribute(mcts_select_kernel<kMW>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
             cudaFuncSetAttribute(mcts_select_kernel<kMWP>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-            cudaFuncSetAttribute(mcts_eval_net_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-            cudaFuncSetAttribute(mcts_late_net_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(mcts_eval_net_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(mcts_late_net_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
             cudaFuncSetAttribute(mcts_backup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
             cudaGetLastError();
             g_attrs_state = want;
@@ -655,6 +699,37 @@ int kv_mcts_set_pipeline(kv_ctx* ctx, int mode) {
     return 0;
 }
 
+// Resignation rule of the game loop (scripts/self_play.py:184-189).  Defaults = the reference's (-0.7, 15);
+// min_plies < 0 switches it off.
+int kv_mcts_set_resign(kv_ctx* ctx, float threshold, int min_plies) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_set_resign: no search context");
+    ctx->mcts->cfg.resign_thr = threshold;
+    ctx->mcts->cfg.resign_min_plies = min_plies;
+    return 0;
+}
+
+// Root prior rule: 0 = softmax + Dirichlet noise over the legal moves, 1 = the reference's mixing over all 4096 indices
+// followed by the legal renormalisation (scripts/self_play.py:150-167), -1 = default (1 when sims == 1, else 0).
+int kv_mcts_set_root_mix(kv_ctx* ctx, int mode) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_set_root_mix: no search context");
+    if (mode < -1 || mode > 1) return kv_fail_msg(ctx, "kv_mcts_set_root_mix: mode must be -1, 0 or 1");
+    ctx->mcts->cfg.root_mix = mode < 0 ? (ctx->mcts->cfg.sims == 1) : mode;
+    return 0;
+}
+
+// Scripted play: d_moves [n_games][stride] move words (0xFFFF = choose as usual) and / or d_values [n_games][stride]
+// (NaN = the evaluator's value) override, per game and ply, the move the game loop plays and the value its resign rule
+// sees.  The arrays stay caller-owned and must outlive their use; (NULL, NULL, 0) clears the script.
+int kv_mcts_set_script(kv_ctx* ctx, const uint16_t* d_moves, const float* d_values, int stride) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_set_script: no search context");
+    if (stride < 0 || (stride == 0 && (d_moves || d_values))) return kv_fail_msg(ctx, "kv_mcts_set_script: bad stride");
+    kv_mcts* m = ctx->mcts;
+    m->A.script_move = stride ? d_moves : nullptr;
+    m->A.script_val = stride ? d_values : nullptr;
+    m->cfg.script_stride = (d_moves || d_values) ? stride : 0;
+    return 0;
+}
+
 int kv_mcts_finish_move(kv_ctx* ctx, void* stream) {
     if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_finish_move: no search context");
     kv_mcts* m = ctx->mcts;
@@ -675,13 +750,13 @@ int kv_mcts_run_move(kv_ctx* ctx, void* stream) {
         // wave 1 expands the root alone; afterwards at most K simulations per wave, fewer when selections collide
         // with leaves still under evaluation: run the minimum, then poll until every game has its S simulations
         int n = 1 + (S - 1 + K - 1) / K;
-        for (int guard = 0; guard < 4 * S + 8; guard++) {
+        unsigned int left = 1;
+        for (int guard = 0; guard < 4 * S + 8 && left; guard++) {
             if (int rc = kv_mcts_run_sims(ctx, n, stream)) return rc;
-            unsigned int left = 0;
             if (int rc = mcts_unfinished(ctx, (cudaStream_t)stream, &left)) return rc;
-            if (!left) break;
             n = 2;
         }
+        if (left) return kv_fail_msg(ctx, "kv_mcts_run_move: games still owe simulations after the wave budget");
     }
     return kv_mcts_finish_move(ctx, stream);
 }
@@ -693,7 +768,7 @@ int kv_mcts_status(kv_ctx* ctx, uint64_t* h_out8, void* stream) {
     KV_CUDA(ctx, cudaMemsetAsync(m->d_status, 0, 16 * sizeof(unsigned long long), st));
     mcts_status_kernel<<<(m->G + 255) / 256, 256, 0, st>>>(m->A, m->G, m->d_status);
     KV_LAUNCH_CHECK(ctx);
-    KV_CUDA(ctx, cudaMemcpyAsync(h_out8, m->d_status, 9 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    KV_CUDA(ctx, cudaMemcpyAsync(h_out8, m->d_status, 10 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     KV_CUDA(ctx, cudaStreamSynchronize(st));
     return 0;
 }

@@ -29,7 +29,18 @@ struct MctsCfg {
     uint32_t cache_mask;  // evaluation cache slots - 1 (power of two), 0 = cache disabled
     int inflight;         // K: simulations in flight per game and wave (>= 1); slot index gs = game * K + j
     uint64_t seed;
+    // resignation (scripts/self_play.py:184-189): after a move, once MORE than resign_min_plies plies were played and the
+    // network's value of the position the move was chosen in (raw output, no perspective flip) is < resign_thr, the game
+    // ends with result -1 if white is to move, else +1.  resign_min_plies < 0: never.  Reference: -0.7 / 15.
+    float resign_thr;
+    int resign_min_plies;
+    // root priors: 0 = softmax over the legal moves, Dirichlet noise over the legal moves (search default);
+    // 1 = the reference's rule (scripts/self_play.py:150-167): softmax over ALL 4096 indices, Dirichlet noise over all
+    //     4096 indices, mix, then renormalise over the legal moves
+    int root_mix;
+    int script_stride;    // plies per game of the script arrays (0: no script)
 };
+constexpr int POLICY_N = 4096;   // policy indices (ai/ai.py:51-57)
 
 // visit counters: low 24 bits real visits, top 8 bits virtual visits of in-flight simulations (0 between waves)
 constexpr uint32_t VL_ONE = 1u << 24;
@@ -106,7 +117,14 @@ struct MctsArrays {
     // under evaluation publishes, so that a leaf of one group can follow a leader of the other group.
     int slot_base = 0;
     uint32_t peer_wave = 0;   // wave id of the other group's wave still in flight (0 = none)
+    // Scripted play (kv_mcts_set_script): replay of recorded games through the engine's game loop.  script_move
+    // [G][script_stride] move words (0xFFFF: choose as usual), matched on (from, to) against the root's legal moves;
+    // script_val [G][script_stride] the value the resign rule sees at that ply (NaN: the evaluator's).
+    const uint16_t* script_move = nullptr;
+    const float* script_val = nullptr;
 };
+constexpr int HDR_OVERFLOW = 1;      // GameHdr.overflow bits: edge pool overflow
+constexpr int HDR_SCRIPT_MISS = 2;   // a scripted move was not legal in its position (game stopped as a draw)
 
 KV_DEV float f_from_bits(uint32_t u) { return kvd_u2f(u); }
 
@@ -364,7 +382,7 @@ KV_DEV int mcts_select_one_warp(const Tables& T, int lane, const MctsCfg& cfg, c
             nm.val = 0.0f;
         } else if (n_edges + n > cfg.edge_cap) {
             nm.val = 0.0f;
-            if (lane == 0) h->overflow = 1;
+            if (lane == 0) h->overflow |= HDR_OVERFLOW;
         } else {
             nm.first_edge = n_edges;
             nm.ne_term = n | NODE_PENDING;
@@ -457,8 +475,56 @@ KV_DEV void mcts_backup_game_warp(int lane, const MctsCfg& cfg, const MctsArrays
 // Finish the pending simulation of game g given the leaf's legal-move logits (n floats, edge order) and the
 // evaluator's white-perspective value: softmax priors (+ root Dirichlet noise), then backup.
 // `logits` is per-warp scratch (shared memory on the device) and is overwritten.
+// Softmax statistics over all POLICY_N logits L(i) (scripts/self_play.py:150 takes the softmax over every index):
+// lane-strided maximum, then lane-strided sum of exp(l - max), both combined by an xor butterfly — the oracle walks
+// the same order.  All lanes return the same (mx, z).
+template <class LogitFn>
+KV_DEV void full_softmax_stats_warp(int lane, LogitFn L, float& mx, float& z) {
+    float m = -3.0e38f;
+    for (int i = lane; i < POLICY_N; i += 32) {
+        const float l = L(i);
+        m = l > m ? l : m;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const float o = shfl_xorf(m, d, lane);
+        m = o > m ? o : m;
+    }
+    float s = 0.0f;
+    for (int i = lane; i < POLICY_N; i += 32) s = s + kvd_expf(L(i) - m);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s = s + shfl_xorf(s, d, lane);
+    mx = m;
+    z = s;
+}
+
+// Root priors by the reference's rule (cfg.root_mix; scripts/self_play.py:150-167): policy = softmax over all 4096
+// logits, noise = Dirichlet(alpha) over all 4096 indices (Gamma variates keyed by seed, game, ply, INDEX), mixed with
+// eps, then the legal entries renormalised.  logits[k] holds the legal moves' logits (edge order) and is overwritten.
+KV_DEV void mcts_root_mix_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, const GameHdr* h, size_t e0, int n,
+                               float* logits, float mx_all, float z_all) {
+    for (int k = lane; k < n; k += 32) logits[k] = kvd_expf(logits[k] - mx_all) / z_all;
+    if (cfg.dir_eps > 0.0f) {
+        const uint64_t key = (uint64_t)h->ply * POLICY_N;
+        float part = 0.0f;
+        for (int i = lane; i < POLICY_N; i += 32) part = part + kvd_gamma_small(cfg.dir_alpha, cfg.seed, h->game_id, key + (uint64_t)i);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) part = part + shfl_xorf(part, d, lane);
+        for (int k = lane; k < n; k += 32) {
+            const float g = kvd_gamma_small(cfg.dir_alpha, cfg.seed, h->game_id, key + (uint64_t)move_index(A.eMv[e0 + k]));
+            logits[k] = (1.0f - cfg.dir_eps) * logits[k] + cfg.dir_eps * (g / part);
+        }
+    }
+    syncwarp();
+    float s = 0.0f;
+    if (lane == 0)
+        for (int k = 0; k < n; k++) s = s + logits[k];
+    s = shflf(s, 0);
+    for (int k = lane; k < n; k += 32) A.eP[e0 + k] = logits[k] / s;
+}
+
 KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int gs, float* logits, float v_white,
-                             bool from_cache = false) {
+                             bool from_cache = false, float mx_all = 0.0f, float z_all = 0.0f) {
     const int g = gs / cfg.inflight;
     GameHdr* h = &A.hdr[g];
     const size_t nbase = (size_t)g * cfg.node_cap, ebase = (size_t)g * cfg.edge_cap;
@@ -467,6 +533,9 @@ KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, 
     const int n = m.ne_term & 0xFFFF;
     const size_t e0 = ebase + m.first_edge;
     const bool wtm = A.node_line[(nbase + c) * LINE_WORDS + 12] & 1;
+    if (c == 0 && cfg.root_mix) {
+        mcts_root_mix_warp(lane, cfg, A, h, e0, n, logits, mx_all, z_all);
+    } else {
     float mx = -3.0e38f;
     for (int k = lane; k < n; k += 32) mx = logits[k] > mx ? logits[k] : mx;
 #pragma unroll
@@ -495,6 +564,7 @@ KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, 
             A.eP[e0 + k] = (1.0f - cfg.dir_eps) * A.eP[e0 + k] + cfg.dir_eps * eta;
             A.eW[e0 + k] = 0.0f;
         }
+    }
     }
     syncwarp();
     const float v = wtm ? v_white : -v_white;
@@ -526,7 +596,10 @@ KV_DEV void mcts_hash_eval_warp(int lane, const MctsCfg& cfg, const MctsArrays& 
     const size_t e0 = (size_t)g * cfg.edge_cap + m.first_edge;
     for (int k = lane; k < n; k += 32) scratch[k] = hash_logit(ph, move_index(A.eMv[e0 + k]));
     syncwarp();
-    mcts_expand_warp(lane, cfg, A, gs, scratch, hash_value(ph));
+    float mx_all = 0.0f, z_all = 0.0f;
+    if (cfg.root_mix && A.pend_node[gs] == 0)
+        full_softmax_stats_warp(lane, [&](int i) { return hash_logit(ph, i); }, mx_all, z_all);
+    mcts_expand_warp(lane, cfg, A, gs, scratch, hash_value(ph), false, mx_all, z_all);
 }
 
 // Hash-evaluator counterpart of the late (cache hit / follower) expansion: the value comes from the cached / leader
@@ -542,7 +615,10 @@ KV_DEV void mcts_hash_late_warp(int lane, const MctsCfg& cfg, const MctsArrays& 
     for (int k = lane; k < n; k += 32) scratch[k] = hash_logit(ph, move_index(A.eMv[e0 + k]));
     syncwarp();
     const float v = src < 0 ? A.feat_game[(size_t)gs * FEAT + 128] : A.feat_slot[(size_t)src * FEAT + 128];
-    mcts_expand_warp(lane, cfg, A, gs, scratch, v, true);
+    float mx_all = 0.0f, z_all = 0.0f;
+    if (cfg.root_mix && A.pend_node[gs] == 0)
+        full_softmax_stats_warp(lane, [&](int i) { return hash_logit(ph, i); }, mx_all, z_all);
+    mcts_expand_warp(lane, cfg, A, gs, scratch, v, true, mx_all, z_all);
 }
 
 // After cfg.sims simulations: pick the move from the root visit counts, record (position, move), play it,
@@ -564,15 +640,51 @@ KV_DEV void mcts_finish_move_warp(const Tables& T, int lane, const MctsCfg& cfg,
     }
     const int n = m.ne_term & 0xFFFF;
     const size_t e0 = ebase + m.first_edge;
+    // the value the resign rule looks at: the evaluator's output for the position the move is chosen in, as the
+    // network returned it (m.val is from the side to move's perspective; the flip is exact) — or the scripted one
+    const bool wtm_root = shfl64(w, 12) & 1;
+    float v_resign = wtm_root ? m.val : -m.val;
+    int forced = -1;
+    if (cfg.script_stride > 0 && ply < cfg.script_stride) {
+        const size_t si = (size_t)g * cfg.script_stride + ply;
+        if (A.script_val) {
+            const float sv = A.script_val[si];
+            if (sv == sv) v_resign = sv;
+        }
+        const int want = A.script_move ? (int)A.script_move[si] : 0xFFFF;
+        if (want != 0xFFFF) {
+            uint32_t hit = 0;
+            for (int k0 = 0; k0 < n; k0 += 32) {   // warp-uniform trip count
+                const int k = k0 + lane;
+                hit = ballot(k < n && ((int)A.eMv[e0 + k] & 0xFFF) == (want & 0xFFF));
+                if (hit) {
+                    forced = k0 + ffs32(hit) - 1;
+                    break;
+                }
+            }
+            if (forced < 0) {   // not a legal move here: stop the game (draw) and flag it
+                if (lane == 0) {
+                    h->done = 1;
+                    h->result = 0;
+                    h->overflow |= HDR_SCRIPT_MISS;
+                }
+                syncwarp();
+                return;
+            }
+        }
+    }
     // total visits
     int tot = 0;
     for (int k = lane; k < n; k += 32) tot += (int)A.eN[e0 + k];
     tot = warp_sum32(tot, lane);
     int pick = 0;
-    if (tot == 0) {
-        // sims == 1: only the root was expanded.  Sample the move from the (noisy) priors — the reference's own
-        // move rule (scripts/self_play.py:147-167: softmax + Dirichlet, legal renormalise, sample).  Sequential
-        // fp32 prefix sum by lane 0, same order as the oracle.
+    if (forced >= 0) {
+        pick = forced;
+    } else if (tot == 0) {
+        // sims == 1: only the root was expanded.  Sample the move from the (noisy) priors — with cfg.root_mix the
+        // distribution of the reference's own move rule (scripts/self_play.py:147-167: softmax and Dirichlet noise
+        // over all 4096 indices, legal renormalise, sample; the generator differs from numpy / random.choices).
+        // Sequential fp32 prefix sum by lane 0, same order as the oracle.
         if (lane == 0) {
             const float u = kvd_u01(kvd_rand24(cfg.seed, h->game_id, (uint64_t)ply, 0xC0FFEEull));
             float sum = 0.0f;
@@ -627,6 +739,8 @@ KV_DEV void mcts_finish_move_warp(const Tables& T, int lane, const MctsCfg& cfg,
         if (lane == 0) A.rec_move[(size_t)g * cfg.rec_cap + ply] = (uint16_t)mvw;
     }
     w = make_move_warp(lane, w, mvw, T_Q);
+    // isDraw() (:21-33, only kings left) is asked right after makeMove, before the next getValidMoves can rewrite the board
+    const bool only_kings = ballot(lane < 12 && lane != 0 && lane != 6 && w != 0ull) == 0;
     const GenOut go = movegen_warp(T, lane, w, mv);
     if (lane < LINE_WORDS) A.root_line[(size_t)g * LINE_WORDS + lane] = w;
     const bool wtm_new = shfl64(w, 12) & 1;
@@ -637,12 +751,19 @@ KV_DEV void mcts_finish_move_warp(const Tables& T, int lane, const MctsCfg& cfg,
         h->n_edges = 0;
         h->sims_done = 0;
         h->n_pend = 0;
-        if (go.n == 0) {
-            h->done = 1;
-            h->result = (go.flags & RF_CHECKMATE) ? (wtm_new ? -1 : 1) : 0;   // self_play.py:217-220
-        } else if ((go.flags & RF_ONLY_KINGS) || np >= cfg.max_plies) {
+        // the reference's tests after a move, in its order (scripts/self_play.py:180-199), then the loop head (:125)
+        if (only_kings) {                                     // isDraw() :180 -> :225
             h->done = 1;
             h->result = 0;
+        } else if (cfg.resign_min_plies >= 0 && np > cfg.resign_min_plies && v_resign < cfg.resign_thr) {
+            h->done = 1;                                      // resignation :185-189
+            h->result = wtm_new ? -1 : 1;
+        } else if (np >= cfg.max_plies) {                     // max_moves :196-199 -> :209-211 (even on a mating move)
+            h->done = 1;
+            h->result = 0;
+        } else if (go.n == 0) {                               // :125 -> checkmate :217-220 / stalemate :221-224
+            h->done = 1;
+            h->result = (go.flags & RF_CHECKMATE) ? (wtm_new ? -1 : 1) : 0;
         }
     }
     syncwarp();

@@ -293,10 +293,33 @@ class Engine:
         """Search waves launched since mcts_create (with K > 1 a move takes a data-dependent number of waves)."""
         return int(self._lib.kv_mcts_waves(self.ctx))
 
+    def mcts_set_resign(self, threshold: float = -0.7, min_plies: int = 15):
+        """Resignation rule of scripts/self_play.py:184-189 (defaults = the reference's); min_plies < 0 = off."""
+        N.check(self.ctx, self._lib.kv_mcts_set_resign(self.ctx, threshold, min_plies), "kv_mcts_set_resign")
+
+    def mcts_set_root_mix(self, mode: int = -1):
+        """Root priors: 0 legal-only softmax + noise, 1 the reference's mixing over all 4096 indices
+        (scripts/self_play.py:150-167), -1 default (1 when sims == 1)."""
+        N.check(self.ctx, self._lib.kv_mcts_set_root_mix(self.ctx, mode), "kv_mcts_set_root_mix")
+
+    def mcts_set_script(self, moves: torch.Tensor | None = None, values: torch.Tensor | None = None):
+        """Scripted play: moves int16 [n_games, stride] move words (-1 = 0xFFFF = choose as usual), values float32
+        [n_games, stride] (NaN = the evaluator's value) on this device; both None clears the script."""
+        stride = 0
+        for t in (moves, values):
+            if t is not None:
+                assert t.is_contiguous() and t.shape[0] == self.mcts_games and t.device == self.device
+                stride = int(t.shape[1])
+        self._script = (moves, values)     # keep the tensors alive while the context points at them
+        N.check(self.ctx, self._lib.kv_mcts_set_script(self.ctx, _ptr(moves) if moves is not None else None,
+                                                       _ptr(values) if values is not None else None, stride),
+                "kv_mcts_set_script")
+
     def mcts_status(self) -> dict:
-        out = np.zeros(9, dtype=np.uint64)
+        out = np.zeros(10, dtype=np.uint64)
         N.check(self.ctx, self._lib.kv_mcts_status(self.ctx, _ptr(out), self._stream()), "kv_mcts_status")
-        keys = ("done", "sims_in_move", "evals", "plies", "overflow", "white_wins", "black_wins", "draws", "cache_hits")
+        keys = ("done", "sims_in_move", "evals", "plies", "overflow", "white_wins", "black_wins", "draws", "cache_hits",
+                "script_misses")
         return {k: int(v) for k, v in zip(keys, out)}
 
     def mcts_roots(self) -> torch.Tensor:

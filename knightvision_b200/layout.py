@@ -39,14 +39,23 @@ START_BOARD = [
 ]
 
 
-def pack_fields(board, white_to_move=True, wk=(7, 4), bk=(0, 4), moved=0, ep=(), clock=0) -> np.ndarray:
-    """Pack reference-style fields into one line (np.uint64[16])."""
+# core/chessEngine.py:85-122 loadFEN writes pawns as 'wP' / 'bP' (upper-case kind): a 13th / 14th piece kind that moves
+# like a pawn (:49) but is no pawn for promotion, e.p. capture, pawn checks or the encoder.  The line has no code for it.
+FEN_PAWNS = {"wP": "wp", "bP": "bp"}
+
+
+def pack_fields(board, white_to_move=True, wk=(7, 4), bk=(0, 4), moved=0, ep=(), clock=0, fen_pawns=False) -> np.ndarray:
+    """Pack reference-style fields into one line (np.uint64[16]).  Unknown piece codes are ignored (what the reference's
+    encoder does, ai/ai.py:26-29); with fen_pawns the 'wP' / 'bP' codes loadFEN produces count as ordinary pawns."""
     w = np.zeros(LINE_WORDS, dtype=np.uint64)
     bbs = [0] * 12
     for r in range(8):
         row = board[r]
         for c in range(8):
-            idx = PIECE_TO_INDEX.get(row[c])
+            code = row[c]
+            if fen_pawns:
+                code = FEN_PAWNS.get(code, code)
+            idx = PIECE_TO_INDEX.get(code)
             if idx is not None:
                 bbs[idx] |= 1 << (r * 8 + c)
     for i in range(12):

@@ -25,7 +25,7 @@ import torch.nn.functional as F
 
 from . import train_ops as T
 from .model import ChessNet
-from .selfplay import SelfPlay, engine_for
+from .selfplay import SelfPlay, engine_for, filter_decisive_device
 
 logger = logging.getLogger(__name__)
 ENTROPY_COEF = 0.01
@@ -113,11 +113,37 @@ class ReplayData:
             yield self.eng.encode(self.lines[idx].contiguous()), self.move[idx], self.reward[idx]
 
 
+def _ddp_active() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def training_graph(net: ChessNet, engine):
+    """The autograd graph of `net` (and, with torch.distributed initialised, its DistributedDataParallel wrapper), built
+    once per network and reused by every train_epochs call: DDP broadcasts the parameters when it is constructed, so
+    rebuilding it per call would re-send 100 MB per generation.  Gradients travel as bf16 (KV_DDP_GRAD_BF16=0: fp32)."""
+    native = os.getenv("KV_TRAIN_NATIVE", "1") != "0"
+    key = (id(engine) if native else None, _ddp_active())
+    cached = getattr(net, "_kv_train_graph", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    graph = TrainGraph(net, engine=engine if native else None)
+    if _ddp_active():
+        graph = nn.parallel.DistributedDataParallel(graph, device_ids=[engine.index], gradient_as_bucket_view=True,
+                                                    bucket_cap_mb=int(os.getenv("KV_DDP_BUCKET_MB", "64")))
+        if os.getenv("KV_DDP_GRAD_BF16", "1") != "0":
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+            graph.register_comm_hook(None, default_hooks.bf16_compress_hook)
+    object.__setattr__(net, "_kv_train_graph", (key, graph))     # not a submodule: state_dict() keeps the reference's keys
+    return graph
+
+
 def train_epochs(net: ChessNet, optimizer, data: ReplayData, epochs: int, batch_size: int, accumulate_steps: int = 2):
-    """scripts/train.py:126-196 without the logging side channels.  Returns the mean loss of the last epoch."""
-    graph = TrainGraph(net, engine=data.eng if os.getenv("KV_TRAIN_NATIVE", "1") != "0" else None)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        graph = nn.parallel.DistributedDataParallel(graph, device_ids=[data.eng.index])
+    """scripts/train.py:126-196 without the logging side channels.  Returns the mean loss of the last epoch.
+    Under DistributedDataParallel the gradient all-reduce runs once per optimizer step (micro-batches that do not step
+    accumulate locally, `no_sync`), and a non-finite loss (train.py:176-178 skips the batch) is skipped by every rank
+    together so that no rank waits for a gradient exchange the others never start."""
+    import contextlib
+    graph = training_graph(net, data.eng)
     net.train()
     last = float("nan")
     ddp = isinstance(graph, nn.parallel.DistributedDataParallel)
@@ -132,23 +158,32 @@ def train_epochs(net: ChessNet, optimizer, data: ReplayData, epochs: int, batch_
             dist.all_reduce(nmin, op=dist.ReduceOp.MIN)
             batches = batches[:int(nmin.item())]
         for i, (boards, moves, outcomes) in enumerate(batches):
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                pol, val = graph(boards)
-            pol = pol.float()
-            loss_policy = F.cross_entropy(pol, moves)
-            loss_value = F.mse_loss(val.squeeze(1).float(), outcomes)
-            logp = F.log_softmax(pol, dim=1)
-            entropy = -(logp.exp() * logp).sum(dim=1).mean()
-            loss = loss_policy + loss_value - ENTROPY_COEF * entropy
-            if not torch.isfinite(loss):
-                continue                                   # train.py:176-178
-            (loss / accumulate_steps).backward()
-            if (i + 1) % accumulate_steps == 0 or i == len(batches) - 1:
+            stepping = (i + 1) % accumulate_steps == 0 or i == len(batches) - 1
+            with (graph.no_sync() if ddp and not stepping else contextlib.nullcontext()):
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    pol, val = graph(boards)
+                pol = pol.float()
+                loss_policy = F.cross_entropy(pol, moves)
+                loss_value = F.mse_loss(val.squeeze(1).float(), outcomes)
+                logp = F.log_softmax(pol, dim=1)
+                entropy = -(logp.exp() * logp).sum(dim=1).mean()
+                loss = loss_policy + loss_value - ENTROPY_COEF * entropy
+                ok = torch.isfinite(loss).to(torch.int32)
+                if ddp:
+                    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok.item()):
+                    (loss / accumulate_steps).backward()
+                    tot += float(loss.item())
+                    nb += 1
+                elif ddp and stepping:
+                    # the skipped batch was the stepping one: exchange what the earlier micro-batches accumulated
+                    for p_ in net.parameters():
+                        if p_.grad is not None:
+                            dist.all_reduce(p_.grad, op=dist.ReduceOp.AVG)
+            if stepping:
                 torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=1.0)
                 optimizer.step()
                 optimizer.zero_grad()
-            tot += float(loss.item())
-            nb += 1
         last = tot / max(nb, 1)
     net.eval()                                             # train.py:444
     net.mark_weights_changed()                             # next forward / self-play re-uploads and re-folds the weights
@@ -234,6 +269,10 @@ def reinforcement_loop(cfg, net: ChessNet | None = None, data: ReplayData | None
         st = sp.play(start, game_id_base=(it * world + rank) * games)
         t3 = now()
         lines, move, reward, _ = sp.records_device()
+        if getattr(cfg.selfplay, "decisive_filter", True):
+            # scripts/learn.py:186 calls generate_self_play_data, which keeps only the records of decisive games once
+            # there are at least 10 of them (scripts/self_play.py:300-311); per rank, as the reference does per call
+            lines, move, reward = filter_decisive_device(lines, move, reward)
         data.extend_packed(lines, move, reward)
         history.append(dict(iteration=it, loss=loss, records=int(lines.shape[0]), plies=st["plies"],
                             white=st["white_wins"], black=st["black_wins"], draws=st["draws"], evals=st["evals"],

@@ -133,7 +133,19 @@ class ChessNet(nn.Module):
 
 
 def fp32_reference_forward(net: ChessNet, x: torch.Tensor):
-    """Plain PyTorch fp32, eval-mode BN: the graph of ai/model.py:51-77.  Test/baseline use only."""
+    """Plain PyTorch fp32, eval-mode BN: the graph of ai/model.py:51-77.  Test/baseline use only.
+    True fp32 on a GPU as well: TF32 is switched off for the duration of the call (cuDNN convolutions and cuBLAS
+    matmuls would otherwise run with 10-bit mantissas, which is not a reference for a 2e-2 tolerance)."""
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        return _fp32_graph(net, x)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+def _fp32_graph(net: ChessNet, x: torch.Tensor):
     def bn(m, t):
         return F.batch_norm(t, m.running_mean, m.running_var, m.weight, m.bias, False, 0.0, m.eps)
     x = x.to(next(net.parameters()).device, torch.float32)

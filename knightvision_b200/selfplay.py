@@ -125,9 +125,24 @@ def self_play(model, num_games, device, max_moves=None, model_path=None):
     return sp.records()
 
 
+MIN_DECISIVE_GAMES = 10   # scripts/self_play.py:305 (it counts records, not games)
+
+
+def filter_decisive(data):
+    """scripts/self_play.py:303-310: keep only the records of won / lost games (reward +-1.0) once there are at least
+    MIN_DECISIVE_GAMES of them; otherwise return everything."""
+    decisive = [s for s in data if s[2] == 1.0 or s[2] == -1.0]
+    return decisive if len(decisive) >= MIN_DECISIVE_GAMES else data
+
+
+def filter_decisive_device(lines, move, reward, game=None):
+    """The same filter on the packed device records (learn loop: no host round trip)."""
+    mask = reward.abs() == 1.0
+    if int(mask.sum()) < MIN_DECISIVE_GAMES:
+        return (lines, move, reward) if game is None else (lines, move, reward, game)
+    out = (lines[mask], move[mask], reward[mask])
+    return out if game is None else out + (game[mask],)
+
+
 def generate_self_play_data(model, num_games, device, max_moves=None):
-    data = self_play(model, num_games, device, max_moves)
-    decisive = [s for s in data if abs(s[2]) == 1]   # scripts/self_play.py:304-310
-    if len(decisive) >= 10:
-        return decisive
-    return data
+    return filter_decisive(self_play(model, num_games, device, max_moves))

@@ -665,7 +665,12 @@ typedef struct {
     float c_puct, dir_alpha, dir_eps;
     int32_t inflight;    /* K simulations in flight per wave (0 or 1: sequential search; > 1: virtual loss) */
     uint64_t seed;
+    float resign_thr;          /* scripts/self_play.py:185: value < thr (reference -0.7) ... */
+    int32_t resign_min_plies;  /* ... once more than this many plies were played (reference 15); < 0: never */
+    int32_t root_mix;          /* 1: root priors by scripts/self_play.py:150-167 (all 4096 indices), 0: legal moves only */
+    int32_t pad;
 } kvo_mcts_cfg;
+#define POLICY_N 4096
 
 typedef struct {
     kvo_state st;
@@ -718,6 +723,50 @@ static void evaluate_leaf(const kvo_mcts_cfg *cfg, onode *nd, oedge *e, int leaf
         e[k].P = hash_logit(ph, kvo_move_index(e[k].mv));
         if (k == 0 || e[k].P > mx) mx = e[k].P;
     }
+    if (leaf == 0 && cfg->root_mix) {
+        /* scripts/self_play.py:150-167: policy = softmax over ALL 4096 logits; noise = Dirichlet(alpha) over all 4096
+         * indices; policy = (1-eps) policy + eps noise; the legal entries renormalised (:159-166).  Reductions in the
+         * order of the device warp: lane-strided partials (lane = index mod 32), then an xor butterfly. */
+        float part[32];
+        for (int l = 0; l < 32; l++) part[l] = -3.0e38f;
+        for (int i = 0; i < POLICY_N; i++) {
+            const float lg = hash_logit(ph, i);
+            if (lg > part[i & 31]) part[i & 31] = lg;
+        }
+        float mxa = part[0];
+        for (int l = 1; l < 32; l++) if (part[l] > mxa) mxa = part[l];
+        for (int l = 0; l < 32; l++) part[l] = 0.0f;
+        for (int i = 0; i < POLICY_N; i++) part[i & 31] = part[i & 31] + kvd_expf(hash_logit(ph, i) - mxa);
+        for (int d = 16; d >= 1; d >>= 1) {
+            float nx[32];
+            for (int l = 0; l < 32; l++) nx[l] = part[l] + part[l ^ d];
+            memcpy(part, nx, sizeof(nx));
+        }
+        const float z = part[0];
+        for (int k = 0; k < n; k++) e[k].P = kvd_expf(e[k].P - mxa) / z;
+        if (cfg->dir_eps > 0.0f) {
+            const uint64_t key = (uint64_t)ply * POLICY_N;
+            for (int l = 0; l < 32; l++) part[l] = 0.0f;
+            for (int i = 0; i < POLICY_N; i++)
+                part[i & 31] = part[i & 31] + kvd_gamma_small(cfg->dir_alpha, cfg->seed, game_id, key + (uint64_t)i);
+            for (int d = 16; d >= 1; d >>= 1) {
+                float nx[32];
+                for (int l = 0; l < 32; l++) nx[l] = part[l] + part[l ^ d];
+                memcpy(part, nx, sizeof(nx));
+            }
+            const float gsum = part[0];
+            for (int k = 0; k < n; k++) {
+                const float g = kvd_gamma_small(cfg->dir_alpha, cfg->seed, game_id, key + (uint64_t)kvo_move_index(e[k].mv));
+                e[k].P = (1.0f - cfg->dir_eps) * e[k].P + cfg->dir_eps * (g / gsum);
+            }
+        }
+        float sum = 0.0f;
+        for (int k = 0; k < n; k++) sum = sum + e[k].P;
+        for (int k = 0; k < n; k++) e[k].P = e[k].P / sum;
+        const float vw0 = hash_value(ph);
+        nd->val = nd->st.white_to_move ? vw0 : -vw0;
+        return;
+    }
     float sum = 0.0f;
     for (int k = 0; k < n; k++) {
         e[k].P = kvd_expf(e[k].P - mx);
@@ -764,7 +813,7 @@ static void backup_path(onode *nodes, oedge *edges, const int *path_n, const int
  * computed). */
 static int mcts_search(const kvo_mcts_cfg *cfg, const kvo_state *root, uint64_t game_id, int ply, const replay_t *rep,
                        uint16_t *root_moves, uint32_t *root_N, float *root_W, float *root_P, int *n_root,
-                       int *out_nodes, int *out_edges, int *overflow) {
+                       int *out_nodes, int *out_edges, int *overflow, float *root_vwhite) {
     const int S = cfg->sims;
     const int K = cfg->inflight > 1 ? cfg->inflight : 1;
     const size_t PL = (size_t)S + 2;   /* path stride */
@@ -896,6 +945,8 @@ static int mcts_search(const kvo_mcts_cfg *cfg, const kvo_state *root, uint64_t 
     }
     int chosen = 0xFFFF;
     *n_root = 0;
+    /* the evaluator's value of the root as the network returned it (white's perspective): what the resign rule reads */
+    if (root_vwhite) *root_vwhite = n_nodes > 0 ? (nodes[0].st.white_to_move ? nodes[0].val : -nodes[0].val) : 0.0f;
     if (n_nodes > 0 && !nodes[0].term) {
         const int n = nodes[0].n_edges;
         const oedge *e = &edges[nodes[0].first_edge];
@@ -954,7 +1005,7 @@ KVO_API int kvo_mcts_search(const kvo_mcts_cfg *cfg, const uint64_t *line, uint6
     replay_t rep = { rep_node_val, rep_node_first, rep_edge_P };
     int n_root, nn, ne, ov;
     int mv = mcts_search(cfg, &s, game_id, ply, rep_node_val ? &rep : NULL, root_moves, root_N, root_W, root_P, &n_root,
-                         &nn, &ne, &ov);
+                         &nn, &ne, &ov, NULL);
     info4[0] = n_root;
     info4[1] = nn;
     info4[2] = ne;
@@ -962,11 +1013,32 @@ KVO_API int kvo_mcts_search(const kvo_mcts_cfg *cfg, const uint64_t *line, uint6
     return mv;
 }
 
-/* Whole self-play game with the hash evaluator (scripts/self_play.py:111-255 control flow, MCTS choosing the move).
+/* test helper: the Gamma(alpha) variates the reference-rule root noise draws for every policy index */
+KVO_API void kvo_root_noise(float alpha, uint64_t seed, uint64_t game_id, int ply, float *out4096) {
+    for (int i = 0; i < POLICY_N; i++)
+        out4096[i] = kvd_gamma_small(alpha, seed, game_id, (uint64_t)ply * POLICY_N + (uint64_t)i);
+}
+
+/* test helper: the hash evaluator's logits for all 4096 policy indices and its white-perspective value */
+KVO_API float kvo_hash_eval(const uint64_t *line, float *logits4096) {
+    const uint64_t ph = pos_hash(line);
+    for (int i = 0; i < POLICY_N; i++) logits4096[i] = hash_logit(ph, i);
+    return hash_value(ph);
+}
+
+/* Whole self-play game (scripts/self_play.py:111-255 control flow; the move comes from the search, or from a script).
+ * After every move the reference tests, in this order: isDraw() = only kings (:180) -> draw; resignation (:185-189:
+ * move_count > resign_min_plies and the model's value of the position the move was chosen in < resign_thr ->
+ * -1 if white is to move, else +1); max_moves (:196) -> draw even if the move mated (:209-211); and at the loop head
+ * no legal move (:125) -> checkmate +-1 (:217-220) or stalemate 0 (:221-224).  The material branch (:229-238) is
+ * unreachable through these exits and would yield 0.
+ * script_moves / script_vals (nullable, script_n entries): per ply a move word to play instead of the search's choice
+ * (matched on from/to; 0xFFFF = none) and the value the resign rule sees (NaN = the evaluator's root value).
  * out_moves[ply] = move word; out_lines[ply][16] = position the move was chosen in; returns the number of plies.
- * *result: +1 white won, -1 black won, 0 draw (self_play.py:211-238). */
-KVO_API int kvo_selfplay_game(const kvo_mcts_cfg *cfg, const uint64_t *start_line, uint64_t game_id, uint16_t *out_moves,
-                              uint64_t *out_lines, int32_t *result) {
+ * *result: +1 white won, -1 black won, 0 draw.  *out_flags: bit 1 = a scripted move was not legal. */
+KVO_API int kvo_selfplay_game2(const kvo_mcts_cfg *cfg, const uint64_t *start_line, uint64_t game_id,
+                               const uint16_t *script_moves, const float *script_vals, int script_n, uint16_t *out_moves,
+                               uint64_t *out_lines, int32_t *result, int32_t *out_flags) {
     kvo_state s;
     kvo_unpack(start_line, &s);
     uint16_t rm[256];
@@ -974,24 +1046,49 @@ KVO_API int kvo_selfplay_game(const kvo_mcts_cfg *cfg, const uint64_t *start_lin
     float rw[256], rp[256];
     int ply = 0;
     *result = 0;
+    if (out_flags) *out_flags = 0;
     for (;;) {
         kvo_state probe = s;
         movelist ml;
         int f;
         int n = valid_moves(&probe, &ml, &f);
         s = probe;   /* getValidMoves may rewrite the state */
-        if (n == 0) {
+        if (n == 0) {                                    /* :125, then :217-224 */
             if (f & RF_CHECKMATE) *result = s.white_to_move ? -1 : 1;
             break;
         }
-        if (f & RF_ONLY_KINGS) break;
-        if (ply >= cfg->max_plies) break;
+        if (ply == 0 && (f & RF_ONLY_KINGS)) break;      /* a start position without pieces: nothing to search */
         int n_root, nn, ne, ov;
-        int mv = mcts_search(cfg, &s, game_id, ply, NULL, rm, rn, rw, rp, &n_root, &nn, &ne, &ov);
+        float vroot = 0.0f;
+        int mv = mcts_search(cfg, &s, game_id, ply, NULL, rm, rn, rw, rp, &n_root, &nn, &ne, &ov, &vroot);
+        if (ply < script_n) {
+            if (script_vals && script_vals[ply] == script_vals[ply]) vroot = script_vals[ply];
+            if (script_moves && script_moves[ply] != 0xFFFF) {
+                int found = -1;
+                for (int k = 0; k < n_root && found < 0; k++)
+                    if ((rm[k] & 0xFFF) == (script_moves[ply] & 0xFFF)) found = k;
+                if (found < 0) {
+                    if (out_flags) *out_flags |= 2;
+                    break;
+                }
+                mv = rm[found];
+            }
+        }
         kvo_pack(&s, out_lines + 16 * (size_t)ply);
         out_moves[ply] = (uint16_t)mv;
         make_move(&s, mv & 63, (mv >> 6) & 63, (mv >> 12) & 7, T_Q);
         ply++;
+        if (only_kings(&s)) break;                                                      /* :180 */
+        if (cfg->resign_min_plies >= 0 && ply > cfg->resign_min_plies && vroot < cfg->resign_thr) {
+            *result = s.white_to_move ? -1 : 1;                                         /* :185-189 */
+            break;
+        }
+        if (ply >= cfg->max_plies) break;                                               /* :196 */
     }
     return ply;
+}
+
+KVO_API int kvo_selfplay_game(const kvo_mcts_cfg *cfg, const uint64_t *start_line, uint64_t game_id, uint16_t *out_moves,
+                              uint64_t *out_lines, int32_t *result) {
+    return kvo_selfplay_game2(cfg, start_line, game_id, NULL, NULL, 0, out_moves, out_lines, result, NULL);
 }

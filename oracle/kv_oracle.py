@@ -99,13 +99,17 @@ def encode(lines: np.ndarray) -> np.ndarray:
 class MctsCfg(ctypes.Structure):
     _fields_ = [("sims", ctypes.c_int32), ("edge_cap", ctypes.c_int32), ("temp_plies", ctypes.c_int32),
                 ("max_plies", ctypes.c_int32), ("c_puct", ctypes.c_float), ("dir_alpha", ctypes.c_float),
-                ("dir_eps", ctypes.c_float), ("inflight", ctypes.c_int32), ("seed", ctypes.c_uint64)]
+                ("dir_eps", ctypes.c_float), ("inflight", ctypes.c_int32), ("seed", ctypes.c_uint64),
+                ("resign_thr", ctypes.c_float), ("resign_min_plies", ctypes.c_int32), ("root_mix", ctypes.c_int32),
+                ("pad", ctypes.c_int32)]
 
 
 def mcts_cfg(sims, edges_per_node=48, temp_plies=0, max_plies=1 << 20, c_puct=1.5, dir_alpha=0.3, dir_eps=0.25, seed=1,
-             inflight=1):
+             inflight=1, resign_thr=-0.7, resign_min_plies=15, root_mix=-1):
+    """Defaults follow kv_mcts_create_k: the reference's resign rule (scripts/self_play.py:184-189) and, when sims == 1,
+    its prior mixing over all 4096 indices (:150-167)."""
     return MctsCfg(sims, max(sims * (edges_per_node or 48), 256), temp_plies, max_plies, c_puct, dir_alpha, dir_eps,
-                   inflight, seed)
+                   inflight, seed, resign_thr, resign_min_plies, int(sims == 1) if root_mix < 0 else root_mix, 0)
 
 
 def mcts_search(cfg, line, game_id=0, ply=0, replay=None):
@@ -129,13 +133,40 @@ def mcts_search(cfg, line, game_id=0, ply=0, replay=None):
                 overflow=int(info[3]))
 
 
-def selfplay_game(cfg, start_line, game_id=0):
+def selfplay_game(cfg, start_line, game_id=0, script_moves=None, script_vals=None, return_flags=False):
+    """One game of the oracle's game loop.  script_moves (u16 words, 0xFFFF = none) / script_vals (f32, NaN = none):
+    per ply the move to play instead of the search's choice and the value the resign rule sees."""
     start_line = np.ascontiguousarray(start_line, dtype=np.uint64)
     mp = int(cfg.max_plies)
     moves = np.zeros(mp, np.uint16)
     lines = np.zeros((mp, 16), np.uint64)
     res = ctypes.c_int32(0)
-    f = lib().kvo_selfplay_game
+    flags = ctypes.c_int32(0)
+    sm = np.ascontiguousarray(script_moves, np.uint16) if script_moves is not None else None
+    sv = np.ascontiguousarray(script_vals, np.float32) if script_vals is not None else None
+    sn = len(sm) if sm is not None else (len(sv) if sv is not None else 0)
+    f = lib().kvo_selfplay_game2
     f.restype = ctypes.c_int
-    n = f(ctypes.byref(cfg), _p(start_line), ctypes.c_uint64(game_id), _p(moves), _p(lines), ctypes.byref(res))
+    n = f(ctypes.byref(cfg), _p(start_line), ctypes.c_uint64(game_id), _p(sm) if sm is not None else None,
+          _p(sv) if sv is not None else None, ctypes.c_int(sn), _p(moves), _p(lines), ctypes.byref(res), ctypes.byref(flags))
+    if return_flags:
+        return moves[:n], lines[:n], int(res.value), int(flags.value)
     return moves[:n], lines[:n], int(res.value)
+
+
+def root_noise(alpha, seed, game_id, ply):
+    """Gamma(alpha) variates of the reference-rule root noise for all 4096 policy indices (key = ply * 4096 + index)."""
+    src = lib().kvo_root_noise
+    out = np.zeros(4096, np.float32)
+    src(ctypes.c_float(alpha), ctypes.c_uint64(seed), ctypes.c_uint64(game_id), ctypes.c_int(ply), _p(out))
+    return out
+
+
+def hash_eval(line):
+    """(logits f32[4096], white-perspective value) of the hash test evaluator for a position."""
+    line = np.ascontiguousarray(line, dtype=np.uint64)
+    out = np.zeros(4096, np.float32)
+    f = lib().kvo_hash_eval
+    f.restype = ctypes.c_float
+    v = f(_p(line), _p(out))
+    return out, float(v)

@@ -78,10 +78,22 @@ def mcts_search(start, sims, id_base=0, ply=0, edges_per_node=48, c_puct=1.5, di
     return moves, N, W, P, info
 
 
+def set_rules(resign_thr=-0.7, resign_min_plies=15, root_mix=-1):
+    """Game-loop rules of the following searches / games (defaults = kv_mcts_create_k's = the reference's)."""
+    lib().kvemu_set_rules(ctypes.c_float(resign_thr), ctypes.c_int(resign_min_plies), ctypes.c_int(root_mix))
+
+
 def selfplay(start, sims, max_plies, temp_plies, id_base=0, edges_per_node=48, c_puct=1.5, dir_alpha=0.3, dir_eps=0.25,
-             seed=1, cache_log2=0, return_counts=False, inflight=1, pipe_order=0):
+             seed=1, cache_log2=0, return_counts=False, inflight=1, pipe_order=0, script_moves=None, script_vals=None,
+             return_flags=False):
     start = np.ascontiguousarray(start, dtype=np.uint64)
     G = start.shape[0]
+    sm = sv = None
+    if script_moves is not None or script_vals is not None:
+        sm = np.ascontiguousarray(script_moves, np.uint16) if script_moves is not None else None
+        sv = np.ascontiguousarray(script_vals, np.float32) if script_vals is not None else None
+        stride = (sm if sm is not None else sv).shape[1]
+        lib().kvemu_set_script(_p(sm) if sm is not None else None, _p(sv) if sv is not None else None, ctypes.c_int(stride))
     moves = np.zeros((G, max_plies), np.uint16); plies = np.zeros(G, np.int32); res = np.zeros(G, np.int32)
     cnt = np.zeros(2, np.int64)
     lib().kvemu_selfplay(ctypes.c_int(G), _p(start), ctypes.c_uint64(id_base), ctypes.c_int(sims),
@@ -89,6 +101,11 @@ def selfplay(start, sims, max_plies, temp_plies, id_base=0, edges_per_node=48, c
                          ctypes.c_float(c_puct), ctypes.c_float(dir_alpha), ctypes.c_float(dir_eps),
                          ctypes.c_uint64(seed), _p(moves), _p(plies), _p(res), ctypes.c_int(cache_log2), _p(cnt),
                          ctypes.c_int(inflight), ctypes.c_int(pipe_order))
+    lib().kvemu_set_script(None, None, ctypes.c_int(0))
+    flags = res >> 8
+    res = ((res & 0xFF) ^ 0x80) - 0x80          # sign-extend the result byte
+    if return_flags:
+        return moves, plies, res, flags
     if return_counts:
         return moves, plies, res, (int(cnt[0]), int(cnt[1]))
     return moves, plies, res

@@ -217,6 +217,13 @@ struct EmuMcts {
     }
 };
 
+// game-loop rules / script applied to the next contexts (kvemu_set_rules, kvemu_set_script); defaults = kv_mcts_create_k's
+static float g_emu_resign_thr = -0.7f;
+static int g_emu_resign_min = 15, g_emu_root_mix = -1;
+static const uint16_t* g_emu_script_moves = nullptr;
+static const float* g_emu_script_vals = nullptr;
+static int g_emu_script_stride = 0;
+
 static EmuMcts* emu_mcts_new(int G, int sims, int edges_per_node, int max_plies, int temp_plies, float c_puct,
                              float dir_alpha, float dir_eps, uint64_t seed, int cache_log2 = 0, int inflight = 1) {
     EmuMcts* m = new EmuMcts();
@@ -236,7 +243,13 @@ static EmuMcts* emu_mcts_new(int G, int sims, int edges_per_node, int max_plies,
     c.dir_alpha = dir_alpha;
     c.dir_eps = dir_eps;
     c.seed = seed;
+    c.resign_thr = g_emu_resign_thr;
+    c.resign_min_plies = g_emu_resign_min;
+    c.root_mix = g_emu_root_mix < 0 ? (sims == 1) : g_emu_root_mix;
+    c.script_stride = (g_emu_script_moves || g_emu_script_vals) ? g_emu_script_stride : 0;
     kv::MctsArrays& A = m->A;
+    A.script_move = c.script_stride ? g_emu_script_moves : nullptr;
+    A.script_val = c.script_stride ? g_emu_script_vals : nullptr;
     const size_t g = (size_t)G, gs = g * (size_t)inflight;
     A.hdr = m->alloc<kv::GameHdr>(g);
     A.root_line = m->alloc<uint64_t>(g * 16);
@@ -426,6 +439,17 @@ static void emu_mcts_finish(EmuMcts* m) {
 
 extern "C" {
 
+__attribute__((visibility("default"))) void kvemu_set_rules(float resign_thr, int resign_min_plies, int root_mix) {
+    g_emu_resign_thr = resign_thr;
+    g_emu_resign_min = resign_min_plies;
+    g_emu_root_mix = root_mix;
+}
+__attribute__((visibility("default"))) void kvemu_set_script(const uint16_t* moves, const float* vals, int stride) {
+    g_emu_script_moves = moves;
+    g_emu_script_vals = vals;
+    g_emu_script_stride = stride;
+}
+
 // One search (sims waves) for G root positions; outputs the root edges of every game ([G][256]) and info [G][4]
 __attribute__((visibility("default"))) void kvemu_mcts_search(int G, const uint64_t* start, uint64_t id_base, int ply0,
                                                                int sims, int edges_per_node, float c_puct,
@@ -477,7 +501,7 @@ __attribute__((visibility("default"))) void kvemu_selfplay(int G, const uint64_t
     }
     for (int g = 0; g < G; g++) {
         out_plies[g] = m->A.hdr[g].ply;
-        out_result[g] = m->A.hdr[g].result;
+        out_result[g] = (m->A.hdr[g].result & 0xFF) | (m->A.hdr[g].overflow << 8);   // low byte: result (two's complement), bits 8+: flags
         for (int p = 0; p < m->A.hdr[g].ply && p < max_plies; p++)
             out_moves[(size_t)g * max_plies + p] = m->A.rec_move[(size_t)g * m->cfg.rec_cap + p];
     }

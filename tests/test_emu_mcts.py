@@ -152,3 +152,46 @@ def test_virtual_loss_selfplay_games_match_oracle():
             cfg = O.mcts_cfg(24, temp_plies=5, max_plies=16, seed=6, inflight=K)
             m, lines, r = O.selfplay_game(cfg, start[g], game_id=9 + g)
             assert len(m) == plies[g] and r == res[g] and np.array_equal(m, moves[g, :plies[g]])
+
+
+def _reference_rule_priors(line, moves, alpha, eps, seed, game_id, ply):
+    """scripts/self_play.py:150-167 in float64: softmax over all 4096 logits, Dirichlet noise over all 4096 indices,
+    (1-eps) p + eps noise, legal entries renormalised."""
+    lg, _ = O.hash_eval(line)
+    p = np.exp(lg.astype(np.float64) - lg.max())
+    p /= p.sum()
+    if eps > 0:
+        g = O.root_noise(alpha, seed, game_id, ply).astype(np.float64)
+        p = (1 - eps) * p + eps * g / g.sum()
+    idx = [O.lib().kvo_move_index(int(m)) for m in moves]
+    w = p[idx]
+    return w / w.sum()
+
+
+def test_reference_rule_mode_priors_and_games():
+    """sims = 1 (no search): root priors mixed the reference's way, whole games bit-exact between the kernel source and
+    the oracle, resignation included (hash values below -0.7 are frequent)."""
+    lines = H.random_playout_positions(n_games=2, max_plies=40, seed=5)
+    roots = np.concatenate([L.start_line()[None], lines[[11, 30, 55]]])
+    for eps in (0.25, 0.0):
+        mv, N, W, P, info = emu.mcts_search(roots, sims=1, id_base=3, ply=7, seed=12, dir_eps=eps)
+        for g in range(len(roots)):
+            n = int(info[g, 0])
+            want = _reference_rule_priors(roots[g], mv[g, :n], 0.3, eps, 12, 3 + g, 7)
+            assert np.allclose(P[g, :n], want, rtol=2e-5, atol=1e-7), (g, eps)
+            assert abs(float(P[g, :n].sum()) - 1.0) < 1e-5
+    # the legal-only mixing (search default) is a different distribution: the switch matters
+    emu.set_rules(root_mix=0)
+    try:
+        _, _, _, P0, info0 = emu.mcts_search(roots[:1], sims=1, id_base=3, ply=7, seed=12)
+    finally:
+        emu.set_rules()
+    assert not np.allclose(P0[0, :20], P[0, :20], rtol=1e-3)
+    start = np.stack([L.start_line()] * 3)
+    moves, plies, res = emu.selfplay(start, sims=1, max_plies=40, temp_plies=0, id_base=9, seed=4)
+    resigned = 0
+    for g in range(3):
+        m, pos, r = O.selfplay_game(O.mcts_cfg(1, max_plies=40, seed=4), start[g], game_id=9 + g)
+        assert len(m) == plies[g] and r == res[g] and np.array_equal(m, moves[g, :plies[g]])
+        resigned += int(plies[g] < 40 and r != 0)
+    assert resigned >= 1

@@ -358,3 +358,86 @@ def test_evaluation_players(eng, monkeypatch):
     other = ChessNet().eval()
     r = P.arena(net, other, n_games=8, sims=8, max_plies=6, device="cuda:0")
     assert r["a_wins"] + r["b_wins"] + r["draws"] == 8 and r["games"] == 8
+
+
+def _reference_rule_priors(logits, moves, alpha, eps, seed, game_id, ply):
+    """scripts/self_play.py:150-167 in float64 (see tests/test_emu_mcts.py)."""
+    p = np.exp(logits.astype(np.float64) - logits.max())
+    p /= p.sum()
+    if eps > 0:
+        g = O.root_noise(alpha, seed, game_id, ply).astype(np.float64)
+        p = (1 - eps) * p + eps * g / g.sum()
+    w = p[[O.lib().kvo_move_index(int(m)) for m in moves]]
+    return w / w.sum()
+
+
+def test_reference_rule_mode_hash_evaluator_bit_exact(eng):
+    """sims = 1: no search, the move is sampled from root priors mixed the reference's way (softmax and Dirichlet noise
+    over all 4096 indices, scripts/self_play.py:150-167), resignation on.  Whole games and priors bit-exact vs the oracle."""
+    G, max_plies = 96, 48
+    eng.mcts_create(G, 1, max_plies=max_plies, temp_plies=0, seed=21, eval_mode=0)
+    eng.mcts_reset(None, game_id_base=300)
+    eng.mcts_run_sims(1)
+    cfg = O.mcts_cfg(1, max_plies=max_plies, seed=21)
+    for g in (0, 41, 95):
+        got = eng.mcts_read_root(g)
+        r = O.mcts_search(cfg, L.start_line(), game_id=300 + g, ply=0)
+        assert np.array_equal(got["moves"], r["moves"]) and np.array_equal(_bits(got["P"]), _bits(r["P"])), g
+        lg, _ = O.hash_eval(L.start_line())
+        assert np.allclose(got["P"], _reference_rule_priors(lg, got["moves"], 0.3, 0.25, 21, 300 + g, 0), rtol=2e-5)
+    eng.mcts_finish_move()
+    for _ in range(max_plies):
+        eng.mcts_run_move()
+    st = eng.mcts_status()
+    assert st["done"] == G
+    lines, move, reward, game = (t.cpu().numpy() for t in eng.mcts_records())
+    lines = lines.view(np.uint64)
+    resigned = 0
+    for g in range(G):
+        m, pos, res = O.selfplay_game(cfg, L.start_line(), game_id=300 + g)
+        sel = game == g
+        assert sel.sum() == len(m), g
+        assert np.array_equal(move[sel], [O.lib().kvo_move_index(int(x)) for x in m]), g
+        assert np.array_equal(lines[sel][:, :12], pos[:, :12]), g
+        assert np.allclose(reward[sel], 1.0 if res > 0 else (-1.0 if res < 0 else 0.2)), g
+        resigned += int(len(m) < max_plies and res != 0)
+    assert resigned > G // 2          # hash values below -0.7 come up within a few plies after move 15
+
+
+def test_reference_rule_mode_network_priors(eng):
+    """Same mode with the real network: the root priors follow the reference's formula on the net's own logits, for a
+    tower evaluation, an in-wave follower and a cache hit alike."""
+    from knightvision_b200.model import ChessNet
+    torch.manual_seed(0)
+    net = ChessNet().eval().attach(eng, max_batch=64)
+    G = 12
+    eng.mcts_create(G, 1, max_plies=6, temp_plies=0, seed=8, eval_mode=1)
+    eng.mcts_enable_cache(12)
+    eng.mcts_reset(None, game_id_base=70)
+    eng.mcts_run_sims(1)
+    st = eng.mcts_status()
+    assert st["evals"] == 1 and st["cache_hits"] == G - 1            # one leader, the rest follow it
+    pol, val = net.forward_lines(torch.from_numpy(L.start_line().view(np.int64)[None]).to(eng.device))
+    lg = pol[0].float().cpu().numpy()
+    for g in (0, 5, 11):
+        got = eng.mcts_read_root(g)
+        want = _reference_rule_priors(lg, got["moves"], 0.3, 0.25, 8, 70 + g, 0)
+        assert np.allclose(got["P"], want, rtol=1e-3, atol=1e-6), g
+    eng.mcts_finish_move()
+    eng.mcts_run_move()                                               # ply 1: positions differ, hits from ply 0 do not apply
+    roots = eng.mcts_roots().cpu().numpy().view(np.uint64)
+    eng.mcts_run_sims(1)
+    pol, _ = net.forward_lines(torch.from_numpy(roots.view(np.int64)).to(eng.device))
+    for g in (1, 7):
+        got = eng.mcts_read_root(g)
+        want = _reference_rule_priors(pol[g].float().cpu().numpy(), got["moves"], 0.3, 0.25, 8, 70 + g, 2)
+        assert np.allclose(got["P"], want, rtol=1e-3, atol=1e-6), g
+    eng.mcts_enable_cache(0)
+
+
+def test_run_move_reports_exhausted_wave_budget(eng):
+    """K > 1: kv_mcts_run_move returns an error instead of silently finishing a move that still owes simulations."""
+    eng.mcts_create(4, 8, max_plies=4, temp_plies=0, seed=1, eval_mode=0, inflight=4)
+    eng.mcts_reset(None, 0)
+    eng.mcts_run_move()                 # the normal case completes
+    assert eng.mcts_status()["plies"] == 4

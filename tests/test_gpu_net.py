@@ -87,6 +87,65 @@ def test_forward_matches_reference_golden(eng, variant):
     assert torch.equal(pol2, pol) and torch.equal(val2, val)
 
 
+def _wide_errors(g, prefix, pol, val):
+    pol = pol.cpu().numpy()
+    n = pol.shape[0]
+    cols = g["cols"][:n].astype(np.int64)
+    d_cols = np.abs(np.take_along_axis(pol, cols, axis=1) - g[prefix + "_cols"]).max()
+    d_top = np.abs(np.take_along_axis(pol, g[prefix + "_top_idx"].astype(np.int64), axis=1) - g[prefix + "_top_val"]).max()
+    d_val = np.abs(val.cpu().numpy() - g[prefix + "_value"]).max()
+    return float(d_cols), float(d_top), float(d_val)
+
+
+@pytest.mark.parametrize("variant", ["init", "bnrand"])
+def test_forward_matches_reference_golden_256_positions(eng, variant, capsys):
+    """tests/golden/net_wide.npz: the UNMODIFIED reference ChessNet in true fp32 on the CPU, 256 positions (208 playout
+    + 48 synthetic), 256 random policy columns + the 8 largest logits + the value per position.  Prints the observed
+    maximum absolute error next to the 2e-2 bound."""
+    from knightvision_b200.engine import lines_to_device
+    g = np.load(H.GOLDEN + "/net_wide.npz")
+    net = _net(bnrand=(variant == "bnrand")).attach(eng, max_batch=256)
+    pol, val = net.forward_lines(lines_to_device(g["lines"], eng.device))
+    d_cols, d_top, d_val = _wide_errors(g, "ref_" + variant, pol, val)
+    with capsys.disabled():
+        print(f"\n[net parity, reference net, {variant}] max |bf16 kernel - fp32 CPU reference| over 256 positions: "
+              f"policy {max(d_cols, d_top):.3e}, value {d_val:.3e} (bound {TOL:.0e})")
+    assert max(d_cols, d_top) < TOL and d_val < TOL, (d_cols, d_top, d_val)
+
+
+def test_tower_20x256_matches_cpu_fp32_golden(eng, capsys):
+    """BASELINE config 5's 20 x 256 tower against a plain torch CPU fp32 run of the same graph (128 positions)."""
+    from knightvision_b200.engine import lines_to_device
+    g = np.load(H.GOLDEN + "/net_wide.npz")
+    n = g["t20_value"].shape[0]
+    net = _net(seed=2, bnrand=True, stem=256, tower=256, blocks=20, conv2=False).attach(eng, max_batch=n)
+    pol, val = net.forward_lines(lines_to_device(g["lines"][:n], eng.device))
+    d_cols, d_top, d_val = _wide_errors(g, "t20", pol, val)
+    with capsys.disabled():
+        print(f"\n[net parity, 20x256 tower] max |bf16 kernel - fp32 CPU| over {n} positions: "
+              f"policy {max(d_cols, d_top):.3e}, value {d_val:.3e} (bound {TOL:.0e})")
+    assert max(d_cols, d_top) < TOL and d_val < TOL, (d_cols, d_top, d_val)
+
+
+def test_torch_references_are_true_fp32(eng):
+    """The torch graphs these tests compare against must not run TF32 (conftest switches it off globally and
+    fp32_reference_forward does so locally): a GPU fp32 run agrees with the CPU fp32 golden to fp32 rounding."""
+    from knightvision_b200.model import fp32_reference_forward
+    assert not torch.backends.cudnn.allow_tf32 and not torch.backends.cuda.matmul.allow_tf32
+    g = np.load(H.GOLDEN + "/net_wide.npz")
+    net = _net(bnrand=True).cuda()
+    x = torch.from_numpy(O.encode(g["lines"][:32])).cuda()
+    torch.backends.cudnn.allow_tf32 = True          # the call must be immune to the global switch
+    try:
+        with torch.no_grad():
+            rp, rv = fp32_reference_forward(net, x)
+    finally:
+        torch.backends.cudnn.allow_tf32 = False
+    sub = {k: g[k][:32] for k in ("cols", "ref_bnrand_cols", "ref_bnrand_top_idx", "ref_bnrand_top_val", "ref_bnrand_value")}
+    d_cols, d_top, d_val = _wide_errors(sub, "ref_bnrand", rp, rv)
+    assert max(d_cols, d_top, d_val) < 2e-4, (d_cols, d_top, d_val)
+
+
 def test_forward_batch_odd_sizes_and_determinism(eng):
     from knightvision_b200.engine import lines_to_device
     from knightvision_b200.model import fp32_reference_forward
