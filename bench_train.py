@@ -29,18 +29,28 @@ def _tower_flops_per_pos(arch):
     return f        # one direction; a training step runs fprop + dgrad + wgrad = 3x
 
 
+ACCUM = int(os.getenv("KV_BENCH_TRAIN_ACCUM", "2"))       # scripts/train.py:183-190 accumulates 2 batches per optimizer step
+
+
 def _step_fn(LR, net, opt, graph):
+    """One optimizer step of the reference's loop: ACCUM micro-batches (loss / ACCUM each), clip 1.0, Adam.  Under
+    DistributedDataParallel only the last micro-batch exchanges gradients (no_sync on the others)."""
+    import contextlib
     import torch
     import torch.nn.functional as F
+    ddp = hasattr(graph, "no_sync")
 
     def step(boards, moves, outcomes):
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            pol, val = graph(boards)
-        pol = pol.float()
-        logp = F.log_softmax(pol, dim=1)
-        loss = F.cross_entropy(pol, moves) + F.mse_loss(val.squeeze(1).float(), outcomes) \
-            - LR.ENTROPY_COEF * (-(logp.exp() * logp).sum(dim=1).mean())
-        loss.backward()
+        loss = None
+        for k in range(ACCUM):
+            with (graph.no_sync() if ddp and k + 1 < ACCUM else contextlib.nullcontext()):
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    pol, val = graph(boards)
+                pol = pol.float()
+                logp = F.log_softmax(pol, dim=1)
+                loss = F.cross_entropy(pol, moves) + F.mse_loss(val.squeeze(1).float(), outcomes) \
+                    - LR.ENTROPY_COEF * (-(logp.exp() * logp).sum(dim=1).mean())
+                (loss / ACCUM).backward()
         torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=1.0)
         opt.step()
         opt.zero_grad(set_to_none=True)
@@ -88,16 +98,29 @@ def run_reference(args):
 
 
 def run(args, rank, world, local_rank):
+    from knightvision_b200.engine import Engine
+    eng = Engine(local_rank)
+    arms = tuple(a for a in os.getenv("KV_BENCH_TRAIN_ARMS", "native,cudnn,cudnn_nhwc").split(",") if a)
+    line = train_record(args, eng, rank, world, local_rank, steps=args.steps, arms=arms, graph=GRAPH)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def train_record(args, eng, rank, world, local_rank, steps, arms=("native",), graph=True):
+    """The training-step record (rank 0 returns the dict, the other ranks None)."""
     import torch
     import torch.distributed as dist
     import torch.nn as nn
     from bench import Clocks, measured_peaks
-    from knightvision_b200 import layout as L
     from knightvision_b200 import learn as LR
-    from knightvision_b200.engine import Engine
     from knightvision_b200.model import ChessNet
 
-    eng = Engine(local_rank)
+    class _A:
+        pass
+    a_ = _A()
+    a_.steps, a_.warmup = steps, args.warmup
+    args = a_
+    GRAPH_ = graph
     dev = eng.device
     arch, name = _arch()
     B = BATCH
@@ -116,7 +139,6 @@ def run(args, rank, world, local_rank):
 
     results = {}
     clk = None
-    arms = tuple(a for a in os.getenv("KV_BENCH_TRAIN_ARMS", "native,cudnn,cudnn_nhwc").split(",") if a)
     if "native" not in arms:
         arms = ("native",) + arms
     for arm in arms:
@@ -126,9 +148,12 @@ def run(args, rank, world, local_rank):
             net = net.to(memory_format=torch.channels_last)
         net.train()
         opt = torch.optim.Adam(net.parameters(), lr=1e-3)
-        graph = LR.TrainGraph(net, engine=eng if arm == "native" else None)
-        if world > 1:
-            graph = nn.parallel.DistributedDataParallel(graph, device_ids=[local_rank])
+        if arm == "native":
+            graph = LR.training_graph(net, eng)      # under torch.distributed: DDP, 64 MB buckets, bf16 gradient exchange
+        else:
+            graph = LR.TrainGraph(net, engine=None)
+            if world > 1:
+                graph = nn.parallel.DistributedDataParallel(graph, device_ids=[local_rank])
         step = _step_fn(LR, net, opt, graph)
         boards = eng.encode(lines)
         for _ in range(max(args.warmup, 3)):
@@ -163,7 +188,7 @@ def run(args, rank, world, local_rank):
             clk = clocks.stop()
         loss_last = lv
         graph_ms = None
-        if GRAPH and world == 1:
+        if GRAPH_ and world == 1:
             # the whole step (encode -> forward -> backward -> clip -> Adam) as ONE CUDA graph: no tracing compiler, the
             # same kernels, launched by the GPU front end instead of ~1 500 host calls
             try:
@@ -196,38 +221,43 @@ def run(args, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         results[arm] = dict(dev_ms=float(t[0]), e2e_ms=float(t[1]), prof=prof, launches=launches, loss=loss_last, graph_ms=graph_ms)
+        if hasattr(net, "_kv_train_graph"):
+            object.__delattr__(net, "_kv_train_graph")
         del graph, net, opt
     if rank != 0:
-        return
+        return None
     peaks = measured_peaks()
     r = results["native"]
     fl = _tower_flops_per_pos(arch)
-    value = world * B * args.steps / (r["dev_ms"] * 1e-3)
+    PB = B * ACCUM                       # positions per optimizer step and GPU
+    value = world * PB * args.steps / (r["dev_ms"] * 1e-3)
     wg_ms, wg_n = r["prof"]["train_wgrad"]
     cv_ms, cv_n = r["prof"]["net_conv"]
-    wg_tf = (B * args.steps * fl) / (wg_ms * 1e-3) / 1e12 if wg_ms else 0.0
-    cv_tf = (2 * B * args.steps * fl) / (cv_ms * 1e-3) / 1e12 if cv_ms else 0.0
+    wg_tf = (PB * args.steps * fl) / (wg_ms * 1e-3) / 1e12 if wg_ms else 0.0
+    cv_tf = (2 * PB * args.steps * fl) / (cv_ms * 1e-3) / 1e12 if cv_ms else 0.0
     line = {
         "metric": "train_positions_per_s", "value": value, "unit": "positions/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": r["dev_ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"training step (scripts/train.py:126-196 loss, clip 1.0, Adam), {name}, batch {B} per GPU, "
+        "config": {"workload": f"optimizer step (scripts/train.py:126-196: loss, {ACCUM} accumulated batches, clip 1.0, Adam), {name}, {ACCUM} x batch {B} per GPU, "
                                "tower convolutions fprop/dgrad/wgrad on tcgen05 kernels, fused BatchNorm+ReLU(+residual) kernels, stem conv / heads / loss / Adam in PyTorch",
-                   "batch_per_gpu": B, "parallelism": f"DDP over {world} GPU(s)" if world > 1 else "single GPU",
+                   "batch_per_gpu": B, "accumulate": ACCUM,
+                   "parallelism": (f"DDP over {world} GPU(s): one bf16 gradient all-reduce per optimizer step (no_sync on the "
+                                   "accumulating micro-batch), 64 MB buckets") if world > 1 else "single GPU",
                    "l2": "activations of one step (> 1 GB) exceed the 126 MB L2; no flush needed"},
-        "cudnn_arm": ({"value": world * B * args.steps / (results["cudnn"]["dev_ms"] * 1e-3), "unit": "positions/s",
+        "cudnn_arm": ({"value": world * PB * args.steps / (results["cudnn"]["dev_ms"] * 1e-3), "unit": "positions/s",
                        "ms_per_step": results["cudnn"]["dev_ms"] / args.steps,
                        "note": "same step in plain PyTorch: cuDNN convolutions + torch BatchNorm, bf16 autocast, channels_first "
                                "as the reference runs it"} if "cudnn" in results else None),
-        "cudnn_nhwc_arm": ({"value": world * B * args.steps / (results["cudnn_nhwc"]["dev_ms"] * 1e-3), "unit": "positions/s",
+        "cudnn_nhwc_arm": ({"value": world * PB * args.steps / (results["cudnn_nhwc"]["dev_ms"] * 1e-3), "unit": "positions/s",
                             "ms_per_step": results["cudnn_nhwc"]["dev_ms"] / args.steps,
                             "note": "same, parameters and activations in channels_last memory (cuDNN's preferred layout)"}
                            if "cudnn_nhwc" in results else None),
         "cuda_graph": {"ms_per_step": {a: results[a]["graph_ms"] for a in results},
-                       "value": (world * B / (r["graph_ms"] * 1e-3)) if isinstance(r["graph_ms"], float) else None,
+                       "value": (world * PB / (r["graph_ms"] * 1e-3)) if isinstance(r["graph_ms"], float) else None,
                        "unit": "positions/s", "note": "the whole step captured as one CUDA graph and replayed (same kernels)"},
         "clocks": clk, "gpu_launches": r["launches"],
-        "e2e": {"value": world * B * args.steps / (r["e2e_ms"] * 1e-3), "unit": "positions/s",
+        "e2e": {"value": world * PB * args.steps / (r["e2e_ms"] * 1e-3), "unit": "positions/s",
                 "h2d_bytes_per_step": B * (128 + 8 + 4), "d2h_bytes_per_step": 4,
                 "api": "pinned host packed records -> device -> kv_encode -> TrainGraph step -> loss.item()"},
         "roofline": {"kernel": "conv3x3_wgrad_kernel (tcgen05 MN-major split-K)", "bound": "tensor", "achieved": wg_tf,
@@ -240,4 +270,4 @@ def run(args, rank, world, local_rank):
         "kernels_ms_per_step": {k: v[0] / args.steps for k, v in r["prof"].items() if v[1]},
         "loss": r["loss"], "loss_cudnn_arm": results["cudnn"]["loss"] if "cudnn" in results else None,
     }
-    print(json.dumps(line), flush=True)
+    return line

@@ -132,6 +132,14 @@ KV_API int kv_net_load(kv_ctx* ctx, const float* h_blob, uint64_t n_floats);
  * broadcast) and call kv_net_commit_weights. */
 KV_API void* kv_net_blob_device_ptr(kv_ctx* ctx);
 KV_API int kv_net_commit_weights(kv_ctx* ctx, void* stream);
+/* The FOLDED weights the kernels read (tower bf16 with BatchNorm folded, biases, stem table, heads) as ONE device
+ * buffer of kv_net_folded_bytes() bytes (52 MB for the reference net: half the fp32 blob).  Weight distribution between
+ * generations (the reference re-loads a checkpoint per worker, scripts/self_play.py:54-77): the trainer's rank commits,
+ * the buffer is NCCL-broadcast into every other rank's buffer, and those ranks call kv_net_adopt_folded (no fold
+ * there; clears the evaluation cache like a commit). */
+KV_API uint64_t kv_net_folded_bytes(kv_ctx* ctx);
+KV_API void* kv_net_folded_device_ptr(kv_ctx* ctx);
+KV_API int kv_net_adopt_folded(kv_ctx* ctx, void* stream);
 /* forward(x) -> (policy logits [n][4096] fp32, value [n] fp32 after tanh); either output may be NULL.
  * Input = board lines (the stem kernel fuses encode_board), or the reference's fp32 one-hot planes. */
 KV_API int kv_net_forward(kv_ctx* ctx, const uint64_t* d_lines, int n, float* d_policy, float* d_value, void* stream);

@@ -39,6 +39,9 @@ SIGNATURES = {
     "kv_net_load": (c_int, [c_void_p, c_void_p, c_u64]),
     "kv_net_blob_device_ptr": (c_void_p, [c_void_p]),
     "kv_net_commit_weights": (c_int, [c_void_p, c_void_p]),
+    "kv_net_folded_bytes": (c_u64, [c_void_p]),
+    "kv_net_folded_device_ptr": (c_void_p, [c_void_p]),
+    "kv_net_adopt_folded": (c_int, [c_void_p, c_void_p]),
     "kv_net_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "kv_net_forward_partial": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, ctypes.POINTER(c_int)]),
     "kv_net_forward_planes": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

@@ -987,14 +987,10 @@ static std::vector<TowerStep> tower_plan(const kv_net* n) {
 void kv_net_destroy(kv_ctx* ctx) {
     kv_net* n = ctx->net;
     if (!n) return;
-    for (auto& L : n->convs) {
-        if (L.w) cudaFree(L.w);
-        if (L.b) cudaFree(L.b);
-    }
     for (int i = 0; i < 3; i++)
         if (n->act[i]) cudaFree(n->act[i]);
-    void* ptrs[] = {n->stem_table, n->stem_bias, n->wh, n->bh, n->wfc, n->bfc, n->w1, n->b1, n->w2, n->b2, n->d_blob,
-                    n->d_flag, n->d_lines_tmp, n->d_layers, n->d_done[0], n->d_done[1]};
+    // the folded weights (tower bf16 + biases, stem table, heads) are slices of one arena
+    void* ptrs[] = {n->d_folded, n->d_blob, n->d_flag, n->d_lines_tmp, n->d_layers, n->d_done[0], n->d_done[1]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (n->side) cudaStreamDestroy(n->side);
@@ -1038,26 +1034,50 @@ int kv_net_create(kv_ctx* ctx, int stem_channels, int tower_channels, int n_bloc
     }
     const int nconv = (n->has_conv2 ? 1 : 0) + 2 * n->blocks;
     n->convs.resize(nconv);
+    // The FOLDED weights — what the kernels read: tower weights bf16 with the BatchNorm scale folded in, fp32 biases,
+    // the stem table, the heads — live in ONE arena (256 B aligned slices), so a generation's weights can travel between
+    // GPUs as a single 52 MB NCCL broadcast of this arena (half the fp32 state_dict blob) with no fold on the receivers.
+    size_t off = 0;
+    auto slice = [&](size_t bytes) {
+        const size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    };
+    std::vector<size_t> o_w(nconv), o_b(nconv);
     for (int l = 0; l < nconv; l++) {
         kv_conv& L = n->convs[l];
         L.cin = (n->has_conv2 && l == 0) ? n->C1 : n->C;
         L.cout = n->C;
-        KV_CUDA(ctx, cudaMalloc(&L.w, (size_t)L.cout * 9 * L.cin * sizeof(bf16)));
-        KV_CUDA(ctx, cudaMalloc(&L.b, (size_t)L.cout * sizeof(float)));
+        o_w[l] = slice((size_t)L.cout * 9 * L.cin * sizeof(bf16));
+        o_b[l] = slice((size_t)L.cout * sizeof(float));
+    }
+    const size_t o_st = slice((size_t)9 * 12 * n->C1 * sizeof(float)), o_sb = slice((size_t)n->C1 * sizeof(float));
+    const size_t o_wh = slice((size_t)3 * n->C * sizeof(float)), o_bh = slice(4 * sizeof(float));
+    const size_t o_wfc = slice((size_t)4096 * 128 * sizeof(float)), o_bfc = slice(4096 * sizeof(float));
+    const size_t o_w1 = slice(512 * 64 * sizeof(float)), o_b1 = slice(512 * sizeof(float));
+    const size_t o_w2 = slice(512 * sizeof(float)), o_b2 = slice(4 * sizeof(float));
+    n->folded_bytes = off;
+    KV_CUDA(ctx, cudaMalloc(&n->d_folded, n->folded_bytes));
+    KV_CUDA(ctx, cudaMemset(n->d_folded, 0, n->folded_bytes));
+    char* fb = static_cast<char*>(n->d_folded);
+    for (int l = 0; l < nconv; l++) {
+        kv_conv& L = n->convs[l];
+        L.w = reinterpret_cast<bf16*>(fb + o_w[l]);
+        L.b = reinterpret_cast<float*>(fb + o_b[l]);
         if (int rc = make_w_map(ctx, &L.map, L.w, L.cout, 9 * L.cin)) return rc;
         if (int rc = make_w_map(ctx, &L.map_half, L.w, L.cout, 9 * L.cin, 128)) return rc;
         if (int rc = make_w_map(ctx, &L.map_q, L.w, L.cout, 9 * L.cin, 64)) return rc;
     }
-    KV_CUDA(ctx, cudaMalloc(&n->stem_table, (size_t)9 * 12 * n->C1 * sizeof(float)));
-    KV_CUDA(ctx, cudaMalloc(&n->stem_bias, (size_t)n->C1 * sizeof(float)));
-    KV_CUDA(ctx, cudaMalloc(&n->wh, (size_t)3 * n->C * sizeof(float)));
-    KV_CUDA(ctx, cudaMalloc(&n->bh, 4 * sizeof(float)));
-    KV_CUDA(ctx, cudaMalloc(&n->wfc, (size_t)4096 * 128 * sizeof(float)));
-    KV_CUDA(ctx, cudaMalloc(&n->bfc, 4096 * sizeof(float)));
-    KV_CUDA(ctx, cudaMalloc(&n->w1, 512 * 64 * sizeof(float)));
-    KV_CUDA(ctx, cudaMalloc(&n->b1, 512 * sizeof(float)));
-    KV_CUDA(ctx, cudaMalloc(&n->w2, 512 * sizeof(float)));
-    KV_CUDA(ctx, cudaMalloc(&n->b2, 4 * sizeof(float)));
+    n->stem_table = reinterpret_cast<float*>(fb + o_st);
+    n->stem_bias = reinterpret_cast<float*>(fb + o_sb);
+    n->wh = reinterpret_cast<float*>(fb + o_wh);
+    n->bh = reinterpret_cast<float*>(fb + o_bh);
+    n->wfc = reinterpret_cast<float*>(fb + o_wfc);
+    n->bfc = reinterpret_cast<float*>(fb + o_bfc);
+    n->w1 = reinterpret_cast<float*>(fb + o_w1);
+    n->b1 = reinterpret_cast<float*>(fb + o_b1);
+    n->w2 = reinterpret_cast<float*>(fb + o_w2);
+    n->b2 = reinterpret_cast<float*>(fb + o_b2);
     KV_CUDA(ctx, cudaMalloc(&n->d_flag, 4 * sizeof(int)));
     KV_CUDA(ctx, cudaMalloc(&n->d_lines_tmp, (size_t)n->cap * 128));
     n->blob_floats = net_blob_floats(n);
@@ -1197,6 +1217,16 @@ int kv_net_commit_weights(kv_ctx* ctx, void* stream) {
     }
     if ((size_t)(p - n->d_blob) != n->blob_floats) return kv_fail_msg(ctx, "kv_net_commit_weights: blob size mismatch");
     n->loaded = true;
+    return kv_mcts_cache_clear(ctx, stream);   // cached features belong to the old weights
+}
+
+// The folded weights as one device buffer (see kv_net_create): after kv_net_commit_weights on the source rank, broadcast
+// these bytes into every other rank's arena and call kv_net_adopt_folded there — no fp32 blob, no fold on the receivers.
+uint64_t kv_net_folded_bytes(kv_ctx* ctx) { return (ctx && ctx->net) ? ctx->net->folded_bytes : 0; }
+void* kv_net_folded_device_ptr(kv_ctx* ctx) { return (ctx && ctx->net) ? ctx->net->d_folded : nullptr; }
+int kv_net_adopt_folded(kv_ctx* ctx, void* stream) {
+    if (!ctx || !ctx->net) return kv_fail_msg(ctx, "kv_net_adopt_folded: no net");
+    ctx->net->loaded = true;
     return kv_mcts_cache_clear(ctx, stream);   // cached features belong to the old weights
 }
 

@@ -28,6 +28,8 @@ struct kv_net {
     float *wh = nullptr, *bh = nullptr;    // head 1x1 convs [3][C], [3]
     float *wfc = nullptr, *bfc = nullptr;  // policy_fc [4096][128], [4096]
     float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;   // value_fc1 [512][64], value_fc2 [512]
+    void* d_folded = nullptr;              // arena holding every folded weight above (one NCCL broadcast moves a generation)
+    size_t folded_bytes = 0;
     float* d_blob = nullptr;               // fp32 state_dict staging (NCCL broadcast target)
     size_t blob_floats = 0;
     int conv_mode = 2;                     // 1: cta_group::1 kernel, 2: cta_group::2 CTA-pair kernel

@@ -154,6 +154,19 @@ class Engine:
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
         return torch.as_tensor(_Holder(), device=self.device)
 
+    def net_folded_tensor(self) -> torch.Tensor:
+        """The folded weights the kernels read (bf16 tower, fp32 biases / stem table / heads) as one uint8 device tensor:
+        the NCCL broadcast payload between generations (half the fp32 blob); receivers call net_adopt_folded()."""
+        n = int(self._lib.kv_net_folded_bytes(self.ctx))
+        ptr = int(self._lib.kv_net_folded_device_ptr(self.ctx))
+
+        class _Holder:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_Holder(), device=self.device)
+
+    def net_adopt_folded(self):
+        N.check(self.ctx, self._lib.kv_net_adopt_folded(self.ctx, self._stream()), "kv_net_adopt_folded")
+
     def net_commit(self):
         N.check(self.ctx, self._lib.kv_net_commit_weights(self.ctx, self._stream()), "kv_net_commit_weights")
 

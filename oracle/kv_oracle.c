@@ -705,6 +705,29 @@ typedef struct {
     const float *rep_edge_P;
 } replay_t;
 
+/* e[k].P holds the legal moves' logits (mx = their maximum): softmax over the legal moves, and at the root the Dirichlet
+ * noise over the legal moves (the arithmetic and its order are the device's, mcts_expand_warp) */
+static void priors_from_logits(const kvo_mcts_cfg *cfg, oedge *e, int n, float mx, int is_root, uint64_t game_id, int ply) {
+    float sum = 0.0f;
+    for (int k = 0; k < n; k++) {
+        e[k].P = kvd_expf(e[k].P - mx);
+        sum = sum + e[k].P;
+    }
+    for (int k = 0; k < n; k++) e[k].P = e[k].P / sum;
+    if (is_root && cfg->dir_eps > 0.0f) {
+        float gs = 0.0f;
+        for (int k = 0; k < n; k++) {
+            e[k].W = kvd_gamma_small(cfg->dir_alpha, cfg->seed, game_id, (uint64_t)ply * 256 + (uint64_t)k);
+            gs = gs + e[k].W;
+        }
+        for (int k = 0; k < n; k++) {
+            const float eta = e[k].W / gs;
+            e[k].P = (1.0f - cfg->dir_eps) * e[k].P + cfg->dir_eps * eta;
+            e[k].W = 0.0f;
+        }
+    }
+}
+
 /* priors and value of a freshly expanded (non-terminal) leaf: replayed device outputs, or the hash evaluator with the
  * softmax / root-noise arithmetic of DESIGN.md 4.3 */
 static void evaluate_leaf(const kvo_mcts_cfg *cfg, onode *nd, oedge *e, int leaf, uint64_t game_id, int ply,
@@ -767,24 +790,7 @@ static void evaluate_leaf(const kvo_mcts_cfg *cfg, onode *nd, oedge *e, int leaf
         nd->val = nd->st.white_to_move ? vw0 : -vw0;
         return;
     }
-    float sum = 0.0f;
-    for (int k = 0; k < n; k++) {
-        e[k].P = kvd_expf(e[k].P - mx);
-        sum = sum + e[k].P;
-    }
-    for (int k = 0; k < n; k++) e[k].P = e[k].P / sum;
-    if (leaf == 0 && cfg->dir_eps > 0.0f) {
-        float gs = 0.0f;
-        for (int k = 0; k < n; k++) {
-            e[k].W = kvd_gamma_small(cfg->dir_alpha, cfg->seed, game_id, (uint64_t)ply * 256 + (uint64_t)k);
-            gs = gs + e[k].W;
-        }
-        for (int k = 0; k < n; k++) {
-            const float eta = e[k].W / gs;
-            e[k].P = (1.0f - cfg->dir_eps) * e[k].P + cfg->dir_eps * eta;
-            e[k].W = 0.0f;
-        }
-    }
+    priors_from_logits(cfg, e, n, mx, leaf == 0, game_id, ply);
     const float vw = hash_value(ph);
     nd->val = nd->st.white_to_move ? vw : -vw;
 }
@@ -799,6 +805,35 @@ static void backup_path(onode *nodes, oedge *edges, const int *path_n, const int
         nodes[path_n[i]].N++;
         nodes[path_n[i]].VL--;
     }
+}
+
+/* the move of a finished search: index into the root's n edges (total = sum of their visit counts) */
+static int choose_move(const kvo_mcts_cfg *cfg, const oedge *e, int n, uint64_t total, uint64_t game_id, int ply) {
+    int pick = 0;
+    if (total == 0) {
+        /* sims == 1: sample from the (noisy) priors, the reference's own move rule (scripts/self_play.py:147-167) */
+        const float u = kvd_u01(kvd_rand24(cfg->seed, game_id, (uint64_t)ply, 0xC0FFEEull));
+        float sum = 0.0f;
+        for (int k = 0; k < n; k++) sum = sum + e[k].P;
+        const float thr = u * sum;
+        float cum = 0.0f;
+        pick = n - 1;
+        for (int k = 0; k < n; k++) {
+            cum = cum + e[k].P;
+            if (cum > thr) { pick = k; break; }
+        }
+    } else if (ply < cfg->temp_plies) {
+        const uint64_t r = ((uint64_t)kvd_rand24(cfg->seed, game_id, (uint64_t)ply, 0xC0FFEEull) * total) >> 24;
+        uint64_t cum = 0;
+        for (int k = 0; k < n; k++) {
+            cum += e[k].N;
+            if (cum > r) { pick = k; break; }
+        }
+    } else {
+        for (int k = 1; k < n; k++)
+            if (e[k].N > e[pick].N) pick = k;
+    }
+    return pick;
 }
 
 /* Runs one search of cfg->sims simulations from `root`; returns the chosen move word (0xFFFF if the root has no
@@ -959,31 +994,7 @@ static int mcts_search(const kvo_mcts_cfg *cfg, const kvo_state *root, uint64_t 
             root_P[k] = e[k].P;
             total += e[k].N;
         }
-        int pick = 0;
-        if (total == 0) {
-            /* sims == 1: sample from the (noisy) priors, the reference's own move rule (scripts/self_play.py:147-167) */
-            const float u = kvd_u01(kvd_rand24(cfg->seed, game_id, (uint64_t)ply, 0xC0FFEEull));
-            float sum = 0.0f;
-            for (int k = 0; k < n; k++) sum = sum + e[k].P;
-            const float thr = u * sum;
-            float cum = 0.0f;
-            pick = n - 1;
-            for (int k = 0; k < n; k++) {
-                cum = cum + e[k].P;
-                if (cum > thr) { pick = k; break; }
-            }
-        } else if (ply < cfg->temp_plies) {
-            const uint64_t r = ((uint64_t)kvd_rand24(cfg->seed, game_id, (uint64_t)ply, 0xC0FFEEull) * total) >> 24;
-            uint64_t cum = 0;
-            for (int k = 0; k < n; k++) {
-                cum += e[k].N;
-                if (cum > r) { pick = k; break; }
-            }
-        } else {
-            for (int k = 1; k < n; k++)
-                if (e[k].N > e[pick].N) pick = k;
-        }
-        chosen = e[pick].mv;
+        chosen = e[choose_move(cfg, e, n, total, game_id, ply)].mv;
     }
     *out_nodes = n_nodes;
     *out_edges = n_edges;
@@ -1091,4 +1102,200 @@ KVO_API int kvo_selfplay_game2(const kvo_mcts_cfg *cfg, const uint64_t *start_li
 KVO_API int kvo_selfplay_game(const kvo_mcts_cfg *cfg, const uint64_t *start_line, uint64_t game_id, uint16_t *out_moves,
                               uint64_t *out_lines, int32_t *result) {
     return kvo_selfplay_game2(cfg, start_line, game_id, NULL, NULL, 0, out_moves, out_lines, result, NULL);
+}
+
+
+/* ==========================================================================================================
+ * Step-wise form of the sequential search (K = 1, legal-move priors) with an EXTERNAL evaluator: select a leaf, hand
+ * its position out, take the evaluator's logits and value back.  bench.py's CPU arm drives many games in lock step so
+ * that the fp32 network (torch CPU kernels) sees a batch, the way the device engine batches its leaves.  Same
+ * arithmetic as mcts_search / kvo_selfplay_game2 (tests/test_oracle_step_api.py feeds it the hash evaluator's logits
+ * and gets the same games bit for bit).
+ * ========================================================================================================== */
+typedef struct {
+    kvo_mcts_cfg cfg;
+    kvo_state st;            /* current position of the game */
+    uint64_t game_id;
+    onode *nodes;
+    oedge *edges;
+    int *path_e, *path_n;
+    int n_nodes, n_edges, sims_done, ply, done, result, overflow;
+    int pend_leaf, pend_depth;
+    uint16_t *rec_moves;     /* moves played so far [max_plies] */
+} kvo_tree;
+
+KVO_API void *kvo_tree_new(const kvo_mcts_cfg *cfg, const uint64_t *start_line, uint64_t game_id) {
+    kvo_tree *t = (kvo_tree *)calloc(1, sizeof(kvo_tree));
+    t->cfg = *cfg;
+    kvo_unpack(start_line, &t->st);
+    t->game_id = game_id;
+    t->nodes = (onode *)calloc((size_t)cfg->sims + 1, sizeof(onode));
+    t->edges = (oedge *)calloc((size_t)cfg->edge_cap, sizeof(oedge));
+    t->path_e = (int *)malloc(sizeof(int) * ((size_t)cfg->sims + 2));
+    t->path_n = (int *)malloc(sizeof(int) * ((size_t)cfg->sims + 2));
+    t->rec_moves = (uint16_t *)calloc((size_t)(cfg->max_plies > 0 ? cfg->max_plies : 1), sizeof(uint16_t));
+    t->pend_leaf = -1;
+    return t;
+}
+
+KVO_API void kvo_tree_free(void *tp) {
+    kvo_tree *t = (kvo_tree *)tp;
+    if (!t) return;
+    free(t->nodes); free(t->edges); free(t->path_e); free(t->path_n); free(t->rec_moves);
+    free(t);
+}
+
+/* Selections until one needs the evaluator.  Returns 1: a leaf is waiting (its line, the policy indices of its legal
+ * moves in edge order and their count are written); 0: the move's simulations are complete, call kvo_tree_finish_move;
+ * -1: the game is over. */
+KVO_API int kvo_tree_select(void *tp, uint64_t *leaf_line16, int32_t *legal_idx256, int32_t *n_legal) {
+    kvo_tree *t = (kvo_tree *)tp;
+    const kvo_mcts_cfg *cfg = &t->cfg;
+    if (t->done) return -1;
+    while (t->sims_done < cfg->sims) {
+        int depth = 0, node = 0, leaf = -1;
+        float v = 0.0f;
+        kvo_state child_st;
+        if (t->n_nodes == 0) {
+            child_st = t->st;
+            leaf = 0;
+        } else {
+            for (;;) {
+                onode *nd = &t->nodes[node];
+                if (nd->term) {
+                    v = nd->val;
+                    nd->N++;
+                    break;
+                }
+                const float sq = KVD_SQRTF((float)nd->N);
+                int best = 0;
+                float bs = 0.0f;
+                for (int k = 0; k < nd->n_edges; k++) {
+                    const oedge *e = &t->edges[nd->first_edge + k];
+                    float sc = kvd_puct(e->W, e->N, e->P, sq, cfg->c_puct);
+                    if (k == 0 || sc > bs) { bs = sc; best = k; }
+                }
+                const int ei = nd->first_edge + best;
+                t->path_n[depth] = node;
+                t->path_e[depth] = ei;
+                depth++;
+                t->edges[ei].VL++;      /* backup_path turns the virtual visit into the real one */
+                nd->VL++;
+                if (t->edges[ei].child < 0) {
+                    child_st = nd->st;
+                    make_move(&child_st, t->edges[ei].mv & 63, (t->edges[ei].mv >> 6) & 63, (t->edges[ei].mv >> 12) & 7, T_Q);
+                    leaf = t->n_nodes;
+                    t->edges[ei].child = leaf;
+                    break;
+                }
+                node = t->edges[ei].child;
+            }
+        }
+        if (leaf >= 0) {
+            onode *nd = &t->nodes[leaf];
+            movelist ml;
+            int f;
+            int n = valid_moves(&child_st, &ml, &f);
+            if (n > 256) n = 256;
+            memset(nd, 0, sizeof(*nd));
+            nd->st = child_st;
+            nd->N = 1;
+            nd->first_edge = -1;
+            t->n_nodes++;
+            if (n == 0) {
+                nd->term = 1;
+                nd->val = (f & RF_CHECKMATE) ? -1.0f : 0.0f;
+            } else if (f & RF_ONLY_KINGS) {
+                nd->term = 1;
+            } else if (t->n_edges + n > cfg->edge_cap) {
+                nd->term = 1;
+                t->overflow = 1;
+            } else {
+                nd->first_edge = t->n_edges;
+                nd->n_edges = n;
+                oedge *e = &t->edges[t->n_edges];
+                t->n_edges += n;
+                for (int k = 0; k < n; k++) {
+                    e[k].mv = pack_move(&ml.m[k]);
+                    e[k].N = 0; e[k].VL = 0; e[k].W = 0.0f; e[k].P = 0.0f; e[k].child = -1;
+                    legal_idx256[k] = kvo_move_index(e[k].mv);
+                }
+                *n_legal = n;
+                kvo_pack(&nd->st, leaf_line16);
+                t->pend_leaf = leaf;
+                t->pend_depth = depth;
+                return 1;
+            }
+            v = nd->val;
+        }
+        backup_path(t->nodes, t->edges, t->path_n, t->path_e, depth, v);
+        t->sims_done++;
+    }
+    return 0;
+}
+
+/* The evaluator's answer for the waiting leaf: logits of its legal moves (edge order) and the white-perspective value */
+KVO_API void kvo_tree_expand(void *tp, const float *legal_logits, float v_white) {
+    kvo_tree *t = (kvo_tree *)tp;
+    if (t->pend_leaf < 0) return;
+    onode *nd = &t->nodes[t->pend_leaf];
+    oedge *e = &t->edges[nd->first_edge];
+    float mx = 0.0f;
+    for (int k = 0; k < nd->n_edges; k++) {
+        e[k].P = legal_logits[k];
+        if (k == 0 || e[k].P > mx) mx = e[k].P;
+    }
+    priors_from_logits(&t->cfg, e, nd->n_edges, mx, t->pend_leaf == 0, t->game_id, t->ply);
+    nd->val = nd->st.white_to_move ? v_white : -v_white;
+    backup_path(t->nodes, t->edges, t->path_n, t->path_e, t->pend_depth, nd->val);
+    t->sims_done++;
+    t->pend_leaf = -1;
+}
+
+/* After the move's simulations: choose, play, apply the game-loop rules (kvo_selfplay_game2's).  Returns 1 while the
+ * game goes on, 0 when it ended. */
+KVO_API int kvo_tree_finish_move(void *tp) {
+    kvo_tree *t = (kvo_tree *)tp;
+    const kvo_mcts_cfg *cfg = &t->cfg;
+    if (t->done) return 0;
+    if (t->n_nodes == 0 || t->nodes[0].term) {
+        t->done = 1;
+        t->result = (t->n_nodes && t->nodes[0].val < 0.0f) ? (t->st.white_to_move ? -1 : 1) : 0;
+        return 0;
+    }
+    const onode *root = &t->nodes[0];
+    const oedge *e = &t->edges[root->first_edge];
+    uint64_t total = 0;
+    for (int k = 0; k < root->n_edges; k++) total += e[k].N;
+    const float vroot = root->st.white_to_move ? root->val : -root->val;
+    const int mv = e[choose_move(cfg, e, root->n_edges, total, t->game_id, t->ply)].mv;
+    t->st = root->st;          /* carries a getValidMoves rewrite, as the reference's state would */
+    if (t->ply < cfg->max_plies) t->rec_moves[t->ply] = (uint16_t)mv;
+    make_move(&t->st, mv & 63, (mv >> 6) & 63, (mv >> 12) & 7, T_Q);
+    t->ply++;
+    t->n_nodes = t->n_edges = t->sims_done = 0;
+    if (only_kings(&t->st)) {
+        t->done = 1;
+    } else if (cfg->resign_min_plies >= 0 && t->ply > cfg->resign_min_plies && vroot < cfg->resign_thr) {
+        t->done = 1;
+        t->result = t->st.white_to_move ? -1 : 1;
+    } else if (t->ply >= cfg->max_plies) {
+        t->done = 1;
+    } else {
+        kvo_state probe = t->st;
+        movelist ml;
+        int f;
+        if (valid_moves(&probe, &ml, &f) == 0) {
+            t->done = 1;
+            t->result = (f & RF_CHECKMATE) ? (t->st.white_to_move ? -1 : 1) : 0;
+        }
+    }
+    return !t->done;
+}
+
+/* info5: ply, done, result, simulations done in the current move, overflow; moves (nullable): the plies played */
+KVO_API void kvo_tree_info(void *tp, int32_t *info5, uint16_t *moves) {
+    kvo_tree *t = (kvo_tree *)tp;
+    info5[0] = t->ply; info5[1] = t->done; info5[2] = t->result; info5[3] = t->sims_done; info5[4] = t->overflow;
+    if (moves) memcpy(moves, t->rec_moves, sizeof(uint16_t) * (size_t)(t->ply < t->cfg.max_plies ? t->ply : t->cfg.max_plies));
 }

@@ -170,3 +170,51 @@ def hash_eval(line):
     f.restype = ctypes.c_float
     v = f(_p(line), _p(out))
     return out, float(v)
+
+
+class Tree:
+    """Step-wise sequential search with an external evaluator (kvo_tree_*): bench.py's CPU arm batches the leaves of many
+    games for the fp32 network.  select() -> (line, legal policy indices) | None when the move's simulations are done."""
+
+    def __init__(self, cfg, start_line, game_id=0):
+        self.cfg = cfg
+        f = lib().kvo_tree_new
+        f.restype = ctypes.c_void_p
+        self._line = np.ascontiguousarray(start_line, dtype=np.uint64)
+        self.h = ctypes.c_void_p(f(ctypes.byref(cfg), _p(self._line), ctypes.c_uint64(game_id)))
+        self._leaf = np.zeros(16, np.uint64)
+        self._idx = np.zeros(256, np.int32)
+        self._n = ctypes.c_int32(0)
+
+    def close(self):
+        if self.h and _lib is not None:
+            _lib.kvo_tree_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def select(self):
+        """1 -> (leaf line u64[16], legal policy indices i32[n]); 0 -> None (call finish_move); game over -> False."""
+        f = lib().kvo_tree_select
+        f.restype = ctypes.c_int
+        r = f(self.h, _p(self._leaf), _p(self._idx), ctypes.byref(self._n))
+        if r == 1:
+            return self._leaf, self._idx[:self._n.value]
+        return None if r == 0 else False
+
+    def expand(self, legal_logits, v_white):
+        lg = np.ascontiguousarray(legal_logits, np.float32)
+        lib().kvo_tree_expand(self.h, _p(lg), ctypes.c_float(v_white))
+
+    def finish_move(self) -> bool:
+        f = lib().kvo_tree_finish_move
+        f.restype = ctypes.c_int
+        return bool(f(self.h))
+
+    def info(self):
+        info = np.zeros(5, np.int32)
+        moves = np.zeros(max(int(self.cfg.max_plies), 1), np.uint16)
+        lib().kvo_tree_info(self.h, _p(info), _p(moves))
+        return dict(ply=int(info[0]), done=bool(info[1]), result=int(info[2]), sims_done=int(info[3]),
+                    overflow=int(info[4]), moves=moves[:int(info[0])])

@@ -416,13 +416,22 @@ def test_reference_rule_mode_network_priors(eng):
     eng.mcts_reset(None, game_id_base=70)
     eng.mcts_run_sims(1)
     st = eng.mcts_status()
-    assert st["evals"] == 1 and st["cache_hits"] == G - 1            # one leader, the rest follow it
+    assert st["evals"] >= 1 and st["evals"] + st["cache_hits"] == G   # leaders (tower) + followers of the same wave
     pol, val = net.forward_lines(torch.from_numpy(L.start_line().view(np.int64)[None]).to(eng.device))
     lg = pol[0].float().cpu().numpy()
+    first = {}
     for g in (0, 5, 11):
         got = eng.mcts_read_root(g)
         want = _reference_rule_priors(lg, got["moves"], 0.3, 0.25, 8, 70 + g, 0)
         assert np.allclose(got["P"], want, rtol=1e-3, atol=1e-6), g
+        first[g] = got["P"].copy()
+    # the same roots again, now served by the cache (late kernel): identical bits
+    eng.mcts_reset(None, game_id_base=70)
+    eng.mcts_run_sims(1)
+    st2 = eng.mcts_status()
+    assert st2["evals"] == 0 and st2["cache_hits"] == G
+    for g in (0, 5, 11):
+        assert np.array_equal(_bits(eng.mcts_read_root(g)["P"]), _bits(first[g])), g
     eng.mcts_finish_move()
     eng.mcts_run_move()                                               # ply 1: positions differ, hits from ply 0 do not apply
     roots = eng.mcts_roots().cpu().numpy().view(np.uint64)
