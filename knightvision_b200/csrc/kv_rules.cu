@@ -16,10 +16,16 @@ namespace kv {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
+#ifndef KV_RULES_MIN_CTAS
+#define KV_RULES_MIN_CTAS 3                  // resident CTAs per SM the register budget is sized for (tuning knob)
+#endif
+constexpr int kW = 16;                       // lanes per board in the rules kernels: two boards per warp
+constexpr int kBoardsPerWarp = 32 / kW;
+constexpr int kGroupsPerCta = kWarpsPerCta * kBoardsPerWarp;
 
 struct __align__(16) RulesSmem {
     Tables tab;
-    uint16_t mv[kWarpsPerCta][MAX_MOVES];
+    uint16_t mv[kGroupsPerCta][MAX_MOVES];   // one move buffer per board in flight
 };
 
 __device__ __forceinline__ void stage_tables(RulesSmem& sm) {
@@ -36,56 +42,64 @@ __device__ __forceinline__ void warp_slice(int n, int gw, int nw, int& lo, int& 
     hi = lo + per < n ? lo + per : n;
 }
 
-__device__ __forceinline__ uint64_t ld_line_word(const uint64_t* line, int lane) {
-    return lane < LINE_WORDS ? __ldg(line + lane) : 0ull;
+// word q of the board line for lane q of its group (0 beyond the line, or when the group has no board)
+__device__ __forceinline__ uint64_t ld_line_word(const uint64_t* line, int q, bool valid) {
+    return (valid && q < LINE_WORDS) ? __ldg(line + q) : 0ull;
 }
 
-__global__ void __launch_bounds__(kThreads, 3) movegen_kernel(uint64_t* __restrict__ lines, int n,
+__global__ void __launch_bounds__(kThreads, KV_RULES_MIN_CTAS) movegen_kernel(uint64_t* __restrict__ lines, int n,
                                                            uint16_t* __restrict__ moves, int stride,
                                                            int32_t* __restrict__ counts, int32_t* __restrict__ flags) {
     __shared__ RulesSmem sm;
     stage_tables(sm);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int q = lane & (kW - 1), grp = lane / kW;
     int lo, hi;
     warp_slice(n, blockIdx.x * kWarpsPerCta + wid, gridDim.x * kWarpsPerCta, lo, hi);
-    uint16_t* mv = sm.mv[wid];
-    for (int i = lo; i < hi; i++) {
-        uint64_t* line = lines + (size_t)i * LINE_WORDS;
-        uint64_t w = ld_line_word(line, lane);
-        const GenOut g = movegen_warp(sm.tab, lane, w, mv);
-        if ((g.flags & RF_STATE_MUTATED) && lane < 12) line[lane] = w;
-        int cnt = g.n < stride ? g.n : stride;
-        if (cnt > MAX_MOVES) cnt = MAX_MOVES;
-        // packed u32 stores: 64 B per 32 moves per request
-        uint32_t* dst = reinterpret_cast<uint32_t*>(moves + (size_t)i * stride);
-        for (int k = lane; 2 * k < cnt; k += 32) {
-            uint32_t lo16 = mv[2 * k], hi16 = (2 * k + 1 < cnt) ? mv[2 * k + 1] : 0u;
-            dst[k] = lo16 | (hi16 << 16);
-        }
-        if (lane == 0) {
-            counts[i] = g.n;
-            flags[i] = g.flags | ((g.n > stride) ? RF_OVERFLOW : 0);
+    uint16_t* mv = sm.mv[wid * kBoardsPerWarp + grp];
+    for (int i0 = lo; i0 < hi; i0 += kBoardsPerWarp) {
+        const int i = i0 + grp;
+        const bool valid = i < hi;
+        uint64_t* line = lines + (size_t)(valid ? i : i0) * LINE_WORDS;
+        uint64_t w = ld_line_word(line, q, valid);
+        const GenOut g = movegen_sub<kW>(sm.tab, lane, w, mv);
+        if (valid) {
+            if ((g.flags & RF_STATE_MUTATED) && q < 12) line[q] = w;
+            int cnt = g.n < stride ? g.n : stride;
+            if (cnt > MAX_MOVES) cnt = MAX_MOVES;
+            // packed u32 stores: 64 B per 32 moves per request
+            uint32_t* dst = reinterpret_cast<uint32_t*>(moves + (size_t)i * stride);
+            for (int k = q; 2 * k < cnt; k += kW) {
+                uint32_t lo16 = mv[2 * k], hi16 = (2 * k + 1 < cnt) ? mv[2 * k + 1] : 0u;
+                dst[k] = lo16 | (hi16 << 16);
+            }
+            if (q == 0) {
+                counts[i] = g.n;
+                flags[i] = g.flags | ((g.n > stride) ? RF_OVERFLOW : 0);
+            }
         }
         __syncwarp();
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) make_moves_kernel(uint64_t* __restrict__ lines, int n,
+__global__ void __launch_bounds__(kThreads, KV_RULES_MIN_CTAS) make_moves_kernel(uint64_t* __restrict__ lines, int n,
                                                               const uint16_t* __restrict__ mvs) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int q = lane & (kW - 1), grp = lane / kW;
     int lo, hi;
     warp_slice(n, blockIdx.x * kWarpsPerCta + wid, gridDim.x * kWarpsPerCta, lo, hi);
-    for (int i = lo; i < hi; i++) {
-        const int m = mvs[i];
-        if (m == 0xFFFF) continue;
-        uint64_t* line = lines + (size_t)i * LINE_WORDS;
-        uint64_t w = ld_line_word(line, lane);
-        w = make_move_warp(lane, w, m, T_Q);
-        if (lane < 13) line[lane] = w;
+    for (int i0 = lo; i0 < hi; i0 += kBoardsPerWarp) {
+        const int i = i0 + grp;
+        const int m = i < hi ? mvs[i] : 0xFFFF;
+        const bool valid = m != 0xFFFF;
+        uint64_t* line = lines + (size_t)(i < hi ? i : i0) * LINE_WORDS;
+        uint64_t w = ld_line_word(line, q, valid);
+        w = make_move_sub<kW>(lane, w, valid ? m : 0, T_Q);
+        if (valid && q < 13) line[q] = w;
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) attacked_kernel(const uint64_t* __restrict__ lines, int n,
+__global__ void __launch_bounds__(kThreads, KV_RULES_MIN_CTAS) attacked_kernel(const uint64_t* __restrict__ lines, int n,
                                                             uint64_t* __restrict__ masks) {
     __shared__ RulesSmem sm;
     stage_tables(sm);
@@ -93,30 +107,34 @@ __global__ void __launch_bounds__(kThreads, 3) attacked_kernel(const uint64_t* _
     int lo, hi;
     warp_slice(n, blockIdx.x * kWarpsPerCta + wid, gridDim.x * kWarpsPerCta, lo, hi);
     for (int i = lo; i < hi; i++) {
-        const uint64_t w = ld_line_word(lines + (size_t)i * LINE_WORDS, lane);
+        const uint64_t w = ld_line_word(lines + (size_t)i * LINE_WORDS, lane, true);
         const uint64_t m = attacked_mask_warp(sm.tab, lane, w);
         if (lane == 0) masks[i] = m;
     }
 }
 
-// ---- perft: one frontier level per launch (body: perft_visit_warp, kv_rules.cuh) ---------------------------
+// ---- perft: one frontier level per launch (body: perft_visit_sub, kv_rules.cuh) ---------------------------
 template <bool LEAF, bool DIGEST>
-__global__ void __launch_bounds__(kThreads, 3) perft_level_kernel(const uint64_t* __restrict__ cur, int m,
+__global__ void __launch_bounds__(kThreads, KV_RULES_MIN_CTAS) perft_level_kernel(const uint64_t* __restrict__ cur, int m,
                                                                uint64_t* __restrict__ next,
                                                                uint32_t* __restrict__ next_count,
                                                                uint64_t* __restrict__ out) {
     __shared__ RulesSmem sm;
     stage_tables(sm);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int q = lane & (kW - 1), grp = lane / kW;
     int lo, hi;
     warp_slice(m, blockIdx.x * kWarpsPerCta + wid, gridDim.x * kWarpsPerCta, lo, hi);
     uint64_t accv = 0;
     int acc_root = -1;
-    for (int i = lo; i < hi; i++) {
-        const uint64_t w = ld_line_word(cur + (size_t)i * LINE_WORDS, lane);
-        perft_visit_warp<LEAF, DIGEST>(sm.tab, lane, w, sm.mv[wid], accv, acc_root, next, next_count, out);
+    uint16_t* mv = sm.mv[wid * kBoardsPerWarp + grp];
+    for (int i0 = lo; i0 < hi; i0 += kBoardsPerWarp) {
+        const int i = i0 + grp;
+        const bool valid = i < hi;
+        const uint64_t w = ld_line_word(cur + (size_t)(valid ? i : i0) * LINE_WORDS, q, valid);
+        perft_visit_sub<kW, LEAF, DIGEST>(sm.tab, lane, w, valid, mv, accv, acc_root, next, next_count, out);
     }
-    perft_acc_flush(accv, acc_root, out, lane);
+    perft_acc_flush(accv, acc_root, out, q);
 }
 
 __global__ void perft_seed_kernel(const uint64_t* __restrict__ roots, int n, uint64_t* __restrict__ dst) {
@@ -145,7 +163,7 @@ __global__ void encode_kernel(const uint64_t* __restrict__ lines, int n, float* 
 }
 
 static int grid_for(kv_ctx* ctx, int n) {
-    int g = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+    int g = (n + kGroupsPerCta - 1) / kGroupsPerCta;
     const int cap = ctx->sm_count * 8;   // 8 CTAs x 8 warps = 64 resident warps per SM
     if (g > cap) g = cap;
     return g < 1 ? 1 : g;

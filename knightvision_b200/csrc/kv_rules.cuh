@@ -1,18 +1,25 @@
-// kv_rules.cuh — KnightVision's custom chess rules as warp-per-board bitboard device code.
+// kv_rules.cuh — KnightVision's custom chess rules as bitboard device code, W lanes per board (W = 16 or 32).
 //
-// One warp owns one board.  The 128-byte board line (16 x u64, see include/kv_b200.h) is loaded with
-// one coalesced request (lane i loads word i) and broadcast by shuffles; every lane then holds the
-// whole position in registers.  Work is spread over lanes by *work item*:
+// A warp holds 32 / W boards; the W lanes of a group own one board.  The 128-byte board line (16 x u64, see
+// include/kv_b200.h) is loaded with one coalesced request per board (lane q of the group loads word q) and broadcast
+// inside the group by shuffles; every lane then holds the whole position in registers.  Work is spread over the
+// group's lanes by *work item*:
 //   - checkForPinsAndChecks  (core/chessEngine.py:325-383): lanes 0-7 walk one king ray each
 //   - getKingMoves/getCastleMoves (:543-601): lanes 0-7 test one king step each on the "king placed"
 //     board, lanes 8-12 test the castle squares, all through attacked()
-//   - getAllPossibleMoves (:433-441): lane l owns squares 2l and 2l+1 (row-major scan order falls out
-//     of a warp prefix sum), emitting moves in the reference's per-piece direction order
+//   - getAllPossibleMoves (:433-441): lane q owns the q-th piece of the side to move in square order (the row-major
+//     scan order of the reference), so every lane that works has a piece; more than W pieces take another round.
+//     The move list falls out of a group prefix sum over the per-piece counts, each piece emitting in the reference's
+//     direction order
+// The rules kernels (perft, movegen, make-move) run W = 16 (two boards per warp: half the warp instructions per
+// board); the tree-search kernels, which own one game per warp, use W = 32 through the *_warp wrappers.
 // squareUnderAttack (:400-415) — "some opponent pseudo-move ENDS on the square", with all its quirks
 // (pawn pushes attack, pawn diagonals onto empty squares do not, opponent castling attacks c/g,
 // nested calls see the re-entrancy guard) — is restated in closed form in attacked().
 // The quirk list this file reproduces on purpose is SURVEY.md §8a-Q.
 //
+// Every warp collective sits in code that all 32 lanes reach together (loops whose trip count depends on a board run
+// until no board of the warp needs another pass).
 // The same source compiles under KV_HOST_EMU (tests/simt_emu) where the warp collectives are routed
 // to a 32-fiber lock-step emulator, so the integer kernels are parity-checked on a box without a GPU.
 #pragma once
@@ -39,11 +46,17 @@ KV_DEV int dir_opp(int d) { return d < 4 ? (d ^ 1) : 11 - d; }
 KV_DEV int first_on_ray(uint64_t b, int d) { return dir_asc(d) ? ctz64(b) : msb64(b); }
 
 // Squares a slider on s reaches in direction d (up to and including the first blocker).
+// Branch-free: towards higher squares the nearest blocker is the lowest set bit l of (ray & occ) and the reach is the
+// ray up to l (l ^ (l - 1) = all bits up to l; all ones when there is no blocker); towards lower squares it is the
+// highest set bit (bit 0 stands in when there is none: the mask is then all ones as well).
 KV_DEV uint64_t ray_att(const Tables& T, int d, int s, uint64_t occ) {
-    uint64_t r = T.ray[d][s];
-    uint64_t b = r & occ;
-    if (b) r ^= T.ray[d][first_on_ray(b, d)];
-    return r;
+    const uint64_t r = T.ray[d][s];
+    const uint64_t b = r & occ;
+    if (dir_asc(d)) {
+        const uint64_t l = b & (0ull - b);
+        return r & (l ^ (l - 1ull));
+    }
+    return r & (~0ull << msb64(b | 1ull));
 }
 KV_DEV uint64_t rook_att(const Tables& T, int s, uint64_t occ) {
     return ray_att(T, 0, s, occ) | ray_att(T, 1, s, occ) | ray_att(T, 2, s, occ) | ray_att(T, 3, s, occ);
@@ -132,12 +145,13 @@ KV_DEV void make_agg(const Pos& p, Agg& g) {
     g.eR = p.e[T_R];
 }
 
-// Broadcast the line (lane i < 16 passes word i in w) to every lane.
-KV_DEV void load_pos(uint64_t w, Pos& p) {
+// Broadcast the line (lane q < 16 of the board's group passes word q in w) to every lane of the group.
+template <int W>
+KV_DEV void load_pos(uint64_t w, Pos& p, int lane) {
     uint64_t bb[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) bb[i] = shfl64(w, i);
-    p.meta = shfl64(w, 12);
+    for (int i = 0; i < 12; i++) bb[i] = sub_shfl64<W>(w, i, lane);
+    p.meta = sub_shfl64<W>(w, 12, lane);
     p.wtm = p.meta & 1;
 #pragma unroll
     for (int i = 0; i < 6; i++) {
@@ -160,8 +174,10 @@ struct KingOut {
 
 // getKingMoves + getCastleMoves for the king-like piece on ks (core/chessEngine.py:543-601), plus the
 // extra in-check filter of getValidMoves (:306-309) when mode == 1.  Warp-collective; result is uniform.
-KV_DEV KingOut king_phase(const Tables& T, int lane, const Pos& p, const Agg& g, int ks, int mode,
+template <int W>
+KV_DEV KingOut king_phase(const Tables& T, int lane_, const Pos& p, const Agg& g, int ks, int mode,
                           uint64_t valid, uint64_t pinned) {
+    const int lane = sub_q<W>(lane_);   // work item index inside the board's group
     const int home = p.wtm ? 60 : 4;
     // One convergent attacked() evaluation for all 13 work items: lanes 0-7 test a king step on the "king placed"
     // board (:556-563), lane 8 the king's own square, lanes 9,10 f,g and 11,12 c,d on the unmodified board (:576-599).
@@ -201,8 +217,8 @@ KV_DEV KingOut king_phase(const Tables& T, int lane, const Pos& p, const Agg& g,
         if (ok) a2 = attacked(T, g, t, p.wtm, p.ep, p.moved, p.akloc);
         ok = ok && !a2;
     }
-    const uint32_t okb = ballot(ok) & 0xFFu;
-    const uint32_t ab = ballot(att) >> 8;
+    const uint32_t okb = sub_ballot<W>(ok, lane_) & 0xFFu;
+    const uint32_t ab = sub_ballot<W>(att, lane_) >> 8;
     KingOut out;
     out.steps = okb;
     out.castle = 0;
@@ -322,31 +338,33 @@ struct GenOut {
     int flags;   // RF_*
 };
 
-// Everything getValidMoves decides, before the moves are laid out in order: per-lane slots (squares 2l, 2l+1).
+// What getValidMoves decides before any piece moves are generated.
 struct GenState {
     Pos p;
     Agg g;
-    Slot sl[2];
+    uint64_t valid, pinned;
     int mode;    // 0 no check, 1 one check, 2 two or more (king moves only)
     int flags;
+    int n_slots; // pieces that generate (mode 2: the king square alone)
 };
 
-// getValidMoves (core/chessEngine.py:277-321), part 1: pins/checks, king phases, per-piece destination sets.
-//   w       lane i < 16: word i of the board line; updated in place when the getKingMoves restore quirk
+// getValidMoves (core/chessEngine.py:277-321), part 1: pins and checks from the king location variable.
+//   w       lane q < 16 of the group: word q of the board line; updated in place when the getKingMoves restore quirk
 //           (:564, stale king location) rewrites the board (flags & RF_STATE_MUTATED)
-KV_DEV void movegen_slots_warp(const Tables& T, int lane, uint64_t& w, GenState& S) {
+template <int W>
+KV_DEV void movegen_prepare(const Tables& T, int lane, uint64_t& w, GenState& S) {
     Pos& p = S.p;
     Agg& g = S.g;
-    Slot* sl = S.sl;
-    load_pos(w, p);
+    const int q = sub_q<W>(lane);
+    load_pos<W>(w, p, lane);
     make_agg(p, g);
     int flags = 0;
 
     // ---- checkForPinsAndChecks: lanes 0-7 one ray each -------------------------------------------------
     uint64_t pinb = 0, validm = 0;
     bool chk = false;
-    if (lane < 8) {
-        const int d = lane;
+    if (q < 8) {
+        const int d = q;
         const uint64_t r = T.ray[d][p.kloc];
         const uint64_t b = r & g.occ;
         if (b) {
@@ -370,12 +388,12 @@ KV_DEV void movegen_slots_warp(const Tables& T, int lane, uint64_t& w, GenState&
             }
         }
     }
-    const uint32_t chkb = ballot(chk);
+    const uint32_t chkb = sub_ballot<W>(chk, lane);
     const uint64_t kn = T.knight7[p.kloc] & g.eN;   // 7-entry table: (-2,+1) is missing
     const int nchecks = popc32(chkb) + popc64(kn);
-    const uint64_t pinned = warp_or64(pinb, lane);
+    const uint64_t pinned = sub_or64<W>(pinb, lane);
     const int src = chkb ? ffs32(chkb) - 1 : 0;
-    uint64_t valid = shfl64(validm, src);
+    uint64_t valid = sub_shfl64<W>(validm, src, lane);
     if (kn) valid = kn;
     const int mode = nchecks == 0 ? 0 : (nchecks == 1 ? 1 : 2);
     if (nchecks) flags |= RF_E3_CHECK;
@@ -393,89 +411,110 @@ KV_DEV void movegen_slots_warp(const Tables& T, int lane, uint64_t& w, GenState&
             p.o[T_K] |= kb;
             make_agg(p, g);
             flags |= RF_STATE_MUTATED;
-            // write the rewritten board back into the line words held by lanes 0-11
-            if (lane < 12) {
+            // write the rewritten board back into the line words held by lanes 0-11 of the group
+            if (q < 12) {
                 w &= ~kb;
-                if (lane == (p.wtm ? 0 : 6)) w |= kb;
+                if (q == (p.wtm ? 0 : 6)) w |= kb;
             }
         }
     }
-
-    // ---- king phases --------------------------------------------------------------------------------
-    sl[0].kind = sl[1].kind = K_NONE;
-    sl[0].tgt = sl[1].tgt = sl[0].epm = sl[1].epm = 0;
-    sl[0].aux = sl[1].aux = 0;
-    {
-        uint64_t kings = mode == 2 ? bit(p.kloc) : p.o[T_K];
-        while (kings) {   // warp-uniform; one iteration on any reachable position
-            const int ks = ctz64(kings);
-            kings &= kings - 1;
-            const KingOut ko = king_phase(T, lane, p, g, ks, mode, valid, pinned);
-            if (lane == (ks >> 1)) {
-                Slot& s = (ks & 1) ? sl[1] : sl[0];
-                s.kind = K_KING;
-                s.tgt = king_steps_to_mask(ks, ko.steps);
-                s.aux = ko.castle;
-            }
-        }
-    }
-
-    // ---- every other piece: lane l owns squares 2l, 2l+1 ---------------------------------------------
-    if (mode != 2) {
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int s = 2 * lane + j;
-            const uint64_t sb = bit(s);
-            Slot& o = j ? sl[1] : sl[0];
-            if (!(g.own & sb) || (p.o[T_K] & sb)) continue;
-            const bool is_pinned = (pinned & sb) != 0;
-            int pd = 0;
-            if (is_pinned)
-                for (int d = 0; d < 8; d++)
-                    if (T.ray[d][p.kloc] & sb) pd = d;
-            uint64_t tgt = 0;
-            if (p.o[T_P] & sb) {
-                o.kind = K_PAWN;
-                const int r = s >> 3, c = s & 7;
-                const int dr = p.wtm ? -1 : 1;
-                const int fwd = dr * 8;
-                const int r1 = r + dr;
-                if (r1 >= 0 && r1 < 8) {
-                    if (!is_pinned || pd == (p.wtm ? D_N : D_S)) {
-                        if (!(g.occ & bit(s + fwd))) {
-                            tgt |= bit(s + fwd);
-                            if (r == (p.wtm ? 6 : 1) && !(g.occ & bit(s + 2 * fwd))) tgt |= bit(s + 2 * fwd);
-                        }
-                    }
-                    if (c > 0 && (!is_pinned || pd == (p.wtm ? D_NW : D_SW))) {
-                        const int t = s + fwd - 1;
-                        if (g.opp & bit(t)) tgt |= bit(t);
-                        else if (t == p.ep) { tgt |= bit(t); o.epm |= bit(t); }
-                    }
-                    if (c < 7 && (!is_pinned || pd == (p.wtm ? D_NE : D_SE))) {
-                        const int t = s + fwd + 1;
-                        if (g.opp & bit(t)) tgt |= bit(t);
-                        else if (t == p.ep) { tgt |= bit(t); o.epm |= bit(t); }
-                    }
-                }
-            } else if (p.o[T_N] & sb) {
-                o.kind = K_KNIGHT;
-                if (!is_pinned) tgt = T.knight[s] & ~g.own;
-            } else {
-                o.kind = K_SLIDER;
-                o.aux = (p.o[T_R] & sb) ? 0x0Fu : ((p.o[T_B] & sb) ? 0xF0u : 0xFFu);
-                if (o.aux & 0x0F) tgt |= rook_att(T, s, g.occ);
-                if (o.aux & 0xF0) tgt |= bishop_att(T, s, g.occ);
-                tgt &= ~g.own;
-                if (is_pinned) tgt &= T.ray[pd][s] | T.ray[dir_opp(pd)][s];
-            }
-            if (mode == 1) tgt &= valid;
-            o.tgt = tgt;
-            o.epm &= tgt;
-        }
-    }
+    S.valid = valid;
+    S.pinned = pinned;
     S.mode = mode;
     S.flags = flags;
+    S.n_slots = mode == 2 ? 1 : popc64(g.own);
+}
+
+// Destination set of the non-king piece of the side to move on square s (:433-441, :604-630 pin filter, :296-311
+// check filter).
+KV_DEV void piece_slot(const Tables& T, const GenState& S, int s, Slot& o) {
+    const Pos& p = S.p;
+    const Agg& g = S.g;
+    const uint64_t sb = bit(s);
+    const bool is_pinned = (S.pinned & sb) != 0;
+    int pd = 0;
+    if (is_pinned)
+        for (int d = 0; d < 8; d++)
+            if (T.ray[d][p.kloc] & sb) pd = d;
+    uint64_t tgt = 0;
+    if (p.o[T_P] & sb) {
+        o.kind = K_PAWN;
+        const int r = s >> 3, c = s & 7;
+        const int dr = p.wtm ? -1 : 1;
+        const int fwd = dr * 8;
+        const int r1 = r + dr;
+        if (r1 >= 0 && r1 < 8) {
+            if (!is_pinned || pd == (p.wtm ? D_N : D_S)) {
+                if (!(g.occ & bit(s + fwd))) {
+                    tgt |= bit(s + fwd);
+                    if (r == (p.wtm ? 6 : 1) && !(g.occ & bit(s + 2 * fwd))) tgt |= bit(s + 2 * fwd);
+                }
+            }
+            if (c > 0 && (!is_pinned || pd == (p.wtm ? D_NW : D_SW))) {
+                const int t = s + fwd - 1;
+                if (g.opp & bit(t)) tgt |= bit(t);
+                else if (t == p.ep) { tgt |= bit(t); o.epm |= bit(t); }
+            }
+            if (c < 7 && (!is_pinned || pd == (p.wtm ? D_NE : D_SE))) {
+                const int t = s + fwd + 1;
+                if (g.opp & bit(t)) tgt |= bit(t);
+                else if (t == p.ep) { tgt |= bit(t); o.epm |= bit(t); }
+            }
+        }
+    } else if (p.o[T_N] & sb) {
+        o.kind = K_KNIGHT;
+        if (!is_pinned) tgt = T.knight[s] & ~g.own;
+    } else {
+        o.kind = K_SLIDER;
+        o.aux = (p.o[T_R] & sb) ? 0x0Fu : ((p.o[T_B] & sb) ? 0xF0u : 0xFFu);
+        if (o.aux & 0x0F) tgt |= rook_att(T, s, g.occ);
+        if (o.aux & 0xF0) tgt |= bishop_att(T, s, g.occ);
+        tgt &= ~g.own;
+        if (is_pinned) tgt &= T.ray[pd][s] | T.ray[dir_opp(pd)][s];
+    }
+    if (S.mode == 1) tgt &= S.valid;
+    o.tgt = tgt;
+    o.epm &= tgt;
+}
+
+// getValidMoves, part 2: the pieces in square order, W per round; per_round(slot, square) is called by every lane of
+// the warp once per round (lanes without a piece pass a K_NONE slot), so it may use collectives.
+template <int W, class F>
+KV_DEV void movegen_rounds(const Tables& T, int lane, GenState& S, F&& per_round) {
+    const Pos& p = S.p;
+    const int q = sub_q<W>(lane);
+    for (int r = 0;; r++) {
+        const int i = r * W + q;
+        const bool act = i < S.n_slots;
+        // every board of the warp takes the same number of rounds (the collectives below need all 32 lanes)
+        if (W == 32) {
+            if (r * W >= S.n_slots) break;
+        } else if (ballot(r * W < S.n_slots) == 0) {
+            break;
+        }
+        Slot sl;
+        sl.kind = K_NONE;
+        sl.tgt = sl.epm = 0;
+        sl.aux = 0;
+        const int s = act ? (S.mode == 2 ? p.kloc : nth_set64(S.g.own, i)) : 0;
+        // king(s) of this round: one collective king_phase each (one on any reachable position)
+        const bool king_slot = act && (S.mode == 2 || (p.o[T_K] & bit(s)));
+        uint32_t kb = sub_ballot<W>(king_slot, lane);
+        while (W == 32 ? kb != 0 : ballot(kb != 0) != 0) {
+            const bool has = kb != 0;
+            const int src = has ? ffs32(kb) - 1 : 0;
+            const int ks = sub_shfl32<W>(s, src, lane);
+            kb &= kb - 1;
+            const KingOut ko = king_phase<W>(T, lane, p, S.g, ks, S.mode, S.valid, S.pinned);
+            if (has && q == src) {
+                sl.kind = K_KING;
+                sl.tgt = king_steps_to_mask(ks, ko.steps);
+                sl.aux = ko.castle;
+            }
+        }
+        if (act && !king_slot) piece_slot(T, S, s, sl);
+        per_round(sl, s);
+    }
 }
 
 // checkForEndConditions (:632-651, repetition excluded) + isDraw's only-kings clause, given the move count n
@@ -493,17 +532,19 @@ KV_DEV int movegen_end_flags(const Tables& T, const GenState& S, int n) {
     return flags;
 }
 
-// getValidMoves with the ordered move list written to mv (shared memory, MAX_MOVES u16:
+// getValidMoves with the ordered move list written to mv (the board's MAX_MOVES u16 of shared memory:
 // from | to<<6 | ep<<12 | castle<<13 | promo<<14).
-KV_DEV GenOut movegen_warp(const Tables& T, int lane, uint64_t& w, uint16_t* mv) {
+template <int W>
+KV_DEV GenOut movegen_sub(const Tables& T, int lane, uint64_t& w, uint16_t* mv) {
     GenState S;
-    movegen_slots_warp(T, lane, w, S);
-    const int c0 = slot_count(S.sl[0]), c1 = slot_count(S.sl[1]);
-    const int incl = warp_incl_scan(c0 + c1, lane);
-    const int n = shfl32(incl, 31);
-    int off = incl - (c0 + c1);
-    off = slot_emit(T, S.p, S.sl[0], (S.mode == 2) ? S.p.kloc : 2 * lane, mv, off);
-    off = slot_emit(T, S.p, S.sl[1], (S.mode == 2) ? S.p.kloc : 2 * lane + 1, mv, off);
+    movegen_prepare<W>(T, lane, w, S);
+    int n = 0;
+    movegen_rounds<W>(T, lane, S, [&](const Slot& sl, int s) {
+        const int c = slot_count(sl);
+        const int incl = sub_incl_scan<W>(c, lane);
+        slot_emit(T, S.p, sl, s, mv, n + incl - c);
+        n += sub_shfl32<W>(incl, W - 1, lane);
+    });
     syncwarp();
     GenOut out;
     out.n = n;
@@ -513,60 +554,68 @@ KV_DEV GenOut movegen_warp(const Tables& T, int lane, uint64_t& w, uint16_t* mv)
 
 // Bulk count without laying the list out (perft leaves): n plus captures | ep<<16 | castles<<32 | promos<<48
 // (a capture = destination occupied or e.p., Move.pieceCaptured != "--", core/chessEngine.py:699-703).
-KV_DEV GenOut movegen_count_warp(const Tables& T, int lane, uint64_t& w, uint64_t& cats) {
+template <int W>
+KV_DEV GenOut movegen_count_sub(const Tables& T, int lane, uint64_t& w, uint64_t& cats) {
     GenState S;
-    movegen_slots_warp(T, lane, w, S);
+    movegen_prepare<W>(T, lane, w, S);
     const uint64_t last = S.p.wtm ? 0xFFull : 0xFFull << 56;
-    uint64_t c = 0;
-    int n = 0;
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-        const Slot& sl = S.sl[j];
-        if (sl.kind == K_NONE) continue;
-        const int ncast = sl.kind == K_KING ? popc32(sl.aux) : 0;
-        n += popc64(sl.tgt) + ncast;
-        const uint64_t cap = (uint64_t)(popc64(sl.tgt & S.g.opp) + popc64(sl.epm));
+    // five 12-bit fields in one word (each <= 256 per lane and <= MAX_MOVES-ish per board): n, captures, ep, castles, promos
+    uint64_t acc = 0;
+    movegen_rounds<W>(T, lane, S, [&](const Slot& sl, int) {
+        if (sl.kind == K_NONE) return;
+        const uint64_t ncast = sl.kind == K_KING ? (uint64_t)popc32(sl.aux) : 0;
+        const uint64_t nep = (uint64_t)popc64(sl.epm);
+        const uint64_t cap = (uint64_t)popc64(sl.tgt & S.g.opp) + nep;
         const uint64_t pro = sl.kind == K_PAWN ? (uint64_t)popc64(sl.tgt & last) : 0;
-        c += cap + ((uint64_t)popc64(sl.epm) << 16) + ((uint64_t)ncast << 32) + (pro << 48);
-    }
-    n = warp_sum32(n, lane);
-    cats = warp_sum64(c, lane);
+        acc += ((uint64_t)popc64(sl.tgt) + ncast) | (cap << 12) | (nep << 24) | (ncast << 36) | (pro << 48);
+    });
+    acc = sub_sum64<W>(acc, lane);
+    const int n = (int)(acc & 0xFFF);
+    cats = ((acc >> 12) & 0xFFF) | (((acc >> 24) & 0xFFF) << 16) | (((acc >> 36) & 0xFFF) << 32) | (((acc >> 48) & 0xFFF) << 48);
     GenOut out;
     out.n = n;
     out.flags = movegen_end_flags(T, S, n);
     return out;
 }
 
+// one board per warp (the tree-search kernels)
+KV_DEV GenOut movegen_warp(const Tables& T, int lane, uint64_t& w, uint16_t* mv) { return movegen_sub<32>(T, lane, w, mv); }
+
 // makeMove (core/chessEngine.py:127-197), no legality check, mailbox write order preserved.
-// Lane l < 12 holds bitboard l in w, lane 12 the meta word; returns the lane's new word.
-KV_DEV uint64_t make_move_warp(int lane, uint64_t w, int mvw, int promo_type) {
+// Lane q < 12 of the board's group holds bitboard q in w, lane 12 the meta word; returns the lane's new word.
+// Convergent for any mix of moves in a warp (every ballot is reached by all lanes).
+template <int W>
+KV_DEV uint64_t make_move_sub(int lane, uint64_t w, int mvw, int promo_type) {
+    const int q = sub_q<W>(lane);
     const int from = mvw & 63, to = (mvw >> 6) & 63, fl = (mvw >> 12) & 7;
     const uint64_t fb = bit(from), tb = bit(to);
-    const bool bbl = lane < 12;
-    const uint32_t has_f = ballot(bbl && (w & fb));
-    const uint32_t has_t = ballot(bbl && (w & tb));
+    const bool bbl = q < 12;
+    const uint32_t has_f = sub_ballot<W>(bbl && (w & fb), lane);
+    const uint32_t has_t = sub_ballot<W>(bbl && (w & tb), lane);
     const int pm = has_f ? ffs32(has_f) - 1 : -1;
     const bool captured = (fl & MF_EP) || has_t;
     const int sr = from >> 3, sc = from & 7, er = to >> 3, ec = to & 7;
     if (bbl) {
         w &= ~fb;                       // board[start] = "--"
         w &= ~tb;                       // board[end] = pieceMoved
-        if (lane == pm) w |= tb;
+        if (q == pm) w |= tb;
         if (fl & MF_EP) w &= ~bit(sr * 8 + ec);   // :152-153
     }
-    if (fl & MF_CASTLE) {               // rook hop, :156-164
+    {                                   // rook hop, :156-164
         int rs = -1, rd = -1;
-        if (ec - sc == 2) {
-            if (ec + 1 < 8) { rs = er * 8 + ec + 1; rd = er * 8 + ec - 1; }
-        } else if (ec - 2 >= 0 && ec + 1 < 8) {
-            rs = er * 8 + ec - 2; rd = er * 8 + ec + 1;
+        if (fl & MF_CASTLE) {
+            if (ec - sc == 2) {
+                if (ec + 1 < 8) { rs = er * 8 + ec + 1; rd = er * 8 + ec - 1; }
+            } else if (ec - 2 >= 0 && ec + 1 < 8) {
+                rs = er * 8 + ec - 2; rd = er * 8 + ec + 1;
+            }
         }
+        const uint32_t has_r = sub_ballot<W>(bbl && rs >= 0 && (w & bit(rs & 63)), lane);
         if (rs >= 0) {
-            const uint32_t has_r = ballot(bbl && (w & bit(rs)));
             const int rp = has_r ? ffs32(has_r) - 1 : -1;
             if (bbl) {
                 w &= ~bit(rd);
-                if (lane == rp) w |= bit(rd);
+                if (q == rp) w |= bit(rd);
                 w &= ~bit(rs);
             }
         }
@@ -575,10 +624,10 @@ KV_DEV uint64_t make_move_warp(int lane, uint64_t w, int mvw, int promo_type) {
         const int pp = ((pm >= 0 && pm < 6) ? 0 : 6) + promo_type;
         if (bbl) {
             w &= ~tb;
-            if (lane == pp) w |= tb;
+            if (q == pp) w |= tb;
         }
     }
-    if (lane == 12) {
+    if (q == 12) {
         uint64_t m = w;
         int moved = (int)((m >> 1) & 63);
         int wk = (int)((m >> 16) & 63), bk = (int)((m >> 24) & 63);
@@ -596,11 +645,12 @@ KV_DEV uint64_t make_move_warp(int lane, uint64_t w, int mvw, int promo_type) {
     }
     return w;
 }
+KV_DEV uint64_t make_move_warp(int lane, uint64_t w, int mvw, int promo_type) { return make_move_sub<32>(lane, w, mvw, promo_type); }
 
 // squareUnderAttack(r, c) for all 64 squares of one board (core/chessEngine.py:400-415): bit r*8+c of the result.
 KV_DEV uint64_t attacked_mask_warp(const Tables& T, int lane, uint64_t w) {
     Pos p;
-    load_pos(w, p);
+    load_pos<32>(w, p, lane);
     Agg g;
     make_agg(p, g);
     const bool a0 = attacked(T, g, 2 * lane, p.wtm, p.ep, p.moved, p.akloc);
@@ -612,7 +662,7 @@ KV_DEV uint64_t attacked_mask_warp(const Tables& T, int lane, uint64_t w) {
     return m;
 }
 
-// ---- perft (kv_perft): one frontier board per warp -----------------------------------------------------
+// ---- perft (kv_perft): one frontier board per group of W lanes ---------------------------------------------
 KV_DEV uint64_t mix64(uint64_t x) {
     x ^= x >> 30;
     x *= 0xbf58476d1ce4e5b9ull;
@@ -622,69 +672,86 @@ KV_DEV uint64_t mix64(uint64_t x) {
     return x;
 }
 // order digest of one move list under path hash `path`: sum_k mix64(path + (k+1)*G + (mv_k << 32))
+template <int W>
 KV_DEV uint64_t list_digest(const uint16_t* mv, int n, uint64_t path, int lane) {
     uint64_t h = 0;
-    for (int k = lane; k < n; k += 32)
+    for (int k = sub_q<W>(lane); k < n; k += W)
         h += mix64(path + (uint64_t)(k + 1) * 0x9E3779B97F4A7C15ull + ((uint64_t)mv[k] << 32));
-    return warp_sum64(h, lane);
+    return sub_sum64<W>(h, lane);
 }
 KV_DEV uint64_t child_path(uint64_t path, int k) { return mix64(path ^ ((uint64_t)(k + 1) * 0xD6E8FEB86659FD93ull)); }
 
-// lane k of the warp owns accumulator k: nodes, captures, ep, castles, promos, digest, movegen calls
-KV_DEV void perft_acc_flush(uint64_t& accv, int root, uint64_t* out, int lane) {
-    if (root >= 0 && lane < 7 && accv) atomic_add_u64(out + (size_t)root * 8 + lane, accv);
+// lane q of the group owns accumulator q: nodes, captures, ep, castles, promos, digest, movegen calls
+KV_DEV void perft_acc_flush(uint64_t& accv, int root, uint64_t* out, int q) {
+    if (root >= 0 && q < 7 && accv) atomic_add_u64(out + (size_t)root * 8 + q, accv);
     accv = 0;
 }
 
-// Visit one frontier board.  LEAF: bulk-count its move list.  Otherwise: write every child board to `next`
-// (slots claimed with one atomic add per parent; the frontier is an unordered multiset and every output is an
-// order-independent sum).  w[13] = root id, w[14] = path hash.
-template <bool LEAF, bool DIGEST = true>
-KV_DEV void perft_visit_warp(const Tables& T, int lane, uint64_t w, uint16_t* mv, uint64_t& accv, int& acc_root,
-                             uint64_t* next, uint32_t* next_count, uint64_t* out) {
-    const int root = (int)(uint32_t)shfl64(w, 13);
-    const uint64_t path = shfl64(w, 14);
+// Visit one frontier board per group (valid = the group has one; a group without still runs the collectives, on an
+// empty line).  LEAF: bulk-count its move list.  Otherwise: write every child board to `next` (slots claimed with one
+// atomic add per parent; the frontier is an unordered multiset and every output is an order-independent sum).
+// w[13] = root id, w[14] = path hash.
+template <int W, bool LEAF, bool DIGEST = true>
+KV_DEV void perft_visit_sub(const Tables& T, int lane, uint64_t w, bool valid, uint16_t* mv, uint64_t& accv, int& acc_root,
+                            uint64_t* next, uint32_t* next_count, uint64_t* out) {
+    const int q = sub_q<W>(lane);
+    const int root_w = (int)(uint32_t)sub_shfl64<W>(w, 13, lane);   // (a collective: outside the conditional)
+    const int root = valid ? root_w : acc_root;
+    const uint64_t path = sub_shfl64<W>(w, 14, lane);
     if (root != acc_root) {
-        perft_acc_flush(accv, acc_root, out, lane);
+        perft_acc_flush(accv, acc_root, out, q);
         acc_root = root;
     }
     if (LEAF && !DIGEST) {   // count-only leaves: no ordered list, no digest
         uint64_t cats = 0;
-        const GenOut g = movegen_count_warp(T, lane, w, cats);
-        if (lane == 0) accv += (unsigned)(g.n < MAX_MOVES ? g.n : MAX_MOVES);
-        if (lane >= 1 && lane <= 4) accv += (cats >> (16 * (lane - 1))) & 0xFFFF;
-        if (lane == 6) accv += 1;
+        const GenOut g = movegen_count_sub<W>(T, lane, w, cats);
+        if (valid) {
+            if (q == 0) accv += (unsigned)(g.n < MAX_MOVES ? g.n : MAX_MOVES);
+            if (q >= 1 && q <= 4) accv += (cats >> (16 * (q - 1))) & 0xFFFF;
+            if (q == 6) accv += 1;
+        }
         return;
     }
     // w reflects the :564 rewrite afterwards, as the reference's makeMove would see it
-    const GenOut g = movegen_warp(T, lane, w, mv);
-    const int n = g.n < MAX_MOVES ? g.n : MAX_MOVES;
-    const uint64_t dig = list_digest(mv, n, path, lane);
+    const GenOut g = movegen_sub<W>(T, lane, w, mv);
+    const int n = valid ? (g.n < MAX_MOVES ? g.n : MAX_MOVES) : 0;
+    const uint64_t dig = list_digest<W>(mv, n, path, lane);
     if (LEAF) {
-        const uint64_t occ = warp_or64(lane < 12 ? w : 0ull, lane);
+        const uint64_t occ = sub_or64<W>(q < 12 ? w : 0ull, lane);
         uint64_t cats = 0;   // captures | ep<<16 | castles<<32 | promos<<48 (each <= 256)
-        for (int k = lane; k < n; k += 32) {
+        for (int k = q; k < n; k += W) {
             const int x = mv[k];
             const int fl = x >> 12;
             const uint64_t cap = ((fl & 1) || ((occ >> ((x >> 6) & 63)) & 1)) ? 1 : 0;
             cats += cap | ((uint64_t)(fl & 1) << 16) | ((uint64_t)((fl >> 1) & 1) << 32) |
                     ((uint64_t)((fl >> 2) & 1) << 48);
         }
-        cats = warp_sum64(cats, lane);
-        if (lane == 0) accv += (unsigned)n;
-        if (lane >= 1 && lane <= 4) accv += (cats >> (16 * (lane - 1))) & 0xFFFF;
+        cats = sub_sum64<W>(cats, lane);
+        if (q == 0) accv += (unsigned)n;
+        if (q >= 1 && q <= 4) accv += (cats >> (16 * (q - 1))) & 0xFFFF;
     } else {
         uint32_t base = 0;
-        if (lane == 0 && n) base = atomic_add_u32(next_count, (uint32_t)n);
-        base = (uint32_t)shfl32((int)base, 0);
-        for (int k = 0; k < n; k++) {
-            uint64_t c = make_move_warp(lane, w, mv[k], T_Q);
-            if (lane == 14) c = child_path(path, k);
-            if (lane < LINE_WORDS) next[(size_t)(base + k) * LINE_WORDS + lane] = c;
+        if (q == 0 && n) base = atomic_add_u32(next_count, (uint32_t)n);
+        base = (uint32_t)sub_shfl32<W>((int)base, 0, lane);
+        int nmax = n;                       // every group makes as many moves as the busiest one of the warp
+        if (W < 32) {
+#pragma unroll
+            for (int m = 16; m >= W; m >>= 1) {
+                const int o = shfl_xor32(nmax, m, lane);
+                nmax = o > nmax ? o : nmax;
+            }
+        }
+        for (int k = 0; k < nmax; k++) {
+            const bool live = k < n;
+            uint64_t c = make_move_sub<W>(lane, w, live ? mv[k] : 0, T_Q);
+            if (q == 14) c = child_path(path, k);
+            if (live && q < LINE_WORDS) next[(size_t)(base + k) * LINE_WORDS + q] = c;
         }
     }
-    if (lane == 5 && DIGEST) accv += dig;
-    if (lane == 6) accv += 1;
+    if (valid) {
+        if (q == 5 && DIGEST) accv += dig;
+        if (q == 6) accv += 1;
+    }
     syncwarp();
 }
 

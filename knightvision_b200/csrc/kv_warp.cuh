@@ -89,6 +89,73 @@ KV_DEV void mem_fence() { __threadfence(); }
 #endif
 
 namespace kv {
+// ---- sub-warp collectives: a warp holds 32 / W boards, W consecutive lanes each (W = 16 or 32).  Built on the
+// full-warp primitives above, so every lane of the warp must reach them together; q = lane & (W - 1) is the lane's
+// index inside its board's group.  xor / up shuffles with distances < W never leave the group.
+template <int W> KV_DEV int sub_q(int lane) { return lane & (W - 1); }
+template <int W> KV_DEV uint64_t sub_shfl64(uint64_t v, int src, int lane) { return shfl64(v, (lane & ~(W - 1)) | src); }
+template <int W> KV_DEV int sub_shfl32(int v, int src, int lane) { return shfl32(v, (lane & ~(W - 1)) | src); }
+template <int W> KV_DEV uint32_t sub_ballot(bool p, int lane) {
+    const uint32_t b = ballot(p);
+    return W == 32 ? b : ((b >> (lane & ~(W - 1) & 31)) & ((W == 32) ? 0xFFFFFFFFu : ((1u << (W & 31)) - 1u)));
+}
+template <int W> KV_DEV uint64_t sub_or64(uint64_t v, int lane) {
+#pragma unroll
+    for (int m = W / 2; m >= 1; m >>= 1) v |= shfl_xor64(v, m, lane);
+    return v;
+}
+template <int W> KV_DEV uint64_t sub_sum64(uint64_t v, int lane) {
+#pragma unroll
+    for (int m = W / 2; m >= 1; m >>= 1) v += shfl_xor64(v, m, lane);
+    return v;
+}
+template <int W> KV_DEV int sub_sum32(int v, int lane) {
+#pragma unroll
+    for (int m = W / 2; m >= 1; m >>= 1) v += shfl_xor32(v, m, lane);
+    return v;
+}
+template <int W> KV_DEV int sub_max32(int v, int lane) {
+#pragma unroll
+    for (int m = W / 2; m >= 1; m >>= 1) {
+        const int o = shfl_xor32(v, m, lane);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+template <int W> KV_DEV int sub_incl_scan(int v, int lane) {
+    const int q = lane & (W - 1);
+#pragma unroll
+    for (int d = 1; d < W; d <<= 1) {
+        const int t = shfl_up32(v, d, lane);
+        if (q >= d) v += t;
+    }
+    return v;
+}
+// index of the i-th (0-based) set bit of m (m has more than i bits set): popcount binary search
+KV_DEV int nth_set64(uint64_t m, int i) {
+    uint32_t x = (uint32_t)m;
+    int pos = 0;
+    const int c = popc32(x);
+    if (i >= c) {
+        i -= c;
+        x = (uint32_t)(m >> 32);
+        pos = 32;
+    }
+#pragma unroll
+    for (int sh = 16; sh >= 1; sh >>= 1) {
+        const uint32_t low = x & ((1u << sh) - 1u);
+        const int cl = popc32(low);
+        if (i >= cl) {
+            i -= cl;
+            x >>= sh;
+            pos += sh;
+        } else {
+            x = low;
+        }
+    }
+    return pos;
+}
+
 // inclusive prefix sum over the warp
 KV_DEV int warp_incl_scan(int v, int lane) {
 #pragma unroll

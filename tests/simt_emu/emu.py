@@ -34,6 +34,11 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+def set_width(w: int):
+    """Lanes per board of movegen / make_moves / perft below: 32 (one board per warp) or 16 (two boards per warp)."""
+    lib().kvemu_set_width(ctypes.c_int(w))
+
+
 def movegen(lines, stride=256):
     lines = np.ascontiguousarray(lines, dtype=np.uint64).copy()
     n = lines.shape[0]

@@ -104,32 +104,99 @@ void run_warp(std::function<void(int)> body) {
 
 static const kv::Tables g_tables = kv::make_tables();
 
-extern "C" {
+// Lanes per board in the rules entry points below: 32 (one board per warp, what the tree-search kernels use) or 16 (two
+// boards per warp, what kv_rules.cu's kernels use).  A trailing odd board leaves the second group without a board.
+static int g_emu_w = 32;
 
-__attribute__((visibility("default"))) void kvemu_movegen(uint64_t* lines, int n, uint16_t* moves, int stride,
-                                                           int32_t* counts, int32_t* flags) {
-    for (int i = 0; i < n; i++) {
-        uint16_t mv[kv::MAX_MOVES];
+template <int W>
+static void emu_movegen_t(uint64_t* lines, int n, uint16_t* moves, int stride, int32_t* counts, int32_t* flags) {
+    constexpr int NB = 32 / W;
+    for (int i0 = 0; i0 < n; i0 += NB) {
+        uint16_t mv[NB][kv::MAX_MOVES];
         memset(mv, 0, sizeof(mv));
-        uint64_t* line = lines + 16 * (size_t)i;
         kv::GenOut out[32];
         uint64_t neww[32];
         kvemu::run_warp([&](int lane) {
-            uint64_t w = lane < 16 ? line[lane] : 0;
-            out[lane] = kv::movegen_warp(g_tables, lane, w, mv);
+            const int grp = lane / W, q = lane % W, i = i0 + grp;
+            uint64_t w = (i < n && q < 16) ? lines[16 * (size_t)i + q] : 0;
+            out[lane] = kv::movegen_sub<W>(g_tables, lane, w, mv[grp]);
             neww[lane] = w;
         });
-        for (int l = 1; l < 32; l++)
-            if (out[l].n != out[0].n || out[l].flags != out[0].flags) {
-                fprintf(stderr, "kvemu: non-uniform movegen result\n");
-                abort();
-            }
-        if (out[0].flags & kv::RF_STATE_MUTATED)
-            for (int l = 0; l < 16; l++) line[l] = neww[l];
-        counts[i] = out[0].n;
-        flags[i] = out[0].flags;
-        for (int k = 0; k < out[0].n && k < stride && k < kv::MAX_MOVES; k++) moves[(size_t)i * stride + k] = mv[k];
+        for (int grp = 0; grp < NB && i0 + grp < n; grp++) {
+            const int i = i0 + grp;
+            uint64_t* line = lines + 16 * (size_t)i;
+            for (int l = 1; l < W; l++)
+                if (out[grp * W + l].n != out[grp * W].n || out[grp * W + l].flags != out[grp * W].flags) {
+                    fprintf(stderr, "kvemu: non-uniform movegen result\n");
+                    abort();
+                }
+            const kv::GenOut o = out[grp * W];
+            if (o.flags & kv::RF_STATE_MUTATED)
+                for (int l = 0; l < 16; l++) line[l] = neww[grp * W + l];
+            counts[i] = o.n;
+            flags[i] = o.flags;
+            for (int k = 0; k < o.n && k < stride && k < kv::MAX_MOVES; k++) moves[(size_t)i * stride + k] = mv[grp][k];
+        }
     }
+}
+
+template <int W>
+static void emu_make_moves_t(uint64_t* lines, int n, const uint16_t* mv) {
+    constexpr int NB = 32 / W;
+    for (int i0 = 0; i0 < n; i0 += NB) {
+        uint64_t neww[32];
+        kvemu::run_warp([&](int lane) {
+            const int grp = lane / W, q = lane % W, i = i0 + grp;
+            const bool valid = i < n && mv[i] != 0xFFFF;
+            uint64_t w = (valid && q < 16) ? lines[16 * (size_t)i + q] : 0;
+            neww[lane] = kv::make_move_sub<W>(lane, w, valid ? mv[i] : 0, kv::T_Q);
+        });
+        for (int grp = 0; grp < NB && i0 + grp < n; grp++)
+            if (mv[i0 + grp] != 0xFFFF)
+                for (int l = 0; l < 16; l++) lines[16 * (size_t)(i0 + grp) + l] = neww[grp * W + l];
+    }
+}
+
+// kv_perft's level loop over host memory (same chunked depth-first / breadth-first-in-chunk order)
+static bool g_emu_digest = true;
+template <int W>
+static void emu_perft_rec(std::vector<uint64_t>& cur, int remaining, uint64_t* out) {
+    constexpr int NB = 32 / W;
+    const int m = (int)(cur.size() / 16);
+    uint16_t mv[NB][kv::MAX_MOVES];
+    const bool leaf = remaining == 1;
+    std::vector<uint64_t> next(leaf ? 0 : (size_t)m * kv::MAX_MOVES * 16);
+    uint32_t cnt = 0;
+    for (int i0 = 0; i0 < m; i0 += NB) {
+        uint64_t acc[32] = {0};
+        kvemu::run_warp([&](int lane) {
+            const int grp = lane / W, q = lane % W, i = i0 + grp;
+            const bool valid = i < m;
+            int acc_root = -1;
+            uint64_t w = (valid && q < 16) ? cur[16 * (size_t)i + q] : 0;
+            if (leaf) {
+                if (g_emu_digest) kv::perft_visit_sub<W, true, true>(g_tables, lane, w, valid, mv[grp], acc[lane], acc_root, nullptr, nullptr, out);
+                else kv::perft_visit_sub<W, true, false>(g_tables, lane, w, valid, mv[grp], acc[lane], acc_root, nullptr, nullptr, out);
+            } else {
+                if (g_emu_digest) kv::perft_visit_sub<W, false, true>(g_tables, lane, w, valid, mv[grp], acc[lane], acc_root, next.data(), &cnt, out);
+                else kv::perft_visit_sub<W, false, false>(g_tables, lane, w, valid, mv[grp], acc[lane], acc_root, next.data(), &cnt, out);
+            }
+            kv::perft_acc_flush(acc[lane], acc_root, out, q);
+        });
+    }
+    if (leaf) return;
+    next.resize((size_t)cnt * 16);
+    if (cnt) emu_perft_rec<W>(next, remaining - 1, out);
+}
+
+extern "C" {
+
+__attribute__((visibility("default"))) void kvemu_set_width(int w) { g_emu_w = (w == 16) ? 16 : 32; }
+
+__attribute__((visibility("default"))) void kvemu_movegen(uint64_t* lines, int n, uint16_t* moves, int stride,
+                                                           int32_t* counts, int32_t* flags) {
+    if (g_emu_w == 16) emu_movegen_t<16>(lines, n, moves, stride, counts, flags);
+    else emu_movegen_t<32>(lines, n, moves, stride, counts, flags);
 }
 
 __attribute__((visibility("default"))) void kvemu_attacked(const uint64_t* lines, int n, uint64_t* masks) {
@@ -144,49 +211,8 @@ __attribute__((visibility("default"))) void kvemu_attacked(const uint64_t* lines
 }
 
 __attribute__((visibility("default"))) void kvemu_make_moves(uint64_t* lines, int n, const uint16_t* mv) {
-    for (int i = 0; i < n; i++) {
-        uint64_t* line = lines + 16 * (size_t)i;
-        uint64_t neww[32];
-        kvemu::run_warp([&](int lane) {
-            uint64_t w = lane < 16 ? line[lane] : 0;
-            neww[lane] = kv::make_move_warp(lane, w, mv[i], kv::T_Q);
-        });
-        for (int l = 0; l < 16; l++) line[l] = neww[l];
-    }
-}
-
-// kv_perft's level loop over host memory (same chunked depth-first / breadth-first-in-chunk order)
-static bool g_emu_digest = true;
-static void emu_perft_rec(std::vector<uint64_t>& cur, int remaining, uint64_t* out) {
-    const int m = (int)(cur.size() / 16);
-    uint16_t mv[kv::MAX_MOVES];
-    if (remaining == 1) {
-        for (int i = 0; i < m; i++) {
-            uint64_t acc[32] = {0};
-            kvemu::run_warp([&](int lane) {
-                int acc_root = -1;
-                uint64_t w = lane < 16 ? cur[16 * (size_t)i + lane] : 0;
-                if (g_emu_digest) kv::perft_visit_warp<true, true>(g_tables, lane, w, mv, acc[lane], acc_root, nullptr, nullptr, out);
-                else kv::perft_visit_warp<true, false>(g_tables, lane, w, mv, acc[lane], acc_root, nullptr, nullptr, out);
-                kv::perft_acc_flush(acc[lane], acc_root, out, lane);
-            });
-        }
-        return;
-    }
-    std::vector<uint64_t> next((size_t)m * kv::MAX_MOVES * 16);
-    uint32_t cnt = 0;
-    for (int i = 0; i < m; i++) {
-        uint64_t acc[32] = {0};
-        kvemu::run_warp([&](int lane) {
-            int acc_root = -1;
-            uint64_t w = lane < 16 ? cur[16 * (size_t)i + lane] : 0;
-            if (g_emu_digest) kv::perft_visit_warp<false, true>(g_tables, lane, w, mv, acc[lane], acc_root, next.data(), &cnt, out);
-            else kv::perft_visit_warp<false, false>(g_tables, lane, w, mv, acc[lane], acc_root, next.data(), &cnt, out);
-            kv::perft_acc_flush(acc[lane], acc_root, out, lane);
-        });
-    }
-    next.resize((size_t)cnt * 16);
-    if (cnt) emu_perft_rec(next, remaining - 1, out);
+    if (g_emu_w == 16) emu_make_moves_t<16>(lines, n, mv);
+    else emu_make_moves_t<32>(lines, n, mv);
 }
 
 __attribute__((visibility("default"))) void kvemu_perft(const uint64_t* roots, int n, int depth, uint64_t* out) {
@@ -199,7 +225,8 @@ __attribute__((visibility("default"))) void kvemu_perft(const uint64_t* roots, i
         cur[16 * (size_t)i + 14] = 0;
         cur[16 * (size_t)i + 15] = 0;
     }
-    emu_perft_rec(cur, depth, out);
+    if (g_emu_w == 16) emu_perft_rec<16>(cur, depth, out);
+    else emu_perft_rec<32>(cur, depth, out);
 }
 
 }  // extern "C"

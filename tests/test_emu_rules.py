@@ -10,6 +10,36 @@ import helpers as H
 from simt_emu import emu
 
 
+@pytest.fixture(params=[32, 16], autouse=True, ids=["warp_per_board", "half_warp_per_board"])
+def lanes_per_board(request):
+    """Every test runs the kernel source both ways: 32 lanes per board (the tree-search kernels) and 16 lanes per board,
+    two boards per warp (kv_rules.cu's perft / movegen / make-move kernels)."""
+    emu.set_width(request.param)
+    yield request.param
+    emu.set_width(32)
+
+
+def test_emu_odd_board_counts_and_mixed_pairs():
+    """Two boards per warp: a trailing odd board, pairs whose boards take different numbers of king passes / piece rounds
+    (wild boards with several kings or more than 16 pieces next to tame ones), pairs with different move counts."""
+    syn = H.synthetic_lines(301, 77, wild=True)
+    tame = H.random_playout_positions(n_games=2, max_plies=80, seed=9)[:150]
+    k = min(len(syn), len(tame))
+    mix = np.empty((2 * k, 16), dtype=np.uint64)
+    mix[0::2] = syn[:k]
+    mix[1::2] = tame[:k]
+    mix = mix[:2 * k - 1]                                   # odd count
+    got = emu.movegen(mix)
+    H.check_movegen_against(mix, got)
+    ok = got[1] > 0
+    mv = np.where(ok, got[0][np.arange(len(mix)), (got[1] - 1).clip(min=0)], 0xFFFF).astype(np.uint16)   # last legal move
+    mv[::7] = 0xFFFF                                        # some boards are skipped
+    out = emu.make_moves(got[3], mv)
+    want = O.make_moves(got[3], mv)
+    want[mv == 0xFFFF] = got[3][mv == 0xFFFF]               # 0xFFFF = leave the board untouched (kv_make_moves)
+    assert np.array_equal(out[:, :13], want[:, :13])
+
+
 @pytest.mark.parametrize("name,step", [("playouts", 4), ("synthetic", 1)])
 def test_emu_movegen_golden(name, step):
     rows = H.load_rows(name)
