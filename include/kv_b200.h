@@ -150,7 +150,7 @@ KV_API int kv_net_forward_planes(kv_ctx* ctx, const float* d_planes, int n, floa
 /* ---- self-play engine: batched PUCT search + game records (replaces the game loop of scripts/self_play.py:111-255;
  *      the tree search itself is new functionality, specified in DESIGN.md §MCTS and oracle/kv_oracle.c) ----------- */
 /* n_games concurrent games on this GPU, `sims` simulations per move (one in flight per game), edges_per_node = edge
- * pool sizing (0 = 48), max_plies = ply cap (draw), temp_plies = plies that sample the move from the visit counts,
+ * pool sizing (0 = 64), max_plies = ply cap (draw), temp_plies = plies that sample the move from the visit counts,
  * eval_mode 0 = hash test evaluator, 1 = the network of kv_net_create (max_boards >= n_games). */
 KV_API int kv_mcts_create(kv_ctx* ctx, int n_games, int sims, int edges_per_node, int max_plies, int temp_plies,
                           float c_puct, float dir_alpha, float dir_eps, uint64_t seed, int eval_mode);

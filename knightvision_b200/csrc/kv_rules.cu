@@ -128,10 +128,13 @@ __global__ void __launch_bounds__(kThreads, KV_RULES_MIN_CTAS) perft_level_kerne
     uint64_t accv = 0;
     int acc_root = -1;
     uint16_t* mv = sm.mv[wid * kBoardsPerWarp + grp];
+    // the next pair's lines are requested before the current pair is visited (the visit is ~1 500 warp instructions)
+    uint64_t wn = ld_line_word(cur + (size_t)(lo + grp < hi ? lo + grp : lo) * LINE_WORDS, q, lo + grp < hi);
     for (int i0 = lo; i0 < hi; i0 += kBoardsPerWarp) {
-        const int i = i0 + grp;
-        const bool valid = i < hi;
-        const uint64_t w = ld_line_word(cur + (size_t)(valid ? i : i0) * LINE_WORDS, q, valid);
+        const bool valid = i0 + grp < hi;
+        const uint64_t w = wn;
+        const int in = i0 + kBoardsPerWarp + grp;
+        wn = ld_line_word(cur + (size_t)(in < hi ? in : lo) * LINE_WORDS, q, in < hi);
         perft_visit_sub<kW, LEAF, DIGEST>(sm.tab, lane, w, valid, mv, accv, acc_root, next, next_count, out);
     }
     perft_acc_flush(accv, acc_root, out, q);

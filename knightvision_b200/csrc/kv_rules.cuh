@@ -148,15 +148,14 @@ KV_DEV void make_agg(const Pos& p, Agg& g) {
 // Broadcast the line (lane q < 16 of the board's group passes word q in w) to every lane of the group.
 template <int W>
 KV_DEV void load_pos(uint64_t w, Pos& p, int lane) {
-    uint64_t bb[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) bb[i] = sub_shfl64<W>(w, i, lane);
     p.meta = sub_shfl64<W>(w, 12, lane);
     p.wtm = p.meta & 1;
+    // side to move first: the shuffle source is chosen by the side bit, so no selects afterwards
+    const int so = p.wtm ? 0 : 6, se = 6 - so;
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-        p.o[i] = p.wtm ? bb[i] : bb[6 + i];
-        p.e[i] = p.wtm ? bb[6 + i] : bb[i];
+        p.o[i] = sub_shfl64<W>(w, so + i, lane);
+        p.e[i] = sub_shfl64<W>(w, se + i, lane);
     }
     p.moved = (int)((p.meta >> 1) & 63);
     p.ep = (int)((p.meta >> 8) & 127);
@@ -185,8 +184,9 @@ KV_DEV KingOut king_phase(const Tables& T, int lane_, const Pos& p, const Agg& g
     int t = 0;
     bool active = false;
     if (lane < 8) {
-        const int dr = (lane < 3) ? -1 : (lane < 5 ? 0 : 1);
-        const int dc = (lane == 0 || lane == 3 || lane == 5) ? -1 : ((lane == 1 || lane == 6) ? 0 : 1);
+        // step k of getKingMoves' order (:544-546): row offset + 1 = {0,0,0,1,1,2,2,2}, column offset + 1 = {0,1,2,0,2,0,1,2}
+        const int dr = (int)((0xA940u >> (2 * lane)) & 3u) - 1;
+        const int dc = (int)((0x9224u >> (2 * lane)) & 3u) - 1;
         const int er = (ks >> 3) + dr, ec = (ks & 7) + dc;
         if (er >= 0 && er < 8 && ec >= 0 && ec < 8) {
             t = er * 8 + ec;
@@ -259,15 +259,12 @@ KV_DEV KingOut king_phase(const Tables& T, int lane_, const Pos& p, const Agg& g
     return out;
 }
 
+// Destination squares of the legal king steps (bit k of `steps` = step k of getKingMoves' order; only on-board steps are
+// ever set).  The eight steps form a 3 x 3 block around ks: lay them out as three board rows with the king's square at
+// bit 9 and shift the block to ks.
 KV_DEV uint64_t king_steps_to_mask(int ks, uint32_t steps) {
-    uint64_t m = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int dr = (k < 3) ? -1 : (k < 5 ? 0 : 1);
-        const int dc = (k == 0 || k == 3 || k == 5) ? -1 : ((k == 1 || k == 6) ? 0 : 1);
-        if ((steps >> k) & 1) m |= bit(((ks >> 3) + dr) * 8 + (ks & 7) + dc);
-    }
-    return m;
+    const uint32_t pat = (steps & 7u) | ((steps & 8u) << 5) | ((steps & 16u) << 6) | ((steps & 0xE0u) << 11);
+    return ks >= 9 ? ((uint64_t)pat << (ks - 9)) : ((uint64_t)pat >> (9 - ks));
 }
 
 enum SlotKind : int { K_NONE = 0, K_PAWN = 1, K_KNIGHT = 2, K_SLIDER = 3, K_KING = 4 };
@@ -552,7 +549,8 @@ KV_DEV GenOut movegen_sub(const Tables& T, int lane, uint64_t& w, uint16_t* mv) 
     return out;
 }
 
-// Bulk count without laying the list out (perft leaves): n plus captures | ep<<16 | castles<<32 | promos<<48
+// Bulk count without laying the list out (perft leaves): n, and in `cats` five 12-bit fields
+// n | captures<<12 | ep<<24 | castles<<36 | promos<<48
 // (a capture = destination occupied or e.p., Move.pieceCaptured != "--", core/chessEngine.py:699-703).
 template <int W>
 KV_DEV GenOut movegen_count_sub(const Tables& T, int lane, uint64_t& w, uint64_t& cats) {
@@ -571,7 +569,7 @@ KV_DEV GenOut movegen_count_sub(const Tables& T, int lane, uint64_t& w, uint64_t
     });
     acc = sub_sum64<W>(acc, lane);
     const int n = (int)(acc & 0xFFF);
-    cats = ((acc >> 12) & 0xFFF) | (((acc >> 24) & 0xFFF) << 16) | (((acc >> 36) & 0xFFF) << 32) | (((acc >> 48) & 0xFFF) << 48);
+    cats = acc;
     GenOut out;
     out.n = n;
     out.flags = movegen_end_flags(T, S, n);
@@ -707,7 +705,7 @@ KV_DEV void perft_visit_sub(const Tables& T, int lane, uint64_t w, bool valid, u
         const GenOut g = movegen_count_sub<W>(T, lane, w, cats);
         if (valid) {
             if (q == 0) accv += (unsigned)(g.n < MAX_MOVES ? g.n : MAX_MOVES);
-            if (q >= 1 && q <= 4) accv += (cats >> (16 * (q - 1))) & 0xFFFF;
+            if (q >= 1 && q <= 4) accv += (cats >> (12 * q)) & 0xFFF;
             if (q == 6) accv += 1;
         }
         return;

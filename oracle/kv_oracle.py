@@ -104,11 +104,11 @@ class MctsCfg(ctypes.Structure):
                 ("pad", ctypes.c_int32)]
 
 
-def mcts_cfg(sims, edges_per_node=48, temp_plies=0, max_plies=1 << 20, c_puct=1.5, dir_alpha=0.3, dir_eps=0.25, seed=1,
+def mcts_cfg(sims, edges_per_node=64, temp_plies=0, max_plies=1 << 20, c_puct=1.5, dir_alpha=0.3, dir_eps=0.25, seed=1,
              inflight=1, resign_thr=-0.7, resign_min_plies=15, root_mix=-1):
     """Defaults follow kv_mcts_create_k: the reference's resign rule (scripts/self_play.py:184-189) and, when sims == 1,
     its prior mixing over all 4096 indices (:150-167)."""
-    return MctsCfg(sims, max(sims * (edges_per_node or 48), 256), temp_plies, max_plies, c_puct, dir_alpha, dir_eps,
+    return MctsCfg(sims, max(sims * (edges_per_node or 64), 256), temp_plies, max_plies, c_puct, dir_alpha, dir_eps,
                    inflight, seed, resign_thr, resign_min_plies, int(sims == 1) if root_mix < 0 else root_mix, 0)
 
 

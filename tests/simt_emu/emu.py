@@ -70,7 +70,7 @@ def perft(roots, depth):
     return out
 
 
-def mcts_search(start, sims, id_base=0, ply=0, edges_per_node=48, c_puct=1.5, dir_alpha=0.3, dir_eps=0.25, seed=1,
+def mcts_search(start, sims, id_base=0, ply=0, edges_per_node=64, c_puct=1.5, dir_alpha=0.3, dir_eps=0.25, seed=1,
                 inflight=1):
     start = np.ascontiguousarray(start, dtype=np.uint64)
     G = start.shape[0]
@@ -88,7 +88,7 @@ def set_rules(resign_thr=-0.7, resign_min_plies=15, root_mix=-1):
     lib().kvemu_set_rules(ctypes.c_float(resign_thr), ctypes.c_int(resign_min_plies), ctypes.c_int(root_mix))
 
 
-def selfplay(start, sims, max_plies, temp_plies, id_base=0, edges_per_node=48, c_puct=1.5, dir_alpha=0.3, dir_eps=0.25,
+def selfplay(start, sims, max_plies, temp_plies, id_base=0, edges_per_node=64, c_puct=1.5, dir_alpha=0.3, dir_eps=0.25,
              seed=1, cache_log2=0, return_counts=False, inflight=1, pipe_order=0, script_moves=None, script_vals=None,
              return_flags=False):
     start = np.ascontiguousarray(start, dtype=np.uint64)

@@ -260,7 +260,7 @@ static EmuMcts* emu_mcts_new(int G, int sims, int edges_per_node, int max_plies,
     kv::MctsCfg& c = m->cfg;
     c.sims = sims;
     c.node_cap = sims;
-    c.edge_cap = sims * (edges_per_node > 0 ? edges_per_node : 48);
+    c.edge_cap = sims * (edges_per_node > 0 ? edges_per_node : 64);
     if (c.edge_cap < kv::MAX_MOVES) c.edge_cap = kv::MAX_MOVES;
     c.temp_plies = temp_plies;
     c.max_plies = max_plies;
