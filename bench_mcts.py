@@ -229,13 +229,18 @@ def run(args, rank, world, local_rank):
             net.mark_weights_changed()
             net.sync_weights()                       # host fp32 parameters -> device staging blob -> fold kernels
         torch.cuda.synchronize()
-        t1 = time.perf_counter()
+        commit = (time.perf_counter() - t0) * 1e3
+        bcast = 0.0
         if world > 1:
+            dist.barrier()                           # the other ranks wait for the fold here, not inside the broadcast timing
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
             dist.broadcast(eng.net_folded_tensor(), src=0)
             if rank != 0:
                 eng.net_adopt_folded()
             torch.cuda.synchronize()
-        return (t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3
+            bcast = (time.perf_counter() - t1) * 1e3
+        return commit, bcast
 
     def timed_moves(n_moves, profile=False):
         """n_moves moves for every game; returns (device ms, status before, status after, per-kernel profile, launches)."""
@@ -265,6 +270,8 @@ def run(args, rank, world, local_rank):
     for _ in range(warm):
         eng.mcts_run_move()
     torch.cuda.synchronize()
+    # first use of the record kernels and of the NCCL point-to-point channels behind gather (connection set-up is seconds)
+    P.gather_records(*eng.mcts_records()[:3], rank * G, eng.mcts_records()[3], dst=0)
     snapshot_h = eng.mcts_roots().cpu().pin_memory()      # positions at the start of the timed region (for B and C)
     clocks.start()
     dev_ms, st0, st1, prof, launches = timed_moves(args.steps, profile=True)
@@ -305,9 +312,15 @@ def run(args, rank, world, local_rank):
     torch.cuda.synchronize()
     tg = time.perf_counter()
     lines_r, move_r, reward_r, game_r = eng.mcts_records()
+    torch.cuda.synchronize()
+    records_ms = (time.perf_counter() - tg) * 1e3
+    if world > 1:
+        dist.barrier()                               # ranks finish their moves at different times: not part of the gather
+    tg = time.perf_counter()
     got = P.gather_records(lines_r, move_r, reward_r, rank * G, game_r, dst=0)
     torch.cuda.synchronize()
     gather_ms = (time.perf_counter() - tg) * 1e3
+    tt = time.perf_counter()
     rec, d2h = 0, 0
     if rank == 0:
         gl, gm, gr, gg = got
@@ -318,6 +331,7 @@ def run(args, rank, world, local_rank):
         d2h = planes.nbytes + gm_h.nbytes + gr_h.nbytes
         del recs, planes
     torch.cuda.synchronize()
+    tuples_ms = (time.perf_counter() - tt) * 1e3
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop()
     e2e_positions = e1["plies"] - e0["plies"]
@@ -372,8 +386,8 @@ def run(args, rank, world, local_rank):
         p_ms, p0, p1, _, _ = timed_moves(POLICY_MODE_PLIES)
         pm = {"ms": p_ms, "positions": p1["plies"] - p0["plies"], "evals": p1["evals"] - p0["evals"]}
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, nocache["ms"] if nocache else 0.0, r_ms, commit_ms, bcast_ms, gather_ms],
-                     dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s * 1e3, nocache["ms"] if nocache else 0.0, r_ms, commit_ms, bcast_ms, gather_ms,
+                      records_ms, tuples_ms], dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(sims_done), float(evals), float(positions), float(rec), float(hits), float(r_sims),
                         float(r_evals), float(e2e_positions), float(st1["overflow"]), float(st0["done"]), float(st1["done"]),
                         float(gather_bytes), float(nocache["sims"] if nocache else 0)], dtype=torch.float64, device=dev)
@@ -383,7 +397,7 @@ def run(args, rank, world, local_rank):
     per_rank_ms = _gather_list(dev_ms / args.steps, world, dev)
     per_rank_mhz = _gather_list(clk.get("sm_mhz") or 0.0, world, dev)
     per_rank_conv = _gather_list(prof["net_conv"][0] / args.steps, world, dev)
-    dev_ms, e2e_ms, nocache_ms, r_ms, commit_ms, bcast_ms, gather_ms = (float(x) for x in t)
+    dev_ms, e2e_ms, nocache_ms, r_ms, commit_ms, bcast_ms, gather_ms, records_ms, tuples_ms = (float(x) for x in t)
     (sims_all, evals_all, pos_all, rec_all, hits_all, r_sims_all, r_evals_all, e2e_pos_all, overflow_all, done0_all,
      done1_all, gather_bytes_all, nocache_sims_all) = (float(x) for x in cnt)
     sub = sub_records(args, eng, rank, world, local_rank) if os.getenv("KV_BENCH_SUB", "1") != "0" else None
@@ -413,7 +427,7 @@ def run(args, rank, world, local_rank):
         "per_rank": {"ms_per_step": per_rank_ms, "sm_mhz_median": per_rank_mhz, "tower_kernel_ms_per_step": per_rank_conv,
                      "note": "value uses the slowest rank (max over ranks); no collective runs inside the timed window"},
         "ceiling": ({"net_evals_per_s_at_kernel_rate": ceiling_evals,
-                     "sims_per_s_at_this_evals_per_sim": ceiling_evals / (evals_all / sims_all) / 1.0 * 1.0 if evals_all else None,
+                     "sims_per_s_at_this_evals_per_sim": ceiling_evals / (evals_all / sims_all) if evals_all else None,
                      "achieved_fraction": (value / world) / (ceiling_evals / (evals_all / sims_all)) if evals_all else None,
                      "evals_per_sim_needed_for_1e6_sims_per_s": ceiling_evals / 1e6,
                      "note": "per GPU: the tensor-core tower bounds evaluations/s; sims/s = evaluations/s / (evaluations per "
@@ -456,7 +470,11 @@ def run(args, rank, world, local_rank):
                 "d2h_bytes_per_step": d2h // e2e_steps, "records_returned": rec_all, "steps": e2e_steps,
                 "commit_ms": commit_ms, "broadcast_ms": bcast_ms,
                 "broadcast_bytes": int(eng._lib.kv_net_folded_bytes(eng.ctx)) if world > 1 else 0,
-                "gather_ms": gather_ms, "gather_bytes": gather_bytes_all,
+                "records_ms": records_ms, "gather_ms": gather_ms, "gather_bytes": gather_bytes_all, "tuples_ms": tuples_ms,
+                "phases_note": ("commit = fp32 parameters (host) -> device -> fold, on the trainer rank; broadcast = NCCL broadcast "
+                                "of the folded blob + adopt; records = per-rank compaction of the game records on the device; "
+                                "gather = NCCL gather of the packed records to rank 0; tuples = kv_encode + D2H + building the "
+                                "reference's tuple list on rank 0 (max over ranks each)"),
                 "api": ("one generation through the public API with host buffers: fp32 parameters (host) -> fold on the trainer "
                         "rank -> NCCL broadcast of the folded bf16 blob -> adopt; pinned host start lines -> kv_mcts_reset -> "
                         "steps x kv_mcts_run_move (cold evaluation cache) -> packed records gathered on rank 0 over NCCL "

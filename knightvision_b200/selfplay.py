@@ -6,7 +6,10 @@
 Every game runs concurrently on the GPU: bitboard rules kernels, a GPU-resident PUCT tree per game and the
 tcgen05 policy/value tower evaluate one leaf per game per wave.  The reference picks each move by sampling the raw
 policy; here the move comes from `KV_SIMS` PUCT simulations (default 800; the tree search is new functionality,
-DESIGN.md §MCTS) with the reference's Dirichlet parameters (DIR_NOISE_EPS / DIR_NOISE_ALPHA, :12-13) at the root.
+DESIGN.md §MCTS) with the reference's Dirichlet parameters (DIR_NOISE_EPS / DIR_NOISE_ALPHA, :12-13) at the root;
+`KV_SIMS=1` is the reference's own rule (no search: the move is sampled from the noisy policy mixed as :150-167 does).
+The game loop's stopping rules are the reference's, in its order (:180-199): only kings, resignation (value < -0.7 after
+more than 15 moves), max_moves, then checkmate / stalemate.
 Record format, reward map (win 1.0 / draw 0.2 / loss -1.0 from white's side, same on every ply, :245-250), error
 behaviour (ValueError without model and path, FileNotFoundError for a missing checkpoint) follow the reference.
 """
@@ -30,6 +33,8 @@ DEFAULT_SIMS = int(os.getenv("KV_SIMS", "800"))
 DEFAULT_PLY_CAP = int(os.getenv("KV_MAX_PLIES", "512"))        # the reference has no cap when max_moves is None
 TEMP_PLIES = int(os.getenv("KV_TEMP_PLIES", "30"))
 C_PUCT = float(os.getenv("KV_CPUCT", "1.5"))
+RESIGN_THRESHOLD = float(os.getenv("KV_RESIGN_THRESHOLD", "-0.7"))   # scripts/self_play.py:185 (value < threshold ...
+RESIGN_MIN_MOVES = int(os.getenv("KV_RESIGN_MIN_MOVES", "15"))       # ... and move_count > 15); a negative count = never
 
 _engines: dict[int, Engine] = {}
 
@@ -61,7 +66,8 @@ class SelfPlay:
     def __init__(self, model: ChessNet, n_games: int, device, sims: int = DEFAULT_SIMS, max_plies: int = DEFAULT_PLY_CAP,
                  temp_plies: int = TEMP_PLIES, c_puct: float = C_PUCT, dir_alpha: float = DIR_NOISE_ALPHA,
                  dir_eps: float = DIR_NOISE_EPS, seed: int = SEED, eval_mode: int = 1, engine: Engine | None = None,
-                 inflight: int | None = None):
+                 inflight: int | None = None, resign_threshold: float = RESIGN_THRESHOLD,
+                 resign_min_moves: int = RESIGN_MIN_MOVES):
         self.eng = engine or engine_for(device)
         self.n_games, self.sims, self.max_plies = n_games, sims, max_plies
         if inflight is None:
@@ -85,6 +91,7 @@ class SelfPlay:
             self.eng.mcts_create(n_games, sims, max_plies, temp_plies, c_puct, dir_alpha, dir_eps, seed, eval_mode,
                                  inflight=inflight)
             self.eng.mcts_geometry_key = geom
+        self.eng.mcts_set_resign(resign_threshold, resign_min_moves)
 
     def play(self, start_lines: torch.Tensor | None = None, game_id_base: int = 0, progress=None) -> dict:
         eng = self.eng
