@@ -149,7 +149,7 @@ def train_record(args, eng, rank, world, local_rank, steps, arms=("native",), gr
         net.train()
         opt = torch.optim.Adam(net.parameters(), lr=1e-3)
         if arm == "native":
-            graph = LR.training_graph(net, eng)      # under torch.distributed: DDP, 64 MB buckets, bf16 gradient exchange
+            graph = LR.training_graph(net, eng)      # under torch.distributed: DDP, 25 MB buckets, one exchange per optimizer step
         else:
             graph = LR.TrainGraph(net, engine=None)
             if world > 1:
@@ -242,8 +242,8 @@ def train_record(args, eng, rank, world, local_rank, steps, arms=("native",), gr
         "config": {"workload": f"optimizer step (scripts/train.py:126-196: loss, {ACCUM} accumulated batches, clip 1.0, Adam), {name}, {ACCUM} x batch {B} per GPU, "
                                "tower convolutions fprop/dgrad/wgrad on tcgen05 kernels, fused BatchNorm+ReLU(+residual) kernels, stem conv / heads / loss / Adam in PyTorch",
                    "batch_per_gpu": B, "accumulate": ACCUM,
-                   "parallelism": (f"DDP over {world} GPU(s): one bf16 gradient all-reduce per optimizer step (no_sync on the "
-                                   "accumulating micro-batch), 64 MB buckets") if world > 1 else "single GPU",
+                   "parallelism": (f"DDP over {world} GPU(s): one fp32 gradient all-reduce per optimizer step (no_sync on the "
+                                   "accumulating micro-batch), 25 MB buckets") if world > 1 else "single GPU",
                    "l2": "activations of one step (> 1 GB) exceed the 126 MB L2; no flush needed"},
         "cudnn_arm": ({"value": world * PB * args.steps / (results["cudnn"]["dev_ms"] * 1e-3), "unit": "positions/s",
                        "ms_per_step": results["cudnn"]["dev_ms"] / args.steps,

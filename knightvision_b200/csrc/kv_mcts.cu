@@ -138,6 +138,28 @@ __device__ __forceinline__ void all_logits(const HeadW& H, const float* hp, floa
     }
 }
 
+// Sum of the 4096 Gamma variates of the reference-rule root noise (key = ply * 4096 + index) with every thread of the
+// CTA, in an order that does not depend on the CTA size (the tower path runs 256 threads, the cache-hit path 128, and a
+// hit must reproduce a miss bit for bit): 256 columns, column c sums indices c, c + 256, ... in order; a butterfly over
+// each group of 32 columns; the eight group sums added in order.  All threads return the sum.  `red`: 8 floats.
+__device__ __forceinline__ float root_noise_sum_cta(const MctsCfg& cfg, const MctsArrays& A, int gs, float* red) {
+    const GameHdr* h = &A.hdr[gs / cfg.inflight];
+    const uint64_t key = (uint64_t)h->ply * POLICY_N;
+    __syncthreads();                       // `red` may still be read by its previous user
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) {      // uniform trip count per warp (blockDim is 128 or 256)
+        float part = 0.f;
+        for (int i = c; i < POLICY_N; i += 256)
+            part = part + kvd_gamma_small(cfg.dir_alpha, cfg.seed, h->game_id, key + (uint64_t)i);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) part = part + __shfl_xor_sync(0xffffffffu, part, d);
+        if ((c & 31) == 0) red[c >> 5] = part;
+    }
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < 8; w++) tot = tot + red[w];
+    return tot;
+}
+
 // CTA per queued leaf: heads on the tower output, logits of the legal moves, then the warp-level expand/backup.
 // ROOTMIX (cfg.root_mix): a root additionally gets all 4096 logits (16 KB of shared memory) for the full softmax.
 template <bool ROOTMIX>
@@ -154,12 +176,16 @@ __global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArr
         const float v_white = kvn::value_mlp(hv, H.w1, H.b1, H.w2, H.b2, red);
         legal_logits(cfg, A, gs, H, hp, logits);
         const bool mix = ROOTMIX && A.pend_node[gs] == 0;
-        if (mix) all_logits(H, hp, lall);
+        float gsum = 0.f;
+        if (mix) {
+            all_logits(H, hp, lall);
+            if (cfg.dir_eps > 0.0f) gsum = root_noise_sum_cta(cfg, A, gs, red);
+        }
         __syncthreads();
         if (threadIdx.x < 32) {
             float mx_all = 0.f, z_all = 0.f;
             if (mix) full_softmax_stats_warp((int)threadIdx.x, [&](int i) { return lall[i]; }, mx_all, z_all);
-            mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, v_white, false, mx_all, z_all);
+            mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, v_white, false, mx_all, z_all, gsum);
             if (cfg.cache_mask) cache_fill_warp((int)threadIdx.x, cfg, A, wave, slot, hp, v_white);
         }
         __syncthreads();   // hp / hv / red / logits are reused by the next leaf
@@ -169,7 +195,7 @@ __global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArr
 // CTA (128 threads) per late entry: features from the cache (already copied per game) or from this wave's leader
 template <bool ROOTMIX>
 __global__ void __launch_bounds__(128) mcts_late_net_kernel(MctsCfg cfg, MctsArrays A, HeadW H) {
-    __shared__ float hp[FEAT], logits[MAX_MOVES];
+    __shared__ float hp[FEAT], logits[MAX_MOVES], red[8];
     __shared__ float lall[ROOTMIX ? POLICY_N : 1];
     const int n_late = (int)*A.n_late;
     for (int li = blockIdx.x; li < n_late; li += gridDim.x) {
@@ -179,12 +205,16 @@ __global__ void __launch_bounds__(128) mcts_late_net_kernel(MctsCfg cfg, MctsArr
         __syncthreads();
         legal_logits(cfg, A, gs, H, hp, logits);
         const bool mix = ROOTMIX && A.pend_node[gs] == 0;
-        if (mix) all_logits(H, hp, lall);
+        float gsum = 0.f;
+        if (mix) {
+            all_logits(H, hp, lall);
+            if (cfg.dir_eps > 0.0f) gsum = root_noise_sum_cta(cfg, A, gs, red);
+        }
         __syncthreads();
         if (threadIdx.x < 32) {
             float mx_all = 0.f, z_all = 0.f;
             if (mix) full_softmax_stats_warp((int)threadIdx.x, [&](int i) { return lall[i]; }, mx_all, z_all);
-            mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, hp[128], true, mx_all, z_all);
+            mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, hp[128], true, mx_all, z_all, gsum);
         }
         __syncthreads();
     }

@@ -501,15 +501,20 @@ KV_DEV void full_softmax_stats_warp(int lane, LogitFn L, float& mx, float& z) {
 // Root priors by the reference's rule (cfg.root_mix; scripts/self_play.py:150-167): policy = softmax over all 4096
 // logits, noise = Dirichlet(alpha) over all 4096 indices (Gamma variates keyed by seed, game, ply, INDEX), mixed with
 // eps, then the legal entries renormalised.  logits[k] holds the legal moves' logits (edge order) and is overwritten.
+// gsum_pre > 0: the sum of the 4096 Gamma variates, already formed by the caller (the network evaluator's CTA computes
+// it with all its threads); otherwise the warp forms it here (lane-strided, butterfly: the order the oracle walks).
 KV_DEV void mcts_root_mix_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, const GameHdr* h, size_t e0, int n,
-                               float* logits, float mx_all, float z_all) {
+                               float* logits, float mx_all, float z_all, float gsum_pre = 0.0f) {
     for (int k = lane; k < n; k += 32) logits[k] = kvd_expf(logits[k] - mx_all) / z_all;
     if (cfg.dir_eps > 0.0f) {
         const uint64_t key = (uint64_t)h->ply * POLICY_N;
-        float part = 0.0f;
-        for (int i = lane; i < POLICY_N; i += 32) part = part + kvd_gamma_small(cfg.dir_alpha, cfg.seed, h->game_id, key + (uint64_t)i);
+        float part = gsum_pre;
+        if (!(gsum_pre > 0.0f)) {
+            part = 0.0f;
+            for (int i = lane; i < POLICY_N; i += 32) part = part + kvd_gamma_small(cfg.dir_alpha, cfg.seed, h->game_id, key + (uint64_t)i);
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) part = part + shfl_xorf(part, d, lane);
+            for (int d = 16; d >= 1; d >>= 1) part = part + shfl_xorf(part, d, lane);
+        }
         for (int k = lane; k < n; k += 32) {
             const float g = kvd_gamma_small(cfg.dir_alpha, cfg.seed, h->game_id, key + (uint64_t)move_index(A.eMv[e0 + k]));
             logits[k] = (1.0f - cfg.dir_eps) * logits[k] + cfg.dir_eps * (g / part);
@@ -524,7 +529,7 @@ KV_DEV void mcts_root_mix_warp(int lane, const MctsCfg& cfg, const MctsArrays& A
 }
 
 KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int gs, float* logits, float v_white,
-                             bool from_cache = false, float mx_all = 0.0f, float z_all = 0.0f) {
+                             bool from_cache = false, float mx_all = 0.0f, float z_all = 0.0f, float gsum_pre = 0.0f) {
     const int g = gs / cfg.inflight;
     GameHdr* h = &A.hdr[g];
     const size_t nbase = (size_t)g * cfg.node_cap, ebase = (size_t)g * cfg.edge_cap;
@@ -534,7 +539,7 @@ KV_DEV void mcts_expand_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, 
     const size_t e0 = ebase + m.first_edge;
     const bool wtm = A.node_line[(nbase + c) * LINE_WORDS + 12] & 1;
     if (c == 0 && cfg.root_mix) {
-        mcts_root_mix_warp(lane, cfg, A, h, e0, n, logits, mx_all, z_all);
+        mcts_root_mix_warp(lane, cfg, A, h, e0, n, logits, mx_all, z_all, gsum_pre);
     } else {
     float mx = -3.0e38f;
     for (int k = lane; k < n; k += 32) mx = logits[k] > mx ? logits[k] : mx;
