@@ -19,7 +19,10 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef KV_RULES_MIN_CTAS
 #define KV_RULES_MIN_CTAS 3                  // resident CTAs per SM the register budget is sized for (tuning knob)
 #endif
-constexpr int kW = 16;                       // lanes per board in the rules kernels: two boards per warp
+#ifndef KV_RULES_LANES
+#define KV_RULES_LANES 8                     // lanes per board in the rules kernels: 8 = four boards per warp (16: two)
+#endif
+constexpr int kW = KV_RULES_LANES;
 constexpr int kBoardsPerWarp = 32 / kW;
 constexpr int kGroupsPerCta = kWarpsPerCta * kBoardsPerWarp;
 
@@ -42,12 +45,21 @@ __device__ __forceinline__ void warp_slice(int n, int gw, int nw, int& lo, int& 
     hi = lo + per < n ? lo + per : n;
 }
 
-// word q of the board line for lane q of its group (0 beyond the line, or when the group has no board)
-__device__ __forceinline__ uint64_t ld_line_word(const uint64_t* line, int q, bool valid) {
-    return (valid && q < LINE_WORDS) ? __ldg(line + q) : 0ull;
+using RLine = Line<kW>;
+
+// the words of the board line lane q of a group keeps (q, q + WL, ...); zeros when the group has no board
+__device__ __forceinline__ RLine ld_line(const uint64_t* line, int q, bool valid) {
+    RLine L;
+#pragma unroll
+    for (int j = 0; j < RLine::NW; j++) {
+        const int idx = q + j * RLine::WL;
+        L.w[j] = (valid && idx < LINE_WORDS) ? __ldg(line + idx) : 0ull;
+    }
+    return L;
 }
 
-__global__ void __launch_bounds__(kThreads, KV_RULES_MIN_CTAS) movegen_kernel(uint64_t* __restrict__ lines, int n,
+// (2 CTAs per SM: with 128 registers the ordered-list path does not spill — measured 610 against 490 M boards/s at 3)
+__global__ void __launch_bounds__(kThreads, 2) movegen_kernel(uint64_t* __restrict__ lines, int n,
                                                            uint16_t* __restrict__ moves, int stride,
                                                            int32_t* __restrict__ counts, int32_t* __restrict__ flags) {
     __shared__ RulesSmem sm;
@@ -61,13 +73,17 @@ __global__ void __launch_bounds__(kThreads, KV_RULES_MIN_CTAS) movegen_kernel(ui
         const int i = i0 + grp;
         const bool valid = i < hi;
         uint64_t* line = lines + (size_t)(valid ? i : i0) * LINE_WORDS;
-        uint64_t w = ld_line_word(line, q, valid);
-        const GenOut g = movegen_sub<kW>(sm.tab, lane, w, mv);
+        RLine L = ld_line(line, q, valid);
+        const GenOut g = movegen_sub<kW>(sm.tab, lane, L, mv);
         if (valid) {
-            if ((g.flags & RF_STATE_MUTATED) && q < 12) line[q] = w;
+            if (g.flags & RF_STATE_MUTATED) {
+#pragma unroll
+                for (int j = 0; j < RLine::NW; j++)
+                    if (q + j * RLine::WL < 12) line[q + j * RLine::WL] = L.w[j];
+            }
             int cnt = g.n < stride ? g.n : stride;
             if (cnt > MAX_MOVES) cnt = MAX_MOVES;
-            // packed u32 stores: 64 B per 32 moves per request
+            // packed u32 stores
             uint32_t* dst = reinterpret_cast<uint32_t*>(moves + (size_t)i * stride);
             for (int k = q; 2 * k < cnt; k += kW) {
                 uint32_t lo16 = mv[2 * k], hi16 = (2 * k + 1 < cnt) ? mv[2 * k + 1] : 0u;
@@ -93,9 +109,13 @@ __global__ void __launch_bounds__(kThreads, KV_RULES_MIN_CTAS) make_moves_kernel
         const int m = i < hi ? mvs[i] : 0xFFFF;
         const bool valid = m != 0xFFFF;
         uint64_t* line = lines + (size_t)(i < hi ? i : i0) * LINE_WORDS;
-        uint64_t w = ld_line_word(line, q, valid);
-        w = make_move_sub<kW>(lane, w, valid ? m : 0, T_Q);
-        if (valid && q < 13) line[q] = w;
+        RLine L = ld_line(line, q, valid);
+        make_move_sub<kW>(lane, L, valid ? m : 0, T_Q);
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < RLine::NW; j++)
+                if (q + j * RLine::WL < 13) line[q + j * RLine::WL] = L.w[j];
+        }
     }
 }
 
@@ -107,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, KV_RULES_MIN_CTAS) attacked_kernel(c
     int lo, hi;
     warp_slice(n, blockIdx.x * kWarpsPerCta + wid, gridDim.x * kWarpsPerCta, lo, hi);
     for (int i = lo; i < hi; i++) {
-        const uint64_t w = ld_line_word(lines + (size_t)i * LINE_WORDS, lane, true);
+        const uint64_t w = lane < LINE_WORDS ? __ldg(lines + (size_t)i * LINE_WORDS + lane) : 0ull;
         const uint64_t m = attacked_mask_warp(sm.tab, lane, w);
         if (lane == 0) masks[i] = m;
     }
@@ -128,14 +148,14 @@ __global__ void __launch_bounds__(kThreads, KV_RULES_MIN_CTAS) perft_level_kerne
     uint64_t accv = 0;
     int acc_root = -1;
     uint16_t* mv = sm.mv[wid * kBoardsPerWarp + grp];
-    // the next pair's lines are requested before the current pair is visited (the visit is ~1 500 warp instructions)
-    uint64_t wn = ld_line_word(cur + (size_t)(lo + grp < hi ? lo + grp : lo) * LINE_WORDS, q, lo + grp < hi);
+    // the next group of lines is requested before the current one is visited
+    RLine Ln = ld_line(cur + (size_t)(lo + grp < hi ? lo + grp : lo) * LINE_WORDS, q, lo + grp < hi);
     for (int i0 = lo; i0 < hi; i0 += kBoardsPerWarp) {
         const bool valid = i0 + grp < hi;
-        const uint64_t w = wn;
+        const RLine L = Ln;
         const int in = i0 + kBoardsPerWarp + grp;
-        wn = ld_line_word(cur + (size_t)(in < hi ? in : lo) * LINE_WORDS, q, in < hi);
-        perft_visit_sub<kW, LEAF, DIGEST>(sm.tab, lane, w, valid, mv, accv, acc_root, next, next_count, out);
+        Ln = ld_line(cur + (size_t)(in < hi ? in : lo) * LINE_WORDS, q, in < hi);
+        perft_visit_sub<kW, LEAF, DIGEST>(sm.tab, lane, L, valid, mv, accv, acc_root, next, next_count, out);
     }
     perft_acc_flush(accv, acc_root, out, q);
 }

@@ -145,17 +145,49 @@ KV_DEV void make_agg(const Pos& p, Agg& g) {
     g.eR = p.e[T_R];
 }
 
-// Broadcast the line (lane q < 16 of the board's group passes word q in w) to every lane of the group.
+// The board line as the W lanes of a group hold it: lane q keeps words q, q + WL, ... (WL = min(W, 16) words per "row"):
+// one word per lane for W >= 16 (lanes 16-31 of a W = 32 group hold nothing), two for W = 8 (words q and q + 8).
 template <int W>
-KV_DEV void load_pos(uint64_t w, Pos& p, int lane) {
-    p.meta = sub_shfl64<W>(w, 12, lane);
+struct Line {
+    static constexpr int WL = W < 16 ? W : 16;
+    static constexpr int NW = 16 / WL;
+    uint64_t w[NW];
+};
+// word i of the line, broadcast to every lane of the group (i is a compile-time constant at every call site)
+template <int W>
+KV_DEV uint64_t line_word(const Line<W>& L, int i, int lane) {
+    return sub_shfl64<W>(L.w[i / Line<W>::WL], i % Line<W>::WL, lane);
+}
+
+// Broadcast the line to every lane of the group, side to move first.
+template <int W>
+KV_DEV void load_pos(const Line<W>& L, Pos& p, int lane) {
+    p.meta = line_word<W>(L, 12, lane);
     p.wtm = p.meta & 1;
-    // side to move first: the shuffle source is chosen by the side bit, so no selects afterwards
-    const int so = p.wtm ? 0 : 6, se = 6 - so;
+    if (Line<W>::NW == 1) {
+        // the shuffle source lane is chosen by the side bit, so no selects afterwards
+        const int so = p.wtm ? 0 : 6, se = 6 - so;
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-        p.o[i] = sub_shfl64<W>(w, so + i, lane);
-        p.e[i] = sub_shfl64<W>(w, se + i, lane);
+        for (int i = 0; i < 6; i++) {
+            p.o[i] = sub_shfl64<W>(L.w[0], so + i, lane);
+            p.e[i] = sub_shfl64<W>(L.w[0], se + i, lane);
+        }
+    } else {
+        // W = 8: bitboards 0-7 are word 0 of lanes 0-7, bitboards 8-11 word 1 of lanes 0-3.  White's six boards are
+        // 0-5 (word 0), black's 6-11 (word 0 of lanes 6, 7; word 1 of lanes 0-3): each lane offers the word the side
+        // bit asks for, the source lane is computed from it
+        const uint64_t w0 = L.w[0], w1 = L.w[Line<W>::NW - 1];
+        const uint64_t vo = p.wtm ? w0 : w1, ve = p.wtm ? w1 : w0;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            p.o[i] = sub_shfl64<W>(w0, p.wtm ? i : 6 + i, lane);
+            p.e[i] = sub_shfl64<W>(w0, p.wtm ? 6 + i : i, lane);
+        }
+#pragma unroll
+        for (int i = 2; i < 6; i++) {
+            p.o[i] = sub_shfl64<W>(vo, p.wtm ? i : i - 2, lane);
+            p.e[i] = sub_shfl64<W>(ve, p.wtm ? i - 2 : i, lane);
+        }
     }
     p.moved = (int)((p.meta >> 1) & 63);
     p.ep = (int)((p.meta >> 8) & 127);
@@ -176,58 +208,76 @@ struct KingOut {
 template <int W>
 KV_DEV KingOut king_phase(const Tables& T, int lane_, const Pos& p, const Agg& g, int ks, int mode,
                           uint64_t valid, uint64_t pinned) {
-    const int lane = sub_q<W>(lane_);   // work item index inside the board's group
     const int home = p.wtm ? 60 : 4;
-    // One convergent attacked() evaluation for all 13 work items: lanes 0-7 test a king step on the "king placed"
-    // board (:556-563), lane 8 the king's own square, lanes 9,10 f,g and 11,12 c,d on the unmodified board (:576-599).
-    Agg h = g;
-    int t = 0;
-    bool active = false;
-    if (lane < 8) {
-        // step k of getKingMoves' order (:544-546): row offset + 1 = {0,0,0,1,1,2,2,2}, column offset + 1 = {0,1,2,0,2,0,1,2}
-        const int dr = (int)((0xA940u >> (2 * lane)) & 3u) - 1;
-        const int dc = (int)((0x9224u >> (2 * lane)) & 3u) - 1;
-        const int er = (ks >> 3) + dr, ec = (ks & 7) + dc;
-        if (er >= 0 && er < 8 && ec >= 0 && ec < 8) {
-            t = er * 8 + ec;
-            const uint64_t tb = bit(t), ksb = bit(ks);
-            if (!(g.own & tb)) {
-                active = true;   // the king placed on t, whatever stood there removed
-                h.occ = (g.occ & ~ksb) | tb;
-                h.own = (g.own & ~ksb) | tb;
-                h.opp = g.opp & ~tb;
-                h.eN = g.eN & ~tb;
-                h.eK = g.eK & ~tb;
-                h.eRQ = g.eRQ & ~tb;
-                h.eBQ = g.eBQ & ~tb;
-                h.eP = g.eP & ~tb;
-                h.eR = g.eR & ~tb;
+    const int f_k = p.wtm ? F_WK : F_BK, f_rk = p.wtm ? F_WRK : F_BRK, f_rq = p.wtm ? F_WRQ : F_BRQ;
+    // castling can only come out if the king stands at home unmoved and a wing has its flag clear, its squares empty
+    // and its rook in the corner; only then are the five squares of work items 8-12 worth testing
+    const bool wing_k = !(p.moved & f_rk) && !(g.occ & (bit(home + 1) | bit(home + 2))) && (p.o[T_R] & bit(home + 3));
+    const bool wing_q = !(p.moved & f_rq) && !(g.occ & (bit(home - 1) | bit(home - 2) | bit(home - 3))) &&
+                        (p.o[T_R] & bit(home - 4));
+    const bool castle_possible = p.kloc == home && !(p.moved & f_k) && (wing_k || wing_q);
+    // 13 work items, W per round: items 0-7 test a king step on the "king placed" board (:556-563), item 8 the king's
+    // own square, items 9,10 f,g and 11,12 c,d on the unmodified board (:576-599).  One convergent attacked() per round.
+    constexpr int ROUNDS = (13 + W - 1) / W;
+    uint32_t okb = 0, ab = 0;
+#pragma unroll
+    for (int rr = 0; rr < ROUNDS; rr++) {
+        const int lane = sub_q<W>(lane_) + rr * W;   // work item index
+        if (ROUNDS > 1 && rr > 0 && ballot(castle_possible) == 0) break;   // no board of the warp can castle
+        Agg h = g;
+        int t = 0;
+        bool active = false;
+        if (lane < 8) {
+            // step k of getKingMoves' order (:544-546): row offset + 1 = {0,0,0,1,1,2,2,2}, column offset + 1 = {0,1,2,0,2,0,1,2}
+            const int dr = (int)((0xA940u >> (2 * lane)) & 3u) - 1;
+            const int dc = (int)((0x9224u >> (2 * lane)) & 3u) - 1;
+            const int er = (ks >> 3) + dr, ec = (ks & 7) + dc;
+            if (er >= 0 && er < 8 && ec >= 0 && ec < 8) {
+                t = er * 8 + ec;
+                const uint64_t tb = bit(t), ksb = bit(ks);
+                if (!(g.own & tb)) {
+                    active = true;   // the king placed on t, whatever stood there removed
+                    h.occ = (g.occ & ~ksb) | tb;
+                    h.own = (g.own & ~ksb) | tb;
+                    h.opp = g.opp & ~tb;
+                    h.eN = g.eN & ~tb;
+                    h.eK = g.eK & ~tb;
+                    h.eRQ = g.eRQ & ~tb;
+                    h.eBQ = g.eBQ & ~tb;
+                    h.eP = g.eP & ~tb;
+                    h.eR = g.eR & ~tb;
+                }
             }
+        } else if (lane < 13) {
+            active = castle_possible;
+            t = lane == 8 ? ks : (lane == 9 ? home + 1 : (lane == 10 ? home + 2 : (lane == 11 ? home - 2 : home - 1)));
         }
-    } else if (lane < 13) {
-        active = true;
-        t = lane == 8 ? ks : (lane == 9 ? home + 1 : (lane == 10 ? home + 2 : (lane == 11 ? home - 2 : home - 1)));
+        bool a1 = false;
+        if (active) a1 = attacked(T, h, t, p.wtm, p.ep, p.moved, p.akloc);
+        bool ok = lane < 8 && active && !a1;
+        const bool att = lane >= 8 && lane < 13 && a1;
+        if (mode == 1) {   // getValidMoves :306-309 re-tests king moves on the unmodified board
+            bool a2 = false;
+            if (ok) a2 = attacked(T, g, t, p.wtm, p.ep, p.moved, p.akloc);
+            ok = ok && !a2;
+        }
+        // item index -> bit index: steps in bits 0-7 of okb, items 8-12 in bits 0-4 of ab
+        const uint32_t bo = sub_ballot<W>(ok, lane_), ba = sub_ballot<W>(att, lane_);
+        if (W >= 16) {
+            okb = bo & 0xFFu;
+            ab = ba >> 8;
+        } else if (rr == 0) {
+            okb = bo & 0xFFu;
+        } else {
+            ab = ba & 0x1Fu;
+        }
     }
-    bool a1 = false;
-    if (active) a1 = attacked(T, h, t, p.wtm, p.ep, p.moved, p.akloc);
-    bool ok = lane < 8 && active && !a1;
-    const bool att = lane >= 8 && lane < 13 && a1;
-    if (mode == 1) {   // getValidMoves :306-309 re-tests king moves on the unmodified board
-        bool a2 = false;
-        if (ok) a2 = attacked(T, g, t, p.wtm, p.ep, p.moved, p.akloc);
-        ok = ok && !a2;
-    }
-    const uint32_t okb = sub_ballot<W>(ok, lane_) & 0xFFu;
-    const uint32_t ab = sub_ballot<W>(att, lane_) >> 8;
     KingOut out;
     out.steps = okb;
     out.castle = 0;
-    const int f_k = p.wtm ? F_WK : F_BK, f_rk = p.wtm ? F_WRK : F_BRK, f_rq = p.wtm ? F_WRQ : F_BRQ;
-    if (!(ab & 1) && p.kloc == home && !(p.moved & f_k)) {
-        bool ck = !(p.moved & f_rk) && !(g.occ & (bit(home + 1) | bit(home + 2))) && !(ab & 2) && !(ab & 4) &&
-                  (p.o[T_R] & bit(home + 3));
-        bool cq = !(p.moved & f_rq) && !(g.occ & (bit(home - 1) | bit(home - 2) | bit(home - 3))) && !(ab & 8) &&
-                  !(ab & 16) && (p.o[T_R] & bit(home - 4));
+    if (castle_possible && !(ab & 1)) {
+        bool ck = wing_k && !(ab & 2) && !(ab & 4);
+        bool cq = wing_q && !(ab & 8) && !(ab & 16);
         if (mode == 1) {
             // getValidMoves :306-310: Move.pieceMoved is board[home]; a king (either colour) is re-tested
             // with squareUnderAttack(to) — already false here — anything else must land on validSquares
@@ -346,14 +396,14 @@ struct GenState {
 };
 
 // getValidMoves (core/chessEngine.py:277-321), part 1: pins and checks from the king location variable.
-//   w       lane q < 16 of the group: word q of the board line; updated in place when the getKingMoves restore quirk
+//   L       the board line as the group's lanes hold it; updated in place when the getKingMoves restore quirk
 //           (:564, stale king location) rewrites the board (flags & RF_STATE_MUTATED)
 template <int W>
-KV_DEV void movegen_prepare(const Tables& T, int lane, uint64_t& w, GenState& S) {
+KV_DEV void movegen_prepare(const Tables& T, int lane, Line<W>& L, GenState& S) {
     Pos& p = S.p;
     Agg& g = S.g;
     const int q = sub_q<W>(lane);
-    load_pos<W>(w, p, lane);
+    load_pos<W>(L, p, lane);
     make_agg(p, g);
     int flags = 0;
 
@@ -408,10 +458,14 @@ KV_DEV void movegen_prepare(const Tables& T, int lane, uint64_t& w, GenState& S)
             p.o[T_K] |= kb;
             make_agg(p, g);
             flags |= RF_STATE_MUTATED;
-            // write the rewritten board back into the line words held by lanes 0-11 of the group
-            if (q < 12) {
-                w &= ~kb;
-                if (q == (p.wtm ? 0 : 6)) w |= kb;
+            // write the rewritten board back into the bitboard words (0-11) the lanes of the group hold
+#pragma unroll
+            for (int j = 0; j < Line<W>::NW; j++) {
+                const int idx = q + j * Line<W>::WL;
+                if (idx < 12) {
+                    L.w[j] &= ~kb;
+                    if (idx == (p.wtm ? 0 : 6)) L.w[j] |= kb;
+                }
             }
         }
     }
@@ -532,9 +586,9 @@ KV_DEV int movegen_end_flags(const Tables& T, const GenState& S, int n) {
 // getValidMoves with the ordered move list written to mv (the board's MAX_MOVES u16 of shared memory:
 // from | to<<6 | ep<<12 | castle<<13 | promo<<14).
 template <int W>
-KV_DEV GenOut movegen_sub(const Tables& T, int lane, uint64_t& w, uint16_t* mv) {
+KV_DEV GenOut movegen_sub(const Tables& T, int lane, Line<W>& L, uint16_t* mv) {
     GenState S;
-    movegen_prepare<W>(T, lane, w, S);
+    movegen_prepare<W>(T, lane, L, S);
     int n = 0;
     movegen_rounds<W>(T, lane, S, [&](const Slot& sl, int s) {
         const int c = slot_count(sl);
@@ -553,9 +607,9 @@ KV_DEV GenOut movegen_sub(const Tables& T, int lane, uint64_t& w, uint16_t* mv) 
 // n | captures<<12 | ep<<24 | castles<<36 | promos<<48
 // (a capture = destination occupied or e.p., Move.pieceCaptured != "--", core/chessEngine.py:699-703).
 template <int W>
-KV_DEV GenOut movegen_count_sub(const Tables& T, int lane, uint64_t& w, uint64_t& cats) {
+KV_DEV GenOut movegen_count_sub(const Tables& T, int lane, Line<W>& L, uint64_t& cats) {
     GenState S;
-    movegen_prepare<W>(T, lane, w, S);
+    movegen_prepare<W>(T, lane, L, S);
     const uint64_t last = S.p.wtm ? 0xFFull : 0xFFull << 56;
     // five 12-bit fields in one word (each <= 256 per lane and <= MAX_MOVES-ish per board): n, captures, ep, castles, promos
     uint64_t acc = 0;
@@ -577,56 +631,85 @@ KV_DEV GenOut movegen_count_sub(const Tables& T, int lane, uint64_t& w, uint64_t
 }
 
 // one board per warp (the tree-search kernels)
-KV_DEV GenOut movegen_warp(const Tables& T, int lane, uint64_t& w, uint16_t* mv) { return movegen_sub<32>(T, lane, w, mv); }
+KV_DEV GenOut movegen_warp(const Tables& T, int lane, uint64_t& w, uint16_t* mv) {
+    Line<32> L;
+    L.w[0] = w;
+    const GenOut g = movegen_sub<32>(T, lane, L, mv);
+    w = L.w[0];
+    return g;
+}
 
 // makeMove (core/chessEngine.py:127-197), no legality check, mailbox write order preserved.
-// Lane q < 12 of the board's group holds bitboard q in w, lane 12 the meta word; returns the lane's new word.
+// The lanes of the board's group hold the line (Line<W>): bitboards are words 0-11, the meta word is 12.
 // Convergent for any mix of moves in a warp (every ballot is reached by all lanes).
 template <int W>
-KV_DEV uint64_t make_move_sub(int lane, uint64_t w, int mvw, int promo_type) {
+KV_DEV void make_move_sub(int lane, Line<W>& L, int mvw, int promo_type) {
+    constexpr int WL = Line<W>::WL, NW = Line<W>::NW;
     const int q = sub_q<W>(lane);
     const int from = mvw & 63, to = (mvw >> 6) & 63, fl = (mvw >> 12) & 7;
     const uint64_t fb = bit(from), tb = bit(to);
-    const bool bbl = q < 12;
-    const uint32_t has_f = sub_ballot<W>(bbl && (w & fb), lane);
-    const uint32_t has_t = sub_ballot<W>(bbl && (w & tb), lane);
-    const int pm = has_f ? ffs32(has_f) - 1 : -1;
+    // which bitboard holds a square: one ballot per word the lanes hold (lowest bitboard index wins, as a mailbox would)
+    auto holder = [&](uint64_t sq_bit, bool enable) {
+        int idx = -1;
+#pragma unroll
+        for (int j = NW - 1; j >= 0; j--) {
+            const uint32_t b = sub_ballot<W>(enable && (q + j * WL) < 12 && (L.w[j] & sq_bit), lane);
+            if (b) idx = j * WL + ffs32(b) - 1;
+        }
+        return idx;
+    };
+    const int pm = holder(fb, true);
+    const bool has_t = holder(tb, true) >= 0;
     const bool captured = (fl & MF_EP) || has_t;
     const int sr = from >> 3, sc = from & 7, er = to >> 3, ec = to & 7;
-    if (bbl) {
-        w &= ~fb;                       // board[start] = "--"
-        w &= ~tb;                       // board[end] = pieceMoved
-        if (q == pm) w |= tb;
-        if (fl & MF_EP) w &= ~bit(sr * 8 + ec);   // :152-153
-    }
-    {                                   // rook hop, :156-164
-        int rs = -1, rd = -1;
-        if (fl & MF_CASTLE) {
-            if (ec - sc == 2) {
-                if (ec + 1 < 8) { rs = er * 8 + ec + 1; rd = er * 8 + ec - 1; }
-            } else if (ec - 2 >= 0 && ec + 1 < 8) {
-                rs = er * 8 + ec - 2; rd = er * 8 + ec + 1;
-            }
+    int rs = -1, rd = -1;               // rook hop, :156-164
+    if (fl & MF_CASTLE) {
+        if (ec - sc == 2) {
+            if (ec + 1 < 8) { rs = er * 8 + ec + 1; rd = er * 8 + ec - 1; }
+        } else if (ec - 2 >= 0 && ec + 1 < 8) {
+            rs = er * 8 + ec - 2; rd = er * 8 + ec + 1;
         }
-        const uint32_t has_r = sub_ballot<W>(bbl && rs >= 0 && (w & bit(rs & 63)), lane);
-        if (rs >= 0) {
-            const int rp = has_r ? ffs32(has_r) - 1 : -1;
-            if (bbl) {
+    }
+#pragma unroll
+    for (int j = 0; j < NW; j++) {
+        const int idx = q + j * WL;
+        if (idx < 12) {
+            uint64_t w = L.w[j];
+            w &= ~fb;                       // board[start] = "--"
+            w &= ~tb;                       // board[end] = pieceMoved
+            if (idx == pm) w |= tb;
+            if (fl & MF_EP) w &= ~bit(sr * 8 + ec);   // :152-153
+            L.w[j] = w;
+        }
+    }
+    const int rp = holder(bit(rs & 63), rs >= 0);   // the rook hop reads the board after the king has moved
+    if (rs >= 0) {
+#pragma unroll
+        for (int j = 0; j < NW; j++) {
+            const int idx = q + j * WL;
+            if (idx < 12) {
+                uint64_t w = L.w[j];
                 w &= ~bit(rd);
-                if (q == rp) w |= bit(rd);
+                if (idx == rp) w |= bit(rd);
                 w &= ~bit(rs);
+                L.w[j] = w;
             }
         }
     }
     if (fl & MF_PROMO) {                // :190-191, promotionChoice defaults to 'Q'
         const int pp = ((pm >= 0 && pm < 6) ? 0 : 6) + promo_type;
-        if (bbl) {
-            w &= ~tb;
-            if (q == pp) w |= tb;
+#pragma unroll
+        for (int j = 0; j < NW; j++) {
+            const int idx = q + j * WL;
+            if (idx < 12) {
+                L.w[j] &= ~tb;
+                if (idx == pp) L.w[j] |= tb;
+            }
         }
     }
-    if (q == 12) {
-        uint64_t m = w;
+    constexpr int MJ = 12 / WL, MQ = 12 % WL;   // where the meta word lives
+    if (q == MQ) {
+        uint64_t m = L.w[MJ];
         int moved = (int)((m >> 1) & 63);
         int wk = (int)((m >> 16) & 63), bk = (int)((m >> 24) & 63);
         int clock = (int)((m >> 32) & 0xFFFF);
@@ -638,17 +721,23 @@ KV_DEV uint64_t make_move_sub(int lane, uint64_t w, int mvw, int promo_type) {
         int ep = EP_NONE;
         if ((pm == 5 || pm == 11) && (sr - er == 2 || er - sr == 2)) ep = ((sr + er) >> 1) * 8 + sc;   // :169-173
         clock = captured ? 0 : (clock + 1 > 0xFFFF ? 0xFFFF : clock + 1);   // :178 resets on captures only
-        w = (m & 0xFFFF000000000000ull) | (uint64_t)(wtm ? 0 : 1) | ((uint64_t)moved << 1) | ((uint64_t)ep << 8) |
-            ((uint64_t)wk << 16) | ((uint64_t)bk << 24) | ((uint64_t)clock << 32);
+        L.w[MJ] = (m & 0xFFFF000000000000ull) | (uint64_t)(wtm ? 0 : 1) | ((uint64_t)moved << 1) | ((uint64_t)ep << 8) |
+                  ((uint64_t)wk << 16) | ((uint64_t)bk << 24) | ((uint64_t)clock << 32);
     }
-    return w;
 }
-KV_DEV uint64_t make_move_warp(int lane, uint64_t w, int mvw, int promo_type) { return make_move_sub<32>(lane, w, mvw, promo_type); }
+KV_DEV uint64_t make_move_warp(int lane, uint64_t w, int mvw, int promo_type) {
+    Line<32> L;
+    L.w[0] = w;
+    make_move_sub<32>(lane, L, mvw, promo_type);
+    return L.w[0];
+}
 
 // squareUnderAttack(r, c) for all 64 squares of one board (core/chessEngine.py:400-415): bit r*8+c of the result.
 KV_DEV uint64_t attacked_mask_warp(const Tables& T, int lane, uint64_t w) {
     Pos p;
-    load_pos<32>(w, p, lane);
+    Line<32> L;
+    L.w[0] = w;
+    load_pos<32>(L, p, lane);
     Agg g;
     make_agg(p, g);
     const bool a0 = attacked(T, g, 2 * lane, p.wtm, p.ep, p.moved, p.akloc);
@@ -690,19 +779,20 @@ KV_DEV void perft_acc_flush(uint64_t& accv, int root, uint64_t* out, int q) {
 // atomic add per parent; the frontier is an unordered multiset and every output is an order-independent sum).
 // w[13] = root id, w[14] = path hash.
 template <int W, bool LEAF, bool DIGEST = true>
-KV_DEV void perft_visit_sub(const Tables& T, int lane, uint64_t w, bool valid, uint16_t* mv, uint64_t& accv, int& acc_root,
+KV_DEV void perft_visit_sub(const Tables& T, int lane, Line<W> L, bool valid, uint16_t* mv, uint64_t& accv, int& acc_root,
                             uint64_t* next, uint32_t* next_count, uint64_t* out) {
+    constexpr int WL = Line<W>::WL, NW = Line<W>::NW;
     const int q = sub_q<W>(lane);
-    const int root_w = (int)(uint32_t)sub_shfl64<W>(w, 13, lane);   // (a collective: outside the conditional)
+    const int root_w = (int)(uint32_t)line_word<W>(L, 13, lane);   // (a collective: outside the conditional)
     const int root = valid ? root_w : acc_root;
-    const uint64_t path = sub_shfl64<W>(w, 14, lane);
+    const uint64_t path = line_word<W>(L, 14, lane);
     if (root != acc_root) {
         perft_acc_flush(accv, acc_root, out, q);
         acc_root = root;
     }
     if (LEAF && !DIGEST) {   // count-only leaves: no ordered list, no digest
         uint64_t cats = 0;
-        const GenOut g = movegen_count_sub<W>(T, lane, w, cats);
+        const GenOut g = movegen_count_sub<W>(T, lane, L, cats);
         if (valid) {
             if (q == 0) accv += (unsigned)(g.n < MAX_MOVES ? g.n : MAX_MOVES);
             if (q >= 1 && q <= 4) accv += (cats >> (12 * q)) & 0xFFF;
@@ -711,11 +801,15 @@ KV_DEV void perft_visit_sub(const Tables& T, int lane, uint64_t w, bool valid, u
         return;
     }
     // w reflects the :564 rewrite afterwards, as the reference's makeMove would see it
-    const GenOut g = movegen_sub<W>(T, lane, w, mv);
+    const GenOut g = movegen_sub<W>(T, lane, L, mv);
     const int n = valid ? (g.n < MAX_MOVES ? g.n : MAX_MOVES) : 0;
     const uint64_t dig = list_digest<W>(mv, n, path, lane);
     if (LEAF) {
-        const uint64_t occ = sub_or64<W>(q < 12 ? w : 0ull, lane);
+        uint64_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < NW; j++)
+            if (q + j * WL < 12) mine |= L.w[j];
+        const uint64_t occ = sub_or64<W>(mine, lane);
         uint64_t cats = 0;   // captures | ep<<16 | castles<<32 | promos<<48 (each <= 256)
         for (int k = q; k < n; k += W) {
             const int x = mv[k];
@@ -741,9 +835,14 @@ KV_DEV void perft_visit_sub(const Tables& T, int lane, uint64_t w, bool valid, u
         }
         for (int k = 0; k < nmax; k++) {
             const bool live = k < n;
-            uint64_t c = make_move_sub<W>(lane, w, live ? mv[k] : 0, T_Q);
-            if (q == 14) c = child_path(path, k);
-            if (live && q < LINE_WORDS) next[(size_t)(base + k) * LINE_WORDS + q] = c;
+            Line<W> C = L;
+            make_move_sub<W>(lane, C, live ? mv[k] : 0, T_Q);
+#pragma unroll
+            for (int j = 0; j < NW; j++) {
+                const int idx = q + j * WL;
+                if (idx == 14) C.w[j] = child_path(path, k);
+                if (live && idx < LINE_WORDS) next[(size_t)(base + k) * LINE_WORDS + idx] = C.w[j];
+            }
         }
     }
     if (valid) {

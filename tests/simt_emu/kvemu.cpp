@@ -104,9 +104,27 @@ void run_warp(std::function<void(int)> body) {
 
 static const kv::Tables g_tables = kv::make_tables();
 
-// Lanes per board in the rules entry points below: 32 (one board per warp, what the tree-search kernels use) or 16 (two
-// boards per warp, what kv_rules.cu's kernels use).  A trailing odd board leaves the second group without a board.
+// Lanes per board in the rules entry points below: 32 (one board per warp, what the tree-search kernels use), 16 or 8
+// (two / four boards per warp, what kv_rules.cu's kernels can be built for).  Trailing boards that do not fill a warp
+// leave groups without a board.
 static int g_emu_w = 32;
+
+template <int W>
+static kv::Line<W> emu_load_line(const uint64_t* line, int q, bool valid) {
+    kv::Line<W> L;
+    for (int j = 0; j < kv::Line<W>::NW; j++) {
+        const int idx = q + j * kv::Line<W>::WL;
+        L.w[j] = (valid && idx < 16) ? line[idx] : 0;
+    }
+    return L;
+}
+template <int W>
+static void emu_store_line(uint64_t* line, int q, const kv::Line<W>& L) {
+    for (int j = 0; j < kv::Line<W>::NW; j++) {
+        const int idx = q + j * kv::Line<W>::WL;
+        if (idx < 16) line[idx] = L.w[j];
+    }
+}
 
 template <int W>
 static void emu_movegen_t(uint64_t* lines, int n, uint16_t* moves, int stride, int32_t* counts, int32_t* flags) {
@@ -115,12 +133,12 @@ static void emu_movegen_t(uint64_t* lines, int n, uint16_t* moves, int stride, i
         uint16_t mv[NB][kv::MAX_MOVES];
         memset(mv, 0, sizeof(mv));
         kv::GenOut out[32];
-        uint64_t neww[32];
+        uint64_t neww[NB][16];
         kvemu::run_warp([&](int lane) {
             const int grp = lane / W, q = lane % W, i = i0 + grp;
-            uint64_t w = (i < n && q < 16) ? lines[16 * (size_t)i + q] : 0;
-            out[lane] = kv::movegen_sub<W>(g_tables, lane, w, mv[grp]);
-            neww[lane] = w;
+            kv::Line<W> L = emu_load_line<W>(lines + 16 * (size_t)(i < n ? i : 0), q, i < n);
+            out[lane] = kv::movegen_sub<W>(g_tables, lane, L, mv[grp]);
+            emu_store_line<W>(neww[grp], q, L);
         });
         for (int grp = 0; grp < NB && i0 + grp < n; grp++) {
             const int i = i0 + grp;
@@ -132,7 +150,7 @@ static void emu_movegen_t(uint64_t* lines, int n, uint16_t* moves, int stride, i
                 }
             const kv::GenOut o = out[grp * W];
             if (o.flags & kv::RF_STATE_MUTATED)
-                for (int l = 0; l < 16; l++) line[l] = neww[grp * W + l];
+                for (int l = 0; l < 16; l++) line[l] = neww[grp][l];
             counts[i] = o.n;
             flags[i] = o.flags;
             for (int k = 0; k < o.n && k < stride && k < kv::MAX_MOVES; k++) moves[(size_t)i * stride + k] = mv[grp][k];
@@ -144,16 +162,17 @@ template <int W>
 static void emu_make_moves_t(uint64_t* lines, int n, const uint16_t* mv) {
     constexpr int NB = 32 / W;
     for (int i0 = 0; i0 < n; i0 += NB) {
-        uint64_t neww[32];
+        uint64_t neww[NB][16];
         kvemu::run_warp([&](int lane) {
             const int grp = lane / W, q = lane % W, i = i0 + grp;
             const bool valid = i < n && mv[i] != 0xFFFF;
-            uint64_t w = (valid && q < 16) ? lines[16 * (size_t)i + q] : 0;
-            neww[lane] = kv::make_move_sub<W>(lane, w, valid ? mv[i] : 0, kv::T_Q);
+            kv::Line<W> L = emu_load_line<W>(lines + 16 * (size_t)(i < n ? i : 0), q, valid);
+            kv::make_move_sub<W>(lane, L, valid ? mv[i] : 0, kv::T_Q);
+            emu_store_line<W>(neww[grp], q, L);
         });
         for (int grp = 0; grp < NB && i0 + grp < n; grp++)
             if (mv[i0 + grp] != 0xFFFF)
-                for (int l = 0; l < 16; l++) lines[16 * (size_t)(i0 + grp) + l] = neww[grp * W + l];
+                for (int l = 0; l < 16; l++) lines[16 * (size_t)(i0 + grp) + l] = neww[grp][l];
     }
 }
 
@@ -173,13 +192,13 @@ static void emu_perft_rec(std::vector<uint64_t>& cur, int remaining, uint64_t* o
             const int grp = lane / W, q = lane % W, i = i0 + grp;
             const bool valid = i < m;
             int acc_root = -1;
-            uint64_t w = (valid && q < 16) ? cur[16 * (size_t)i + q] : 0;
+            kv::Line<W> L = emu_load_line<W>(cur.data() + 16 * (size_t)(valid ? i : 0), q, valid);
             if (leaf) {
-                if (g_emu_digest) kv::perft_visit_sub<W, true, true>(g_tables, lane, w, valid, mv[grp], acc[lane], acc_root, nullptr, nullptr, out);
-                else kv::perft_visit_sub<W, true, false>(g_tables, lane, w, valid, mv[grp], acc[lane], acc_root, nullptr, nullptr, out);
+                if (g_emu_digest) kv::perft_visit_sub<W, true, true>(g_tables, lane, L, valid, mv[grp], acc[lane], acc_root, nullptr, nullptr, out);
+                else kv::perft_visit_sub<W, true, false>(g_tables, lane, L, valid, mv[grp], acc[lane], acc_root, nullptr, nullptr, out);
             } else {
-                if (g_emu_digest) kv::perft_visit_sub<W, false, true>(g_tables, lane, w, valid, mv[grp], acc[lane], acc_root, next.data(), &cnt, out);
-                else kv::perft_visit_sub<W, false, false>(g_tables, lane, w, valid, mv[grp], acc[lane], acc_root, next.data(), &cnt, out);
+                if (g_emu_digest) kv::perft_visit_sub<W, false, true>(g_tables, lane, L, valid, mv[grp], acc[lane], acc_root, next.data(), &cnt, out);
+                else kv::perft_visit_sub<W, false, false>(g_tables, lane, L, valid, mv[grp], acc[lane], acc_root, next.data(), &cnt, out);
             }
             kv::perft_acc_flush(acc[lane], acc_root, out, q);
         });
@@ -191,11 +210,12 @@ static void emu_perft_rec(std::vector<uint64_t>& cur, int remaining, uint64_t* o
 
 extern "C" {
 
-__attribute__((visibility("default"))) void kvemu_set_width(int w) { g_emu_w = (w == 16) ? 16 : 32; }
+__attribute__((visibility("default"))) void kvemu_set_width(int w) { g_emu_w = (w == 16 || w == 8) ? w : 32; }
 
 __attribute__((visibility("default"))) void kvemu_movegen(uint64_t* lines, int n, uint16_t* moves, int stride,
                                                            int32_t* counts, int32_t* flags) {
-    if (g_emu_w == 16) emu_movegen_t<16>(lines, n, moves, stride, counts, flags);
+    if (g_emu_w == 8) emu_movegen_t<8>(lines, n, moves, stride, counts, flags);
+    else if (g_emu_w == 16) emu_movegen_t<16>(lines, n, moves, stride, counts, flags);
     else emu_movegen_t<32>(lines, n, moves, stride, counts, flags);
 }
 
@@ -211,7 +231,8 @@ __attribute__((visibility("default"))) void kvemu_attacked(const uint64_t* lines
 }
 
 __attribute__((visibility("default"))) void kvemu_make_moves(uint64_t* lines, int n, const uint16_t* mv) {
-    if (g_emu_w == 16) emu_make_moves_t<16>(lines, n, mv);
+    if (g_emu_w == 8) emu_make_moves_t<8>(lines, n, mv);
+    else if (g_emu_w == 16) emu_make_moves_t<16>(lines, n, mv);
     else emu_make_moves_t<32>(lines, n, mv);
 }
 
@@ -225,7 +246,8 @@ __attribute__((visibility("default"))) void kvemu_perft(const uint64_t* roots, i
         cur[16 * (size_t)i + 14] = 0;
         cur[16 * (size_t)i + 15] = 0;
     }
-    if (g_emu_w == 16) emu_perft_rec<16>(cur, depth, out);
+    if (g_emu_w == 8) emu_perft_rec<8>(cur, depth, out);
+    else if (g_emu_w == 16) emu_perft_rec<16>(cur, depth, out);
     else emu_perft_rec<32>(cur, depth, out);
 }
 

@@ -10,10 +10,10 @@ import helpers as H
 from simt_emu import emu
 
 
-@pytest.fixture(params=[32, 16], autouse=True, ids=["warp_per_board", "half_warp_per_board"])
+@pytest.fixture(params=[32, 16, 8], autouse=True, ids=["32_lanes_per_board", "16_lanes_per_board", "8_lanes_per_board"])
 def lanes_per_board(request):
-    """Every test runs the kernel source both ways: 32 lanes per board (the tree-search kernels) and 16 lanes per board,
-    two boards per warp (kv_rules.cu's perft / movegen / make-move kernels)."""
+    """Every test runs the kernel source three ways: 32 lanes per board (the tree-search kernels), 16 (two boards per warp)
+    and 8 (four boards per warp: what kv_rules.cu's perft / movegen / make-move kernels are built for)."""
     emu.set_width(request.param)
     yield request.param
     emu.set_width(32)
