@@ -116,28 +116,6 @@ __device__ __forceinline__ void legal_logits(const MctsCfg& cfg, const MctsArray
     }
 }
 
-// All 4096 policy logits of one position into shared memory (cfg.root_mix roots only: the reference's softmax runs
-// over every index, scripts/self_play.py:150).  Same per-row arithmetic as legal_logits (8 lanes x 16 features, fixed
-// butterfly), so a legal move's entry equals its legal_logits value bit for bit.
-__device__ __forceinline__ void all_logits(const HeadW& H, const float* hp, float* out) {
-    const int part = threadIdx.x & 7, per = blockDim.x >> 3;
-    const float* f = hp + part * 16;
-    for (int r0 = 0; r0 < POLICY_N; r0 += per) {
-        const int idx = r0 + (int)(threadIdx.x >> 3);
-        const float4* wr = reinterpret_cast<const float4*>(H.wfc + (size_t)idx * 128 + part * 16);
-        float a = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const float4 w = __ldg(wr + i);
-            a += w.x * f[4 * i] + w.y * f[4 * i + 1] + w.z * f[4 * i + 2] + w.w * f[4 * i + 3];
-        }
-        a += __shfl_xor_sync(0xffffffffu, a, 1);
-        a += __shfl_xor_sync(0xffffffffu, a, 2);
-        a += __shfl_xor_sync(0xffffffffu, a, 4);
-        if (part == 0) out[idx] = a + __ldg(H.bfc + idx);
-    }
-}
-
 // Sum of the 4096 Gamma variates of the reference-rule root noise (key = ply * 4096 + index) with every thread of the
 // CTA, in an order that does not depend on the CTA size (the tower path runs 256 threads, the cache-hit path 128, and a
 // hit must reproduce a miss bit for bit): 256 columns, column c sums indices c, c + 256, ... in order; a butterfly over
@@ -161,13 +139,10 @@ __device__ __forceinline__ float root_noise_sum_cta(const MctsCfg& cfg, const Mc
 }
 
 // CTA per queued leaf: heads on the tower output, logits of the legal moves, then the warp-level expand/backup.
-// ROOTMIX (cfg.root_mix): a root additionally gets all 4096 logits (16 KB of shared memory) for the full softmax.
-template <bool ROOTMIX>
 __global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArrays A, const __nv_bfloat16* __restrict__ act,
                                                             HeadW H, uint32_t wave) {
     __shared__ float hp[128], hv[64], red[8], logits[MAX_MOVES];
     __shared__ __align__(16) float swh[3 * 512];
-    __shared__ float lall[ROOTMIX ? POLICY_N : 1];
     const int n_eval = (int)*A.n_eval;
     for (int slot = blockIdx.x; slot < n_eval; slot += gridDim.x) {   // grid-stride: see mcts_select_kernel
         const int gs = A.eval_game[slot];
@@ -175,17 +150,9 @@ __global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArr
         __syncthreads();
         const float v_white = kvn::value_mlp(hv, H.w1, H.b1, H.w2, H.b2, red);
         legal_logits(cfg, A, gs, H, hp, logits);
-        const bool mix = ROOTMIX && A.pend_node[gs] == 0;
-        float gsum = 0.f;
-        if (mix) {
-            all_logits(H, hp, lall);
-            if (cfg.dir_eps > 0.0f) gsum = root_noise_sum_cta(cfg, A, gs, red);
-        }
         __syncthreads();
         if (threadIdx.x < 32) {
-            float mx_all = 0.f, z_all = 0.f;
-            if (mix) full_softmax_stats_warp((int)threadIdx.x, [&](int i) { return lall[i]; }, mx_all, z_all);
-            mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, v_white, false, mx_all, z_all, gsum);
+            mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, v_white);
             if (cfg.cache_mask) cache_fill_warp((int)threadIdx.x, cfg, A, wave, slot, hp, v_white);
         }
         __syncthreads();   // hp / hv / red / logits are reused by the next leaf
@@ -193,10 +160,8 @@ __global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArr
 }
 
 // CTA (128 threads) per late entry: features from the cache (already copied per game) or from this wave's leader
-template <bool ROOTMIX>
 __global__ void __launch_bounds__(128) mcts_late_net_kernel(MctsCfg cfg, MctsArrays A, HeadW H) {
-    __shared__ float hp[FEAT], logits[MAX_MOVES], red[8];
-    __shared__ float lall[ROOTMIX ? POLICY_N : 1];
+    __shared__ float hp[FEAT], logits[MAX_MOVES];
     const int n_late = (int)*A.n_late;
     for (int li = blockIdx.x; li < n_late; li += gridDim.x) {
         const int gs = A.late_game[li], src = A.late_src[li];
@@ -204,17 +169,164 @@ __global__ void __launch_bounds__(128) mcts_late_net_kernel(MctsCfg cfg, MctsArr
         for (int i = threadIdx.x; i < FEAT; i += blockDim.x) hp[i] = f[i];
         __syncthreads();
         legal_logits(cfg, A, gs, H, hp, logits);
-        const bool mix = ROOTMIX && A.pend_node[gs] == 0;
-        float gsum = 0.f;
-        if (mix) {
-            all_logits(H, hp, lall);
-            if (cfg.dir_eps > 0.0f) gsum = root_noise_sum_cta(cfg, A, gs, red);
+        __syncthreads();
+        if (threadIdx.x < 32) mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, hp[128], true);
+        __syncthreads();
+    }
+}
+
+// ---- cfg.root_mix (the reference's prior rule, scripts/self_play.py:150-167): the root's softmax runs over ALL 4096
+// logits and its Dirichlet noise over all 4096 indices.  These variants of the two evaluator kernels take kRM leaves per
+// CTA pass, so that the 2 MB policy_fc matrix is read once per kRM leaves, and form
+//   (mx, z)  softmax statistics over the 4096 logits, ONLINE: the lane that owns a row keeps a running (max, sum) pair
+//            per leaf over its rows in order (row r0 + t/8, 32 rows per pass), the 32 owners' pairs are then combined
+//            by one warp (butterfly maximum, rescale, butterfly sum)
+//   gsum     the 4096-term Gamma sum (root_noise_sum_cta)
+// Both kernels run 256 threads and the per-leaf arithmetic does not depend on which leaves share a pass, so a root served
+// by the evaluation cache gets the very bits of a root that went through the tower.
+constexpr int kRM = 4;
+struct RootMixSmem {
+    float hp[kRM][FEAT];
+    float hv[64];
+    float logits[kRM][MAX_MOVES];
+    float pm[kRM][32], pz[kRM][32];
+    float red[8];
+    float vw[kRM], gsum[kRM], mx[kRM], z[kRM];
+    int gs[kRM];
+};
+
+__device__ __forceinline__ void rootmix_stats(const MctsCfg& cfg, const MctsArrays& A, const HeadW& H, RootMixSmem& sm, int nb) {
+    const int part = threadIdx.x & 7, own = threadIdx.x >> 3;   // 8 lanes per row, 32 rows per pass (256 threads)
+    float m[kRM], z[kRM];
+#pragma unroll
+    for (int r = 0; r < kRM; r++) {
+        m[r] = -3.0e38f;
+        z[r] = 0.f;
+    }
+    for (int r0 = 0; r0 < POLICY_N; r0 += 32) {
+        const int idx = r0 + own;
+        const float4* wr = reinterpret_cast<const float4*>(H.wfc + (size_t)idx * 128 + part * 16);
+        float4 w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = __ldg(wr + i);
+        const float bias = __ldg(H.bfc + idx);
+#pragma unroll
+        for (int r = 0; r < kRM; r++) {
+            const float* f = sm.hp[r] + part * 16;
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; i++) a += w[i].x * f[4 * i] + w[i].y * f[4 * i + 1] + w[i].z * f[4 * i + 2] + w[i].w * f[4 * i + 3];
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            const float l = a + bias;
+            if (l > m[r]) {
+                z[r] = z[r] * kvd_expf(m[r] - l) + 1.0f;
+                m[r] = l;
+            } else {
+                z[r] = z[r] + kvd_expf(l - m[r]);
+            }
+        }
+    }
+    if (part == 0) {
+#pragma unroll
+        for (int r = 0; r < kRM; r++) {
+            sm.pm[r][own] = m[r];
+            sm.pz[r][own] = z[r];
+        }
+    }
+    __syncthreads();
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (wid < nb) {   // warp r combines leaf r's 32 partial pairs
+        const float ml = sm.pm[wid][lane];
+        float M = ml;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const float o = __shfl_xor_sync(0xffffffffu, M, d);
+            M = o > M ? o : M;
+        }
+        float zz = sm.pz[wid][lane] * kvd_expf(ml - M);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) zz = zz + __shfl_xor_sync(0xffffffffu, zz, d);
+        if (lane == 0) {
+            sm.mx[wid] = M;
+            sm.z[wid] = zz;
+        }
+    }
+    for (int r = 0; r < nb; r++) {
+        const float g = cfg.dir_eps > 0.0f ? root_noise_sum_cta(cfg, A, sm.gs[r], sm.red) : 0.f;
+        if (threadIdx.x == 0) sm.gsum[r] = g;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) mcts_eval_rootmix_kernel(MctsCfg cfg, MctsArrays A, const __nv_bfloat16* __restrict__ act,
+                                                                HeadW H, uint32_t wave) {
+    __shared__ RootMixSmem sm;
+    __shared__ __align__(16) float swh[3 * 512];
+    const int n_eval = (int)*A.n_eval;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int s0 = blockIdx.x * kRM; s0 < n_eval; s0 += gridDim.x * kRM) {
+        const int nb = n_eval - s0 < kRM ? n_eval - s0 : kRM;
+        bool any_root = false;
+        for (int r = 0; r < kRM; r++) {
+            if (r < nb) {
+                const int slot = s0 + r, gs = A.eval_game[slot];
+                any_root |= A.pend_node[gs] == 0;
+                kvn::head_features(act + (size_t)slot * 64 * H.C, H.C, H.wh, H.bh, sm.hp[r], sm.hv, swh);
+                __syncthreads();
+                const float v_white = kvn::value_mlp(sm.hv, H.w1, H.b1, H.w2, H.b2, sm.red);
+                legal_logits(cfg, A, gs, H, sm.hp[r], sm.logits[r]);
+                if (threadIdx.x == 0) {
+                    sm.vw[r] = v_white;
+                    sm.gs[r] = gs;
+                }
+                __syncthreads();
+            } else {
+                for (int i = threadIdx.x; i < 128; i += blockDim.x) sm.hp[r][i] = 0.f;   // defined input for the shared pass
+            }
         }
         __syncthreads();
-        if (threadIdx.x < 32) {
-            float mx_all = 0.f, z_all = 0.f;
-            if (mix) full_softmax_stats_warp((int)threadIdx.x, [&](int i) { return lall[i]; }, mx_all, z_all);
-            mcts_expand_warp((int)threadIdx.x, cfg, A, gs, logits, hp[128], true, mx_all, z_all, gsum);
+        if (any_root) rootmix_stats(cfg, A, H, sm, nb);
+        if (wid < nb) {   // warp r finishes leaf r
+            const int gs = sm.gs[wid];
+            const bool root = A.pend_node[gs] == 0;
+            mcts_expand_warp(lane, cfg, A, gs, sm.logits[wid], sm.vw[wid], false, root ? sm.mx[wid] : 0.f, root ? sm.z[wid] : 0.f,
+                             root ? sm.gsum[wid] : 0.f);
+            if (cfg.cache_mask) cache_fill_warp(lane, cfg, A, wave, s0 + wid, sm.hp[wid], sm.vw[wid]);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) mcts_late_rootmix_kernel(MctsCfg cfg, MctsArrays A, HeadW H) {
+    __shared__ RootMixSmem sm;
+    const int n_late = (int)*A.n_late;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int l0 = blockIdx.x * kRM; l0 < n_late; l0 += gridDim.x * kRM) {
+        const int nb = n_late - l0 < kRM ? n_late - l0 : kRM;
+        bool any_root = false;
+        for (int r = 0; r < kRM; r++) {
+            if (r < nb) {
+                const int gs = A.late_game[l0 + r], src = A.late_src[l0 + r];
+                any_root |= A.pend_node[gs] == 0;
+                const float* f = src < 0 ? A.feat_game + (size_t)gs * FEAT : A.feat_slot + (size_t)src * FEAT;
+                for (int i = threadIdx.x; i < FEAT; i += blockDim.x) sm.hp[r][i] = f[i];
+                if (threadIdx.x == 0) sm.gs[r] = gs;
+                __syncthreads();
+                legal_logits(cfg, A, gs, H, sm.hp[r], sm.logits[r]);
+                if (threadIdx.x == 0) sm.vw[r] = sm.hp[r][128];
+            } else {
+                for (int i = threadIdx.x; i < 128; i += blockDim.x) sm.hp[r][i] = 0.f;
+            }
+        }
+        __syncthreads();
+        if (any_root) rootmix_stats(cfg, A, H, sm, nb);
+        if (wid < nb) {
+            const int gs = sm.gs[wid];
+            const bool root = A.pend_node[gs] == 0;
+            mcts_expand_warp(lane, cfg, A, gs, sm.logits[wid], sm.vw[wid], true, root ? sm.mx[wid] : 0.f, root ? sm.z[wid] : 0.f,
+                             root ? sm.gsum[wid] : 0.f);
         }
         __syncthreads();
     }
@@ -574,8 +686,9 @@ static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1
             if (int rc = wait_peer(m->ev_late, m->late_rec)) return rc;
         {
             KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
-            if (m->cfg.root_mix) mcts_eval_net_kernel<true><<<piped ? imin(GS, sms) : GS, 256, 0, st>>>(m->cfg, A, act, H, wave);
-            else mcts_eval_net_kernel<false><<<piped ? imin(GS, sms) : GS, 256, 0, st>>>(m->cfg, A, act, H, wave);
+            if (m->cfg.root_mix)
+                mcts_eval_rootmix_kernel<<<piped ? imin((GS + kRM - 1) / kRM, sms) : (GS + kRM - 1) / kRM, 256, 0, st>>>(m->cfg, A, act, H, wave);
+            else mcts_eval_net_kernel<<<piped ? imin(GS, sms) : GS, 256, 0, st>>>(m->cfg, A, act, H, wave);
         }
         KV_LAUNCH_CHECK(ctx);
         if (cache) {
@@ -583,8 +696,9 @@ static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1
             if (int rc = wait_peer(m->ev_eval, m->eval_rec)) return rc;
             {
                 KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
-                if (m->cfg.root_mix) mcts_late_net_kernel<true><<<piped ? imin(GS, 3 * sms) : GS, 128, 0, st>>>(m->cfg, A, H);
-                else mcts_late_net_kernel<false><<<piped ? imin(GS, 3 * sms) : GS, 128, 0, st>>>(m->cfg, A, H);
+                if (m->cfg.root_mix)
+                    mcts_late_rootmix_kernel<<<piped ? imin((GS + kRM - 1) / kRM, sms) : (GS + kRM - 1) / kRM, 256, 0, st>>>(m->cfg, A, H);
+                else mcts_late_net_kernel<<<piped ? imin(GS, 3 * sms) : GS, 128, 0, st>>>(m->cfg, A, H);
             }
             KV_LAUNCH_CHECK(ctx);
             if (int rc = mark(m->ev_late, m->late_rec)) return rc;
@@ -645,8 +759,8 @@ static int mcts_run_waves(kv_ctx* ctx, int n_waves, cudaStream_t st) {
             const int carve = want ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault;
             cudaFuncSetAttribute(mcts_select_kernel<kMW>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
             cudaFuncSetAttribute(mcts_select_kernel<kMWP>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-            cudaFuncSetAttribute(mcts_eval_net_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-            cudaFuncSetAttribute(mcts_late_net_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(mcts_eval_net_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(mcts_late_net_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
             cudaFuncSetAttribute(mcts_backup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
             cudaGetLastError();
             g_attrs_state = want;
