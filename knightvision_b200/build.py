@@ -35,7 +35,7 @@ def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = glob.glob(os.path.join(CSRC, "*")) + [os.path.join(HERE, "..", "include", "kv_b200.h")]
+    deps = glob.glob(os.path.join(CSRC, "*")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
 

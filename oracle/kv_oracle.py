@@ -16,8 +16,8 @@ _SO = os.path.join(_HERE, "libkv_oracle.so")
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "kv_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    deps = [os.path.join(_HERE, "kv_oracle.c"), os.path.join(_HERE, "..", "include", "kv_detmath.h")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(d) for d in deps):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libkv_oracle.so"])
     return _SO
 

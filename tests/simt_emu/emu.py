@@ -15,7 +15,8 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    deps = [os.path.join(HERE, "kvemu.cpp")] + glob.glob(os.path.join(ROOT, "knightvision_b200", "csrc", "*.cuh"))
+    deps = ([os.path.join(HERE, "kvemu.cpp")] + glob.glob(os.path.join(ROOT, "knightvision_b200", "csrc", "*.cuh"))
+            + glob.glob(os.path.join(ROOT, "knightvision_b200", "csrc", "*.h")) + glob.glob(os.path.join(ROOT, "include", "*.h")))
     if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
                                "-ffp-contract=off", "-fvisibility=hidden", "-o", SO,
