@@ -60,6 +60,7 @@ SIGNATURES = {
                                  ctypes.c_float, c_u64, c_int, c_int]),
     "kv_mcts_waves": (ctypes.c_int64, [c_void_p]),
     "kv_mcts_set_pipeline": (c_int, [c_void_p, c_int]),
+    "kv_mcts_set_eval_split": (c_int, [c_void_p, c_int]),
     "kv_mcts_set_resign": (c_int, [c_void_p, ctypes.c_float, c_int]),
     "kv_mcts_set_root_mix": (c_int, [c_void_p, c_int]),
     "kv_mcts_set_script": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),

@@ -159,6 +159,123 @@ __global__ void __launch_bounds__(256) mcts_eval_net_kernel(MctsCfg cfg, MctsArr
     }
 }
 
+// ---- the same evaluation as two kernels (opt-in: kv_mcts_set_eval_split(1) / KV_MCTS_EVAL_SPLIT=1) ----------------------
+// ncu at bench state (profiles/r02_ncu_mcts_kernels_bench_state.txt) shows the one-CTA-per-leaf kernel moving 257 MB of
+// last-layer activations at 1.6 TB/s and 481 MB from L2 to L1, most of it the 128 KB value-MLP matrix re-read by every
+// leaf's CTA.  Split: (1) a streaming kernel that turns a leaf's 64 x C activations into its 128 policy + 64 value
+// features (head_buf), (2) a kernel that finishes kEB leaves per CTA — the value MLP for all of them from one pass over
+// w1, then one warp per leaf for the legal logits, priors and backup.  Same expressions in the same order as the kernel
+// above: bit-identical results (tests/test_gpu_mcts.py::test_split_evaluator_matches_single_kernel).
+// Measured at bench state (4 096 games x 800 sims, tools/bench_eval_split.py): expand kernels 184 -> 165 ms per move, and
+// the tower 5 968 -> 5 990 ms — the step as a whole does not move (515.0 k vs 514.9 k sims/s): under the power cap the
+// time the tree kernels give back is taken by a lower tower clock.  Hence opt-in.
+constexpr int kEB = 8;      // leaves per CTA of the second kernel
+constexpr int HEADF = 192;  // 128 policy features + 64 value features per leaf
+
+__global__ void __launch_bounds__(256) mcts_head_kernel(MctsArrays A, const __nv_bfloat16* __restrict__ act, HeadW H,
+                                                        float* __restrict__ head_buf) {
+    __shared__ float hp[128], hv[64];
+    __shared__ __align__(16) float swh[3 * 512];
+    const int n_eval = (int)*A.n_eval;
+    for (int slot = blockIdx.x; slot < n_eval; slot += gridDim.x) {
+        kvn::head_features(act + (size_t)slot * 64 * H.C, H.C, H.wh, H.bh, hp, hv, swh);
+        __syncthreads();
+        if (threadIdx.x < HEADF)
+            head_buf[(size_t)slot * HEADF + threadIdx.x] = threadIdx.x < 128 ? hp[threadIdx.x] : hv[threadIdx.x - 128];
+        __syncthreads();
+    }
+}
+
+// legal-move logits of one leaf by ONE warp (same per-move arithmetic as legal_logits: 8 lanes x 16 features, butterfly)
+__device__ __forceinline__ void legal_logits_warp(int lane, const MctsCfg& cfg, const MctsArrays& A, int gs, const HeadW& H,
+                                                  const float* hp, float* logits) {
+    const int g = gs / cfg.inflight;
+    const NodeMeta m = A.node_meta[(size_t)g * cfg.node_cap + A.pend_node[gs]];
+    const int n = m.ne_term & 0xFFFF;
+    const size_t e0 = (size_t)g * cfg.edge_cap + m.first_edge;
+    const int part = lane & 7;
+    for (int k0 = 0; k0 < n; k0 += 4) {   // uniform trip count: the shuffles below need the whole warp
+        const int k = k0 + (lane >> 3);
+        float a = 0.f;
+        int idx = 0;
+        if (k < n) {
+            idx = move_index(A.eMv[e0 + k]);
+            const float4* wr = reinterpret_cast<const float4*>(H.wfc + (size_t)idx * 128 + part * 16);
+            const float* f = hp + part * 16;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float4 w = __ldg(wr + i);
+                a += w.x * f[4 * i] + w.y * f[4 * i + 1] + w.z * f[4 * i + 2] + w.w * f[4 * i + 3];
+            }
+        }
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (k < n && part == 0) logits[k] = a + __ldg(H.bfc + idx);
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(256) mcts_eval_batch_kernel(MctsCfg cfg, MctsArrays A, const float* __restrict__ head_buf,
+                                                              HeadW H, uint32_t wave) {
+    __shared__ float hf[kEB][HEADF], logits[kEB][MAX_MOVES], red[kEB][8], vw[kEB];
+    const int n_eval = (int)*A.n_eval;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int s0 = blockIdx.x * kEB; s0 < n_eval; s0 += gridDim.x * kEB) {
+        const int nb = n_eval - s0 < kEB ? n_eval - s0 : kEB;
+        for (int i = threadIdx.x; i < kEB * HEADF; i += blockDim.x) {
+            const int l = i / HEADF;
+            hf[l][i - l * HEADF] = l < nb ? head_buf[(size_t)(s0 + l) * HEADF + (i - l * HEADF)] : 0.f;
+        }
+        __syncthreads();
+        // value_fc1 64 -> 512 + relu, value_fc2 512 -> 1 (kv_heads.cuh value_mlp, same association), all kEB leaves per
+        // pass over the transposed w1: thread j owns units j and j + 256
+        float part[kEB];
+#pragma unroll
+        for (int l = 0; l < kEB; l++) part[l] = 0.f;
+        for (int j = threadIdx.x; j < 512; j += blockDim.x) {
+            float a[kEB];
+            const float bj = __ldg(H.b1 + j);
+#pragma unroll
+            for (int l = 0; l < kEB; l++) a[l] = bj;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const float wx = __ldg(H.w1 + (4 * i + 0) * 512 + j), wy = __ldg(H.w1 + (4 * i + 1) * 512 + j);
+                const float wz = __ldg(H.w1 + (4 * i + 2) * 512 + j), ww = __ldg(H.w1 + (4 * i + 3) * 512 + j);
+#pragma unroll
+                for (int l = 0; l < kEB; l++) {
+                    const float* hv = hf[l] + 128;
+                    a[l] += wx * hv[4 * i] + wy * hv[4 * i + 1] + wz * hv[4 * i + 2] + ww * hv[4 * i + 3];
+                }
+            }
+            const float w2j = __ldg(H.w2 + j);
+#pragma unroll
+            for (int l = 0; l < kEB; l++) part[l] += fmaxf(a[l], 0.f) * w2j;
+        }
+#pragma unroll
+        for (int l = 0; l < kEB; l++) {
+            float p = part[l];
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) p += __shfl_xor_sync(0xffffffffu, p, m);
+            if (lane == 0) red[l][wid] = p;
+        }
+        __syncthreads();
+        if (threadIdx.x < kEB) {
+            float tot = 0.f;
+            for (int w = 0; w < 8; w++) tot += red[threadIdx.x][w];
+            vw[threadIdx.x] = tanhf(tot + __ldg(H.b2));
+        }
+        __syncthreads();
+        if (wid < nb) {   // warp l finishes leaf l
+            const int slot = s0 + wid, gs = A.eval_game[slot];
+            legal_logits_warp(lane, cfg, A, gs, H, hf[wid], logits[wid]);
+            mcts_expand_warp(lane, cfg, A, gs, logits[wid], vw[wid]);
+            if (cfg.cache_mask) cache_fill_warp(lane, cfg, A, wave, slot, hf[wid], vw[wid]);
+        }
+        __syncthreads();
+    }
+}
+
 // CTA (128 threads) per late entry: features from the cache (already copied per game) or from this wave's leader
 __global__ void __launch_bounds__(128) mcts_late_net_kernel(MctsCfg cfg, MctsArrays A, HeadW H) {
     __shared__ float hp[FEAT], logits[MAX_MOVES];
@@ -437,6 +554,8 @@ struct kv_mcts {
     unsigned int* d_unfinished = nullptr;
     unsigned int* h_unfinished = nullptr;   // pinned
     long waves_run = 0;
+    float* head_buf = nullptr;   // [G*K][192] head features of the wave's evaluated leaves (split evaluator)
+    int eval_split = -1;         // -1 default (on unless KV_MCTS_EVAL_SPLIT=0), 0 one kernel per leaf, 1 split
     void* cache_mem = nullptr;
     size_t cache_slots = 0;
     // pipelined search: two game groups on two streams (see mcts_wave_group)
@@ -547,6 +666,7 @@ int kv_mcts_create_k(kv_ctx* ctx, int n_games, int sims, int edges_per_node, int
     if (dalloc(ctx, m, &A.late_src, GS)) return -1;
     if (dalloc(ctx, m, &A.feat_game, GS * FEAT)) return -1;
     if (dalloc(ctx, m, &A.feat_slot, GS * FEAT)) return -1;
+    if (eval_mode == 1 && dalloc(ctx, m, &m->head_buf, GS * HEADF)) return -1;
     if (dalloc(ctx, m, &m->d_unfinished, 4)) return -1;
     KV_CUDA(ctx, cudaMallocHost((void**)&m->h_unfinished, 16));
     A.cache = nullptr;
@@ -686,9 +806,20 @@ static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1
             if (int rc = wait_peer(m->ev_late, m->late_rec)) return rc;
         {
             KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
-            if (m->cfg.root_mix)
+            static const int split_env = [] {
+                const char* e = getenv("KV_MCTS_EVAL_SPLIT");
+                return e ? atoi(e) : 0;   // opt-in: it shortens the evaluator by 10 % and the step by nothing (power cap)
+            }();
+            const bool split = (m->eval_split >= 0 ? m->eval_split : split_env) != 0 && !piped;
+            if (m->cfg.root_mix) {
                 mcts_eval_rootmix_kernel<<<piped ? imin((GS + kRM - 1) / kRM, sms) : (GS + kRM - 1) / kRM, 256, 0, st>>>(m->cfg, A, act, H, wave);
-            else mcts_eval_net_kernel<<<piped ? imin(GS, sms) : GS, 256, 0, st>>>(m->cfg, A, act, H, wave);
+            } else if (split) {
+                float* hb = m->head_buf + (size_t)s0 * HEADF;
+                mcts_head_kernel<<<GS, 256, 0, st>>>(A, act, H, hb);
+                mcts_eval_batch_kernel<<<(GS + kEB - 1) / kEB, 256, 0, st>>>(m->cfg, A, hb, H, wave);
+            } else {
+                mcts_eval_net_kernel<<<piped ? imin(GS, sms) : GS, 256, 0, st>>>(m->cfg, A, act, H, wave);
+            }
         }
         KV_LAUNCH_CHECK(ctx);
         if (cache) {
@@ -871,6 +1002,15 @@ int kv_mcts_set_script(kv_ctx* ctx, const uint16_t* d_moves, const float* d_valu
     m->A.script_move = stride ? d_moves : nullptr;
     m->A.script_val = stride ? d_values : nullptr;
     m->cfg.script_stride = (d_moves || d_values) ? stride : 0;
+    return 0;
+}
+
+// Evaluator schedule of the tower path: 1 = head-features kernel + batched finish kernel, 0 = one kernel per leaf, -1 =
+// default (0 unless KV_MCTS_EVAL_SPLIT=1).  Bit-identical results.
+int kv_mcts_set_eval_split(kv_ctx* ctx, int mode) {
+    if (!ctx || !ctx->mcts) return kv_fail_msg(ctx, "kv_mcts_set_eval_split: no search context");
+    if (mode < -1 || mode > 1) return kv_fail_msg(ctx, "kv_mcts_set_eval_split: mode must be -1, 0 or 1");
+    ctx->mcts->eval_split = mode;
     return 0;
 }
 

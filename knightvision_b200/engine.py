@@ -302,6 +302,11 @@ class Engine:
         tower): -1 default (off unless KV_MCTS_PIPELINE=1), 0 off, 1 on.  Search results are identical either way."""
         N.check(self.ctx, self._lib.kv_mcts_set_pipeline(self.ctx, mode), "kv_mcts_set_pipeline")
 
+    def mcts_set_eval_split(self, mode: int = -1):
+        """Evaluator schedule after the tower: 0 one kernel per leaf (default), 1 head-features kernel + batched finish
+        kernel.  Results are identical either way (and so is the power-capped step time)."""
+        N.check(self.ctx, self._lib.kv_mcts_set_eval_split(self.ctx, mode), "kv_mcts_set_eval_split")
+
     def mcts_waves(self) -> int:
         """Search waves launched since mcts_create (with K > 1 a move takes a data-dependent number of waves)."""
         return int(self._lib.kv_mcts_waves(self.ctx))

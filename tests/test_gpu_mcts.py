@@ -450,3 +450,34 @@ def test_run_move_reports_exhausted_wave_budget(eng):
     eng.mcts_reset(None, 0)
     eng.mcts_run_move()                 # the normal case completes
     assert eng.mcts_status()["plies"] == 4
+
+
+def test_split_evaluator_matches_single_kernel(eng):
+    """The two-kernel evaluator (head features, then eight leaves per CTA with a batched value MLP) gives the same games,
+    visit counts, W and prior bits as the one-CTA-per-leaf kernel, with and without the evaluation cache."""
+    from knightvision_b200.model import ChessNet
+    torch.manual_seed(0)
+    ChessNet().eval().attach(eng, max_batch=256)
+    G, sims, moves = 173, 40, 4           # not a multiple of 8: a partly filled last CTA
+    out = {}
+    for split in (0, 1):
+        for log2 in (0, 16):
+            eng.mcts_create(G, sims, max_plies=moves, temp_plies=4, seed=13, eval_mode=1)
+            eng.mcts_set_eval_split(split)
+            eng.mcts_enable_cache(log2)
+            eng.mcts_reset(None, game_id_base=50)
+            for i in range(moves):
+                eng.mcts_run_sims(sims)
+                if i == moves - 1:
+                    roots = [eng.mcts_read_root(g) for g in (0, G // 2, G - 1)]
+                eng.mcts_finish_move()
+            out[(split, log2)] = (tuple(t.cpu().numpy() for t in eng.mcts_records()), roots)
+    base_rec, base_roots = out[(0, 0)]
+    for key, (rec, roots) in out.items():
+        for a, b in zip(base_rec, rec):
+            assert np.array_equal(a, b), key
+        for ra, rb in zip(base_roots, roots):
+            assert np.array_equal(ra["N"], rb["N"]) and np.array_equal(_bits(ra["W"]), _bits(rb["W"])), key
+            assert np.array_equal(_bits(ra["P"]), _bits(rb["P"])), key
+    eng.mcts_enable_cache(0)
+    eng.mcts_set_eval_split(-1)
