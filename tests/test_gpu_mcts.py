@@ -481,3 +481,32 @@ def test_split_evaluator_matches_single_kernel(eng):
             assert np.array_equal(_bits(ra["P"]), _bits(rb["P"])), key
     eng.mcts_enable_cache(0)
     eng.mcts_set_eval_split(-1)
+
+
+def test_full_size_move_4096_games_800_sims_cache_transparent(eng):
+    """BASELINE config 3 at full size: one move of 4 096 games x 800 simulations from random positions, with the
+    evaluation cache and without it — the same moves for every game (argmax of the visit counts), every game played
+    exactly one ply, no edge-pool overflow, and simulations = games x 800 on the device's counters."""
+    from knightvision_b200.model import ChessNet
+    torch.manual_seed(0)
+    ChessNet().eval().attach(eng, max_batch=4096)
+    G, sims = 4096, 800
+    eng.mcts_create(G, sims, max_plies=8, temp_plies=0, seed=3, eval_mode=1)
+    start = eng.random_positions(G, 40, 99)
+    moves = {}
+    for log2 in (22, 0):
+        eng.mcts_enable_cache(log2)
+        eng.mcts_reset(start, 0)
+        eng.mcts_run_sims(sims)
+        st = eng.mcts_status()
+        assert st["sims_in_move"] == G * sims and st["overflow"] == 0
+        assert st["evals"] + st["cache_hits"] <= G * sims and (st["cache_hits"] > 0) == (log2 > 0)
+        r = eng.mcts_read_root(G - 1)
+        assert int(r["N"].sum()) == sims - 1
+        eng.mcts_finish_move()
+        assert eng.mcts_status()["plies"] == G
+        lines, move, reward, game = eng.mcts_records()
+        assert game.cpu().tolist() == list(range(G))
+        moves[log2] = move.cpu().numpy()
+    assert np.array_equal(moves[22], moves[0])
+    eng.mcts_enable_cache(0)
