@@ -136,3 +136,17 @@ def test_gpu_game_loop_matches_reference_games():
             assert np.array_equal(planes, O.encode(lines[sel]))
         eng.mcts_set_script(None, None)
     eng.close()
+
+
+def test_decisive_filter_on_packed_device_records_matches_reference():
+    """learn.reinforcement_loop filters the packed records (scripts/learn.py:186 -> generate_self_play_data): same rule."""
+    import torch
+    from knightvision_b200.selfplay import filter_decisive_device
+    for f in cases()["decisive_filter"]:
+        n = len(f["rewards"])
+        lines = torch.arange(n * 16, dtype=torch.int64).reshape(n, 16)
+        move = torch.arange(n, dtype=torch.int32)
+        reward = torch.tensor(f["rewards"], dtype=torch.float32)
+        l2, m2, r2 = filter_decisive_device(lines, move, reward)
+        assert m2.tolist() == f["kept"] and l2[:, 0].tolist() == [16 * k for k in f["kept"]]
+        assert r2.tolist() == [pytest.approx(f["rewards"][k]) for k in f["kept"]]
