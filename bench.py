@@ -347,7 +347,7 @@ def rules_record(args, eng, rank, world, steps):
                                "kv_movegen over all of them per step; kv_make_moves plays the first legal move of each",
                    "avg_legal_moves": avg_moves, "l2": "board lines + move lists (671 MB) exceed the 126 MB L2"},
         "ms_per_step": mg_ms / steps,
-        "roofline": {"kernel": "movegen_kernel (warp per board)", "bound": "hbm", "achieved": mg_gbs, "peak": peaks["hbm"],
+        "roofline": {"kernel": "movegen_kernel (8 lanes per board, four boards per warp)", "bound": "hbm", "achieved": mg_gbs, "peak": peaks["hbm"],
                      "unit": "GB/s", "frac": mg_gbs / peaks["hbm"], "traffic": (ncu or {}).get("movegen_dram_bytes"),
                      "peak_source": peaks["source"], "issue_active_pct": (ncu or {}).get("movegen_issue_pct"),
                      "ncu_source": (ncu or {}).get("source"),
