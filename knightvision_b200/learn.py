@@ -133,7 +133,9 @@ def training_graph(net: ChessNet, engine):
         return cached[1]
     graph = TrainGraph(net, engine=engine if native else None)
     if _ddp_active():
-        graph = nn.parallel.DistributedDataParallel(graph, device_ids=[engine.index], gradient_as_bucket_view=True,
+        on_gpu = next(net.parameters()).is_cuda
+        graph = nn.parallel.DistributedDataParallel(graph, device_ids=[engine.index] if on_gpu else None,
+                                                    gradient_as_bucket_view=True,
                                                     bucket_cap_mb=int(os.getenv("KV_DDP_BUCKET_MB", "25")))
         if os.getenv("KV_DDP_GRAD_BF16", "0") != "0":
             from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
@@ -165,7 +167,7 @@ def train_epochs(net: ChessNet, optimizer, data: ReplayData, epochs: int, batch_
         for i, (boards, moves, outcomes) in enumerate(batches):
             stepping = (i + 1) % accumulate_steps == 0 or i == len(batches) - 1
             with (graph.no_sync() if ddp and not stepping else contextlib.nullcontext()):
-                with torch.autocast("cuda", dtype=torch.bfloat16):
+                with torch.autocast(boards.device.type, dtype=torch.bfloat16, enabled=boards.is_cuda):
                     pol, val = graph(boards)
                 pol = pol.float()
                 loss_policy = F.cross_entropy(pol, moves)
