@@ -1,7 +1,8 @@
 // kv_rules.cu — rules kernels (move generation, make-move, perft, encode) and their C-ABI entry points.
 //
-// All kernels are warp-per-board over the 128-byte board line: one coalesced 128 B request per board,
-// attack tables (5.5 KB) staged once per CTA in shared memory, per-warp move buffers in shared memory.
+// The rules kernels give 8 lanes to a board (four boards per warp, kv_rules.cuh): the 128-byte board line is two
+// coalesced 64 B requests per board (lane q keeps words q and q + 8), attack tables (5.5 KB) are staged once per CTA
+// in shared memory, every board in flight has its own move buffer in shared memory.
 // They are integer/bit kernels: HBM traffic is ~170 B per board, so they are bounded by issue rate,
 // not bandwidth (DESIGN.md §kernels gives both figures).
 #include <cstring>

@@ -1,4 +1,4 @@
-// kv_warp.cuh — warp-collective wrappers used by the warp-per-board kernels.
+// kv_warp.cuh — warp-collective wrappers (full warp and W-lane groups) used by the rules and tree-search kernels.
 //
 // On the device these are the sm_100a intrinsics.  When KV_HOST_EMU is defined (tests/simt_emu only —
 // a CI harness that runs the *kernel source* lane-by-lane on the CPU so the integer kernels can be

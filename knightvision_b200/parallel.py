@@ -1,8 +1,10 @@
 """Multi-GPU plumbing for self-play: one process per GPU, `torch.distributed` (NCCL over NVLink 5 / NVSwitch on the
 GPU box, gloo in CPU tests).  Games are independent, so the simulation path has NO collective: rank r owns the game
 ids [r*G, (r+1)*G).  Collectives appear exactly twice per generation:
-  broadcast_weights   the fp32 state_dict blob (101.6 MB for the reference net) from the trainer rank into every
-                      rank's device staging buffer; each rank then folds BN / converts to bf16 on its own GPU
+  broadcast_weights   a weight blob from the trainer rank into every rank's device buffer: either the FOLDED blob the
+                      kernels read (Engine.net_folded_tensor(): tower bf16 with BatchNorm folded, 49.6 MB for the reference
+                      net; receivers call net_adopt_folded(), no fold there — what bench.py times), or the fp32 state_dict
+                      blob (Engine.net_blob_tensor(), 101.6 MB; every rank then folds with net_commit())
   gather_records      variable-length gather of packed records (96 B bitboards + move + reward per position)
 The reference's only multi-GPU construct is nn.DataParallel (ai/model_utils.py:26-28); this replaces it.
 """
