@@ -152,7 +152,8 @@ def cpu_baseline(sims, budget_s=15.0, start_lines=None):
                        f"({done_s} simulations, {done_e} network evaluations, {t:.1f} s): sequential oracle "
                        f"(oracle/kv_oracle.c) + the reference net graph in fp32 on torch CPU kernels, {arm.threads} threads, "
                        "leaves of a wave batched, positions evaluated once"),
-            "net_evals_per_s": done_e / t, "evals_per_sim": done_e / done_s if done_s else None}
+            "net_evals_per_s": done_e / t, "evals_per_sim": done_e / done_s if done_s else None,
+            "value_per_core": done_s / t / max(arm.threads, 1)}
 
 
 def run_reference(args):
@@ -176,7 +177,9 @@ def run_reference(args):
                        f"search ({tot_s} simulations, {tot_e} network evaluations in {tot_t:.1f} s): sequential oracle "
                        f"(oracle/kv_oracle.c) + the reference net graph in fp32 on torch CPU kernels, {arm.threads} threads, "
                        "leaves of a wave batched, positions evaluated once"),
-            "net_evals_per_s": tot_e / tot_t, "evals_per_sim": tot_e / tot_s if tot_s else None}
+            "net_evals_per_s": tot_e / tot_t, "evals_per_sim": tot_e / tot_s if tot_s else None,
+            "value_per_core": value / max(arm.threads, 1),
+            "note": "uses every host core of the box it runs on: boxes with more GPUs have more cores, so compare per core"}
     line = {"impl": "reference", "metric": "mcts_sims_per_s", "value": value, "unit": "sims/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
