@@ -99,18 +99,29 @@ KVD_FN uint32_t kvd_rand24(uint64_t seed, uint64_t a, uint64_t b, uint64_t c) {
     h = kvd_mix64(h + c * 0xE7037ED1A0B428DBull);
     return (uint32_t)(h >> 40);
 }
+/* 48 uniform bits from one hash (two 24-bit uniforms per call) */
+KVD_FN uint64_t kvd_rand48(uint64_t seed, uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t h = kvd_mix64(seed ^ 0x9E3779B97F4A7C15ull);
+    h = kvd_mix64(h + a * 0xD6E8FEB86659FD93ull);
+    h = kvd_mix64(h + b * 0xA0761D6478BD642Full);
+    h = kvd_mix64(h + c * 0xE7037ED1A0B428DBull);
+    return h >> 16;
+}
 /* uniform in (0,1): (bits + 0.5) / 2^24, exact in fp32 */
 KVD_FN float kvd_u01(uint32_t bits24) { return ((float)bits24 + 0.5f) * 5.9604644775390625e-8f; }
 
-/* Gamma(alpha, 1) for 0 < alpha < 1, Ahrens-Dieter GS rejection, at most 24 rounds (counter c = 2*round, +1) */
+/* Gamma(alpha, 1) for 0 < alpha < 1, Ahrens-Dieter GS rejection, at most 24 rounds; both uniforms of a round come from
+ * one hash (counter c = round): the hash is most of the cost, and the reference-rule root noise draws 4096 variates per
+ * position */
 KVD_FN float kvd_gamma_small(float alpha, uint64_t seed, uint64_t a, uint64_t b) {
     const float e = 2.718281828459045f;
     const float bb = (e + alpha) / e;
     const float inv_alpha = 1.0f / alpha;
     float x = 0.5f;
     for (int round = 0; round < 24; round++) {
-        float u1 = kvd_u01(kvd_rand24(seed, a, b, (uint64_t)(2 * round)));
-        float u2 = kvd_u01(kvd_rand24(seed, a, b, (uint64_t)(2 * round + 1)));
+        const uint64_t r48 = kvd_rand48(seed, a, b, (uint64_t)round);
+        float u1 = kvd_u01((uint32_t)(r48 >> 24));
+        float u2 = kvd_u01((uint32_t)(r48 & 0xFFFFFFu));
         float p = bb * u1;
         if (p <= 1.0f) {
             x = kvd_expf(kvd_logf(p) * inv_alpha);

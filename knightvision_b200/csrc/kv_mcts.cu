@@ -295,92 +295,111 @@ __global__ void __launch_bounds__(128) mcts_late_net_kernel(MctsCfg cfg, MctsArr
 // ---- cfg.root_mix (the reference's prior rule, scripts/self_play.py:150-167): the root's softmax runs over ALL 4096
 // logits and its Dirichlet noise over all 4096 indices.  These variants of the two evaluator kernels take kRM leaves per
 // CTA pass, so that the 2 MB policy_fc matrix is read once per kRM leaves, and form
-//   (mx, z)  softmax statistics over the 4096 logits, ONLINE: the lane that owns a row keeps a running (max, sum) pair
-//            per leaf over its rows in order (row r0 + t/8, 32 rows per pass), the 32 owners' pairs are then combined
-//            by one warp (butterfly maximum, rescale, butterfly sum)
+//   (mx, z)  softmax statistics over the 4096 logits: the logits of the kRM leaves go to shared memory (64 KB, dynamic),
+//            then two warps per leaf form the maximum and the sum of exponentials (lane-strided, butterfly, halves in order)
 //   gsum     the 4096-term Gamma sum (root_noise_sum_cta)
 // Both kernels run 256 threads and the per-leaf arithmetic does not depend on which leaves share a pass, so a root served
 // by the evaluation cache gets the very bits of a root that went through the tower.
 constexpr int kRM = 4;
+constexpr int kRootMixDyn = kRM * POLICY_N * (int)sizeof(float);   // dynamic shared memory of the two kernels (64 KB)
 struct RootMixSmem {
     float hp[kRM][FEAT];
     float hv[64];
     float logits[kRM][MAX_MOVES];
-    float pm[kRM][32], pz[kRM][32];
+    float pm[kRM][2], pz[kRM][2];
     float red[8];
     float vw[kRM], gsum[kRM], mx[kRM], z[kRM];
     int gs[kRM];
 };
 
-__device__ __forceinline__ void rootmix_stats(const MctsCfg& cfg, const MctsArrays& A, const HeadW& H, RootMixSmem& sm, int nb) {
+// lall: kRM x 4096 floats of dynamic shared memory (64 KB)
+__device__ __forceinline__ void rootmix_stats(const MctsCfg& cfg, const MctsArrays& A, const HeadW& H, RootMixSmem& sm, int nb,
+                                              float* lall) {
     const int part = threadIdx.x & 7, own = threadIdx.x >> 3;   // 8 lanes per row, 32 rows per pass (256 threads)
-    float m[kRM], z[kRM];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // all 4096 logits of the kRM leaves: every policy_fc row is loaded once and used kRM times (fused multiply-adds: these
+    // values only feed the softmax statistics, which no CPU code has to reproduce)
+    // every CTA starts at its own row block (the logits are stored by index, so the order does not matter): otherwise
+    // the ~300 resident CTAs walk the same 2 MB matrix in lock step and queue up on the same L2 lines; the next block's
+    // weights are requested before the current block is used
+    // the lane's 16 features of every leaf live in registers for the whole pass (read from shared memory inside the loop
+    // they cost a 4-way bank conflict per load: eight 64-byte-strided addresses per warp fall into two bank groups)
+    float f[kRM][16];
 #pragma unroll
-    for (int r = 0; r < kRM; r++) {
-        m[r] = -3.0e38f;
-        z[r] = 0.f;
+    for (int r = 0; r < kRM; r++)
+#pragma unroll
+        for (int j = 0; j < 16; j++) f[r][j] = sm.hp[r][part * 16 + j];
+    const int start = (int)((blockIdx.x * 416u) & (POLICY_N - 1)) & ~31;
+    float4 wn[4];
+    {
+        const float4* wr = reinterpret_cast<const float4*>(H.wfc + (size_t)(start + own) * 128 + part * 16);
+#pragma unroll
+        for (int i = 0; i < 4; i++) wn[i] = __ldg(wr + i);
     }
-    for (int r0 = 0; r0 < POLICY_N; r0 += 32) {
-        const int idx = r0 + own;
-        const float4* wr = reinterpret_cast<const float4*>(H.wfc + (size_t)idx * 128 + part * 16);
+    for (int rr = 0; rr < POLICY_N; rr += 32) {
+        const int idx = ((start + rr) & (POLICY_N - 1)) + own;
         float4 w[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) w[i] = __ldg(wr + i);
+        for (int i = 0; i < 4; i++) w[i] = wn[i];
+        if (rr + 32 < POLICY_N) {
+            const int nidx = ((start + rr + 32) & (POLICY_N - 1)) + own;
+            const float4* wr = reinterpret_cast<const float4*>(H.wfc + (size_t)nidx * 128 + part * 16);
+#pragma unroll
+            for (int i = 0; i < 4; i++) wn[i] = __ldg(wr + i);
+        }
         const float bias = __ldg(H.bfc + idx);
 #pragma unroll
         for (int r = 0; r < kRM; r++) {
-            const float* f = sm.hp[r] + part * 16;
             float a = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; i++) a += w[i].x * f[4 * i] + w[i].y * f[4 * i + 1] + w[i].z * f[4 * i + 2] + w[i].w * f[4 * i + 3];
+            for (int i = 0; i < 4; i++) {
+                a = fmaf(w[i].x, f[r][4 * i], a);
+                a = fmaf(w[i].y, f[r][4 * i + 1], a);
+                a = fmaf(w[i].z, f[r][4 * i + 2], a);
+                a = fmaf(w[i].w, f[r][4 * i + 3], a);
+            }
             a += __shfl_xor_sync(0xffffffffu, a, 1);
             a += __shfl_xor_sync(0xffffffffu, a, 2);
             a += __shfl_xor_sync(0xffffffffu, a, 4);
-            const float l = a + bias;
-            if (l > m[r]) {
-                z[r] = z[r] * kvd_expf(m[r] - l) + 1.0f;
-                m[r] = l;
-            } else {
-                z[r] = z[r] + kvd_expf(l - m[r]);
-            }
-        }
-    }
-    if (part == 0) {
-#pragma unroll
-        for (int r = 0; r < kRM; r++) {
-            sm.pm[r][own] = m[r];
-            sm.pz[r][own] = z[r];
+            if (part == 0) lall[r * POLICY_N + idx] = a + bias;
         }
     }
     __syncthreads();
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (wid < nb) {   // warp r combines leaf r's 32 partial pairs
-        const float ml = sm.pm[wid][lane];
-        float M = ml;
+    // statistics: warp w takes half h = w / 4 of leaf r = w % 4 (lane-strided, butterfly), the two halves combined in order
+    const int r = wid & 3, hbase = (wid >> 2) * (POLICY_N / 2);
+    const float* lr = lall + r * POLICY_N + hbase;
+    float m = -3.0e38f;
+    for (int i = lane; i < POLICY_N / 2; i += 32) m = lr[i] > m ? lr[i] : m;
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) {
-            const float o = __shfl_xor_sync(0xffffffffu, M, d);
-            M = o > M ? o : M;
-        }
-        float zz = sm.pz[wid][lane] * kvd_expf(ml - M);
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) zz = zz + __shfl_xor_sync(0xffffffffu, zz, d);
-        if (lane == 0) {
-            sm.mx[wid] = M;
-            sm.z[wid] = zz;
-        }
+    for (int d = 16; d >= 1; d >>= 1) {
+        const float o = __shfl_xor_sync(0xffffffffu, m, d);
+        m = o > m ? o : m;
     }
-    for (int r = 0; r < nb; r++) {
-        const float g = cfg.dir_eps > 0.0f ? root_noise_sum_cta(cfg, A, sm.gs[r], sm.red) : 0.f;
-        if (threadIdx.x == 0) sm.gsum[r] = g;
+    if (lane == 0) sm.pm[r][wid >> 2] = m;
+    __syncthreads();
+    const float M = sm.pm[r][0] > sm.pm[r][1] ? sm.pm[r][0] : sm.pm[r][1];
+    float z = 0.f;
+    for (int i = lane; i < POLICY_N / 2; i += 32) z = z + kvd_expf(lr[i] - M);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) z = z + __shfl_xor_sync(0xffffffffu, z, d);
+    if (lane == 0) sm.pz[r][wid >> 2] = z;
+    __syncthreads();
+    if (threadIdx.x < kRM) {
+        sm.mx[threadIdx.x] = sm.pm[threadIdx.x][0] > sm.pm[threadIdx.x][1] ? sm.pm[threadIdx.x][0] : sm.pm[threadIdx.x][1];
+        sm.z[threadIdx.x] = sm.pz[threadIdx.x][0] + sm.pz[threadIdx.x][1];
+    }
+    for (int rr = 0; rr < nb; rr++) {
+        const float g = cfg.dir_eps > 0.0f ? root_noise_sum_cta(cfg, A, sm.gs[rr], sm.red) : 0.f;
+        if (threadIdx.x == 0) sm.gsum[rr] = g;
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) mcts_eval_rootmix_kernel(MctsCfg cfg, MctsArrays A, const __nv_bfloat16* __restrict__ act,
+__global__ void __launch_bounds__(256, 2) mcts_eval_rootmix_kernel(MctsCfg cfg, MctsArrays A, const __nv_bfloat16* __restrict__ act,
                                                                 HeadW H, uint32_t wave) {
     __shared__ RootMixSmem sm;
     __shared__ __align__(16) float swh[3 * 512];
+    extern __shared__ float lall_dyn[];
     const int n_eval = (int)*A.n_eval;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int s0 = blockIdx.x * kRM; s0 < n_eval; s0 += gridDim.x * kRM) {
@@ -404,7 +423,7 @@ __global__ void __launch_bounds__(256) mcts_eval_rootmix_kernel(MctsCfg cfg, Mct
             }
         }
         __syncthreads();
-        if (any_root) rootmix_stats(cfg, A, H, sm, nb);
+        if (any_root) rootmix_stats(cfg, A, H, sm, nb, lall_dyn);
         if (wid < nb) {   // warp r finishes leaf r
             const int gs = sm.gs[wid];
             const bool root = A.pend_node[gs] == 0;
@@ -416,8 +435,9 @@ __global__ void __launch_bounds__(256) mcts_eval_rootmix_kernel(MctsCfg cfg, Mct
     }
 }
 
-__global__ void __launch_bounds__(256) mcts_late_rootmix_kernel(MctsCfg cfg, MctsArrays A, HeadW H) {
+__global__ void __launch_bounds__(256, 2) mcts_late_rootmix_kernel(MctsCfg cfg, MctsArrays A, HeadW H) {
     __shared__ RootMixSmem sm;
+    extern __shared__ float lall_dyn[];
     const int n_late = (int)*A.n_late;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int l0 = blockIdx.x * kRM; l0 < n_late; l0 += gridDim.x * kRM) {
@@ -438,7 +458,7 @@ __global__ void __launch_bounds__(256) mcts_late_rootmix_kernel(MctsCfg cfg, Mct
             }
         }
         __syncthreads();
-        if (any_root) rootmix_stats(cfg, A, H, sm, nb);
+        if (any_root) rootmix_stats(cfg, A, H, sm, nb, lall_dyn);
         if (wid < nb) {
             const int gs = sm.gs[wid];
             const bool root = A.pend_node[gs] == 0;
@@ -812,7 +832,7 @@ static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1
             }();
             const bool split = (m->eval_split >= 0 ? m->eval_split : split_env) != 0 && !piped;
             if (m->cfg.root_mix) {
-                mcts_eval_rootmix_kernel<<<piped ? imin((GS + kRM - 1) / kRM, sms) : (GS + kRM - 1) / kRM, 256, 0, st>>>(m->cfg, A, act, H, wave);
+                mcts_eval_rootmix_kernel<<<piped ? imin((GS + kRM - 1) / kRM, sms) : (GS + kRM - 1) / kRM, 256, kRootMixDyn, st>>>(m->cfg, A, act, H, wave);
             } else if (split) {
                 float* hb = m->head_buf + (size_t)s0 * HEADF;
                 mcts_head_kernel<<<GS, 256, 0, st>>>(A, act, H, hb);
@@ -828,7 +848,7 @@ static int mcts_wave_group(kv_ctx* ctx, cudaStream_t st, int grp, int g0, int g1
             {
                 KvTimed t_(ctx, KVK_MCTS_EXPAND, st);
                 if (m->cfg.root_mix)
-                    mcts_late_rootmix_kernel<<<piped ? imin((GS + kRM - 1) / kRM, sms) : (GS + kRM - 1) / kRM, 256, 0, st>>>(m->cfg, A, H);
+                    mcts_late_rootmix_kernel<<<piped ? imin((GS + kRM - 1) / kRM, sms) : (GS + kRM - 1) / kRM, 256, kRootMixDyn, st>>>(m->cfg, A, H);
                 else mcts_late_net_kernel<<<piped ? imin(GS, 3 * sms) : GS, 128, 0, st>>>(m->cfg, A, H);
             }
             KV_LAUNCH_CHECK(ctx);
@@ -893,6 +913,8 @@ static int mcts_run_waves(kv_ctx* ctx, int n_waves, cudaStream_t st) {
             cudaFuncSetAttribute(mcts_eval_net_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
             cudaFuncSetAttribute(mcts_late_net_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
             cudaFuncSetAttribute(mcts_backup_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(mcts_eval_rootmix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRootMixDyn);
+            cudaFuncSetAttribute(mcts_late_rootmix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRootMixDyn);
             cudaGetLastError();
             g_attrs_state = want;
         }
