@@ -326,13 +326,12 @@ def run(args, rank, world, local_rank):
     tt = time.perf_counter()
     rec, d2h = 0, 0
     if rank == 0:
+        from knightvision_b200.selfplay import records_to_tuples
         gl, gm, gr, gg = got
-        planes = eng.encode(gl.contiguous()).cpu().numpy()          # D2H: the reference's float planes
-        gm_h, gr_h = gm.cpu().numpy(), gr.cpu().numpy()
-        recs = [(planes[i], int(gm_h[i]), float(gr_h[i])) for i in range(len(gm_h))]
+        recs = records_to_tuples(eng, gl, gm, gr)                   # D2H: the reference's float planes + move + reward
         rec = len(recs)
-        d2h = planes.nbytes + gm_h.nbytes + gr_h.nbytes
-        del recs, planes
+        d2h = rec * (12 * 64 * 4 + 4 + 4)
+        del recs
     torch.cuda.synchronize()
     tuples_ms = (time.perf_counter() - tt) * 1e3
     e2e_s = time.perf_counter() - t0

@@ -114,10 +114,14 @@ class SelfPlay:
         lines, move, reward, game = self.eng.mcts_records()
         if lines.shape[0] == 0:
             return []
-        planes = self.eng.encode(lines).cpu().numpy()
-        mv = move.cpu().numpy()
-        rw = reward.cpu().numpy()
-        return [(planes[i], int(mv[i]), float(rw[i])) for i in range(len(mv))]
+        return records_to_tuples(self.eng, lines, move, reward)
+
+
+def records_to_tuples(eng, lines, move, reward):
+    """Packed device records -> the reference's list of (np.float32 (12,8,8), int, float) tuples (scripts/self_play.py:253):
+    planes by the encode kernel, one device-to-host copy per field, the tuples zipped from views of the host arrays."""
+    planes = eng.encode(lines.contiguous()).cpu().numpy()
+    return list(zip(planes, move.cpu().tolist(), reward.cpu().tolist()))
 
 
 def self_play(model, num_games, device, max_moves=None, model_path=None):
